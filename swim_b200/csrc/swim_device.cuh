@@ -1,0 +1,629 @@
+// swim_device.cuh — sm_100a device code of the SWIM bulk simulator.
+//
+// One simulated node == one `Store` (reference Types.hs:53-60). Per round every node runs
+//   tick  : suspicion countdown (Core.hs:141 FIXME) + kRandomMembers/shuffle target and
+//           proxy selection (Core.hs:69-74, Util.hs:36-42) + probeNode' (Core.hs:243-269)
+//           + piggyback send (Core.hs:127-138)
+//   recv  : process / suspectOrDeadNode' / aliveNode (Core.hs:89-121,142-218)
+//
+// Mapping to the hardware (integer / indexing work, HBM+L2 bound, no tensor cores):
+//   * a warp owns 32 consecutive nodes. Phase A is lane-per-node: each lane streams its
+//     node's packed state row with 128-bit loads (a warp reads 1 KB contiguous), builds the
+//     alive bitmask with SWAR, draws with Philox4x32-10 and picks the r-th alive slot.
+//   * nodes that have work beyond the read-only probe (timer expiry, failed probe,
+//     non-empty piggyback buffer, mail) are found with __ballot_sync and handled
+//     warp-per-node: lane s owns view slot s, the piggyback buffer is staged in shared
+//     memory, membership lookups are a ballot over the id row.
+//   * mail is delivered without atomics or sorting: the sender raises a byte flag on the
+//     static in-edge (i -> j) of the receiver's sorted in-list; the receiver walks its
+//     flags in ascending sender order and pulls the sender's snapshot.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/swim.h"
+
+namespace swim {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// Philox counter purposes
+enum : uint32_t { P_SELECT = 0, P_LOSS = 1, P_SCALAR = 2, P_TOPO = 3 };
+
+struct SimDev {
+  uint32_t N, first, n, cap;
+  uint32_t k, fanout, B, S, T, loss_ppm;
+  uint32_t key0, key1;
+  uint32_t round;
+  uint32_t world, rank, per; // per = nodes per shard
+  uint8_t *alive;            // [N]
+  uint32_t *self_inc;        // [n]
+  uint32_t *seqno;           // [n]
+  uint32_t *nbr;             // [n*cap]
+  uint8_t *vst;              // [n*cap] liveness | timer<<2
+  uint32_t *vinc;            // [n*cap]
+  uint32_t *vlast;           // [n*cap]
+  uint4 *pb;                 // [n*B] {member, inc, from, kind | ttl<<8}
+  uint8_t *pb_cnt;           // [n]
+  uint4 *out;                // [n*B] snapshot sent this round
+  uint8_t *out_cnt;          // [n]
+  uint32_t *ridx;            // [n*cap] index of edge (i,s) in the receiver's in-list
+  uint32_t *in_off;          // [n+1]
+  uint32_t *in_src;          // [E] sender ids, ascending per receiver
+  uint8_t *eflag;            // [E] 1 = sender mailed this round
+  uint8_t *mail;             // [n] receiver has mail
+  uint32_t *any_mail;        // [2] round-parity "somebody sent" flag
+  unsigned long long *ctr;   // [SWIM_CTR__COUNT]
+};
+
+// ------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ uint32_t word_of(uint4 v, int i) {
+  return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+// randomR (0, L-1) (Util.hs:40) on the Philox stream
+__device__ __forceinline__ uint32_t bounded(uint32_t x, uint32_t L) { return __umulhi(x, L); }
+
+// position of the r-th (0-based) set bit of m; requires r < popc(m)
+__device__ __forceinline__ uint32_t nth_set(uint32_t m, uint32_t r) {
+  uint32_t pos = 0, c;
+  c = __popc(m & 0xFFFFu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
+  c = __popc(m & 0xFFu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
+  c = __popc(m & 0xFu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
+  c = __popc(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
+  if (r >= (m & 1u)) pos += 1;
+  return pos;
+}
+
+// `shuffle` (Util.hs:36-42) on a W-word bitmask of candidate slots: pick the r-th remaining
+// candidate in ascending slot order and remove it (order preserved by construction).
+template <int W>
+__device__ __forceinline__ uint32_t pick_remove(uint32_t (&m)[W], uint32_t r) {
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    uint32_t c = __popc(m[w]);
+    if (r < c) {
+      uint32_t b = nth_set(m[w], r);
+      m[w] &= ~(1u << b);
+      return w * 32 + b;
+    }
+    r -= c;
+  }
+  return 0; // unreachable when r < total
+}
+
+// ------------------------------------------------------------------ records
+__device__ __forceinline__ uint4 make_rec(uint32_t member, uint32_t inc, uint32_t from, uint32_t kind) {
+  return make_uint4(member, inc, from, kind);
+}
+__device__ __forceinline__ uint32_t rec_kind(uint4 r) { return r.w & 0xFFu; }
+__device__ __forceinline__ uint32_t rec_ttl(uint4 r) { return (r.w >> 8) & 0xFFu; }
+
+// Warp-cooperative piggyback buffer in shared memory: lane q < cnt owns record q, newest
+// first. This is the `Broadcast` branch of disseminate (Core.hs:131) that the reference
+// leaves as `enqueue _msg = return ()` (Core.hs:136-138).
+struct PbStage {
+  uint4 *s;     // shared memory, 32 entries for this warp
+  uint32_t cnt; // uniform across the warp
+  bool dirty;
+};
+
+__device__ __forceinline__ void pb_load(PbStage &p, const SimDev &d, uint32_t l, int lane) {
+  p.cnt = d.pb_cnt[l];
+  p.dirty = false;
+  __syncwarp();
+  if ((uint32_t)lane < p.cnt) p.s[lane] = d.pb[(size_t)l * d.B + lane];
+  __syncwarp();
+}
+
+__device__ __forceinline__ void pb_store(PbStage &p, const SimDev &d, uint32_t l, int lane) {
+  if (!p.dirty) return;
+  __syncwarp();
+  if ((uint32_t)lane < p.cnt) d.pb[(size_t)l * d.B + lane] = p.s[lane];
+  if (lane == 0) d.pb_cnt[l] = (uint8_t)p.cnt;
+}
+
+__device__ __forceinline__ void pb_enqueue(PbStage &p, const SimDev &d, uint4 rec, int lane,
+                                           uint32_t &dropped) {
+  rec.w = (rec.w & 0xFFu) | (d.T << 8);
+  uint4 mine = make_uint4(0, 0, 0, 0);
+  bool have = (uint32_t)lane < p.cnt;
+  if (have) mine = p.s[lane];
+  unsigned same = __ballot_sync(kFull, have && mine.x == rec.x);
+  uint32_t pos = same ? (uint32_t)(__ffs(same) - 1) : p.cnt; // slot that disappears
+  uint32_t ncnt = same ? p.cnt : p.cnt + 1;
+  if (!same && p.cnt == d.B) { pos = d.B - 1; ncnt = d.B; if (lane == 0) ++dropped; }
+  __syncwarp();
+  if (have && (uint32_t)lane < pos) p.s[lane + 1] = mine; // shift older records down
+  if (lane == 0) p.s[0] = rec;                           // newest first
+  p.cnt = ncnt;
+  p.dirty = true;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------ view row, warp-per-node
+// lane owns slots {w*32 + lane}.
+template <int W>
+struct Row {
+  uint32_t nb[W];
+  uint32_t inc[W];
+  uint32_t st[W];     // packed liveness | timer<<2
+  uint32_t touched;   // bit w: slot (w, lane) changed this call -> write st, inc, last
+};
+
+template <int W>
+__device__ __forceinline__ void row_load(Row<W> &r, const SimDev &d, uint32_t l, int lane) {
+  size_t base = (size_t)l * d.cap + lane;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    r.nb[w] = d.nbr[base + w * 32];
+    r.st[w] = d.vst[base + w * 32];
+    r.inc[w] = d.vinc[base + w * 32];
+  }
+  r.touched = 0;
+}
+
+template <int W>
+__device__ __forceinline__ void row_store(const Row<W> &r, const SimDev &d, uint32_t l, int lane) {
+  size_t base = (size_t)l * d.cap + lane;
+#pragma unroll
+  for (int w = 0; w < W; ++w)
+    if (r.touched & (1u << w)) {
+      d.vst[base + w * 32] = (uint8_t)r.st[w];
+      d.vinc[base + w * 32] = r.inc[w];
+      d.vlast[base + w * 32] = d.round;
+    }
+}
+
+// suspectOrDeadNode' (Core.hs:142-187) + aliveNode's known-member completion [Q7], for one
+// record delivered to node `self`. Every lane returns the same verdict:
+//   0 = `Nothing`; 1 = `Just` *rb (re-broadcast); 2 = unknown member + Alive (Core.hs:206-216
+//   would insert; bulk rounds ignore, the scalar call inserts).
+template <int W>
+__device__ __forceinline__ int row_apply(Row<W> &r, const SimDev &d, uint32_t self, uint32_t &self_inc,
+                                         uint4 rec, uint4 &rb, int lane, uint32_t &refutes) {
+  const uint32_t kind = rec_kind(rec);
+  if (rec.x == self) {
+    // own entry is virtual: (Alive, storeIncarnation)
+    if (kind == SWIM_MSG_ALIVE) return 0;
+    if (rec.y < self_inc) return 0;                 // Core.hs:151 stale incarnation
+    uint32_t base = self_inc > rec.y ? self_inc : rec.y;
+    self_inc = base + 1;                            // Core.hs:155-166; [Q9] terminating bump
+    if (lane == 0) ++refutes;
+    rb = make_rec(self, base + 1, 0, SWIM_MSG_ALIVE);
+    return 1;
+  }
+  // Core.hs:144-145 `find ((== name) . memberName) ms` as a ballot over the id row
+  int hw = -1, hl = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    unsigned hit = __ballot_sync(kFull, r.nb[w] == rec.x && (r.st[w] & 3u) != SWIM_VACANT);
+    if (hit && hw < 0) { hw = w; hl = __ffs(hit) - 1; }
+  }
+  if (hw < 0) return kind == SWIM_MSG_ALIVE ? 2 : 0; // Core.hs:147-148 unknown: ignore
+  uint32_t st_s = 0, inc_s = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    uint32_t a = __shfl_sync(kFull, r.st[w], hl), b = __shfl_sync(kFull, r.inc[w], hl);
+    if (w == hw) { st_s = a; inc_s = b; }
+  }
+  const uint32_t live = st_s & 3u;
+  uint32_t nst;
+  if (kind == SWIM_MSG_SUSPECT) {
+    if (rec.y < inc_s || live != SWIM_ALIVE) return 0; // Core.hs:151,183
+    nst = SWIM_SUSPECT | (d.S << 2);                   // [Q8] arm the countdown
+  } else if (kind == SWIM_MSG_DEAD) {
+    if (rec.y < inc_s || live == SWIM_DEAD) return 0;  // Core.hs:151,184
+    nst = SWIM_DEAD;
+  } else {
+    if (rec.y <= inc_s) return 0;                      // [Q7] Alive(i) applies iff i > j
+    nst = SWIM_ALIVE;
+  }
+  if (lane == hl) {
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+      if (w == hw) { r.st[w] = nst; r.inc[w] = rec.y; r.touched |= 1u << w; } // Core.hs:171-177
+  }
+  rb = rec; // Core.hs:179 `return $ Just msg`: the identical message (deadFrom intact)
+  return 1;
+}
+
+// ------------------------------------------------------------------ counters
+struct Ctr {
+  uint32_t v[SWIM_CTR__COUNT];
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int i = 0; i < SWIM_CTR__COUNT; ++i) v[i] = 0;
+  }
+  __device__ __forceinline__ void flush(unsigned long long *g, int lane) {
+#pragma unroll
+    for (int i = 0; i < SWIM_CTR__COUNT; ++i) {
+      uint32_t x = __reduce_add_sync(kFull, v[i]);
+      if (lane == 0 && x) atomicAdd(&g[i], (unsigned long long)x);
+    }
+  }
+};
+
+// =================================================================== K1: tick
+// SWAR helpers on 4 packed state bytes
+__device__ __forceinline__ uint32_t gather4(uint32_t a) { // bit0 of each byte -> 4-bit nibble
+  return (a * 0x01020408u) >> 24 & 0xFu;
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) tick_kernel(SimDev d) {
+  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  if (warp == 0 && lane == 0) d.any_mail[(d.round + 1) & 1] = 0;
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+
+  for (uint32_t base = warp * 32; base < d.n; base += nwarps * 32) {
+    // ---------------- phase A: lane-per-node
+    const uint32_t l = base + lane;
+    const bool up = l < d.n && d.alive[d.first + l] != 0; // a crashed process does nothing
+    uint32_t am[W];       // alive bitmask per 32-slot word, after the countdown
+    bool work = false;    // needs the warp-per-node path
+    bool expired = false; // some suspicion timer hit zero
+    bool acked = true;
+    uint32_t tslot = 0, tnode = 0, L = 0;
+    uint4 x = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int w = 0; w < W; ++w) am[w] = 0;
+    if (up) {
+      uint4 *rowp = reinterpret_cast<uint4 *>(d.vst + (size_t)l * d.cap);
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        uint4 q[2] = {rowp[2 * w], rowp[2 * w + 1]};
+        uint32_t *v = reinterpret_cast<uint32_t *>(q);
+        uint32_t any_sus = 0, mask = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t b0 = v[j] & 0x01010101u, b1 = (v[j] >> 1) & 0x01010101u;
+          uint32_t sus = b0 & ~b1;  // liveness == Suspect
+          uint32_t alv = ~(b0 | b1) & 0x01010101u; // liveness == Alive
+          any_sus |= sus;
+          v[j] -= sus << 2;         // [Q8] countdown: timer -= 1 (timer >= 1 while Suspect)
+          uint32_t t = v[j] & 0xFCFCFCFCu; // timer fields
+          uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u; // zero timers
+          if (sus & (z >> 7)) expired = true;
+          mask |= gather4(alv) << (4 * j);
+        }
+        am[w] = mask;
+        L += __popc(mask);
+        if (any_sus) { rowp[2 * w] = q[0]; rowp[2 * w + 1] = q[1]; }
+      }
+      work = expired || d.pb_cnt[l] != 0;
+      if (L) {
+        // kRandomMembers store 1 [] (Core.hs:239, [Q11]): first draw of the first block
+        x = philox4x32_10(make_uint4(d.round, d.first + l, P_SELECT, 0), d.key0, d.key1);
+        uint32_t tmp[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) tmp[w] = am[w];
+        tslot = pick_remove<W>(tmp, bounded(x.x, L));
+        tnode = d.nbr[(size_t)l * d.cap + tslot];
+        ++c.v[SWIM_CTR_PINGS];                        // Ping (Core.hs:246)
+        acked = d.alive[tnode] != 0;                  // Ack iff the target process is up
+        if (acked && d.loss_ppm) {
+          uint4 y = philox4x32_10(make_uint4(d.round, d.first + l, P_LOSS, 0), d.key0, d.key1);
+          acked = !(bounded(y.x, 1000000u) < d.loss_ppm);
+        }
+        work |= !acked;
+      }
+    }
+    // ---------------- phase B: warp-per-node for nodes with work
+    __syncwarp(); // phase A's countdown stores are ordered before the row loads below
+    unsigned todo = __ballot_sync(kFull, work);
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t ln = base + b, self = d.first + ln;
+      const bool b_expired = __shfl_sync(kFull, expired, b);
+      const bool b_acked = __shfl_sync(kFull, acked, b);
+      const uint32_t b_L = __shfl_sync(kFull, L, b);
+      const uint32_t b_tslot = __shfl_sync(kFull, tslot, b);
+      const uint32_t b_tnode = __shfl_sync(kFull, tnode, b);
+      uint4 bx;
+      bx.x = __shfl_sync(kFull, x.x, b); bx.y = __shfl_sync(kFull, x.y, b);
+      bx.z = __shfl_sync(kFull, x.z, b); bx.w = __shfl_sync(kFull, x.w, b);
+      uint32_t bam[W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) bam[w] = __shfl_sync(kFull, am[w], b);
+
+      Row<W> row;
+      row_load<W>(row, d, ln, lane); // lane b's countdown stores are visible after the shuffles' sync
+      pb_load(pbs, d, ln, lane);
+
+      // T1 [Q8]: expired Suspect -> Dead, broadcast Dead(inc, member, from = self), slot order
+      if (b_expired) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && (row.st[w] >> 2) == 0);
+          if (lane < 32 && (em >> lane & 1u)) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
+          while (em) {
+            int s = __ffs(em) - 1;
+            em &= em - 1;
+            uint32_t m = __shfl_sync(kFull, row.nb[w], s), i = __shfl_sync(kFull, row.inc[w], s);
+            pb_enqueue(pbs, d, make_rec(m, i, self, SWIM_MSG_DEAD), lane, c.v[SWIM_CTR_PB_DROPPED]);
+            if (lane == 0) ++c.v[SWIM_CTR_DEAD_TIMEOUT];
+          }
+        }
+      }
+      // kRandomMembers store k [] (Core.hs:249): a fresh shuffle over the same alive list;
+      // neither self nor the target is excluded. Draws 1..k of the SELECT stream.
+      uint32_t prox[SWIM_MAX_K];
+      uint32_t np = 0;
+      if (b_L) {
+        uint32_t tmp[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) tmp[w] = bam[w];
+        uint4 blk = bx;
+        np = d.k < b_L ? d.k : b_L;
+        for (uint32_t j = 0; j < np; ++j) {
+          uint32_t dr = 1 + j;
+          if (dr == 4) blk = philox4x32_10(make_uint4(d.round, self, P_SELECT, 1), d.key0, d.key1);
+          prox[j] = pick_remove<W>(tmp, bounded(word_of(blk, dr & 3), b_L - j));
+        }
+      }
+      // T3: unlessAck -> IndirectPings (Core.hs:247-250), unlessAck -> suspectNode (251-254)
+      if (b_L && !b_acked) {
+        if (lane == 0) { ++c.v[SWIM_CTR_DIRECT_FAIL]; c.v[SWIM_CTR_INDIRECT_PINGS] += np; }
+        bool ok = false;
+        const bool t_up = d.alive[b_tnode] != 0;
+        if ((uint32_t)lane < np && t_up) {
+          uint32_t pn = d.nbr[(size_t)ln * d.cap + prox[lane]];
+          ok = d.alive[pn] != 0;
+          if (ok && d.loss_ppm) {
+            uint32_t leg = 1 + lane;
+            uint4 y = philox4x32_10(make_uint4(d.round, self, P_LOSS, leg >> 2), d.key0, d.key1);
+            ok = !(bounded(word_of(y, leg & 3), 1000000u) < d.loss_ppm);
+          }
+        }
+        if (!__any_sync(kFull, ok)) {
+          // Suspect (memberIncarnation m) (memberName m) with m captured at probe start
+          const int tw = b_tslot >> 5, tl = b_tslot & 31;
+          uint32_t tinc = 0;
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            uint32_t v = __shfl_sync(kFull, row.inc[w], tl);
+            if (w == tw) tinc = v;
+          }
+          uint4 rb;
+          uint32_t dummy_inc = 0xFFFFFFFFu; // a probe never targets self
+          if (row_apply<W>(row, d, self, dummy_inc, make_rec(b_tnode, tinc, 0, SWIM_MSG_SUSPECT), rb, lane,
+                           c.v[SWIM_CTR_REFUTES]) == 1) {
+            pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // yield . Broadcast (Core.hs:254)
+            if (lane == 0) ++c.v[SWIM_CTR_SUSPECT_LOCAL];
+          }
+        }
+      }
+      row_store<W>(row, d, ln, lane);
+      // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
+      if (b_L && pbs.cnt) {
+        uint32_t nr = 1;
+        uint32_t rslot = b_tslot; // lane f carries recipient f
+        for (uint32_t j = 0; j < np && nr < d.fanout; ++j)
+          if (prox[j] != b_tslot) { if ((uint32_t)lane == nr) rslot = prox[j]; ++nr; }
+        if ((uint32_t)lane < nr) {
+          size_t e = (size_t)ln * d.cap + rslot;
+          uint32_t dst = d.nbr[e];
+          d.eflag[d.ridx[e]] = 1;      // raise the in-edge flag (i -> dst)
+          d.mail[dst - d.first] = 1;   // single-shard delivery
+        }
+        if (lane == 0) {
+          d.any_mail[d.round & 1] = 1;
+          d.out_cnt[ln] = (uint8_t)pbs.cnt;
+          c.v[SWIM_CTR_MSGS] += nr;
+          c.v[SWIM_CTR_RECS_SENT] += nr * pbs.cnt;
+        }
+        // snapshot, then one transmission is spent on every record
+        uint4 mine = make_uint4(0, 0, 0, 0);
+        const bool have = (uint32_t)lane < pbs.cnt;
+        if (have) { mine = pbs.s[lane]; d.out[(size_t)ln * d.B + lane] = mine; }
+        const bool keep = have && rec_ttl(mine) > 1;
+        const unsigned km = __ballot_sync(kFull, keep);
+        __syncwarp();
+        if (keep) {
+          mine.w -= 1u << 8;
+          pbs.s[__popc(km & ((1u << lane) - 1))] = mine;
+        }
+        pbs.cnt = __popc(km);
+        pbs.dirty = true;
+        __syncwarp();
+      }
+      pb_store(pbs, d, ln, lane);
+    }
+  }
+  c.flush(d.ctr, lane);
+}
+
+// =================================================================== K2: receive
+template <int W>
+__global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
+  if (d.any_mail[d.round & 1] == 0) return; // nobody sent this round
+  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+
+  for (uint32_t base = warp * 32; base < d.n; base += nwarps * 32) {
+    const uint32_t l = base + lane;
+    unsigned todo = __ballot_sync(kFull, l < d.n && d.mail[l] != 0);
+    while (todo) {
+      const int b = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t ln = base + b, self = d.first + ln;
+      const bool up = d.alive[self] != 0; // datagrams to a crashed process are lost
+      if (lane == 0) d.mail[ln] = 0;
+      Row<W> row;
+      uint32_t self_inc = 0, self_inc0 = 0;
+      if (up) {
+        row_load<W>(row, d, ln, lane);
+        pb_load(pbs, d, ln, lane);
+        self_inc = self_inc0 = d.self_inc[ln];
+      }
+      const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
+      for (uint32_t eb = e0; eb < e1; eb += 32) {
+        const uint32_t e = eb + lane;
+        const bool f = e < e1 && d.eflag[e] != 0;
+        uint32_t src = 0;
+        if (f) { d.eflag[e] = 0; src = d.in_src[e]; }
+        unsigned fm = __ballot_sync(kFull, f);
+        if (!up) continue;
+        while (fm) { // ascending sender id: the in-list is sorted
+          const int q = __ffs(fm) - 1;
+          fm &= fm - 1;
+          const uint32_t sl = __shfl_sync(kFull, src, q) - d.first;
+          const uint32_t cnt = d.out_cnt[sl];
+          uint4 mine = make_uint4(0, 0, 0, 0);
+          if ((uint32_t)lane < cnt) mine = d.out[(size_t)sl * d.B + lane];
+          if (lane == 0) ++c.v[SWIM_CTR_MSGS_RECV];
+          for (uint32_t r = 0; r < cnt; ++r) { // records in buffer order (newest first)
+            uint4 rec;
+            rec.x = __shfl_sync(kFull, mine.x, r); rec.y = __shfl_sync(kFull, mine.y, r);
+            rec.z = __shfl_sync(kFull, mine.z, r); rec.w = __shfl_sync(kFull, mine.w, r);
+            uint4 rb;
+            if (row_apply<W>(row, d, self, self_inc, rec, rb, lane, c.v[SWIM_CTR_REFUTES]) == 1) {
+              pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // maybeBroadcast (Core.hs:119-121)
+              if (lane == 0) ++c.v[SWIM_CTR_RECS_APPLIED];
+            }
+          }
+        }
+      }
+      if (up) {
+        row_store<W>(row, d, ln, lane);
+        pb_store(pbs, d, ln, lane);
+        if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
+      }
+    }
+  }
+  c.flush(d.ctr, lane);
+}
+
+// =================================================================== events (phase E)
+struct DevEvent {
+  uint32_t node;
+  uint32_t kind;
+  uint4 rec; // SWIM_EV_INJECT
+};
+
+template <int W>
+__global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEvent *ev, uint32_t n_ev) {
+  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+  // same-node events stay in list order: a node's events all belong to one warp
+  for (uint32_t x = 0; x < n_ev; ++x) {
+    const uint32_t node = ev[x].node;
+    if (node % nwarps != warp) continue;
+    const uint32_t kind = ev[x].kind;
+    const bool local = node >= d.first && node < d.first + d.n;
+    const uint32_t ln = node - d.first;
+    if (kind == SWIM_EV_CRASH) {
+      if (lane == 0) d.alive[node] = 0;
+    } else if (kind == SWIM_EV_REJOIN) {
+      const bool was_up = d.alive[node] != 0;
+      __syncwarp();
+      if (!was_up) {
+        if (lane == 0) d.alive[node] = 1;
+        if (local) { // restart with incarnation + 1 and announce Alive
+          uint32_t inc = d.self_inc[ln] + 1;
+          __syncwarp();
+          if (lane == 0) d.self_inc[ln] = inc;
+          pb_load(pbs, d, ln, lane);
+          pb_enqueue(pbs, d, make_rec(node, inc, 0, SWIM_MSG_ALIVE), lane, c.v[SWIM_CTR_PB_DROPPED]);
+          pb_store(pbs, d, ln, lane);
+        }
+      }
+    } else if (local && d.alive[node] != 0) { // SWIM_EV_INJECT: one datagram through `process`
+      Row<W> row;
+      row_load<W>(row, d, ln, lane);
+      pb_load(pbs, d, ln, lane);
+      uint32_t self_inc = d.self_inc[ln];
+      const uint32_t self_inc0 = self_inc;
+      uint4 rb;
+      if (row_apply<W>(row, d, node, self_inc, ev[x].rec, rb, lane, c.v[SWIM_CTR_REFUTES]) == 1) {
+        pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]);
+        if (lane == 0) ++c.v[SWIM_CTR_RECS_APPLIED];
+      }
+      row_store<W>(row, d, ln, lane);
+      pb_store(pbs, d, ln, lane);
+      if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
+    }
+    __syncwarp();
+  }
+  c.flush(d.ctr, lane);
+}
+
+// =================================================================== digest / convergence
+__device__ __forceinline__ uint64_t fmix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+__device__ __forceinline__ uint64_t dg(uint64_t arr, uint64_t idx, uint64_t val) {
+  return fmix64(fmix64(idx + (arr << 56)) ^ val);
+}
+
+static __global__ void __launch_bounds__(kThreads) digest_kernel(SimDev d, unsigned long long *out) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint64_t acc = 0;
+  for (uint32_t l = warp; l < d.n; l += nwarps) {
+    const uint64_t g = d.first + l;
+    const uint32_t cnt = d.pb_cnt[l];
+    if (lane == 0) {
+      acc += dg(SWIM_ARR_ALIVE, g, d.alive[g]);
+      acc += dg(SWIM_ARR_SELF_INC, g, d.self_inc[l]);
+      acc += dg(SWIM_ARR_SEQNO, g, d.seqno[l]);
+      acc += dg(SWIM_ARR_PB_CNT, g, cnt);
+    }
+    for (uint32_t s = lane; s < d.cap; s += 32) {
+      const size_t x = (size_t)l * d.cap + s;
+      const uint64_t gi = g * d.cap + s;
+      acc += dg(SWIM_ARR_NBR, gi, d.nbr[x]);
+      acc += dg(SWIM_ARR_VST, gi, d.vst[x]);
+      acc += dg(SWIM_ARR_VINC, gi, d.vinc[x]);
+      acc += dg(SWIM_ARR_VLAST, gi, d.vlast[x]);
+    }
+    if ((uint32_t)lane < cnt) {
+      const uint4 r = d.pb[(size_t)l * d.B + lane];
+      const uint64_t gi = (g * d.B + lane) * 2;
+      acc += dg(SWIM_ARR_PB, gi, (uint64_t)r.x | ((uint64_t)r.y << 32));
+      acc += dg(SWIM_ARR_PB, gi + 1, (uint64_t)r.z | ((uint64_t)(r.w & 0xFFu) << 32) | ((uint64_t)((r.w >> 8) & 0xFFu) << 40));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
+  if (lane == 0 && acc) atomicAdd(out, (unsigned long long)acc);
+}
+
+static __global__ void __launch_bounds__(kThreads) mismatch_kernel(SimDev d, unsigned long long *out) {
+  const size_t total = (size_t)d.n * d.cap;
+  uint32_t bad = 0;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x) {
+    const uint32_t l = (uint32_t)(x / d.cap);
+    const uint32_t st = d.vst[x] & 3u;
+    if (st == SWIM_VACANT || !d.alive[d.first + l]) continue;
+    bad += d.alive[d.nbr[x]] ? st != SWIM_ALIVE : st != SWIM_DEAD;
+  }
+  bad = __reduce_add_sync(kFull, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, (unsigned long long)bad);
+}
+
+} // namespace swim

@@ -1,0 +1,43 @@
+// swim_host.h — the handle behind swim_sim_t (include/swim.h). Host-only bookkeeping plus the
+// SimDev block of device pointers handed to every kernel by value.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "swim_device.cuh"
+
+struct swim_sim {
+  swim_config_t cfg{};
+  swim::SimDev dev{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  bool timed = false;
+  uint32_t round = 0;
+  bool view_set = false;
+  bool edges_dirty = false; // scalar calls changed a row's membership
+  bool connected = false;   // multi-shard exchange ready
+  uint64_t n_edges = 0;
+  uint64_t scalar_calls = 0;
+  std::vector<void *> allocs;
+  uint32_t *d_in_src = nullptr;
+  uint8_t *d_eflag = nullptr;
+  void *d_events = nullptr;
+  size_t d_events_cap = 0;
+  unsigned long long *d_scratch = nullptr;
+  std::vector<swim_event_t> events; // pending, sorted by round (stable)
+  std::string last_error;
+  void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
+};
+
+namespace swim {
+void set_error(swim_sim *sim, const char *fmt, ...);
+uint32_t shard_first(uint32_t N, uint32_t world, uint32_t rank);
+int rebuild_edges_from_device(swim_sim *sim);
+int dist_exchange(swim_sim *sim);
+void dist_teardown(swim_sim *sim);
+} // namespace swim

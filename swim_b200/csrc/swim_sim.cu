@@ -1,0 +1,522 @@
+// swim_sim.cu — host side of the C ABI (include/swim.h): handle, HBM layout, round driver.
+// Replaces the process wiring of Core.main (reference Core.hs:272-287): instead of three
+// conduits and a ticker thread per OS process, one handle owns N stores in HBM and
+// swim_sim_step runs the protocol period for all of them.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "swim_device.cuh"
+#include "swim_host.h"
+
+using namespace swim;
+
+namespace swim {
+thread_local std::string g_last_error;
+
+void set_error(swim_sim *sim, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (sim) sim->last_error = buf;
+}
+} // namespace swim
+
+#define CUDA_TRY(sim, call)                                                             \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      set_error(sim, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? SWIM_ENODEV : SWIM_ECUDA; \
+    }                                                                                   \
+  } while (0)
+
+extern "C" uint32_t swim_abi_version(void) { return SWIM_ABI_VERSION; }
+
+extern "C" const char *swim_strerror(int code) {
+  switch (code) {
+    case SWIM_OK: return "ok";
+    case SWIM_EINVAL: return "invalid argument";
+    case SWIM_ENOMEM: return "out of memory";
+    case SWIM_ECUDA: return "CUDA error";
+    case SWIM_ERANGE: return "value out of range";
+    case SWIM_EDECODE: return "decode error";
+    case SWIM_ENODEV: return "no CUDA device (swim-b200 has no CPU fallback)";
+    case SWIM_ENCCL: return "NCCL error";
+    case SWIM_ECAP: return "capacity exceeded";
+    case SWIM_ESTATE: return "invalid state";
+  }
+  return "unknown error";
+}
+
+extern "C" const char *swim_last_error(const swim_sim_t *sim) {
+  return sim ? sim->last_error.c_str() : g_last_error.c_str();
+}
+
+extern "C" int swim_config_default(swim_config_t *cfg) {
+  if (!cfg) return SWIM_EINVAL;
+  memset(cfg, 0, sizeof *cfg);
+  cfg->abi_version = SWIM_ABI_VERSION;
+  cfg->n_nodes = 32;
+  cfg->view_cap = 32;
+  cfg->k_indirect = 3; // reference default numToGossip = 10 (Util.hs:48); BASELINE configs use k = 3
+  cfg->fanout = 4;
+  cfg->pb_cap = 8;
+  cfg->suspicion_rounds = 5;
+  cfg->retransmit = 8;
+  cfg->loss_ppm = 0;
+  cfg->seed = 0x5EED0001ull;
+  cfg->rank = 0;
+  cfg->world = 1;
+  cfg->device = -1;
+  cfg->base_port = 4000;
+  return SWIM_OK;
+}
+
+static int validate(const swim_config_t *c) {
+  if (!c || c->abi_version != SWIM_ABI_VERSION) return SWIM_EINVAL;
+  if (c->n_nodes == 0 || c->world == 0 || c->rank >= c->world) return SWIM_EINVAL;
+  if (c->view_cap != 32 && c->view_cap != 64 && c->view_cap != 128 && c->view_cap != 256) return SWIM_EINVAL;
+  if (c->k_indirect > SWIM_MAX_K || c->fanout < 1 || c->fanout > 1 + c->k_indirect) return SWIM_EINVAL;
+  if (c->pb_cap < 1 || c->pb_cap > SWIM_MAX_PB) return SWIM_EINVAL;
+  if (c->suspicion_rounds < 1 || c->suspicion_rounds > SWIM_MAX_TIMER) return SWIM_EINVAL;
+  if (c->retransmit < 1 || c->retransmit > 255 || c->loss_ppm > 1000000u) return SWIM_EINVAL;
+  return SWIM_OK;
+}
+
+namespace swim {
+uint32_t shard_first(uint32_t N, uint32_t world, uint32_t rank) {
+  uint64_t per = ((uint64_t)N + world - 1) / world, f = per * rank;
+  return (uint32_t)(f > N ? N : f);
+}
+} // namespace swim
+
+template <typename T>
+static int dalloc(swim_sim *sim, T **p, size_t count, int fill) {
+  if (count == 0) count = 1;
+  CUDA_TRY(sim, cudaMalloc((void **)p, count * sizeof(T)));
+  CUDA_TRY(sim, cudaMemset(*p, fill, count * sizeof(T)));
+  sim->allocs.push_back((void *)*p);
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
+  if (!out) return SWIM_EINVAL;
+  *out = nullptr;
+  int rc = validate(cfg);
+  if (rc) { set_error(nullptr, "swim_sim_create: invalid config"); return rc; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(nullptr, "swim_sim_create: no CUDA device (%s); swim-b200 has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return SWIM_ENODEV;
+  }
+  swim_sim *sim = new (std::nothrow) swim_sim();
+  if (!sim) return SWIM_ENOMEM;
+  sim->cfg = *cfg;
+  if (cfg->device >= 0) {
+    rc = [&]() { CUDA_TRY(sim, cudaSetDevice(cfg->device)); return SWIM_OK; }();
+    if (rc) { g_last_error = sim->last_error; delete sim; return rc; }
+  }
+  cudaGetDevice(&sim->device);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, sim->device);
+  sim->sm_count = prop.multiProcessorCount;
+  SimDev &d = sim->dev;
+  memset(&d, 0, sizeof d);
+  d.N = cfg->n_nodes; d.cap = cfg->view_cap; d.k = cfg->k_indirect; d.fanout = cfg->fanout;
+  d.B = cfg->pb_cap; d.S = cfg->suspicion_rounds; d.T = cfg->retransmit; d.loss_ppm = cfg->loss_ppm;
+  d.key0 = (uint32_t)cfg->seed; d.key1 = (uint32_t)(cfg->seed >> 32);
+  d.world = cfg->world; d.rank = cfg->rank;
+  d.per = (uint32_t)(((uint64_t)d.N + d.world - 1) / d.world);
+  d.first = shard_first(d.N, d.world, d.rank);
+  d.n = shard_first(d.N, d.world, d.rank + 1) - d.first;
+  const size_t n = d.n, slots = n * d.cap;
+  rc = [&]() -> int {
+    int r;
+    CUDA_TRY(sim, cudaStreamCreateWithFlags(&sim->own_stream, cudaStreamNonBlocking));
+    sim->stream = sim->own_stream;
+    CUDA_TRY(sim, cudaEventCreate(&sim->ev_start));
+    CUDA_TRY(sim, cudaEventCreate(&sim->ev_stop));
+    if ((r = dalloc(sim, &d.alive, d.N, 1))) return r;       // every node up
+    if ((r = dalloc(sim, &d.self_inc, n, 0))) return r;      // Util.hs:80
+    if ((r = dalloc(sim, &d.seqno, n, 0))) return r;         // Util.hs:79
+    if ((r = dalloc(sim, &d.nbr, slots, 0xFF))) return r;    // Util.hs:78 empty member map
+    if ((r = dalloc(sim, &d.vst, slots, 0))) return r;
+    CUDA_TRY(sim, cudaMemset(d.vst, SWIM_VACANT, slots ? slots : 1));
+    if ((r = dalloc(sim, &d.vinc, slots, 0))) return r;
+    if ((r = dalloc(sim, &d.vlast, slots, 0))) return r;
+    if ((r = dalloc(sim, &d.pb, n * d.B, 0))) return r;
+    if ((r = dalloc(sim, &d.pb_cnt, n, 0))) return r;
+    if ((r = dalloc(sim, &d.out, n * d.B, 0))) return r;
+    if ((r = dalloc(sim, &d.out_cnt, n, 0))) return r;
+    if ((r = dalloc(sim, &d.ridx, slots, 0))) return r;
+    if ((r = dalloc(sim, &d.in_off, n + 1, 0))) return r;
+    if ((r = dalloc(sim, &d.mail, n, 0))) return r;
+    if ((r = dalloc(sim, &d.any_mail, 2, 0))) return r;
+    if ((r = dalloc(sim, &d.ctr, SWIM_CTR__COUNT, 0))) return r;
+    if ((r = dalloc(sim, &sim->d_scratch, 8, 0))) return r;
+    return SWIM_OK;
+  }();
+  if (rc) { g_last_error = sim->last_error; swim_sim_destroy(sim); return rc; }
+  *out = sim;
+  return SWIM_OK;
+}
+
+extern "C" void swim_sim_destroy(swim_sim_t *sim) {
+  if (!sim) return;
+  cudaSetDevice(sim->device);
+  if (sim->own_stream) cudaStreamSynchronize(sim->own_stream);
+  swim::dist_teardown(sim);
+  for (void *p : sim->allocs) cudaFree(p);
+  if (sim->d_in_src) cudaFree(sim->d_in_src);
+  if (sim->d_eflag) cudaFree(sim->d_eflag);
+  if (sim->d_events) cudaFree(sim->d_events);
+  if (sim->ev_start) cudaEventDestroy(sim->ev_start);
+  if (sim->ev_stop) cudaEventDestroy(sim->ev_stop);
+  if (sim->own_stream) cudaStreamDestroy(sim->own_stream);
+  delete sim;
+}
+
+extern "C" int swim_sim_local_range(const swim_sim_t *sim, uint32_t *first, uint32_t *count) {
+  if (!sim || !first || !count) return SWIM_EINVAL;
+  *first = sim->dev.first;
+  *count = sim->dev.n;
+  return SWIM_OK;
+}
+
+// Build the in-edge index of the local nodes from the global id matrix and upload it.
+// in-list of receiver j = senders i (ascending) that have j in their row; the flag of edge
+// (i -> j) lives at in_off[j] + position; ridx[i, s] is that position for local senders.
+static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
+  SimDev &d = sim->dev;
+  const uint32_t N = d.N, cap = d.cap;
+  // global in-degree, then per-shard exclusive offsets
+  std::vector<uint32_t> deg((size_t)N + 1, 0);
+  for (size_t x = 0, tot = (size_t)N * cap; x < tot; ++x)
+    if (nbr[x] != SWIM_NO_MEMBER) deg[nbr[x]]++;
+  std::vector<uint64_t> goff((size_t)N + 1);
+  uint64_t acc = 0;
+  for (uint32_t j = 0; j <= N; ++j) {
+    if (j % d.per == 0) acc = 0; // offsets restart at every shard boundary
+    goff[j] = acc;
+    if (j < N) acc += deg[j];
+  }
+  // goff[j] for j at a shard boundary is 0; the shard's edge count is needed separately
+  uint64_t E = 0;
+  for (uint32_t j = d.first; j < d.first + d.n; ++j) E += deg[j];
+  if (E > 0xFFFFFFFFull) { set_error(sim, "in-edge count %llu exceeds 2^32", (unsigned long long)E); return SWIM_ERANGE; }
+  std::vector<uint32_t> in_off((size_t)d.n + 1), in_src((size_t)E ? (size_t)E : 1), ridx((size_t)d.n * cap, 0);
+  for (uint32_t l = 0; l < d.n; ++l) in_off[l] = (uint32_t)goff[d.first + l];
+  in_off[d.n] = (uint32_t)E;
+  std::vector<uint32_t> cursor((size_t)N, 0); // edges seen so far per receiver
+  for (uint32_t i = 0; i < N; ++i) {
+    const bool mine = i >= d.first && i < d.first + d.n;
+    for (uint32_t s = 0; s < cap; ++s) {
+      const uint32_t j = nbr[(size_t)i * cap + s];
+      if (j == SWIM_NO_MEMBER) continue;
+      const uint32_t pos = cursor[j]++;
+      if (j >= d.first && j < d.first + d.n) in_src[(size_t)goff[j] + pos] = i;
+      if (mine) ridx[(size_t)(i - d.first) * cap + s] = (uint32_t)goff[j] + pos;
+    }
+  }
+  if (sim->d_in_src) { cudaFree(sim->d_in_src); sim->d_in_src = nullptr; }
+  if (sim->d_eflag) { cudaFree(sim->d_eflag); sim->d_eflag = nullptr; }
+  const size_t Ea = E ? (size_t)E : 1;
+  CUDA_TRY(sim, cudaMalloc((void **)&sim->d_in_src, Ea * 4));
+  CUDA_TRY(sim, cudaMalloc((void **)&sim->d_eflag, Ea));
+  CUDA_TRY(sim, cudaMemset(sim->d_eflag, 0, Ea));
+  CUDA_TRY(sim, cudaMemcpy(sim->d_in_src, in_src.data(), Ea * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(sim, cudaMemcpy(d.in_off, in_off.data(), ((size_t)d.n + 1) * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(sim, cudaMemcpy(d.ridx, ridx.data(), ridx.size() * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(sim, cudaMemset(d.mail, 0, d.n ? d.n : 1));
+  d.in_src = sim->d_in_src;
+  d.eflag = sim->d_eflag;
+  sim->n_edges = E;
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_set_view(swim_sim_t *sim, const uint32_t *nbr) {
+  if (!sim || !nbr) return SWIM_EINVAL;
+  SimDev &d = sim->dev;
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  // validate the local rows: ascending, distinct, in range, never self, vacancies last
+  for (uint32_t l = 0; l < d.n; ++l) {
+    const uint32_t *row = nbr + (size_t)(d.first + l) * d.cap;
+    uint32_t prev = 0;
+    bool seen = false, vacant = false;
+    for (uint32_t s = 0; s < d.cap; ++s) {
+      const uint32_t m = row[s];
+      if (m == SWIM_NO_MEMBER) { vacant = true; continue; }
+      if (vacant || m >= d.N || m == d.first + l || (seen && m <= prev)) {
+        set_error(sim, "swim_sim_set_view: row %u slot %u is not a sorted set of ids != self", d.first + l, s);
+        return SWIM_EINVAL;
+      }
+      prev = m; seen = true;
+    }
+  }
+  const size_t slots = (size_t)d.n * d.cap;
+  std::vector<uint8_t> st(slots ? slots : 1);
+  const uint32_t *mine = nbr + (size_t)d.first * d.cap;
+  for (size_t x = 0; x < slots; ++x) st[x] = mine[x] == SWIM_NO_MEMBER ? SWIM_VACANT : SWIM_ALIVE;
+  CUDA_TRY(sim, cudaMemcpy(d.nbr, mine, slots * 4, cudaMemcpyHostToDevice));
+  CUDA_TRY(sim, cudaMemcpy(d.vst, st.data(), slots, cudaMemcpyHostToDevice));
+  CUDA_TRY(sim, cudaMemset(d.vinc, 0, slots * 4));
+  CUDA_TRY(sim, cudaMemset(d.vlast, 0, slots * 4));
+  int rc = build_in_edges(sim, nbr);
+  if (rc) return rc;
+  sim->view_set = true;
+  sim->edges_dirty = false;
+  return SWIM_OK;
+}
+
+// Rebuild the in-edge index from the device rows (after scalar calls changed memberships).
+namespace swim {
+int rebuild_edges_from_device(swim_sim *sim) {
+  SimDev &d = sim->dev;
+  if (d.world != 1) { set_error(sim, "view membership changes are single-shard only"); return SWIM_ESTATE; }
+  std::vector<uint32_t> nbr((size_t)d.N * d.cap);
+  CUDA_TRY(sim, cudaMemcpy(nbr.data(), d.nbr, nbr.size() * 4, cudaMemcpyDeviceToHost));
+  int rc = build_in_edges(sim, nbr.data());
+  if (rc) return rc;
+  sim->edges_dirty = false;
+  return SWIM_OK;
+}
+} // namespace swim
+
+// ------------------------------------------------------------------ events
+extern "C" int swim_sim_inject(swim_sim_t *sim, const swim_event_t *ev, size_t n) {
+  if (!sim || (!ev && n)) return SWIM_EINVAL;
+  for (size_t x = 0; x < n; ++x) {
+    if (ev[x].round <= sim->round || ev[x].node >= sim->dev.N || ev[x].kind > SWIM_EV_INJECT) {
+      set_error(sim, "swim_sim_inject: event %zu invalid (round %u <= %u, node %u, kind %u)", x, ev[x].round,
+                sim->round, ev[x].node, ev[x].kind);
+      return SWIM_EINVAL;
+    }
+    if (ev[x].kind == SWIM_EV_INJECT) {
+      const swim_message_t &m = ev[x].msg;
+      if (m.kind != SWIM_MSG_SUSPECT && m.kind != SWIM_MSG_ALIVE && m.kind != SWIM_MSG_DEAD) {
+        set_error(sim, "swim_sim_inject: only Suspect/Alive/Dead can be injected");
+        return SWIM_EINVAL;
+      }
+      if (m.incarnation < 0 || m.incarnation > 0xFFFFFFFFll) return SWIM_ERANGE;
+    }
+  }
+  sim->events.insert(sim->events.end(), ev, ev + n);
+  std::stable_sort(sim->events.begin(), sim->events.end(),
+                   [](const swim_event_t &a, const swim_event_t &b) { return a.round < b.round; });
+  return SWIM_OK;
+}
+
+// ------------------------------------------------------------------ round driver
+static int grid_for(const swim_sim *sim, size_t warps_needed) {
+  size_t blocks = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  size_t cap = (size_t)sim->sm_count * (2048 / kThreads);
+  if (blocks < 1) blocks = 1;
+  return (int)std::min(blocks, cap);
+}
+
+template <int W>
+static int run_rounds(swim_sim *sim, uint32_t rounds) {
+  SimDev &d = sim->dev;
+  const int grid = grid_for(sim, ((size_t)d.n + 31) / 32);
+  // upload the events that fall inside this call
+  size_t n_ev = 0;
+  while (n_ev < sim->events.size() && sim->events[n_ev].round <= sim->round + rounds) ++n_ev;
+  if (n_ev) {
+    std::vector<DevEvent> dev(n_ev);
+    for (size_t x = 0; x < n_ev; ++x) {
+      const swim_event_t &e = sim->events[x];
+      dev[x].node = e.node;
+      dev[x].kind = e.kind;
+      dev[x].rec = make_uint4(e.msg.node, (uint32_t)e.msg.incarnation,
+                              e.msg.kind == SWIM_MSG_DEAD ? e.msg.dead_from : 0u, e.msg.kind);
+    }
+    if (n_ev > sim->d_events_cap) {
+      if (sim->d_events) { CUDA_TRY(sim, cudaStreamSynchronize(sim->stream)); cudaFree(sim->d_events); sim->d_events = nullptr; }
+      sim->d_events_cap = n_ev * 2;
+      CUDA_TRY(sim, cudaMalloc((void **)&sim->d_events, sim->d_events_cap * sizeof(DevEvent)));
+    }
+    // stream-ordered, blocking w.r.t. the (pageable) host vector
+    CUDA_TRY(sim, cudaMemcpyAsync(sim->d_events, dev.data(), n_ev * sizeof(DevEvent), cudaMemcpyHostToDevice, sim->stream));
+    CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  }
+  size_t ev_pos = 0;
+  for (uint32_t r = 0; r < rounds; ++r) {
+    d.round = ++sim->round;
+    size_t ev_end = ev_pos;
+    while (ev_end < n_ev && sim->events[ev_end].round == d.round) ++ev_end;
+    if (ev_end > ev_pos) {
+      const uint32_t cnt = (uint32_t)(ev_end - ev_pos);
+      const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count);
+      event_kernel<W><<<eg, kThreads, 0, sim->stream>>>(d, (const DevEvent *)sim->d_events + ev_pos, cnt);
+      ev_pos = ev_end;
+    }
+    tick_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
+    if (d.world > 1) {
+      int rc = swim::dist_exchange(sim);
+      if (rc) return rc;
+    }
+    recv_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
+  }
+  sim->events.erase(sim->events.begin(), sim->events.begin() + n_ev);
+  CUDA_TRY(sim, cudaGetLastError());
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_step_async(swim_sim_t *sim, uint32_t rounds) {
+  if (!sim) return SWIM_EINVAL;
+  if (!sim->view_set) { set_error(sim, "swim_sim_step: no view installed (swim_sim_set_view / swim_set_members)"); return SWIM_ESTATE; }
+  cudaSetDevice(sim->device);
+  if (sim->edges_dirty) {
+    int rc = swim::rebuild_edges_from_device(sim);
+    if (rc) return rc;
+  }
+  if (sim->dev.world > 1 && !sim->connected) { set_error(sim, "swim_sim_step: world > 1 needs swim_sim_connect"); return SWIM_ESTATE; }
+  CUDA_TRY(sim, cudaEventRecord(sim->ev_start, sim->stream));
+  int rc;
+  switch (sim->dev.cap / 32) {
+    case 1: rc = run_rounds<1>(sim, rounds); break;
+    case 2: rc = run_rounds<2>(sim, rounds); break;
+    case 4: rc = run_rounds<4>(sim, rounds); break;
+    default: rc = run_rounds<8>(sim, rounds); break;
+  }
+  if (rc) return rc;
+  CUDA_TRY(sim, cudaEventRecord(sim->ev_stop, sim->stream));
+  sim->timed = true;
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_sync(swim_sim_t *sim) {
+  if (!sim) return SWIM_EINVAL;
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_step(swim_sim_t *sim, uint32_t rounds) {
+  int rc = swim_sim_step_async(sim, rounds);
+  if (rc) return rc;
+  return swim_sim_sync(sim);
+}
+
+extern "C" int swim_sim_set_stream(swim_sim_t *sim, void *cuda_stream) {
+  if (!sim) return SWIM_EINVAL;
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  sim->stream = cuda_stream ? (cudaStream_t)cuda_stream : sim->own_stream;
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_last_step_ms(const swim_sim_t *sim, float *ms) {
+  if (!sim || !ms) return SWIM_EINVAL;
+  if (!sim->timed) return SWIM_ESTATE;
+  cudaError_t e = cudaEventElapsedTime(ms, sim->ev_start, sim->ev_stop);
+  return e == cudaSuccess ? SWIM_OK : SWIM_ECUDA;
+}
+
+extern "C" int swim_sim_round(const swim_sim_t *sim, uint32_t *round) {
+  if (!sim || !round) return SWIM_EINVAL;
+  *round = sim->round;
+  return SWIM_OK;
+}
+
+// ------------------------------------------------------------------ bulk state access
+static void *array_ptr(const swim_sim *sim, int arr, size_t *bytes) {
+  const SimDev &d = sim->dev;
+  const size_t n = d.n, slots = n * d.cap;
+  switch (arr) {
+    case SWIM_ARR_ALIVE: *bytes = d.N; return d.alive;
+    case SWIM_ARR_SELF_INC: *bytes = n * 4; return d.self_inc;
+    case SWIM_ARR_SEQNO: *bytes = n * 4; return d.seqno;
+    case SWIM_ARR_NBR: *bytes = slots * 4; return d.nbr;
+    case SWIM_ARR_VST: *bytes = slots; return d.vst;
+    case SWIM_ARR_VINC: *bytes = slots * 4; return d.vinc;
+    case SWIM_ARR_VLAST: *bytes = slots * 4; return d.vlast;
+    case SWIM_ARR_PB: *bytes = n * d.B * sizeof(swim_record_t); return d.pb;
+    case SWIM_ARR_PB_CNT: *bytes = n; return d.pb_cnt;
+  }
+  *bytes = 0;
+  return nullptr;
+}
+
+extern "C" int swim_sim_array_bytes(const swim_sim_t *sim, int arr, size_t *bytes) {
+  if (!sim || !bytes) return SWIM_EINVAL;
+  return array_ptr(sim, arr, bytes) ? SWIM_OK : SWIM_EINVAL;
+}
+
+extern "C" int swim_sim_get_array(swim_sim_t *sim, int arr, void *buf, size_t bytes) {
+  if (!sim || !buf) return SWIM_EINVAL;
+  size_t want;
+  void *p = array_ptr(sim, arr, &want);
+  if (!p || want != bytes) { set_error(sim, "swim_sim_get_array(%d): expected %zu bytes, got %zu", arr, want, bytes); return SWIM_EINVAL; }
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  CUDA_TRY(sim, cudaMemcpy(buf, p, bytes, cudaMemcpyDeviceToHost));
+  if (arr == SWIM_ARR_PB) { // entries at or beyond the count are defined to read as zero
+    std::vector<uint8_t> cnt(sim->dev.n ? sim->dev.n : 1);
+    CUDA_TRY(sim, cudaMemcpy(cnt.data(), sim->dev.pb_cnt, sim->dev.n, cudaMemcpyDeviceToHost));
+    swim_record_t *r = (swim_record_t *)buf;
+    for (uint32_t l = 0; l < sim->dev.n; ++l)
+      for (uint32_t q = cnt[l]; q < sim->dev.B; ++q) memset(&r[(size_t)l * sim->dev.B + q], 0, sizeof *r);
+  }
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_set_array(swim_sim_t *sim, int arr, const void *buf, size_t bytes) {
+  if (!sim || !buf) return SWIM_EINVAL;
+  if (arr == SWIM_ARR_NBR) { set_error(sim, "swim_sim_set_array: use swim_sim_set_view for SWIM_ARR_NBR"); return SWIM_EINVAL; }
+  size_t want;
+  void *p = array_ptr(sim, arr, &want);
+  if (!p || want != bytes) { set_error(sim, "swim_sim_set_array(%d): expected %zu bytes, got %zu", arr, want, bytes); return SWIM_EINVAL; }
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  CUDA_TRY(sim, cudaMemcpy(p, buf, bytes, cudaMemcpyHostToDevice));
+  return SWIM_OK;
+}
+
+static int reduce_u64(swim_sim *sim, int which, uint64_t *out) {
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaMemsetAsync(sim->d_scratch, 0, 8, sim->stream));
+  const SimDev &d = sim->dev;
+  if (which == 0) {
+    digest_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+  } else {
+    const size_t total = (size_t)d.n * d.cap;
+    mismatch_kernel<<<grid_for(sim, (total + 31) / 32 / 4 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+  }
+  CUDA_TRY(sim, cudaGetLastError());
+  unsigned long long v = 0;
+  CUDA_TRY(sim, cudaMemcpyAsync(&v, sim->d_scratch, 8, cudaMemcpyDeviceToHost, sim->stream));
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  *out = v;
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_digest(swim_sim_t *sim, uint64_t *digest) {
+  if (!sim || !digest) return SWIM_EINVAL;
+  return reduce_u64(sim, 0, digest);
+}
+
+extern "C" int swim_sim_mismatches(swim_sim_t *sim, uint64_t *count) {
+  if (!sim || !count) return SWIM_EINVAL;
+  return reduce_u64(sim, 1, count);
+}
+
+extern "C" int swim_sim_counters(swim_sim_t *sim, uint64_t *out, size_t n) {
+  if (!sim || !out) return SWIM_EINVAL;
+  cudaSetDevice(sim->device);
+  unsigned long long v[SWIM_CTR__COUNT];
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  CUDA_TRY(sim, cudaMemcpy(v, sim->dev.ctr, sizeof v, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n && i < SWIM_CTR__COUNT; ++i) out[i] = v[i];
+  return SWIM_OK;
+}

@@ -1,0 +1,156 @@
+"""Bulk simulator front end: N simulated `Store`s (reference Types.hs:53-60) stepped on the GPU.
+
+Replaces the process wiring of `Core.main` (Core.hs:272-287): `Simulator.step(r)` runs r
+protocol periods (failureDetector Core.hs:233-241 + handleUDPMessage Core.hs:79-121 +
+disseminate Core.hs:127-138) for every node."""
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from ._lib import SwimError, check, lib
+
+
+def default_config(**kw) -> A.Config:
+    """parseConfig (Util.hs:44-50) + the simulator knobs; keyword overrides."""
+    cfg = A.Config()
+    check(lib().swim_config_default(C.byref(cfg)), "swim_config_default")
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(f"swim_config_t has no field {k}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+def generate_topology(kind, n_nodes, view_cap=32, degree=32, seed=1):
+    """Synthetic view graph [N, view_cap] (ids ascending, NO_MEMBER padded). Host only."""
+    out = np.empty((n_nodes, view_cap), dtype=np.uint32)
+    kind = {"complete": A.TOPO_COMPLETE, "random": A.TOPO_RANDOM, "ring": A.TOPO_RING}.get(kind, kind)
+    check(lib().swim_topology_generate(kind, n_nodes, view_cap, degree, seed, out.ctypes.data),
+          "swim_topology_generate")
+    return out
+
+
+def make_events(rounds, nodes, kinds, msg_kind=None, msg_node=None, msg_inc=None, msg_from=None):
+    """Pack an event trace into the swim_event_t layout."""
+    n = len(nodes)
+    ev = np.zeros(n, dtype=A.EVENT_DTYPE)
+    ev["round"] = rounds
+    ev["node"] = nodes
+    ev["kind"] = kinds
+    if msg_kind is not None:
+        ev["msg_kind"] = msg_kind
+        ev["msg_node"] = msg_node
+        ev["msg_incarnation"] = msg_inc
+        ev["msg_dead_from"] = 0 if msg_from is None else msg_from
+    return ev
+
+
+def crash_events(round_, nodes):
+    nodes = np.asarray(nodes, dtype=np.uint32)
+    return make_events(np.full(len(nodes), round_, np.uint32), nodes, np.full(len(nodes), A.EV_CRASH, np.uint8))
+
+
+class Simulator:
+    def __init__(self, cfg: A.Config = None, **kw):
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        h = C.c_void_p()
+        check(lib().swim_sim_create(C.byref(self.cfg), C.byref(h)), "swim_sim_create")
+        self._h = h
+        f, n = C.c_uint32(), C.c_uint32()
+        check(lib().swim_sim_local_range(h, C.byref(f), C.byref(n)), "swim_sim_local_range", h)
+        self.first, self.n_local = f.value, n.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().swim_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- bulk path
+    def set_view(self, nbr):
+        nbr = np.ascontiguousarray(nbr, dtype=np.uint32)
+        if nbr.size != self.cfg.n_nodes * self.cfg.view_cap:
+            raise ValueError("nbr must be the global [N, view_cap] id matrix")
+        check(lib().swim_sim_set_view(self._h, nbr.ctypes.data), "swim_sim_set_view", self._h)
+
+    def inject(self, events):
+        events = np.ascontiguousarray(events, dtype=A.EVENT_DTYPE)
+        check(lib().swim_sim_inject(self._h, events.ctypes.data, len(events)), "swim_sim_inject", self._h)
+
+    def step(self, rounds=1):
+        check(lib().swim_sim_step(self._h, rounds), "swim_sim_step", self._h)
+
+    def step_async(self, rounds=1):
+        check(lib().swim_sim_step_async(self._h, rounds), "swim_sim_step_async", self._h)
+
+    def sync(self):
+        check(lib().swim_sim_sync(self._h), "swim_sim_sync", self._h)
+
+    def set_stream(self, cuda_stream):
+        check(lib().swim_sim_set_stream(self._h, C.c_void_p(cuda_stream)), "swim_sim_set_stream", self._h)
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        check(lib().swim_sim_last_step_ms(self._h, C.byref(ms)), "swim_sim_last_step_ms", self._h)
+        return ms.value
+
+    @property
+    def round(self):
+        r = C.c_uint32()
+        check(lib().swim_sim_round(self._h, C.byref(r)), "swim_sim_round", self._h)
+        return r.value
+
+    def get_array(self, arr):
+        nb = C.c_size_t()
+        check(lib().swim_sim_array_bytes(self._h, arr, C.byref(nb)), "swim_sim_array_bytes", self._h)
+        dt = A.ARRAY_DTYPES[arr]
+        out = np.zeros(nb.value // dt.itemsize, dtype=dt)
+        check(lib().swim_sim_get_array(self._h, arr, out.ctypes.data, nb.value), "swim_sim_get_array", self._h)
+        return out
+
+    def set_array(self, arr, data):
+        data = np.ascontiguousarray(data, dtype=A.ARRAY_DTYPES[arr])
+        check(lib().swim_sim_set_array(self._h, arr, data.ctypes.data, data.nbytes), "swim_sim_set_array",
+              self._h)
+
+    def digest(self):
+        d = C.c_uint64()
+        check(lib().swim_sim_digest(self._h, C.byref(d)), "swim_sim_digest", self._h)
+        return d.value
+
+    def mismatches(self):
+        d = C.c_uint64()
+        check(lib().swim_sim_mismatches(self._h, C.byref(d)), "swim_sim_mismatches", self._h)
+        return d.value
+
+    def counters(self):
+        out = np.zeros(A.CTR_COUNT, dtype=np.uint64)
+        check(lib().swim_sim_counters(self._h, out.ctypes.data, A.CTR_COUNT), "swim_sim_counters", self._h)
+        return out
+
+    def state(self):
+        """All bulk arrays as a dict (the checkable form of dumpStore, Util.hs:64-74)."""
+        return {A.ARRAY_NAMES[a]: self.get_array(a) for a in range(A.ARR_COUNT)}
+
+    # ---- multi-GPU
+    def connect(self, unique_id: bytes):
+        buf = (C.c_uint8 * A.NCCL_ID_BYTES).from_buffer_copy(unique_id)
+        check(lib().swim_sim_connect(self._h, buf), "swim_sim_connect", self._h)
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * A.NCCL_ID_BYTES)()
+    check(lib().swim_nccl_unique_id(buf), "swim_nccl_unique_id")
+    return bytes(buf)

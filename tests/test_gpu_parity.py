@@ -1,0 +1,128 @@
+"""GPU parity: the CUDA path (through the C ABI) must equal the CPU oracle bit for bit on every
+state array, counter and digest, after every round, on the same seed and event trace."""
+import numpy as np
+import pytest
+
+from helpers import assert_same_state, crash_events, default_config, generate_topology, make_pair, random_events
+from swim_b200 import _abi as A
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c1_every_round():
+    """BASELINE config C1: N=32 complete view (D=31), k=3, B=8, S=5, nodes {7,19} crash at round 10."""
+    cfg = default_config(n_nodes=32, seed=0x5EED0001 + 1)
+    nbr = generate_topology("complete", 32, 32)
+    sim, orc = make_pair(cfg, nbr)
+    ev = crash_events(10, [7, 19])
+    sim.inject(ev)
+    orc.inject(ev)
+    for r in range(100):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"round {r + 1}")
+    assert sim.mismatches() == 0  # converged: both crashed nodes Dead everywhere
+    c = sim.counters()
+    assert c[A.CTR_DEAD_TIMEOUT] > 0 and c[A.CTR_RECS_APPLIED] > 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_small(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 200))
+    cap = 32
+    deg = int(rng.integers(1, min(n - 1, cap) + 1))
+    k = int(rng.integers(0, 8))
+    cfg = default_config(n_nodes=n, view_cap=cap, k_indirect=k, fanout=int(rng.integers(1, k + 2)),
+                         pb_cap=int(rng.integers(1, 33)), suspicion_rounds=int(rng.integers(1, 12)),
+                         retransmit=int(rng.integers(1, 12)), loss_ppm=int(rng.choice([0, 0, 50000, 300000])),
+                         seed=int(rng.integers(0, 2 ** 63)))
+    kind = rng.choice(["random", "ring"]) if deg < n - 1 else "complete"
+    nbr = generate_topology(str(kind), n, cap, deg, seed=seed + 1)
+    sim, orc = make_pair(cfg, nbr)
+    rounds = 40
+    ev = random_events(rng, n, rounds, n_crash=max(1, n // 10), n_rejoin=max(1, n // 30), n_inject=n // 4)
+    sim.inject(ev)
+    orc.inject(ev)
+    for r in range(rounds):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"seed {seed} round {r + 1}")
+
+
+@pytest.mark.parametrize("cap", [64, 128, 256])
+def test_wide_rows(cap):
+    """view_cap > 32: a lane owns several slots of the row."""
+    rng = np.random.default_rng(cap)
+    n = 300
+    deg = cap - 7
+    cfg = default_config(n_nodes=n, view_cap=cap, k_indirect=5, fanout=4, pb_cap=16, suspicion_rounds=3,
+                         retransmit=5, loss_ppm=20000, seed=cap)
+    nbr = generate_topology("random", n, cap, deg, seed=3)
+    sim, orc = make_pair(cfg, nbr)
+    ev = random_events(rng, n, 30, n_crash=30, n_rejoin=10, n_inject=40)
+    sim.inject(ev)
+    orc.inject(ev)
+    for r in range(30):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"cap {cap} round {r + 1}")
+
+
+def test_multi_round_steps_equal_single_steps():
+    cfg = default_config(n_nodes=500, seed=99, loss_ppm=10000)
+    nbr = generate_topology("random", 500, 32, 20, seed=5)
+    sim, orc = make_pair(cfg, nbr)
+    ev = crash_events(3, list(range(0, 500, 17)))
+    sim.inject(ev)
+    orc.inject(ev)
+    sim.step(64)
+    orc.step(64)
+    assert_same_state(sim, orc, "after 64 rounds in one call")
+
+
+def test_c2_digest():
+    """BASELINE config C2: N=65,536, D=32 random views, k=3, 1 % crash at round 10."""
+    n = 65536
+    cfg = default_config(n_nodes=n, seed=0x5EED0001 + 2)
+    nbr = generate_topology("random", n, 32, 32, seed=2)
+    sim, orc = make_pair(cfg, nbr)
+    rng = np.random.default_rng(2)
+    ev = crash_events(10, rng.choice(n, size=n // 100, replace=False))
+    sim.inject(ev)
+    orc.inject(ev)
+    for chunk in (9, 1, 5, 1, 1, 23, 60):
+        sim.step(chunk)
+        orc.step(chunk)
+        assert sim.digest() == orc.digest(), f"digest differs at round {sim.round}"
+        assert sim.counters().tolist() == orc.counters().tolist()
+    assert_same_state(sim, orc, "C2 round 100")
+
+
+def test_c3_properties():
+    """BASELINE config C3 (N=1,048,576): size-independent properties at full size.
+    determinism (two runs, same digest), counters consistent, no false positives without loss."""
+    n = 1 << 20
+    cfg = default_config(n_nodes=n, seed=0x5EED0001 + 3)
+    nbr = generate_topology("random", n, 32, 32, seed=3)
+    rng = np.random.default_rng(3)
+    crashed = rng.choice(n, size=n // 1000, replace=False)
+    from swim_b200.sim import Simulator
+    digests = []
+    for rep in range(2):
+        sim = Simulator(cfg)
+        sim.set_view(nbr)
+        sim.inject(crash_events(10, crashed))
+        sim.step(40)
+        digests.append(sim.digest())
+        c = sim.counters()
+        st = sim.get_array(A.ARR_VST).reshape(n, 32) & 3
+        alive = sim.get_array(A.ARR_ALIVE)
+        sim.close()
+    assert digests[0] == digests[1]
+    assert c[A.CTR_PINGS] == 9 * n + 31 * (n - len(crashed))
+    assert c[A.CTR_REFUTES] == 0
+    # no loss => only crashed members are ever non-Alive
+    nonalive_members = np.unique(nbr[st != A.ALIVE])
+    assert alive[nonalive_members].max(initial=0) == 0
+    assert c[A.CTR_SUSPECT_LOCAL] > 0 and c[A.CTR_DEAD_TIMEOUT] > 0
