@@ -270,6 +270,17 @@ int swim_sim_mismatches(swim_sim_t *sim, uint64_t *count);
  * with CUDA events on the handle's stream. */
 int swim_sim_last_step_ms(const swim_sim_t *sim, float *ms);
 
+/* Number of kernels this handle has launched since create (bench.py's `gpu_launches`). */
+int swim_sim_launch_count(const swim_sim_t *sim, uint64_t *count);
+
+/* Per-kernel device timing: when enabled, every kernel of swim_sim_step is bracketed by CUDA
+ * events on the handle's stream; swim_sim_profile_ms returns the cumulative milliseconds per
+ * phase since it was enabled: out[0]=events, out[1]=tick, out[2]=exchange, out[3]=receive,
+ * and the number of rounds profiled in out[4]. Costs two event records per kernel. */
+#define SWIM_PROFILE_SLOTS 5
+int swim_sim_set_profile(swim_sim_t *sim, int enable);
+int swim_sim_profile_ms(swim_sim_t *sim, double *out, size_t n);
+
 /* ---- multi-GPU plumbing (one process per GPU; ranks own contiguous node ranges) ------
  * The per-round exchange is one all-to-all of cross-shard piggyback envelopes (the UDP
  * hop of Core.hs:280,286). Rank 0 obtains an id, the host side broadcasts the bytes

@@ -58,6 +58,9 @@ def lib():
     sig("swim_sim_counters", i, vp, vp, sz)
     sig("swim_sim_mismatches", i, vp, P(u64))
     sig("swim_sim_last_step_ms", i, vp, P(C.c_float))
+    sig("swim_sim_launch_count", i, vp, P(u64))
+    sig("swim_sim_set_profile", i, vp, i)
+    sig("swim_sim_profile_ms", i, vp, vp, sz)
     sig("swim_nccl_unique_id", i, vp)
     sig("swim_sim_connect", i, vp, vp)
     for name, args in {

@@ -29,8 +29,15 @@ struct swim_sim {
   void *d_events = nullptr;
   size_t d_events_cap = 0;
   unsigned long long *d_scratch = nullptr;
+  void *d_sargs = nullptr; // scalar-call argument block (swim_scalar.cu)
   std::vector<swim_event_t> events; // pending, sorted by round (stable)
   std::string last_error;
+  uint64_t launches = 0;
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events; // pool, reused
+  std::vector<std::pair<int, int>> prof_marks; // (phase, index of start event); stop = start + 1
+  size_t prof_used = 0;
+  double prof_ms[SWIM_PROFILE_SLOTS] = {0, 0, 0, 0, 0};
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };
 
@@ -39,5 +46,8 @@ void set_error(swim_sim *sim, const char *fmt, ...);
 uint32_t shard_first(uint32_t N, uint32_t world, uint32_t rank);
 int rebuild_edges_from_device(swim_sim *sim);
 int dist_exchange(swim_sim *sim);
+int prof_begin(swim_sim *sim, int phase);
+void prof_end(swim_sim *sim, int mark);
+int prof_collect(swim_sim *sim);
 void dist_teardown(swim_sim *sim);
 } // namespace swim

@@ -179,6 +179,7 @@ extern "C" void swim_sim_destroy(swim_sim_t *sim) {
   if (sim->d_in_src) cudaFree(sim->d_in_src);
   if (sim->d_eflag) cudaFree(sim->d_eflag);
   if (sim->d_events) cudaFree(sim->d_events);
+  for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   if (sim->ev_start) cudaEventDestroy(sim->ev_start);
   if (sim->ev_stop) cudaEventDestroy(sim->ev_stop);
   if (sim->own_stream) cudaStreamDestroy(sim->own_stream);
@@ -357,15 +358,26 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     if (ev_end > ev_pos) {
       const uint32_t cnt = (uint32_t)(ev_end - ev_pos);
       const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count);
+      int mk = prof_begin(sim, 0);
       event_kernel<W><<<eg, kThreads, 0, sim->stream>>>(d, (const DevEvent *)sim->d_events + ev_pos, cnt);
+      prof_end(sim, mk);
+      ++sim->launches;
       ev_pos = ev_end;
     }
+    int mk = prof_begin(sim, 1);
     tick_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
+    prof_end(sim, mk);
     if (d.world > 1) {
+      mk = prof_begin(sim, 2);
       int rc = swim::dist_exchange(sim);
       if (rc) return rc;
+      prof_end(sim, mk);
     }
+    mk = prof_begin(sim, 3);
     recv_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
+    prof_end(sim, mk);
+    sim->launches += 2;
+    if (sim->profile) sim->prof_ms[4] += 1;
   }
   sim->events.erase(sim->events.begin(), sim->events.begin() + n_ev);
   CUDA_TRY(sim, cudaGetLastError());
@@ -426,6 +438,63 @@ extern "C" int swim_sim_last_step_ms(const swim_sim_t *sim, float *ms) {
 extern "C" int swim_sim_round(const swim_sim_t *sim, uint32_t *round) {
   if (!sim || !round) return SWIM_EINVAL;
   *round = sim->round;
+  return SWIM_OK;
+}
+
+// ------------------------------------------------------------------ per-kernel profiling
+namespace swim {
+int prof_begin(swim_sim *sim, int phase) {
+  if (!sim->profile) return -1;
+  if (sim->prof_used + 2 > sim->prof_events.size()) {
+    for (int x = 0; x < 2; ++x) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return -1;
+      sim->prof_events.push_back(e);
+    }
+  }
+  const int idx = (int)sim->prof_used;
+  sim->prof_used += 2;
+  cudaEventRecord(sim->prof_events[idx], sim->stream);
+  sim->prof_marks.push_back({phase, idx});
+  return idx;
+}
+void prof_end(swim_sim *sim, int mark) {
+  if (mark >= 0) cudaEventRecord(sim->prof_events[mark + 1], sim->stream);
+}
+int prof_collect(swim_sim *sim) {
+  if (sim->prof_marks.empty()) return SWIM_OK;
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  for (auto &m : sim->prof_marks) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, sim->prof_events[m.second], sim->prof_events[m.second + 1]) == cudaSuccess)
+      sim->prof_ms[m.first] += ms;
+  }
+  sim->prof_marks.clear();
+  sim->prof_used = 0;
+  return SWIM_OK;
+}
+} // namespace swim
+
+extern "C" int swim_sim_set_profile(swim_sim_t *sim, int enable) {
+  if (!sim) return SWIM_EINVAL;
+  int rc = swim::prof_collect(sim);
+  if (rc) return rc;
+  sim->profile = enable != 0;
+  if (enable) for (double &v : sim->prof_ms) v = 0;
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_profile_ms(swim_sim_t *sim, double *out, size_t n) {
+  if (!sim || !out) return SWIM_EINVAL;
+  int rc = swim::prof_collect(sim);
+  if (rc) return rc;
+  for (size_t x = 0; x < n && x < SWIM_PROFILE_SLOTS; ++x) out[x] = sim->prof_ms[x];
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_launch_count(const swim_sim_t *sim, uint64_t *count) {
+  if (!sim || !count) return SWIM_EINVAL;
+  *count = sim->launches;
   return SWIM_OK;
 }
 
@@ -494,6 +563,7 @@ static int reduce_u64(swim_sim *sim, int which, uint64_t *out) {
     mismatch_kernel<<<grid_for(sim, (total + 31) / 32 / 4 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
   }
   CUDA_TRY(sim, cudaGetLastError());
+  ++sim->launches;
   unsigned long long v = 0;
   CUDA_TRY(sim, cudaMemcpyAsync(&v, sim->d_scratch, 8, cudaMemcpyDeviceToHost, sim->stream));
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));

@@ -140,6 +140,20 @@ class Simulator:
         check(lib().swim_sim_counters(self._h, out.ctypes.data, A.CTR_COUNT), "swim_sim_counters", self._h)
         return out
 
+    def launch_count(self):
+        d = C.c_uint64()
+        check(lib().swim_sim_launch_count(self._h, C.byref(d)), "swim_sim_launch_count", self._h)
+        return d.value
+
+    def set_profile(self, enable=True):
+        check(lib().swim_sim_set_profile(self._h, int(enable)), "swim_sim_set_profile", self._h)
+
+    def profile_ms(self):
+        """Cumulative per-phase device ms since set_profile(True): events, tick, exchange, recv, rounds."""
+        out = (C.c_double * 5)()
+        check(lib().swim_sim_profile_ms(self._h, out, 5), "swim_sim_profile_ms", self._h)
+        return dict(zip(["events", "tick", "exchange", "recv", "rounds"], list(out)))
+
     def state(self):
         """All bulk arrays as a dict (the checkable form of dumpStore, Util.hs:64-74)."""
         return {A.ARRAY_NAMES[a]: self.get_array(a) for a in range(A.ARR_COUNT)}
