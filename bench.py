@@ -188,7 +188,10 @@ def run_cuda(args):
 
     # ------------------------------------------------ device-resident timing (value)
     sim = fresh()
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: its handle is what the library launches on, so the torch events
+    # below bracket the kernels (handle 0 would mean "the handle's private stream" to the C ABI)
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
     sim.set_stream(stream.cuda_stream)
     sim.step(args.warmup)
     c0, l0 = sim.counters(), sim.launch_count()

@@ -95,7 +95,7 @@ bool put_body(Out &o, const swim_wire_message_t &m) {
       put_key(o, "port"); put_int(o, m.port);
       return true;
     case SWIM_MSG_DEAD:
-      o.u8(0x83); put_key(o, "tag"); put_key(o, "Dead");
+      o.u8(0x84); put_key(o, "tag"); put_key(o, "Dead");
       put_key(o, "incarnation"); put_int(o, m.incarnation);
       put_key(o, "node"); put_str(o, m.node, nn);
       put_key(o, "deadFrom"); put_str(o, m.dead_from, nf);
