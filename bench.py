@@ -233,20 +233,21 @@ def run_cuda(args):
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    tick_ms = prof["tick"] / max(1.0, prof["rounds"])
+    tick_ms = prof["tick_scan"] / max(1.0, prof["rounds"])
     n_local = n // world
     achieved = ab_tick * n_local / (tick_ms * 1e-3) / 1e9 if tick_ms > 0 else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "tick_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "tick_kernel<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "tick_scan_kernel<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
                 "traffic": traffic,
                 "algorithmic_bytes_per_launch": ab_tick * n_local,
                 "ab_per_node_round": {"round": ab_round, "tick": ab_tick, "m_bar": m_bar, "b_bar": b_bar},
-                "tick_ms_per_launch": tick_ms, "recv_ms_per_launch": prof["recv"] / max(1.0, prof["rounds"]),
+                "tick_ms_per_launch": tick_ms, "tick_work_ms_per_launch": prof["tick_work"] / max(1.0, prof["rounds"]),
+                "recv_ms_per_launch": prof["recv"] / max(1.0, prof["rounds"]),
                 "exchange_ms_per_round": prof["exchange"] / max(1.0, prof["rounds"]),
                 "note": "achieved uses SURVEY §8(d)'s canonical bytes; the kernel packs liveness+timer into one "
                         "byte per slot and reads incarnations/buffers only on events, so real DRAM traffic "

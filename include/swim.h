@@ -275,9 +275,10 @@ int swim_sim_launch_count(const swim_sim_t *sim, uint64_t *count);
 
 /* Per-kernel device timing: when enabled, every kernel of swim_sim_step is bracketed by CUDA
  * events on the handle's stream; swim_sim_profile_ms returns the cumulative milliseconds per
- * phase since it was enabled: out[0]=events, out[1]=tick, out[2]=exchange, out[3]=receive,
- * and the number of rounds profiled in out[4]. Costs two event records per kernel. */
-#define SWIM_PROFILE_SLOTS 5
+ * phase since it was enabled: out[0]=events, out[1]=tick scan (K1a), out[2]=exchange,
+ * out[3]=receive (K2), out[4]=tick work (K1b), and the number of rounds profiled in out[5].
+ * Costs two event records per kernel. */
+#define SWIM_PROFILE_SLOTS 6
 int swim_sim_set_profile(swim_sim_t *sim, int enable);
 int swim_sim_profile_ms(swim_sim_t *sim, double *out, size_t n);
 

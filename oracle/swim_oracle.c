@@ -700,7 +700,9 @@ EXPORT int oracle_set_members(oracle_t *o, uint32_t node, const swim_member_t *m
   for (uint32_t s = 0; s < o->cap; ++s) {
     size_t x = (size_t)l * o->cap + s;
     if (s < n) {
-      o->nbr[x] = tmp[s].id; o->state[x] = tmp[s].liveness; o->timer[x] = tmp[s].timer;
+      /* the countdown only exists while Suspect; a Suspect member given without one is armed with S */
+      o->nbr[x] = tmp[s].id; o->state[x] = tmp[s].liveness;
+      o->timer[x] = tmp[s].liveness != SWIM_SUSPECT ? 0 : tmp[s].timer ? tmp[s].timer : (uint8_t)o->S;
       o->vinc[x] = tmp[s].incarnation; o->vlast[x] = (uint32_t)tmp[s].last_change;
     } else {
       o->nbr[x] = SWIM_NO_MEMBER; o->state[x] = SWIM_VACANT; o->timer[x] = 0; o->vinc[x] = 0; o->vlast[x] = 0;

@@ -53,10 +53,21 @@ struct SimDev {
   uint32_t *in_off;          // [n+1]
   uint32_t *in_src;          // [E] sender ids, ascending per receiver
   uint8_t *eflag;            // [E] 1 = sender mailed this round
-  uint8_t *mail;             // [n] receiver has mail
-  uint32_t *any_mail;        // [2] round-parity "somebody sent" flag
+  uint32_t *mail;            // [n] round of the receiver's latest mail (dedupes the receiver list)
+  uint32_t *tdead;           // [n*W] bit s: the member in slot s is a crashed process
+  uint32_t *obs_off;         // [N+1] observers of member m among this shard's rows ...
+  uint32_t *obs_slot;        // [n*cap] ... as linear slot indices l*cap + s
+  uint32_t *wl, *wl_cnt;     // work list of K1b [n], its round-parity counters [2]
+  uint32_t *rl, *rl_cnt;     // receiver list of K2 [n], its round-parity counters [2]
+  // cross-shard exchange (world > 1)
+  uint4 *xsend;              // [world][xcap] envelopes {ridx, cnt, src, -} + B records, bucketed by rank
+  uint32_t *xsend_cnt;       // [world + 1]; the last word is the bucket-overflow flag
+  uint4 *xrecv;              // received envelopes, all source ranks back to back
+  uint32_t *eslot;           // [E] exchange-buffer slot of the envelope raised on in-edge e
+  uint32_t xcap;             // envelopes per destination bucket
   unsigned long long *ctr;   // [SWIM_CTR__COUNT]
 };
+
 
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -257,34 +268,34 @@ struct Ctr {
 };
 
 // =================================================================== K1: tick
-// SWAR helpers on 4 packed state bytes
-__device__ __forceinline__ uint32_t gather4(uint32_t a) { // bit0 of each byte -> 4-bit nibble
-  return (a * 0x01020408u) >> 24 & 0xFu;
+// SWAR helper: bit0 of each of 4 bytes -> 4-bit nibble
+__device__ __forceinline__ uint32_t gather4(uint32_t a) { return (a * 0x01020408u) >> 24 & 0xFu; }
+
+__device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t self, uint32_t leg) {
+  if (!d.loss_ppm) return false;
+  uint4 y = philox4x32_10(make_uint4(d.round, self, P_LOSS, leg >> 2), d.key0, d.key1);
+  return bounded(word_of(y, leg & 3), 1000000u) < d.loss_ppm;
 }
 
+// K1a — lane-per-node streaming pass over every node of the shard. Reads per node: 1 B up flag,
+// 1 B buffer count, 4*W B crashed-member bitmap, 32*W B packed state row (two 128-bit loads per
+// 32 slots; a warp covers 1 KB contiguous). Does the suspicion countdown in place (SWAR), builds
+// the alive bitmask, draws the probe target with Philox and tests it against the crashed-member
+// bitmap. Nodes that need more than that (timer expiry, failed probe, non-empty piggyback buffer)
+// are appended to the round's work list for K1b.
 template <int W>
-__global__ void __launch_bounds__(kThreads) tick_kernel(SimDev d) {
-  __shared__ uint4 s_pb[kWarpsPerBlock][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
-  if (warp == 0 && lane == 0) d.any_mail[(d.round + 1) & 1] = 0;
-  Ctr c; c.clear();
-  PbStage pbs; pbs.s = s_pb[wib];
-
+__global__ void __launch_bounds__(kThreads, 6) tick_scan_kernel(SimDev d) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t *wl_cnt = d.wl_cnt + (d.round & 1);
+  uint32_t pings = 0;
   for (uint32_t base = warp * 32; base < d.n; base += nwarps * 32) {
-    // ---------------- phase A: lane-per-node
     const uint32_t l = base + lane;
-    const bool up = l < d.n && d.alive[d.first + l] != 0; // a crashed process does nothing
-    uint32_t am[W];       // alive bitmask per 32-slot word, after the countdown
-    bool work = false;    // needs the warp-per-node path
-    bool expired = false; // some suspicion timer hit zero
-    bool acked = true;
-    uint32_t tslot = 0, tnode = 0, L = 0;
-    uint4 x = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int w = 0; w < W; ++w) am[w] = 0;
-    if (up) {
+    bool work = false;
+    if (l < d.n && d.alive[d.first + l] != 0) { // a crashed process does nothing
+      work = d.pb_cnt[l] != 0;
       uint4 *rowp = reinterpret_cast<uint4 *>(d.vst + (size_t)l * d.cap);
+      uint32_t am[W], L = 0;
 #pragma unroll
       for (int w = 0; w < W; ++w) {
         uint4 q[2] = {rowp[2 * w], rowp[2 * w + 1]};
@@ -292,229 +303,284 @@ __global__ void __launch_bounds__(kThreads) tick_kernel(SimDev d) {
         uint32_t any_sus = 0, mask = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          uint32_t b0 = v[j] & 0x01010101u, b1 = (v[j] >> 1) & 0x01010101u;
-          uint32_t sus = b0 & ~b1;  // liveness == Suspect
-          uint32_t alv = ~(b0 | b1) & 0x01010101u; // liveness == Alive
-          any_sus |= sus;
-          v[j] -= sus << 2;         // [Q8] countdown: timer -= 1 (timer >= 1 while Suspect)
-          uint32_t t = v[j] & 0xFCFCFCFCu; // timer fields
-          uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u; // zero timers
-          if (sus & (z >> 7)) expired = true;
-          mask |= gather4(alv) << (4 * j);
+          const uint32_t b0 = v[j] & 0x01010101u, b1 = (v[j] >> 1) & 0x01010101u;
+          any_sus |= b0 & ~b1;                                      // liveness == Suspect
+          mask |= gather4(~(b0 | b1) & 0x01010101u) << (4 * j);     // liveness == Alive
+        }
+        if (any_sus) { // [Q8] countdown: timer -= 1 on Suspect slots (timer >= 1 while Suspect)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t sus = v[j] & ~(v[j] >> 1) & 0x01010101u;
+            v[j] -= sus << 2;
+            const uint32_t t = v[j] & 0xFCFCFCFCu;
+            const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u; // zero timers
+            work |= (sus & (z >> 7)) != 0;                          // a timer expired
+          }
+          rowp[2 * w] = q[0];
+          rowp[2 * w + 1] = q[1];
         }
         am[w] = mask;
         L += __popc(mask);
-        if (any_sus) { rowp[2 * w] = q[0]; rowp[2 * w + 1] = q[1]; }
       }
-      work = expired || d.pb_cnt[l] != 0;
       if (L) {
-        // kRandomMembers store 1 [] (Core.hs:239, [Q11]): first draw of the first block
-        x = philox4x32_10(make_uint4(d.round, d.first + l, P_SELECT, 0), d.key0, d.key1);
-        uint32_t tmp[W];
-#pragma unroll
-        for (int w = 0; w < W; ++w) tmp[w] = am[w];
-        tslot = pick_remove<W>(tmp, bounded(x.x, L));
-        tnode = d.nbr[(size_t)l * d.cap + tslot];
-        ++c.v[SWIM_CTR_PINGS];                        // Ping (Core.hs:246)
-        acked = d.alive[tnode] != 0;                  // Ack iff the target process is up
-        if (acked && d.loss_ppm) {
-          uint4 y = philox4x32_10(make_uint4(d.round, d.first + l, P_LOSS, 0), d.key0, d.key1);
-          acked = !(bounded(y.x, 1000000u) < d.loss_ppm);
-        }
+        // kRandomMembers store 1 [] (Core.hs:239, [Q11]): first draw of the SELECT stream
+        const uint4 x = philox4x32_10(make_uint4(d.round, d.first + l, P_SELECT, 0), d.key0, d.key1);
+        const uint32_t tslot = pick_remove<W>(am, bounded(x.x, L));
+        ++pings;                                                    // Ping (Core.hs:246)
+        bool acked = (d.tdead[(size_t)l * W + (tslot >> 5)] >> (tslot & 31) & 1u) == 0; // target process up
+        if (acked && d.loss_ppm) acked = !leg_lost(d, d.first + l, 0);
         work |= !acked;
       }
     }
-    // ---------------- phase B: warp-per-node for nodes with work
-    __syncwarp(); // phase A's countdown stores are ordered before the row loads below
-    unsigned todo = __ballot_sync(kFull, work);
-    while (todo) {
-      const int b = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t ln = base + b, self = d.first + ln;
-      const bool b_expired = __shfl_sync(kFull, expired, b);
-      const bool b_acked = __shfl_sync(kFull, acked, b);
-      const uint32_t b_L = __shfl_sync(kFull, L, b);
-      const uint32_t b_tslot = __shfl_sync(kFull, tslot, b);
-      const uint32_t b_tnode = __shfl_sync(kFull, tnode, b);
-      uint4 bx;
-      bx.x = __shfl_sync(kFull, x.x, b); bx.y = __shfl_sync(kFull, x.y, b);
-      bx.z = __shfl_sync(kFull, x.z, b); bx.w = __shfl_sync(kFull, x.w, b);
-      uint32_t bam[W];
-#pragma unroll
-      for (int w = 0; w < W; ++w) bam[w] = __shfl_sync(kFull, am[w], b);
+    const unsigned todo = __ballot_sync(kFull, work);
+    if (todo) {
+      uint32_t pos = 0;
+      if (lane == 0) pos = atomicAdd(wl_cnt, (uint32_t)__popc(todo));
+      pos = __shfl_sync(kFull, pos, 0);
+      if (work) d.wl[pos + __popc(todo & ((1u << lane) - 1))] = l;
+    }
+  }
+  pings = __reduce_add_sync(kFull, pings);
+  if (lane == 0 && pings) atomicAdd(&d.ctr[SWIM_CTR_PINGS], (unsigned long long)pings);
+}
 
-      Row<W> row;
-      row_load<W>(row, d, ln, lane); // lane b's countdown stores are visible after the shuffles' sync
-      pb_load(pbs, d, ln, lane);
+// K1b — warp-per-node over the work list: timer expiry -> Dead, probe escalation (k proxies),
+// local suspicion, piggyback send. Lane s owns view slot s; the piggyback buffer is staged in
+// shared memory. Everything K1a derived is recomputed from the row with warp ballots.
+template <int W>
+__global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
+  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  const uint32_t n_work = d.wl_cnt[d.round & 1];
+  if (warp == 0 && lane == 0) { d.wl_cnt[(d.round + 1) & 1] = 0; }
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+  uint32_t *rl_cnt = d.rl_cnt + (d.round & 1);
 
-      // T1 [Q8]: expired Suspect -> Dead, broadcast Dead(inc, member, from = self), slot order
-      if (b_expired) {
+  for (uint32_t item = warp; item < n_work; item += nwarps) {
+    const uint32_t ln = d.wl[item], self = d.first + ln;
+    Row<W> row;
+    row_load<W>(row, d, ln, lane);
+    pb_load(pbs, d, ln, lane);
+    uint32_t td[W], am[W], L = 0;
 #pragma unroll
-        for (int w = 0; w < W; ++w) {
-          unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && (row.st[w] >> 2) == 0);
-          if (lane < 32 && (em >> lane & 1u)) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
-          while (em) {
-            int s = __ffs(em) - 1;
-            em &= em - 1;
-            uint32_t m = __shfl_sync(kFull, row.nb[w], s), i = __shfl_sync(kFull, row.inc[w], s);
-            pb_enqueue(pbs, d, make_rec(m, i, self, SWIM_MSG_DEAD), lane, c.v[SWIM_CTR_PB_DROPPED]);
-            if (lane == 0) ++c.v[SWIM_CTR_DEAD_TIMEOUT];
-          }
-        }
-      }
-      // kRandomMembers store k [] (Core.hs:249): a fresh shuffle over the same alive list;
-      // neither self nor the target is excluded. Draws 1..k of the SELECT stream.
-      uint32_t prox[SWIM_MAX_K];
-      uint32_t np = 0;
-      if (b_L) {
-        uint32_t tmp[W];
+    for (int w = 0; w < W; ++w) {
+      td[w] = d.tdead[(size_t)ln * W + w];
+      am[w] = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE);
+      L += __popc(am[w]);
+    }
+    // T1 [Q8]: expired Suspect -> Dead, broadcast Dead(inc, member, from = self), slot order
 #pragma unroll
-        for (int w = 0; w < W; ++w) tmp[w] = bam[w];
-        uint4 blk = bx;
-        np = d.k < b_L ? d.k : b_L;
-        for (uint32_t j = 0; j < np; ++j) {
-          uint32_t dr = 1 + j;
-          if (dr == 4) blk = philox4x32_10(make_uint4(d.round, self, P_SELECT, 1), d.key0, d.key1);
-          prox[j] = pick_remove<W>(tmp, bounded(word_of(blk, dr & 3), b_L - j));
-        }
+    for (int w = 0; w < W; ++w) {
+      unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && (row.st[w] >> 2) == 0);
+      if (em >> lane & 1u) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
+      while (em) {
+        const int s = __ffs(em) - 1;
+        em &= em - 1;
+        const uint32_t m = __shfl_sync(kFull, row.nb[w], s), i = __shfl_sync(kFull, row.inc[w], s);
+        pb_enqueue(pbs, d, make_rec(m, i, self, SWIM_MSG_DEAD), lane, c.v[SWIM_CTR_PB_DROPPED]);
+        if (lane == 0) ++c.v[SWIM_CTR_DEAD_TIMEOUT];
       }
-      // T3: unlessAck -> IndirectPings (Core.hs:247-250), unlessAck -> suspectNode (251-254)
-      if (b_L && !b_acked) {
+    }
+    uint32_t tslot = 0, np = 0, prox[SWIM_MAX_K];
+    if (L) {
+      // target: draw 0; proxies: kRandomMembers store k [] (Core.hs:249), a fresh shuffle over the
+      // same alive list (neither self nor the target excluded), draws 1..k of the SELECT stream
+      uint4 blk = philox4x32_10(make_uint4(d.round, self, P_SELECT, 0), d.key0, d.key1);
+      uint32_t tmp[W];
+#pragma unroll
+      for (int w = 0; w < W; ++w) tmp[w] = am[w];
+      tslot = pick_remove<W>(tmp, bounded(blk.x, L));
+#pragma unroll
+      for (int w = 0; w < W; ++w) tmp[w] = am[w];
+      np = d.k < L ? d.k : L;
+      for (uint32_t j = 0; j < np; ++j) {
+        const uint32_t dr = 1 + j;
+        if (dr == 4) blk = philox4x32_10(make_uint4(d.round, self, P_SELECT, 1), d.key0, d.key1);
+        prox[j] = pick_remove<W>(tmp, bounded(word_of(blk, dr & 3), L - j));
+      }
+      // T3: Ping (Core.hs:246); unlessAck -> IndirectPings (247-250); unlessAck -> suspectNode (251-254)
+      const bool t_up = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;
+      const bool acked = t_up && !leg_lost(d, self, 0);
+      if (!acked) {
         if (lane == 0) { ++c.v[SWIM_CTR_DIRECT_FAIL]; c.v[SWIM_CTR_INDIRECT_PINGS] += np; }
         bool ok = false;
-        const bool t_up = d.alive[b_tnode] != 0;
         if ((uint32_t)lane < np && t_up) {
-          uint32_t pn = d.nbr[(size_t)ln * d.cap + prox[lane]];
-          ok = d.alive[pn] != 0;
-          if (ok && d.loss_ppm) {
-            uint32_t leg = 1 + lane;
-            uint4 y = philox4x32_10(make_uint4(d.round, self, P_LOSS, leg >> 2), d.key0, d.key1);
-            ok = !(bounded(word_of(y, leg & 3), 1000000u) < d.loss_ppm);
-          }
+          const uint32_t ps = prox[lane];
+          ok = (td[ps >> 5] >> (ps & 31) & 1u) == 0 && !leg_lost(d, self, 1 + lane);
         }
         if (!__any_sync(kFull, ok)) {
           // Suspect (memberIncarnation m) (memberName m) with m captured at probe start
-          const int tw = b_tslot >> 5, tl = b_tslot & 31;
-          uint32_t tinc = 0;
+          const int tw = tslot >> 5, tl = tslot & 31;
+          uint32_t tinc = 0, tnode = 0;
 #pragma unroll
           for (int w = 0; w < W; ++w) {
-            uint32_t v = __shfl_sync(kFull, row.inc[w], tl);
-            if (w == tw) tinc = v;
+            const uint32_t a = __shfl_sync(kFull, row.inc[w], tl), b = __shfl_sync(kFull, row.nb[w], tl);
+            if (w == tw) { tinc = a; tnode = b; }
           }
           uint4 rb;
-          uint32_t dummy_inc = 0xFFFFFFFFu; // a probe never targets self
-          if (row_apply<W>(row, d, self, dummy_inc, make_rec(b_tnode, tinc, 0, SWIM_MSG_SUSPECT), rb, lane,
+          uint32_t no_self_inc = 0xFFFFFFFFu; // a probe never targets self
+          if (row_apply<W>(row, d, self, no_self_inc, make_rec(tnode, tinc, 0, SWIM_MSG_SUSPECT), rb, lane,
                            c.v[SWIM_CTR_REFUTES]) == 1) {
             pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // yield . Broadcast (Core.hs:254)
             if (lane == 0) ++c.v[SWIM_CTR_SUSPECT_LOCAL];
           }
         }
       }
-      row_store<W>(row, d, ln, lane);
-      // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
-      if (b_L && pbs.cnt) {
-        uint32_t nr = 1;
-        uint32_t rslot = b_tslot; // lane f carries recipient f
-        for (uint32_t j = 0; j < np && nr < d.fanout; ++j)
-          if (prox[j] != b_tslot) { if ((uint32_t)lane == nr) rslot = prox[j]; ++nr; }
-        if ((uint32_t)lane < nr) {
-          size_t e = (size_t)ln * d.cap + rslot;
-          uint32_t dst = d.nbr[e];
-          d.eflag[d.ridx[e]] = 1;      // raise the in-edge flag (i -> dst)
-          d.mail[dst - d.first] = 1;   // single-shard delivery
-        }
-        if (lane == 0) {
-          d.any_mail[d.round & 1] = 1;
-          d.out_cnt[ln] = (uint8_t)pbs.cnt;
-          c.v[SWIM_CTR_MSGS] += nr;
-          c.v[SWIM_CTR_RECS_SENT] += nr * pbs.cnt;
-        }
-        // snapshot, then one transmission is spent on every record
-        uint4 mine = make_uint4(0, 0, 0, 0);
-        const bool have = (uint32_t)lane < pbs.cnt;
-        if (have) { mine = pbs.s[lane]; d.out[(size_t)ln * d.B + lane] = mine; }
-        const bool keep = have && rec_ttl(mine) > 1;
-        const unsigned km = __ballot_sync(kFull, keep);
-        __syncwarp();
-        if (keep) {
-          mine.w -= 1u << 8;
-          pbs.s[__popc(km & ((1u << lane) - 1))] = mine;
-        }
-        pbs.cnt = __popc(km);
-        pbs.dirty = true;
-        __syncwarp();
-      }
-      pb_store(pbs, d, ln, lane);
     }
+    row_store<W>(row, d, ln, lane);
+    // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
+    if (L && pbs.cnt) {
+      uint32_t nr = 1, rslot = tslot; // lane f carries recipient f
+      for (uint32_t j = 0; j < np && nr < d.fanout; ++j)
+        if (prox[j] != tslot) { if ((uint32_t)lane == nr) rslot = prox[j]; ++nr; }
+      uint32_t xs = 0xFFFFFFFFu; // exchange-bucket slot when lane f's recipient lives on another shard
+      if ((uint32_t)lane < nr) {
+        const size_t e = (size_t)ln * d.cap + rslot;
+        const uint32_t dst = d.nbr[e], ridx = d.ridx[e];
+        const uint32_t owner = d.world == 1 ? 0u : dst / d.per;
+        if (owner == d.rank) {
+          d.eflag[ridx] = 1; // raise the in-edge flag (i -> dst)
+          if (atomicExch(&d.mail[dst - d.first], d.round) != d.round) d.rl[atomicAdd(rl_cnt, 1u)] = dst - d.first;
+        } else {
+          const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
+          if (k < d.xcap) {
+            xs = owner * d.xcap + k;
+            d.xsend[(size_t)xs * (1 + d.B)] = make_uint4(ridx, pbs.cnt, self, dst - owner * d.per);
+          } else {
+            d.xsend_cnt[d.world] = 1; // overflow: reported by the host as SWIM_ECAP, never silent
+          }
+        }
+      }
+      if (lane == 0) {
+        d.out_cnt[ln] = (uint8_t)pbs.cnt;
+        c.v[SWIM_CTR_MSGS] += nr;
+        c.v[SWIM_CTR_RECS_SENT] += nr * pbs.cnt;
+      }
+      // snapshot, then one transmission is spent on every record
+      uint4 mine = make_uint4(0, 0, 0, 0);
+      const bool have = (uint32_t)lane < pbs.cnt;
+      if (have) { mine = pbs.s[lane]; d.out[(size_t)ln * d.B + lane] = mine; }
+      unsigned xm = __ballot_sync(kFull, xs != 0xFFFFFFFFu);
+      while (xm) { // cross-shard envelopes carry the records themselves
+        const int f = __ffs(xm) - 1;
+        xm &= xm - 1;
+        const uint32_t slot = __shfl_sync(kFull, xs, f);
+        if (have) d.xsend[(size_t)slot * (1 + d.B) + 1 + lane] = mine;
+      }
+      const bool keep = have && rec_ttl(mine) > 1;
+      const unsigned km = __ballot_sync(kFull, keep);
+      __syncwarp();
+      if (keep) {
+        mine.w -= 1u << 8;
+        pbs.s[__popc(km & ((1u << lane) - 1))] = mine;
+      }
+      pbs.cnt = __popc(km);
+      pbs.dirty = true;
+      __syncwarp();
+    }
+    pb_store(pbs, d, ln, lane);
   }
   c.flush(d.ctr, lane);
 }
 
 // =================================================================== K2: receive
+// warp-per-receiver over the round's receiver list. Loads that do not depend on each other are
+// issued together: (row, buffer, in-list bounds) -> (edge flags, sender ids) -> (sender snapshots).
 template <int W>
 __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
-  if (d.any_mail[d.round & 1] == 0) return; // nobody sent this round
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  const uint32_t n_recv = d.rl_cnt[d.round & 1];
+  if (warp == 0 && lane == 0) d.rl_cnt[(d.round + 1) & 1] = 0;
+  if (n_recv == 0) return;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
 
-  for (uint32_t base = warp * 32; base < d.n; base += nwarps * 32) {
-    const uint32_t l = base + lane;
-    unsigned todo = __ballot_sync(kFull, l < d.n && d.mail[l] != 0);
-    while (todo) {
-      const int b = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const uint32_t ln = base + b, self = d.first + ln;
-      const bool up = d.alive[self] != 0; // datagrams to a crashed process are lost
-      if (lane == 0) d.mail[ln] = 0;
-      Row<W> row;
-      uint32_t self_inc = 0, self_inc0 = 0;
-      if (up) {
-        row_load<W>(row, d, ln, lane);
-        pb_load(pbs, d, ln, lane);
-        self_inc = self_inc0 = d.self_inc[ln];
-      }
-      const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
-      for (uint32_t eb = e0; eb < e1; eb += 32) {
-        const uint32_t e = eb + lane;
-        const bool f = e < e1 && d.eflag[e] != 0;
-        uint32_t src = 0;
-        if (f) { d.eflag[e] = 0; src = d.in_src[e]; }
-        unsigned fm = __ballot_sync(kFull, f);
-        if (!up) continue;
-        while (fm) { // ascending sender id: the in-list is sorted
-          const int q = __ffs(fm) - 1;
-          fm &= fm - 1;
-          const uint32_t sl = __shfl_sync(kFull, src, q) - d.first;
-          const uint32_t cnt = d.out_cnt[sl];
-          uint4 mine = make_uint4(0, 0, 0, 0);
-          if ((uint32_t)lane < cnt) mine = d.out[(size_t)sl * d.B + lane];
-          if (lane == 0) ++c.v[SWIM_CTR_MSGS_RECV];
-          for (uint32_t r = 0; r < cnt; ++r) { // records in buffer order (newest first)
-            uint4 rec;
-            rec.x = __shfl_sync(kFull, mine.x, r); rec.y = __shfl_sync(kFull, mine.y, r);
-            rec.z = __shfl_sync(kFull, mine.z, r); rec.w = __shfl_sync(kFull, mine.w, r);
-            uint4 rb;
-            if (row_apply<W>(row, d, self, self_inc, rec, rb, lane, c.v[SWIM_CTR_REFUTES]) == 1) {
-              pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // maybeBroadcast (Core.hs:119-121)
-              if (lane == 0) ++c.v[SWIM_CTR_RECS_APPLIED];
-            }
+  for (uint32_t item = warp; item < n_recv; item += nwarps) {
+    const uint32_t ln = d.rl[item], self = d.first + ln;
+    const bool up = d.alive[self] != 0; // datagrams to a crashed process are lost
+    const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
+    Row<W> row;
+    uint32_t self_inc = 0, self_inc0 = 0;
+    if (up) {
+      row_load<W>(row, d, ln, lane);
+      pb_load(pbs, d, ln, lane);
+      self_inc = self_inc0 = d.self_inc[ln];
+    }
+    for (uint32_t eb = e0; eb < e1; eb += 32) {
+      const uint32_t e = eb + lane;
+      uint32_t f = 0, src = 0;
+      if (e < e1) { f = d.eflag[e]; src = d.in_src[e]; }
+      if (f) d.eflag[e] = 0;
+      unsigned fm = __ballot_sync(kFull, f != 0);
+      if (!up) continue;
+      while (fm) { // ascending sender id: the in-list is sorted
+        const int q = __ffs(fm) - 1;
+        fm &= fm - 1;
+        const uint32_t s_id = __shfl_sync(kFull, src, q), s_kind = __shfl_sync(kFull, f, q);
+        uint32_t cnt;
+        uint4 mine = make_uint4(0, 0, 0, 0);
+        if (s_kind == 1) { // sender on this shard: pull its snapshot
+          const uint32_t sl = s_id - d.first;
+          if ((uint32_t)lane < d.B) mine = d.out[(size_t)sl * d.B + lane];
+          cnt = d.out_cnt[sl];
+        } else {           // sender on another shard: the envelope arrived in the exchange buffer
+          const uint32_t slot = d.eslot[eb + q];
+          const uint4 *env = d.xrecv + (size_t)slot * (1 + d.B);
+          if ((uint32_t)lane < d.B) mine = env[1 + lane];
+          cnt = env[0].y;
+        }
+        if (lane == 0) ++c.v[SWIM_CTR_MSGS_RECV];
+        for (uint32_t r = 0; r < cnt; ++r) { // records in buffer order (newest first)
+          uint4 rec;
+          rec.x = __shfl_sync(kFull, mine.x, r); rec.y = __shfl_sync(kFull, mine.y, r);
+          rec.z = __shfl_sync(kFull, mine.z, r); rec.w = __shfl_sync(kFull, mine.w, r);
+          uint4 rb;
+          if (row_apply<W>(row, d, self, self_inc, rec, rb, lane, c.v[SWIM_CTR_REFUTES]) == 1) {
+            pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // maybeBroadcast (Core.hs:119-121)
+            if (lane == 0) ++c.v[SWIM_CTR_RECS_APPLIED];
           }
         }
       }
-      if (up) {
-        row_store<W>(row, d, ln, lane);
-        pb_store(pbs, d, ln, lane);
-        if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
-      }
+    }
+    if (up) {
+      row_store<W>(row, d, ln, lane);
+      pb_store(pbs, d, ln, lane);
+      if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
     }
   }
   c.flush(d.ctr, lane);
 }
 
 // =================================================================== events (phase E)
+// Keep the crashed-member bitmaps in step with alive[]: every row of this shard that lists
+// `node` has the corresponding bit set (crash) or cleared (rejoin).
+__device__ __forceinline__ void mark_observers(const SimDev &d, uint32_t node, bool crashed, int lane) {
+  const uint32_t W = d.cap >> 5;
+  for (uint32_t x = d.obs_off[node] + lane, end = d.obs_off[node + 1]; x < end; x += 32) {
+    const uint32_t slot = d.obs_slot[x], l = slot / d.cap, s = slot % d.cap;
+    uint32_t *word = d.tdead + (size_t)l * W + (s >> 5);
+    if (crashed) atomicOr(word, 1u << (s & 31)); else atomicAnd(word, ~(1u << (s & 31)));
+  }
+}
+
+// Rebuild every crashed-member bitmap from alive[] (after bulk edits of alive[] or of the rows).
+static __global__ void __launch_bounds__(kThreads) tdead_rebuild_kernel(SimDev d) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t W = d.cap >> 5;
+  for (uint32_t l = warp; l < d.n; l += nwarps)
+    for (uint32_t w = 0; w < W; ++w) {
+      const size_t x = (size_t)l * d.cap + w * 32 + lane;
+      const bool dead = (d.vst[x] & 3u) != SWIM_VACANT && d.alive[d.nbr[x]] == 0;
+      const unsigned m = __ballot_sync(kFull, dead);
+      if (lane == 0) d.tdead[(size_t)l * W + w] = m;
+    }
+}
+
 struct DevEvent {
   uint32_t node;
   uint32_t kind;
@@ -537,11 +603,13 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
     const uint32_t ln = node - d.first;
     if (kind == SWIM_EV_CRASH) {
       if (lane == 0) d.alive[node] = 0;
+      mark_observers(d, node, true, lane);
     } else if (kind == SWIM_EV_REJOIN) {
       const bool was_up = d.alive[node] != 0;
       __syncwarp();
       if (!was_up) {
         if (lane == 0) d.alive[node] = 1;
+        mark_observers(d, node, false, lane);
         if (local) { // restart with incarnation + 1 and announce Alive
           uint32_t inc = d.self_inc[ln] + 1;
           __syncwarp();

@@ -20,6 +20,7 @@ struct swim_sim {
   uint32_t round = 0;
   bool view_set = false;
   bool edges_dirty = false; // scalar calls changed a row's membership
+  bool tdead_dirty = true;  // crashed-member bitmaps must be rebuilt from alive[]
   bool connected = false;   // multi-shard exchange ready
   uint64_t n_edges = 0;
   uint64_t scalar_calls = 0;
@@ -37,7 +38,7 @@ struct swim_sim {
   std::vector<cudaEvent_t> prof_events; // pool, reused
   std::vector<std::pair<int, int>> prof_marks; // (phase, index of start event); stop = start + 1
   size_t prof_used = 0;
-  double prof_ms[SWIM_PROFILE_SLOTS] = {0, 0, 0, 0, 0};
+  double prof_ms[SWIM_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0};
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };
 

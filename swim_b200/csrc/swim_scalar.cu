@@ -257,7 +257,9 @@ extern "C" int swim_set_members(swim_sim_t *sim, uint32_t node, const swim_membe
   std::vector<uint32_t> nb(d.cap, SWIM_NO_MEMBER), inc(d.cap, 0), last(d.cap, 0);
   std::vector<uint8_t> st(d.cap, SWIM_VACANT);
   for (size_t x = 0; x < n; ++x) {
-    nb[x] = v[x].id; st[x] = (uint8_t)(v[x].liveness | (v[x].timer << 2)); inc[x] = v[x].incarnation;
+    // the countdown only exists while Suspect; a Suspect member given without one is armed with S
+    const uint32_t timer = v[x].liveness != SWIM_SUSPECT ? 0u : v[x].timer ? v[x].timer : d.S;
+    nb[x] = v[x].id; st[x] = (uint8_t)(v[x].liveness | (timer << 2)); inc[x] = v[x].incarnation;
     last[x] = (uint32_t)v[x].last_change;
   }
   const size_t base = (size_t)(node - d.first) * d.cap;

@@ -160,7 +160,13 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.ridx, slots, 0))) return r;
     if ((r = dalloc(sim, &d.in_off, n + 1, 0))) return r;
     if ((r = dalloc(sim, &d.mail, n, 0))) return r;
-    if ((r = dalloc(sim, &d.any_mail, 2, 0))) return r;
+    if ((r = dalloc(sim, &d.tdead, slots / 32, 0))) return r;
+    if ((r = dalloc(sim, &d.obs_off, (size_t)d.N + 1, 0))) return r;
+    if ((r = dalloc(sim, &d.obs_slot, slots, 0))) return r;
+    if ((r = dalloc(sim, &d.wl, n, 0))) return r;
+    if ((r = dalloc(sim, &d.wl_cnt, 2, 0))) return r;
+    if ((r = dalloc(sim, &d.rl, n, 0))) return r;
+    if ((r = dalloc(sim, &d.rl_cnt, 2, 0))) return r;
     if ((r = dalloc(sim, &d.ctr, SWIM_CTR__COUNT, 0))) return r;
     if ((r = dalloc(sim, &sim->d_scratch, 8, 0))) return r;
     return SWIM_OK;
@@ -228,6 +234,21 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
       if (mine) ridx[(size_t)(i - d.first) * cap + s] = (uint32_t)goff[j] + pos;
     }
   }
+  // observers: for every member id m, the local slots (l*cap + s) that hold m — the transpose of
+  // the local rows, used to keep the crashed-member bitmaps current on crash / rejoin events
+  {
+    std::vector<uint32_t> obs_off((size_t)N + 1, 0), obs_slot((size_t)d.n * cap ? (size_t)d.n * cap : 1);
+    const uint32_t *rows = nbr + (size_t)d.first * cap;
+    for (size_t x = 0, tot = (size_t)d.n * cap; x < tot; ++x)
+      if (rows[x] != SWIM_NO_MEMBER) obs_off[rows[x] + 1]++;
+    for (uint32_t m = 0; m < N; ++m) obs_off[m + 1] += obs_off[m];
+    std::vector<uint32_t> cur(obs_off.begin(), obs_off.end() - 1);
+    for (size_t x = 0, tot = (size_t)d.n * cap; x < tot; ++x)
+      if (rows[x] != SWIM_NO_MEMBER) obs_slot[cur[rows[x]]++] = (uint32_t)x;
+    CUDA_TRY(sim, cudaMemcpy(d.obs_off, obs_off.data(), obs_off.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(sim, cudaMemcpy(d.obs_slot, obs_slot.data(), (size_t)d.n * cap * 4, cudaMemcpyHostToDevice));
+  }
+  sim->tdead_dirty = true;
   if (sim->d_in_src) { cudaFree(sim->d_in_src); sim->d_in_src = nullptr; }
   if (sim->d_eflag) { cudaFree(sim->d_eflag); sim->d_eflag = nullptr; }
   const size_t Ea = E ? (size_t)E : 1;
@@ -237,7 +258,7 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
   CUDA_TRY(sim, cudaMemcpy(sim->d_in_src, in_src.data(), Ea * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(sim, cudaMemcpy(d.in_off, in_off.data(), ((size_t)d.n + 1) * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(sim, cudaMemcpy(d.ridx, ridx.data(), ridx.size() * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(sim, cudaMemset(d.mail, 0, d.n ? d.n : 1));
+  CUDA_TRY(sim, cudaMemset(d.mail, 0, (d.n ? d.n : 1) * sizeof(uint32_t)));
   d.in_src = sim->d_in_src;
   d.eflag = sim->d_eflag;
   sim->n_edges = E;
@@ -329,6 +350,12 @@ template <int W>
 static int run_rounds(swim_sim *sim, uint32_t rounds) {
   SimDev &d = sim->dev;
   const int grid = grid_for(sim, ((size_t)d.n + 31) / 32);
+  const int wgrid = grid_for(sim, (size_t)d.n); // warp-per-item kernels: at most one resident wave
+  if (sim->tdead_dirty) {
+    tdead_rebuild_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+    ++sim->launches;
+    sim->tdead_dirty = false;
+  }
   // upload the events that fall inside this call
   size_t n_ev = 0;
   while (n_ev < sim->events.size() && sim->events[n_ev].round <= sim->round + rounds) ++n_ev;
@@ -365,7 +392,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       ev_pos = ev_end;
     }
     int mk = prof_begin(sim, 1);
-    tick_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
+    tick_scan_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
+    prof_end(sim, mk);
+    mk = prof_begin(sim, 4);
+    tick_work_kernel<W><<<wgrid, kThreads, 0, sim->stream>>>(d);
     prof_end(sim, mk);
     if (d.world > 1) {
       mk = prof_begin(sim, 2);
@@ -374,10 +404,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       prof_end(sim, mk);
     }
     mk = prof_begin(sim, 3);
-    recv_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
+    recv_kernel<W><<<wgrid, kThreads, 0, sim->stream>>>(d);
     prof_end(sim, mk);
-    sim->launches += 2;
-    if (sim->profile) sim->prof_ms[4] += 1;
+    sim->launches += 3;
+    if (sim->profile) sim->prof_ms[5] += 1;
   }
   sim->events.erase(sim->events.begin(), sim->events.begin() + n_ev);
   CUDA_TRY(sim, cudaGetLastError());
@@ -549,6 +579,7 @@ extern "C" int swim_sim_set_array(swim_sim_t *sim, int arr, const void *buf, siz
   cudaSetDevice(sim->device);
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   CUDA_TRY(sim, cudaMemcpy(p, buf, bytes, cudaMemcpyHostToDevice));
+  if (arr == SWIM_ARR_ALIVE) sim->tdead_dirty = true; // crashed-member bitmaps follow alive[]
   return SWIM_OK;
 }
 

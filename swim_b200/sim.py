@@ -149,10 +149,10 @@ class Simulator:
         check(lib().swim_sim_set_profile(self._h, int(enable)), "swim_sim_set_profile", self._h)
 
     def profile_ms(self):
-        """Cumulative per-phase device ms since set_profile(True): events, tick, exchange, recv, rounds."""
-        out = (C.c_double * 5)()
-        check(lib().swim_sim_profile_ms(self._h, out, 5), "swim_sim_profile_ms", self._h)
-        return dict(zip(["events", "tick", "exchange", "recv", "rounds"], list(out)))
+        """Cumulative per-phase device ms since set_profile(True)."""
+        out = (C.c_double * 6)()
+        check(lib().swim_sim_profile_ms(self._h, out, 6), "swim_sim_profile_ms", self._h)
+        return dict(zip(["events", "tick_scan", "exchange", "recv", "tick_work", "rounds"], list(out)))
 
     def state(self):
         """All bulk arrays as a dict (the checkable form of dumpStore, Util.hs:64-74)."""

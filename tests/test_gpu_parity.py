@@ -126,3 +126,27 @@ def test_c3_properties():
     nonalive_members = np.unique(nbr[st != A.ALIVE])
     assert alive[nonalive_members].max(initial=0) == 0
     assert c[A.CTR_SUSPECT_LOCAL] > 0 and c[A.CTR_DEAD_TIMEOUT] > 0
+
+
+def test_set_array_alive_rebuilds_crash_bitmaps():
+    """Bulk edits of alive[] (swim_sim_set_array) must reach the per-row crashed-member bitmaps."""
+    n = 400
+    cfg = default_config(n_nodes=n, seed=5)
+    nbr = generate_topology("random", n, 32, 16, seed=8)
+    sim, orc = make_pair(cfg, nbr)
+    sim.step(2)
+    orc.step(2)
+    alive = sim.get_array(A.ARR_ALIVE)
+    alive[::7] = 0
+    sim.set_array(A.ARR_ALIVE, alive)
+    orc.set_array(A.ARR_ALIVE, alive)
+    for r in range(12):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"after alive edit, round {r + 3}")
+    alive[::7] = 1
+    sim.set_array(A.ARR_ALIVE, alive)
+    orc.set_array(A.ARR_ALIVE, alive)
+    sim.step(10)
+    orc.step(10)
+    assert_same_state(sim, orc, "after revive")
