@@ -30,6 +30,20 @@ sys.path.insert(0, ROOT)
 
 from swim_b200 import _abi as A  # noqa: E402
 
+def usable_cpus():
+    """CPUs this process may actually use (affinity mask and cgroup quota), for the CPU arm."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(int(q) / int(per))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
+os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
+
 N_PER_GPU = 1 << 20
 CRASH_ROUND = 10
 CRASH_PPM = 1000  # 0.1 %
@@ -70,7 +84,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -167,15 +181,13 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from swim_b200.sim import Simulator, default_config, nccl_unique_id
+    from swim_b200 import dist as sdist
+    from swim_b200.sim import Simulator, default_config
     cfg_kw, nbr, events, n = workload(world, args.nodes_per_gpu)
 
     def fresh(inject=True):
         sim = Simulator(default_config(rank=rank, world=world, device=local, **cfg_kw))
-        if world > 1:
-            ids = [nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(ids, src=0)
-            sim.connect(ids[0])
+        sdist.connect(sim)
         sim.set_view(nbr)
         if inject:
             sim.inject(events)
@@ -193,9 +205,9 @@ def run_cuda(args):
     stream = torch.cuda.Stream()
     assert stream.cuda_stream != 0
     sim.set_stream(stream.cuda_stream)
+    clocks = ClockSampler(local) if rank == 0 else None  # runs until the end of the e2e region
     sim.step(args.warmup)
     c0, l0 = sim.counters(), sim.launch_count()
-    clocks = ClockSampler(local) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
@@ -204,7 +216,6 @@ def run_cuda(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     c1, l1 = sim.counters(), sim.launch_count()
-    clk = clocks.stop() if clocks else None
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,6 +305,7 @@ def run_cuda(args):
                "what": "per round: swim_sim_inject(host events) + swim_sim_step(1) + swim_sim_counters + "
                        "swim_sim_digest + swim_sim_mismatches (host wall clock, max over ranks)"}
         sim.close()
+    clk = clocks.stop() if clocks else None
 
     # ------------------------------------------------ convergence metric (second half of BASELINE's metric)
     conv = None
@@ -341,7 +353,7 @@ def run_cuda(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=448)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--nodes-per-gpu", type=int, default=N_PER_GPU)

@@ -54,7 +54,8 @@ struct SimDev {
   uint32_t *in_src;          // [E] sender ids, ascending per receiver
   uint8_t *eflag;            // [E] 1 = sender mailed this round
   uint32_t *mail;            // [n] round of the receiver's latest mail (dedupes the receiver list)
-  uint32_t *tdead;           // [n*W] bit s: the member in slot s is a crashed process
+  uint4 *meta;               // [n*W] per 32 slots: {alive bitmap, suspect bitmap, crashed-member bitmap,
+                             //        flags: byte0 = process up, byte1 = piggyback count (word 0 only)}
   uint32_t *obs_off;         // [N+1] observers of member m among this shard's rows ...
   uint32_t *obs_slot;        // [n*cap] ... as linear slot indices l*cap + s
   uint32_t *wl, *wl_cnt;     // work list of K1b [n], its round-parity counters [2]
@@ -132,10 +133,13 @@ struct PbStage {
 };
 
 __device__ __forceinline__ void pb_load(PbStage &p, const SimDev &d, uint32_t l, int lane) {
+  // count and records are fetched together (records speculatively: B lanes, whatever the count)
+  uint4 mine = make_uint4(0, 0, 0, 0);
+  if ((uint32_t)lane < d.B) mine = d.pb[(size_t)l * d.B + lane];
   p.cnt = d.pb_cnt[l];
   p.dirty = false;
   __syncwarp();
-  if ((uint32_t)lane < p.cnt) p.s[lane] = d.pb[(size_t)l * d.B + lane];
+  if ((uint32_t)lane < p.cnt) p.s[lane] = mine;
   __syncwarp();
 }
 
@@ -143,7 +147,10 @@ __device__ __forceinline__ void pb_store(PbStage &p, const SimDev &d, uint32_t l
   if (!p.dirty) return;
   __syncwarp();
   if ((uint32_t)lane < p.cnt) d.pb[(size_t)l * d.B + lane] = p.s[lane];
-  if (lane == 0) d.pb_cnt[l] = (uint8_t)p.cnt;
+  if (lane == 0) {
+    d.pb_cnt[l] = (uint8_t)p.cnt;
+    reinterpret_cast<uint8_t *>(d.meta + (size_t)l * (d.cap >> 5))[13] = (uint8_t)p.cnt; // flags byte 1
+  }
 }
 
 __device__ __forceinline__ void pb_enqueue(PbStage &p, const SimDev &d, uint4 rec, int lane,
@@ -171,7 +178,8 @@ struct Row {
   uint32_t nb[W];
   uint32_t inc[W];
   uint32_t st[W];     // packed liveness | timer<<2
-  uint32_t touched;   // bit w: slot (w, lane) changed this call -> write st, inc, last
+  uint32_t touched;   // bit w: slot (w, lane) changed liveness/incarnation -> write st, inc, last
+  uint32_t ticked;    // bit w: only the countdown of slot (w, lane) changed -> write st
 };
 
 template <int W>
@@ -184,18 +192,34 @@ __device__ __forceinline__ void row_load(Row<W> &r, const SimDev &d, uint32_t l,
     r.inc[w] = d.vinc[base + w * 32];
   }
   r.touched = 0;
+  r.ticked = 0;
 }
 
 template <int W>
 __device__ __forceinline__ void row_store(const Row<W> &r, const SimDev &d, uint32_t l, int lane) {
   size_t base = (size_t)l * d.cap + lane;
 #pragma unroll
-  for (int w = 0; w < W; ++w)
+  for (int w = 0; w < W; ++w) {
     if (r.touched & (1u << w)) {
       d.vst[base + w * 32] = (uint8_t)r.st[w];
       d.vinc[base + w * 32] = r.inc[w];
       d.vlast[base + w * 32] = d.round;
+    } else if (r.ticked & (1u << w)) {
+      d.vst[base + w * 32] = (uint8_t)r.st[w];
     }
+  }
+  if (__any_sync(kFull, r.touched != 0)) { // liveness changed somewhere: refresh the row's bitmaps
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const unsigned am = __ballot_sync(kFull, (r.st[w] & 3u) == SWIM_ALIVE);
+      const unsigned sm = __ballot_sync(kFull, (r.st[w] & 3u) == SWIM_SUSPECT);
+      if (lane == 0) {
+        uint32_t *m = reinterpret_cast<uint32_t *>(d.meta + (size_t)l * W + w);
+        m[0] = am;
+        m[1] = sm;
+      }
+    }
+  }
 }
 
 // suspectOrDeadNode' (Core.hs:142-187) + aliveNode's known-member completion [Q7], for one
@@ -277,14 +301,14 @@ __device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t self, uint32_
   return bounded(word_of(y, leg & 3), 1000000u) < d.loss_ppm;
 }
 
-// K1a — lane-per-node streaming pass over every node of the shard. Reads per node: 1 B up flag,
-// 1 B buffer count, 4*W B crashed-member bitmap, 32*W B packed state row (two 128-bit loads per
-// 32 slots; a warp covers 1 KB contiguous). Does the suspicion countdown in place (SWAR), builds
-// the alive bitmask, draws the probe target with Philox and tests it against the crashed-member
-// bitmap. Nodes that need more than that (timer expiry, failed probe, non-empty piggyback buffer)
-// are appended to the round's work list for K1b.
+// K1a — lane-per-node streaming pass over every node of the shard: ONE 16-byte load per node
+// (per 32 slots): the alive / suspect / crashed-member bitmaps and the flags word. Draws the probe
+// target with Philox4x32-10 (kRandomMembers store 1 [], Core.hs:239), picks the r-th alive slot
+// (shuffle, Util.hs:36-42) and tests it against the crashed-member bitmap (Ping/Ack, Core.hs:246).
+// Nodes that need more — a Suspect slot to count down, a failed probe, a non-empty piggyback
+// buffer — are appended to the round's work list (warp-aggregated atomicAdd) for K1b.
 template <int W>
-__global__ void __launch_bounds__(kThreads, 6) tick_scan_kernel(SimDev d) {
+__global__ void __launch_bounds__(kThreads, 8) tick_scan_kernel(SimDev d) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t *wl_cnt = d.wl_cnt + (d.round & 1);
@@ -292,44 +316,25 @@ __global__ void __launch_bounds__(kThreads, 6) tick_scan_kernel(SimDev d) {
   for (uint32_t base = warp * 32; base < d.n; base += nwarps * 32) {
     const uint32_t l = base + lane;
     bool work = false;
-    if (l < d.n && d.alive[d.first + l] != 0) { // a crashed process does nothing
-      work = d.pb_cnt[l] != 0;
-      uint4 *rowp = reinterpret_cast<uint4 *>(d.vst + (size_t)l * d.cap);
-      uint32_t am[W], L = 0;
+    if (l < d.n) {
+      uint32_t am[W], td[W], sus = 0, L = 0, flags = 0;
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        uint4 q[2] = {rowp[2 * w], rowp[2 * w + 1]};
-        uint32_t *v = reinterpret_cast<uint32_t *>(q);
-        uint32_t any_sus = 0, mask = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t b0 = v[j] & 0x01010101u, b1 = (v[j] >> 1) & 0x01010101u;
-          any_sus |= b0 & ~b1;                                      // liveness == Suspect
-          mask |= gather4(~(b0 | b1) & 0x01010101u) << (4 * j);     // liveness == Alive
-        }
-        if (any_sus) { // [Q8] countdown: timer -= 1 on Suspect slots (timer >= 1 while Suspect)
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t sus = v[j] & ~(v[j] >> 1) & 0x01010101u;
-            v[j] -= sus << 2;
-            const uint32_t t = v[j] & 0xFCFCFCFCu;
-            const uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u; // zero timers
-            work |= (sus & (z >> 7)) != 0;                          // a timer expired
-          }
-          rowp[2 * w] = q[0];
-          rowp[2 * w + 1] = q[1];
-        }
-        am[w] = mask;
-        L += __popc(mask);
+        const uint4 m = d.meta[(size_t)l * W + w];
+        am[w] = m.x; sus |= m.y; td[w] = m.z;
+        if (w == 0) flags = m.w;
+        L += __popc(m.x);
       }
-      if (L) {
-        // kRandomMembers store 1 [] (Core.hs:239, [Q11]): first draw of the SELECT stream
-        const uint4 x = philox4x32_10(make_uint4(d.round, d.first + l, P_SELECT, 0), d.key0, d.key1);
-        const uint32_t tslot = pick_remove<W>(am, bounded(x.x, L));
-        ++pings;                                                    // Ping (Core.hs:246)
-        bool acked = (d.tdead[(size_t)l * W + (tslot >> 5)] >> (tslot & 31) & 1u) == 0; // target process up
-        if (acked && d.loss_ppm) acked = !leg_lost(d, d.first + l, 0);
-        work |= !acked;
+      if (flags & 0xFFu) { // a crashed process does nothing
+        work = (flags & 0xFF00u) != 0 || sus != 0; // piggyback to send, or a countdown to run [Q8]
+        if (L) {
+          const uint4 x = philox4x32_10(make_uint4(d.round, d.first + l, P_SELECT, 0), d.key0, d.key1);
+          const uint32_t tslot = pick_remove<W>(am, bounded(x.x, L));
+          ++pings;                                                          // Ping (Core.hs:246)
+          bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;          // Ack iff the target is up
+          if (acked && d.loss_ppm) acked = !leg_lost(d, d.first + l, 0);
+          work |= !acked;
+        }
       }
     }
     const unsigned todo = __ballot_sync(kFull, work);
@@ -366,13 +371,15 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
     uint32_t td[W], am[W], L = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
-      td[w] = d.tdead[(size_t)ln * W + w];
+      td[w] = d.meta[(size_t)ln * W + w].z;
       am[w] = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE);
       L += __popc(am[w]);
     }
-    // T1 [Q8]: expired Suspect -> Dead, broadcast Dead(inc, member, from = self), slot order
+    // T1 [Q8]: countdown on every Suspect slot; expired -> Dead, broadcast Dead(inc, member,
+    // from = self) in slot order
 #pragma unroll
     for (int w = 0; w < W; ++w) {
+      if ((row.st[w] & 3u) == SWIM_SUSPECT) { row.st[w] -= 4u; row.ticked |= 1u << w; } // timer >= 1 while Suspect
       unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && (row.st[w] >> 2) == 0);
       if (em >> lane & 1u) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
       while (em) {
@@ -562,22 +569,28 @@ __device__ __forceinline__ void mark_observers(const SimDev &d, uint32_t node, b
   const uint32_t W = d.cap >> 5;
   for (uint32_t x = d.obs_off[node] + lane, end = d.obs_off[node + 1]; x < end; x += 32) {
     const uint32_t slot = d.obs_slot[x], l = slot / d.cap, s = slot % d.cap;
-    uint32_t *word = d.tdead + (size_t)l * W + (s >> 5);
+    uint32_t *word = reinterpret_cast<uint32_t *>(d.meta + (size_t)l * W + (s >> 5)) + 2;
     if (crashed) atomicOr(word, 1u << (s & 31)); else atomicAnd(word, ~(1u << (s & 31)));
   }
 }
 
-// Rebuild every crashed-member bitmap from alive[] (after bulk edits of alive[] or of the rows).
-static __global__ void __launch_bounds__(kThreads) tdead_rebuild_kernel(SimDev d) {
+// Rebuild every per-node meta record from the primary arrays (after bulk edits of alive[], rows
+// or buffers through the ABI): bitmaps from the row's liveness, crashed members from alive[nbr].
+static __global__ void __launch_bounds__(kThreads) derive_meta_kernel(SimDev d) {
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t W = d.cap >> 5;
   for (uint32_t l = warp; l < d.n; l += nwarps)
     for (uint32_t w = 0; w < W; ++w) {
       const size_t x = (size_t)l * d.cap + w * 32 + lane;
-      const bool dead = (d.vst[x] & 3u) != SWIM_VACANT && d.alive[d.nbr[x]] == 0;
-      const unsigned m = __ballot_sync(kFull, dead);
-      if (lane == 0) d.tdead[(size_t)l * W + w] = m;
+      const uint32_t live = d.vst[x] & 3u;
+      const unsigned am = __ballot_sync(kFull, live == SWIM_ALIVE);
+      const unsigned sm = __ballot_sync(kFull, live == SWIM_SUSPECT);
+      const unsigned td = __ballot_sync(kFull, live != SWIM_VACANT && d.alive[d.nbr[x]] == 0);
+      if (lane == 0) {
+        const uint32_t flags = w == 0 ? (d.alive[d.first + l] ? 1u : 0u) | ((uint32_t)d.pb_cnt[l] << 8) : 0u;
+        d.meta[(size_t)l * W + w] = make_uint4(am, sm, td, flags);
+      }
     }
 }
 
@@ -602,13 +615,19 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
     const bool local = node >= d.first && node < d.first + d.n;
     const uint32_t ln = node - d.first;
     if (kind == SWIM_EV_CRASH) {
-      if (lane == 0) d.alive[node] = 0;
+      if (lane == 0) {
+        d.alive[node] = 0;
+        if (local) reinterpret_cast<uint8_t *>(d.meta + (size_t)ln * (d.cap >> 5))[12] = 0; // flags byte 0: up
+      }
       mark_observers(d, node, true, lane);
     } else if (kind == SWIM_EV_REJOIN) {
       const bool was_up = d.alive[node] != 0;
       __syncwarp();
       if (!was_up) {
-        if (lane == 0) d.alive[node] = 1;
+        if (lane == 0) {
+          d.alive[node] = 1;
+          if (local) reinterpret_cast<uint8_t *>(d.meta + (size_t)ln * (d.cap >> 5))[12] = 1;
+        }
         mark_observers(d, node, false, lane);
         if (local) { // restart with incarnation + 1 and announce Alive
           uint32_t inc = d.self_inc[ln] + 1;

@@ -27,6 +27,7 @@ struct swim_sim {
   std::vector<void *> allocs;
   uint32_t *d_in_src = nullptr;
   uint8_t *d_eflag = nullptr;
+  uint32_t *d_eslot = nullptr; // exchange-buffer slot per in-edge (world > 1)
   void *d_events = nullptr;
   size_t d_events_cap = 0;
   unsigned long long *d_scratch = nullptr;
@@ -47,6 +48,7 @@ void set_error(swim_sim *sim, const char *fmt, ...);
 uint32_t shard_first(uint32_t N, uint32_t world, uint32_t rank);
 int rebuild_edges_from_device(swim_sim *sim);
 int dist_exchange(swim_sim *sim);
+int dist_alloc_edges(swim_sim *sim);
 int prof_begin(swim_sim *sim, int phase);
 void prof_end(swim_sim *sim, int mark);
 int prof_collect(swim_sim *sim);

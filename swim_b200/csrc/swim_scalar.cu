@@ -216,7 +216,7 @@ int apply_message(swim_sim *sim, uint32_t node, uint8_t want, const swim_message
   rc = run_scalar(sim, a);
   if (rc) { if (rc == SWIM_ECAP) set_error(sim, "view row of node %u is full", node); return rc; }
   *has_out = a.verdict != 0;
-  if (a.verdict == 3) { sim->edges_dirty = true; sim->view_set = true; }
+  if (a.verdict == 3) { sim->edges_dirty = true; sim->view_set = true; sim->tdead_dirty = true; }
   if (a.verdict) {
     if ((a.rb.w & 0xFF) == msg->kind && a.rb.x == msg->node) *out = *msg; // `Just msg`: the identical message
     else msg_of_rec(sim, a.rb, out);                                       // the Alive refutation (Core.hs:162-166)
@@ -270,6 +270,7 @@ extern "C" int swim_set_members(swim_sim_t *sim, uint32_t node, const swim_membe
   CUDA_TRY(sim, cudaMemcpy(d.vinc + base, inc.data(), d.cap * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(sim, cudaMemcpy(d.vlast + base, last.data(), d.cap * 4, cudaMemcpyHostToDevice));
   sim->edges_dirty = true;
+  sim->tdead_dirty = true;
   sim->view_set = true;
   return SWIM_OK;
 }
@@ -304,6 +305,7 @@ extern "C" int swim_remove_dead_nodes(swim_sim_t *sim, uint32_t node) {
   a.op = OP_REMOVE_DEAD; a.node = node;
   if ((rc = run_scalar(sim, a))) return rc;
   sim->edges_dirty = true;
+  sim->tdead_dirty = true;
   return SWIM_OK;
 }
 

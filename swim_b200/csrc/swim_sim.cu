@@ -160,7 +160,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.ridx, slots, 0))) return r;
     if ((r = dalloc(sim, &d.in_off, n + 1, 0))) return r;
     if ((r = dalloc(sim, &d.mail, n, 0))) return r;
-    if ((r = dalloc(sim, &d.tdead, slots / 32, 0))) return r;
+    if ((r = dalloc(sim, &d.meta, slots / 32, 0))) return r;
     if ((r = dalloc(sim, &d.obs_off, (size_t)d.N + 1, 0))) return r;
     if ((r = dalloc(sim, &d.obs_slot, slots, 0))) return r;
     if ((r = dalloc(sim, &d.wl, n, 0))) return r;
@@ -262,7 +262,7 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
   d.in_src = sim->d_in_src;
   d.eflag = sim->d_eflag;
   sim->n_edges = E;
-  return SWIM_OK;
+  return swim::dist_alloc_edges(sim);
 }
 
 extern "C" int swim_sim_set_view(swim_sim_t *sim, const uint32_t *nbr) {
@@ -346,13 +346,24 @@ static int grid_for(const swim_sim *sim, size_t warps_needed) {
   return (int)std::min(blocks, cap);
 }
 
+// one resident wave of a persistent kernel: SMs x (CTAs the occupancy calculator allows per SM)
+template <typename K>
+static int wave_grid(const swim_sim *sim, K kernel, size_t warps_needed) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  size_t blocks = (warps_needed + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  if (blocks < 1) blocks = 1;
+  return (int)std::min(blocks, (size_t)sim->sm_count * per_sm);
+}
+
 template <int W>
 static int run_rounds(swim_sim *sim, uint32_t rounds) {
   SimDev &d = sim->dev;
-  const int grid = grid_for(sim, ((size_t)d.n + 31) / 32);
-  const int wgrid = grid_for(sim, (size_t)d.n); // warp-per-item kernels: at most one resident wave
+  const int grid = wave_grid(sim, tick_scan_kernel<W>, ((size_t)d.n + 31) / 32);
+  const int wgrid = wave_grid(sim, tick_work_kernel<W>, (size_t)d.n);
+  const int rgrid = wave_grid(sim, recv_kernel<W>, (size_t)d.n);
   if (sim->tdead_dirty) {
-    tdead_rebuild_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+    derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
     ++sim->launches;
     sim->tdead_dirty = false;
   }
@@ -404,7 +415,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       prof_end(sim, mk);
     }
     mk = prof_begin(sim, 3);
-    recv_kernel<W><<<wgrid, kThreads, 0, sim->stream>>>(d);
+    recv_kernel<W><<<rgrid, kThreads, 0, sim->stream>>>(d);
     prof_end(sim, mk);
     sim->launches += 3;
     if (sim->profile) sim->prof_ms[5] += 1;
@@ -579,7 +590,7 @@ extern "C" int swim_sim_set_array(swim_sim_t *sim, int arr, const void *buf, siz
   cudaSetDevice(sim->device);
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   CUDA_TRY(sim, cudaMemcpy(p, buf, bytes, cudaMemcpyHostToDevice));
-  if (arr == SWIM_ARR_ALIVE) sim->tdead_dirty = true; // crashed-member bitmaps follow alive[]
+  if (arr == SWIM_ARR_ALIVE || arr == SWIM_ARR_VST || arr == SWIM_ARR_PB_CNT) sim->tdead_dirty = true; // meta is derived state
   return SWIM_OK;
 }
 

@@ -46,6 +46,18 @@ def make_events(rounds, nodes, kinds, msg_kind=None, msg_node=None, msg_inc=None
     return ev
 
 
+def concat_events(parts):
+    """np.concatenate drops the padding of the swim_event_t layout; this keeps it."""
+    parts = [np.asarray(p) for p in parts]
+    out = np.zeros(sum(len(p) for p in parts), dtype=A.EVENT_DTYPE)
+    pos = 0
+    for p in parts:
+        for name in A.EVENT_DTYPE.names:
+            out[name][pos:pos + len(p)] = p[name]
+        pos += len(p)
+    return out
+
+
 def crash_events(round_, nodes):
     nodes = np.asarray(nodes, dtype=np.uint32)
     return make_events(np.full(len(nodes), round_, np.uint32), nodes, np.full(len(nodes), A.EV_CRASH, np.uint8))

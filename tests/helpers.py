@@ -3,7 +3,7 @@ the C ABI) and on the CPU oracle, and compare every state array bit for bit."""
 import numpy as np
 
 from swim_b200 import _abi as A
-from swim_b200.sim import crash_events, default_config, generate_topology, make_events  # noqa: F401
+from swim_b200.sim import concat_events, crash_events, default_config, generate_topology, make_events  # noqa: F401
 
 
 def make_pair(cfg, nbr):
@@ -49,4 +49,4 @@ def random_events(rng, n_nodes, rounds, n_crash, n_rejoin=0, n_inject=0):
                                msg_node=rng.integers(0, n_nodes, size=n_inject).astype(np.uint32),
                                msg_inc=rng.integers(0, 4, size=n_inject).astype(np.int64),
                                msg_from=rng.integers(0, n_nodes, size=n_inject).astype(np.uint32)))
-    return np.concatenate(evs)
+    return concat_events(evs)

@@ -109,7 +109,7 @@ def test_scalar_api_matches_oracle_on_random_sequences():
     """swim_suspect_node / swim_dead_node / swim_alive_node / swim_handle_message / kRandomMembers /
     removeDeadNodes on the device == the oracle, message by message."""
     import ctypes as C
-    from oracle.oracle import Oracle
+    from oracle.oracle import Oracle, OracleError
     from swim_b200._lib import check, lib
     from swim_b200.sim import Simulator, default_config
     rng = np.random.default_rng(11)
@@ -134,10 +134,11 @@ def test_scalar_api_matches_oracle_on_random_sequences():
             rc = fns[kind](sim._h, node, C.byref(m), C.byref(out), C.byref(has))
             try:
                 exp = [orc.suspect_node, orc.dead_node, orc.alive_node][kind - 3](node, m)
-                assert rc == 0
-            except Exception as e:  # row full: both sides must fail the same way
-                assert rc == e.code == A.ECAP
+            except OracleError as e:  # row full: both sides must fail the same way
+                assert (rc, e.code) == (A.ECAP, A.ECAP), (step, kind, who, rc, e.code, len(orc.get_members(node)),
+                                                          len(_members(sim, node, cap)))
                 continue
+            assert rc == 0, (step, kind, who, rc, lib().swim_last_error(sim._h))
             assert bool(has.value) == (exp is not None), (step, kind, who)
             if exp is not None:
                 assert (out.kind, out.node, out.incarnation, out.dead_from) == (exp.kind, exp.node, exp.incarnation, exp.dead_from)
