@@ -154,12 +154,12 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def config_dict(cfg_kw, n, n_gpus):
+def config_dict(cfg_kw, n, n_gpus, exchange_mode="single"):
     return {"workload": f"C3 x{n_gpus}: N={n} simulated nodes ({n // n_gpus}/GPU), D=32 uniform-random views, k=3, "
                         f"fanout=4, B=8, S=5, T=8, {CRASH_PPM / 1e4:.1f}% crash at round {CRASH_ROUND}; step = 1 round",
             "n_nodes": n, "view_degree": 32, "k_indirect": 3, "fanout": 4, "pb_cap": 8, "suspicion_rounds": 5,
             "retransmit": 8, "crash_round": CRASH_ROUND, "seed": SEED,
-            "parallelism": f"shard{n_gpus}" if n_gpus > 1 else "single",
+            "parallelism": f"shard{n_gpus}" if n_gpus > 1 else "single", "exchange": exchange_mode,
             "l2": "no flush between rounds: consecutive rounds of one simulation share state by definition; "
                   "state arrays total 0.5 GB/GPU (> 126 MB L2), the per-round hot set (packed state rows 32 MB "
                   "+ flags) is L2-resident by design"}
@@ -185,10 +185,12 @@ def run_cuda(args):
     from swim_b200.sim import Simulator, default_config
     cfg_kw, nbr, events, n = workload(world, args.nodes_per_gpu)
 
+    exchange = {"mode": "single"}
+
     def fresh(inject=True):
         sim = Simulator(default_config(rank=rank, world=world, device=local, **cfg_kw))
-        sdist.connect(sim)
         sim.set_view(nbr)
+        exchange["mode"] = sdist.connect(sim, args.exchange)
         if inject:
             sim.inject(events)
         return sim
@@ -342,7 +344,7 @@ def run_cuda(args):
         line = {"metric": "simulated node-rounds/sec", "value": value, "unit": "node-rounds/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
-                "data": "synthetic", "config": config_dict(cfg_kw, n, world), "clocks": clk, "e2e": e2e,
+                "data": "synthetic", "config": config_dict(cfg_kw, n, world, exchange["mode"]), "clocks": clk, "e2e": e2e,
                 "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "convergence": conv,
                 "counters_timed_region": dict(zip(A.CTR_NAMES, [int(x) for x in ctr_delta]))}
         print(json.dumps(line))
@@ -359,6 +361,8 @@ def main():
     ap.add_argument("--nodes-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--converge-limit", type=int, default=1200)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--exchange", default=None, choices=[None, "p2p", "nccl"],
+                    help="cross-shard exchange: fused peer-memory (default) or staged NCCL all-to-all")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

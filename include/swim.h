@@ -290,6 +290,17 @@ int swim_sim_profile_ms(swim_sim_t *sim, double *out, size_t n);
 int swim_nccl_unique_id(uint8_t id[SWIM_NCCL_ID_BYTES]);
 int swim_sim_connect(swim_sim_t *sim, const uint8_t id[SWIM_NCCL_ID_BYTES]);
 
+/* Fused exchange over peer memory (preferred when all ranks share one NVLink/NVSwitch box):
+ * instead of staging envelopes for NCCL, K1b raises the in-edge flag and appends the receiver
+ * directly in the owner GPU's memory, and K2 pulls the sender's snapshot from the sender GPU's
+ * memory; two device-side cross-GPU barriers per round replace the collective. Call after
+ * swim_sim_set_view: every rank exports a blob (CUDA IPC handles of its mail arrays), the host
+ * side all-gathers the blobs in rank order, every rank connects. Without this call (only
+ * swim_sim_connect) the staged NCCL all-to-all is used. */
+#define SWIM_IPC_BLOB_BYTES 512
+int swim_sim_ipc_export(swim_sim_t *sim, uint8_t blob[SWIM_IPC_BLOB_BYTES]);
+int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs /* world x SWIM_IPC_BLOB_BYTES */);
+
 /* ====================== scalar API: Core.hs function parity ==========================
  * Each call acts on ONE simulated node's store, executing the same device code as the
  * bulk path (a one-warp launch), so the reference's unit tests (test/Spec.hs) can be

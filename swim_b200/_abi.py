@@ -16,6 +16,7 @@ MAX_K, MAX_PB, MAX_TIMER, MAX_VIEW = 7, 32, 63, 256
 ACK_PAYLOAD_MAX = 16
 NAME_MAX = 255
 NCCL_ID_BYTES = 128
+IPC_BLOB_BYTES = 512
 
 EV_CRASH, EV_REJOIN, EV_INJECT = 0, 1, 2
 TOPO_COMPLETE, TOPO_RANDOM, TOPO_RING = 0, 1, 2

@@ -63,6 +63,8 @@ def lib():
     sig("swim_sim_profile_ms", i, vp, vp, sz)
     sig("swim_nccl_unique_id", i, vp)
     sig("swim_sim_connect", i, vp, vp)
+    sig("swim_sim_ipc_export", i, vp, vp)
+    sig("swim_sim_ipc_connect", i, vp, vp)
     for name, args in {
         "swim_get_members": (vp, u32, vp, sz, P(sz)),
         "swim_set_members": (vp, u32, vp, sz),

@@ -28,6 +28,7 @@ namespace swim {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
+#define SWIM_MAX_WORLD 8
 
 // Philox counter purposes
 enum : uint32_t { P_SELECT = 0, P_LOSS = 1, P_SCALAR = 2, P_TOPO = 3 };
@@ -60,7 +61,17 @@ struct SimDev {
   uint32_t *obs_slot;        // [n*cap] ... as linear slot indices l*cap + s
   uint32_t *wl, *wl_cnt;     // work list of K1b [n], its round-parity counters [2]
   uint32_t *rl, *rl_cnt;     // receiver list of K2 [n], its round-parity counters [2]
-  // cross-shard exchange (world > 1)
+  // cross-shard delivery over peer memory (NVLink): the same arrays of every rank, mapped here
+  // with CUDA IPC; entry [rank] is this rank's own array. Filled for world == 1 too (one entry).
+  uint8_t *eflag_p[SWIM_MAX_WORLD];
+  uint32_t *mail_p[SWIM_MAX_WORLD];
+  uint32_t *rl_p[SWIM_MAX_WORLD];
+  uint32_t *rl_cnt_p[SWIM_MAX_WORLD];
+  const uint4 *out_p[SWIM_MAX_WORLD];
+  const uint8_t *out_cnt_p[SWIM_MAX_WORLD];
+  uint32_t *bar_p[SWIM_MAX_WORLD]; // cross-GPU barrier words [world] of every rank
+  uint32_t p2p;                    // 1 = fused peer-memory exchange, 0 = staged NCCL all-to-all
+  // staged exchange through NCCL (baseline path)
   uint4 *xsend;              // [world][xcap] envelopes {ridx, cnt, src, -} + B records, bucketed by rank
   uint32_t *xsend_cnt;       // [world + 1]; the last word is the bucket-overflow flag
   uint4 *xrecv;              // received envelopes, all source ranks back to back
@@ -447,14 +458,26 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
         const size_t e = (size_t)ln * d.cap + rslot;
         const uint32_t dst = d.nbr[e], ridx = d.ridx[e];
         const uint32_t owner = d.world == 1 ? 0u : dst / d.per;
+        const uint32_t dl = dst - owner * d.per;
         if (owner == d.rank) {
           d.eflag[ridx] = 1; // raise the in-edge flag (i -> dst)
-          if (atomicExch(&d.mail[dst - d.first], d.round) != d.round) d.rl[atomicAdd(rl_cnt, 1u)] = dst - d.first;
+          if (d.p2p && d.world > 1) {
+            if (atomicExch_system(&d.mail[dl], d.round) != d.round) d.rl[atomicAdd_system(rl_cnt, 1u)] = dl;
+          } else if (atomicExch(&d.mail[dl], d.round) != d.round) {
+            d.rl[atomicAdd(rl_cnt, 1u)] = dl;
+          }
+        } else if (d.p2p) {
+          // fused exchange: the flag and the receiver-list entry are written straight into the
+          // owner GPU's memory over NVLink; the receiver will pull our snapshot from ours
+          d.eflag_p[owner][ridx] = 1;
+          if (atomicExch_system(&d.mail_p[owner][dl], d.round) != d.round)
+            d.rl_p[owner][atomicAdd_system(&d.rl_cnt_p[owner][d.round & 1], 1u)] = dl;
+          __threadfence_system(); // peer-memory stores are ordered before this kernel's end + the barrier flag
         } else {
           const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
           if (k < d.xcap) {
             xs = owner * d.xcap + k;
-            d.xsend[(size_t)xs * (1 + d.B)] = make_uint4(ridx, pbs.cnt, self, dst - owner * d.per);
+            d.xsend[(size_t)xs * (1 + d.B)] = make_uint4(ridx, pbs.cnt, self, dl);
           } else {
             d.xsend_cnt[d.world] = 1; // overflow: reported by the host as SWIM_ECAP, never silent
           }
@@ -530,10 +553,10 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
         const uint32_t s_id = __shfl_sync(kFull, src, q), s_kind = __shfl_sync(kFull, f, q);
         uint32_t cnt;
         uint4 mine = make_uint4(0, 0, 0, 0);
-        if (s_kind == 1) { // sender on this shard: pull its snapshot
-          const uint32_t sl = s_id - d.first;
-          if ((uint32_t)lane < d.B) mine = d.out[(size_t)sl * d.B + lane];
-          cnt = d.out_cnt[sl];
+        if (s_kind == 1) { // pull the sender's snapshot (from a peer GPU's memory if it lives there)
+          const uint32_t s_rank = d.world == 1 ? 0u : s_id / d.per, sl = s_id - s_rank * d.per;
+          if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][(size_t)sl * d.B + lane];
+          cnt = d.out_cnt_p[s_rank][sl];
         } else {           // sender on another shard: the envelope arrived in the exchange buffer
           const uint32_t slot = d.eslot[eb + q];
           const uint4 *env = d.xrecv + (size_t)slot * (1 + d.B);
@@ -560,6 +583,26 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
     }
   }
   c.flush(d.ctr, lane);
+}
+
+// =================================================================== cross-GPU barrier
+// Every rank stores `stamp` into word [rank] of every peer's barrier array (NVLink store), then
+// waits until all words of its own array reached `stamp`. Runs as a one-warp kernel in stream order,
+// so everything the previous kernel wrote to peer memory is ordered before the flag. The wait is
+// bounded: a missing peer sets *err instead of hanging the GPU.
+static __global__ void peer_barrier_kernel(SimDev d, uint32_t stamp, uint32_t *err) {
+  const uint32_t q = threadIdx.x;
+  if (q >= d.world) return;
+  __threadfence_system();
+  volatile uint32_t *theirs = d.bar_p[q] + d.rank;
+  *theirs = stamp;
+  volatile uint32_t *mine = d.bar_p[d.rank] + q;
+  const long long t0 = clock64();
+  while ((int32_t)(*mine - stamp) < 0) {
+    if (clock64() - t0 > 6000000000ll) { *err = 1; break; } // ~3 s at 2 GHz
+    __nanosleep(100);
+  }
+  __threadfence_system();
 }
 
 // =================================================================== events (phase E)

@@ -147,7 +147,70 @@ extern "C" int swim_sim_connect(swim_sim_t *sim, const uint8_t *id) {
   return SWIM_OK;
 }
 
+// ------------------------------------------------------------------ fused exchange over peer memory
+namespace {
+struct IpcBlob {
+  uint32_t magic, rank, n, n_edges_lo;
+  cudaIpcMemHandle_t h[7]; // eflag, mail, rl, rl_cnt, out, out_cnt, bar
+};
+static_assert(sizeof(IpcBlob) <= SWIM_IPC_BLOB_BYTES, "blob too small");
+constexpr uint32_t kBlobMagic = 0x53574D49u; // "SWMI"
+} // namespace
+
+extern "C" int swim_sim_ipc_export(swim_sim_t *sim, uint8_t *blob) {
+  if (!sim || !blob) return SWIM_EINVAL;
+  if (!sim->view_set) { set_error(sim, "swim_sim_ipc_export: install the view first (swim_sim_set_view)"); return SWIM_ESTATE; }
+  cudaSetDevice(sim->device);
+  SimDev &d = sim->dev;
+  IpcBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = kBlobMagic; b.rank = d.rank; b.n = d.n; b.n_edges_lo = (uint32_t)sim->n_edges;
+  void *ptrs[7] = {d.eflag, d.mail, d.rl, d.rl_cnt, d.out, d.out_cnt, sim->d_bar};
+  for (int x = 0; x < 7; ++x) CUDA_TRY(sim, cudaIpcGetMemHandle(&b.h[x], ptrs[x]));
+  memset(blob, 0, SWIM_IPC_BLOB_BYTES);
+  memcpy(blob, &b, sizeof b);
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
+  if (!sim || !blobs) return SWIM_EINVAL;
+  SimDev &d = sim->dev;
+  if (d.world == 1) { sim->connected = true; return SWIM_OK; }
+  if (d.p2p) return SWIM_OK;
+  cudaSetDevice(sim->device);
+  for (uint32_t r = 0; r < d.world; ++r) {
+    IpcBlob b;
+    memcpy(&b, blobs + (size_t)r * SWIM_IPC_BLOB_BYTES, sizeof b);
+    if (b.magic != kBlobMagic || b.rank != r) { set_error(sim, "swim_sim_ipc_connect: blob %u is not rank %u's export", r, r); return SWIM_EINVAL; }
+    if (r == d.rank) continue;
+    void *p[7];
+    for (int x = 0; x < 7; ++x) {
+      CUDA_TRY(sim, cudaIpcOpenMemHandle(&p[x], b.h[x], cudaIpcMemLazyEnablePeerAccess));
+      sim->ipc_opened.push_back(p[x]);
+    }
+    d.eflag_p[r] = (uint8_t *)p[0]; d.mail_p[r] = (uint32_t *)p[1]; d.rl_p[r] = (uint32_t *)p[2];
+    d.rl_cnt_p[r] = (uint32_t *)p[3]; d.out_p[r] = (const uint4 *)p[4]; d.out_cnt_p[r] = (const uint8_t *)p[5];
+    d.bar_p[r] = (uint32_t *)p[6];
+  }
+  d.p2p = 1;
+  sim->connected = true;
+  return SWIM_OK;
+}
+
 namespace swim {
+
+void refresh_peer_tables(swim_sim *sim) { // entry [rank] always aliases this rank's own arrays
+  SimDev &d = sim->dev;
+  const uint32_t r = d.rank;
+  d.eflag_p[r] = d.eflag; d.mail_p[r] = d.mail; d.rl_p[r] = d.rl; d.rl_cnt_p[r] = d.rl_cnt;
+  d.out_p[r] = d.out; d.out_cnt_p[r] = d.out_cnt; d.bar_p[r] = sim->d_bar;
+}
+
+int dist_barrier(swim_sim *sim) {
+  peer_barrier_kernel<<<1, 32, 0, sim->stream>>>(sim->dev, ++sim->bar_stamp, sim->d_bar_err);
+  ++sim->launches;
+  return SWIM_OK;
+}
 
 int dist_alloc_edges(swim_sim *sim) { // eslot follows the in-edge count
   SimDev &d = sim->dev;
@@ -202,6 +265,8 @@ int dist_exchange(swim_sim *sim) {
 }
 
 void dist_teardown(swim_sim *sim) {
+  for (void *p : sim->ipc_opened) cudaIpcCloseMemHandle(p);
+  sim->ipc_opened.clear();
   Dist *x = (Dist *)sim->dist;
   if (!x) return;
   if (x->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(x->comm);

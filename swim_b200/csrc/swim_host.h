@@ -40,6 +40,10 @@ struct swim_sim {
   std::vector<std::pair<int, int>> prof_marks; // (phase, index of start event); stop = start + 1
   size_t prof_used = 0;
   double prof_ms[SWIM_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0};
+  uint32_t *d_bar = nullptr;     // [world] cross-GPU barrier words of this rank
+  uint32_t *d_bar_err = nullptr; // set by a barrier that timed out
+  uint32_t bar_stamp = 0;
+  std::vector<void *> ipc_opened; // peer mappings to close
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };
 
@@ -49,6 +53,8 @@ uint32_t shard_first(uint32_t N, uint32_t world, uint32_t rank);
 int rebuild_edges_from_device(swim_sim *sim);
 int dist_exchange(swim_sim *sim);
 int dist_alloc_edges(swim_sim *sim);
+int dist_barrier(swim_sim *sim);
+void refresh_peer_tables(swim_sim *sim);
 int prof_begin(swim_sim *sim, int phase);
 void prof_end(swim_sim *sim, int mark);
 int prof_collect(swim_sim *sim);

@@ -81,7 +81,7 @@ extern "C" int swim_config_default(swim_config_t *cfg) {
 
 static int validate(const swim_config_t *c) {
   if (!c || c->abi_version != SWIM_ABI_VERSION) return SWIM_EINVAL;
-  if (c->n_nodes == 0 || c->world == 0 || c->rank >= c->world) return SWIM_EINVAL;
+  if (c->n_nodes == 0 || c->world == 0 || c->world > SWIM_MAX_WORLD || c->rank >= c->world) return SWIM_EINVAL;
   if (c->view_cap != 32 && c->view_cap != 64 && c->view_cap != 128 && c->view_cap != 256) return SWIM_EINVAL;
   if (c->k_indirect > SWIM_MAX_K || c->fanout < 1 || c->fanout > 1 + c->k_indirect) return SWIM_EINVAL;
   if (c->pb_cap < 1 || c->pb_cap > SWIM_MAX_PB) return SWIM_EINVAL;
@@ -169,6 +169,8 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.rl_cnt, 2, 0))) return r;
     if ((r = dalloc(sim, &d.ctr, SWIM_CTR__COUNT, 0))) return r;
     if ((r = dalloc(sim, &sim->d_scratch, 8, 0))) return r;
+    if ((r = dalloc(sim, &sim->d_bar, SWIM_MAX_WORLD, 0))) return r;
+    if ((r = dalloc(sim, &sim->d_bar_err, 1, 0))) return r;
     return SWIM_OK;
   }();
   if (rc) { g_last_error = sim->last_error; swim_sim_destroy(sim); return rc; }
@@ -268,6 +270,7 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
 extern "C" int swim_sim_set_view(swim_sim_t *sim, const uint32_t *nbr) {
   if (!sim || !nbr) return SWIM_EINVAL;
   SimDev &d = sim->dev;
+  if (d.p2p) { set_error(sim, "swim_sim_set_view: peers already mapped this rank's arrays (set the view before swim_sim_ipc_connect)"); return SWIM_ESTATE; }
   cudaSetDevice(sim->device);
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   // validate the local rows: ascending, distinct, in range, never self, vacancies last
@@ -405,12 +408,18 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     int mk = prof_begin(sim, 1);
     tick_scan_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
     prof_end(sim, mk);
+    if (d.world > 1 && d.p2p) { // every peer is done pulling last round's snapshots from this rank
+      mk = prof_begin(sim, 2);
+      int rc = swim::dist_barrier(sim);
+      if (rc) return rc;
+      prof_end(sim, mk);
+    }
     mk = prof_begin(sim, 4);
     tick_work_kernel<W><<<wgrid, kThreads, 0, sim->stream>>>(d);
     prof_end(sim, mk);
-    if (d.world > 1) {
+    if (d.world > 1) { // the exchange step: flags raised on every rank (p2p) / envelopes moved (NCCL)
       mk = prof_begin(sim, 2);
-      int rc = swim::dist_exchange(sim);
+      int rc = d.p2p ? swim::dist_barrier(sim) : swim::dist_exchange(sim);
       if (rc) return rc;
       prof_end(sim, mk);
     }
@@ -433,7 +442,8 @@ extern "C" int swim_sim_step_async(swim_sim_t *sim, uint32_t rounds) {
     int rc = swim::rebuild_edges_from_device(sim);
     if (rc) return rc;
   }
-  if (sim->dev.world > 1 && !sim->connected) { set_error(sim, "swim_sim_step: world > 1 needs swim_sim_connect"); return SWIM_ESTATE; }
+  if (sim->dev.world > 1 && !sim->connected) { set_error(sim, "swim_sim_step: world > 1 needs swim_sim_ipc_connect or swim_sim_connect"); return SWIM_ESTATE; }
+  swim::refresh_peer_tables(sim);
   CUDA_TRY(sim, cudaEventRecord(sim->ev_start, sim->stream));
   int rc;
   switch (sim->dev.cap / 32) {
@@ -452,6 +462,11 @@ extern "C" int swim_sim_sync(swim_sim_t *sim) {
   if (!sim) return SWIM_EINVAL;
   cudaSetDevice(sim->device);
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  if (sim->dev.world > 1 && sim->dev.p2p) {
+    uint32_t err = 0;
+    CUDA_TRY(sim, cudaMemcpy(&err, sim->d_bar_err, 4, cudaMemcpyDeviceToHost));
+    if (err) { set_error(sim, "a cross-GPU barrier timed out (a peer rank stopped stepping)"); return SWIM_ESTATE; }
+  }
   return SWIM_OK;
 }
 

@@ -36,15 +36,42 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
-def connect(sim):
-    """Rank 0 creates the NCCL unique id, everyone receives it and joins (swim_sim_connect)."""
+def connect(sim, mode=None):
+    """Wire up the per-round exchange of a sharded simulator; call AFTER sim.set_view().
+    mode "p2p" (default): fused exchange over peer memory — every rank exports CUDA IPC handles of
+    its mail arrays, the blobs are all-gathered, every rank maps its peers (swim_sim_ipc_connect).
+    mode "nccl": staged all-to-all — rank 0 creates the NCCL unique id, everyone joins
+    (swim_sim_connect). If peer mapping fails on any rank, all ranks fall back to "nccl".
+    Returns the mode in use."""
     import torch.distributed as dist
+    from ._lib import SwimError
     from .sim import nccl_unique_id
     if sim.cfg.world == 1:
-        return
+        return "single"
+    mode = mode or os.environ.get("SWIM_EXCHANGE", "p2p")
+    if mode == "p2p":
+        ok = 1
+        try:
+            blob = sim.ipc_export()
+        except SwimError:
+            blob, ok = b"", 0
+        blobs = [None] * dist.get_world_size()
+        dist.all_gather_object(blobs, blob)
+        if ok and all(blobs):
+            try:
+                sim.ipc_connect(blobs)
+            except SwimError:
+                ok = 0
+        else:
+            ok = 0
+        if int(global_sum([ok])[0]) == dist.get_world_size():
+            dist.barrier()
+            return "p2p"
+        mode = "nccl"
     ids = [nccl_unique_id() if dist.get_rank() == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     sim.connect(ids[0])
+    return "nccl"
 
 
 def _device():

@@ -172,8 +172,20 @@ class Simulator:
 
     # ---- multi-GPU
     def connect(self, unique_id: bytes):
+        """Staged exchange: join the NCCL communicator (swim_sim_connect)."""
         buf = (C.c_uint8 * A.NCCL_ID_BYTES).from_buffer_copy(unique_id)
         check(lib().swim_sim_connect(self._h, buf), "swim_sim_connect", self._h)
+
+    def ipc_export(self) -> bytes:
+        buf = (C.c_uint8 * A.IPC_BLOB_BYTES)()
+        check(lib().swim_sim_ipc_export(self._h, buf), "swim_sim_ipc_export", self._h)
+        return bytes(buf)
+
+    def ipc_connect(self, blobs):
+        """Fused exchange over peer memory: blobs = every rank's ipc_export(), in rank order."""
+        raw = b"".join(blobs)
+        buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+        check(lib().swim_sim_ipc_connect(self._h, buf), "swim_sim_ipc_connect", self._h)
 
 
 def nccl_unique_id() -> bytes:

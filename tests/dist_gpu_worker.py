@@ -21,8 +21,9 @@ def main():
     cfg = default_config(n_nodes=int(data["n"]), k_indirect=3, fanout=4, pb_cap=6, suspicion_rounds=4, retransmit=5,
                          loss_ppm=int(data["loss"]), seed=int(data["seed"]), rank=rank, world=world, device=local)
     sim = Simulator(cfg)
-    sdist.connect(sim)
     sim.set_view(data["nbr"])
+    mode = sdist.connect(sim, str(data["mode"]))
+    assert mode == str(data["mode"]), f"asked for {data['mode']} exchange, got {mode}"
     sim.inject(np.ascontiguousarray(data["events"]).reshape(-1).view(A.EVENT_DTYPE))
     chunks = [int(c) for c in data["chunks"]]
     digests = []

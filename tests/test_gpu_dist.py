@@ -19,7 +19,7 @@ def _gpus():
     return torch.cuda.device_count()
 
 
-def _run(tmp_path, world, n, rounds_chunks, loss, deg, gather=True, n_crash=None):
+def _run(tmp_path, world, n, rounds_chunks, loss, deg, gather=True, n_crash=None, mode="p2p"):
     from oracle.oracle import Oracle
     rng = np.random.default_rng(world * 100 + n)
     seed = 4242
@@ -27,7 +27,7 @@ def _run(tmp_path, world, n, rounds_chunks, loss, deg, gather=True, n_crash=None
     total = sum(rounds_chunks)
     events = random_events(rng, n, total, n_crash=n_crash or max(2, n // 12), n_rejoin=max(1, n // 40), n_inject=n // 10)
     np.savez(tmp_path / "case.npz", n=n, seed=seed, loss=loss, nbr=nbr, chunks=np.array(rounds_chunks),
-             gather=int(gather), events=np.frombuffer(events.tobytes(), dtype=np.uint8))
+             gather=int(gather), mode=mode, events=np.frombuffer(events.tobytes(), dtype=np.uint8))
     out = tmp_path / "result.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000),
@@ -50,15 +50,17 @@ def _run(tmp_path, world, n, rounds_chunks, loss, deg, gather=True, n_crash=None
     assert ref.counters()[A.CTR_MSGS_RECV] > 0
 
 
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_cuda_equals_oracle_small(tmp_path, world):
+def test_sharded_cuda_equals_oracle_small(tmp_path, world, mode):
     if _gpus() < world:
         pytest.skip(f"needs {world} GPUs")
-    _run(tmp_path, world, n=1003, rounds_chunks=[1] * 12 + [20], loss=20000, deg=24)
+    _run(tmp_path, world, n=1003, rounds_chunks=[1] * 12 + [20], loss=20000, deg=24, mode=mode)
 
 
-def test_sharded_cuda_equals_oracle_64k(tmp_path):
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_sharded_cuda_equals_oracle_64k(tmp_path, mode):
     world = min(_gpus(), 4)
     if world < 2:
         pytest.skip("needs 2 GPUs")
-    _run(tmp_path, world, n=65536, rounds_chunks=[5, 5, 10, 20], loss=0, deg=32, gather=False, n_crash=655)
+    _run(tmp_path, world, n=65536, rounds_chunks=[5, 5, 10, 20], loss=0, deg=32, gather=False, n_crash=655, mode=mode)

@@ -133,7 +133,7 @@ def test_scalar_api_matches_oracle_on_random_sequences():
             out, has = A.Message(), C.c_int()
             rc = fns[kind](sim._h, node, C.byref(m), C.byref(out), C.byref(has))
             try:
-                exp = [orc.suspect_node, orc.dead_node, orc.alive_node][kind - 3](node, m)
+                exp = {A.MSG_SUSPECT: orc.suspect_node, A.MSG_DEAD: orc.dead_node, A.MSG_ALIVE: orc.alive_node}[kind](node, m)
             except OracleError as e:  # row full: both sides must fail the same way
                 assert (rc, e.code) == (A.ECAP, A.ECAP), (step, kind, who, rc, e.code, len(orc.get_members(node)),
                                                           len(_members(sim, node, cap)))
