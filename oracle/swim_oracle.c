@@ -77,8 +77,10 @@ EXPORT void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t
   philox4x32_10(ctr, key, out);
 }
 
-/* counter layout: (a, node, purpose, block); key = seed lo, hi */
-enum { P_SELECT = 0, P_LOSS = 1, P_SCALAR = 2, P_TOPO = 3 };
+/* counter layout: (a, id, purpose, block); key = seed lo, hi. The target draw and the
+ * direct-leg loss draw of node i are word (i & 3) of the block with id = i >> 2 (four nodes share a
+ * block); proxy draws and indirect-leg loss draws use per-node blocks. */
+enum { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5 };
 
 /* bounded draw: floor(x * L / 2^32) — `randomR (0, L-1)` of Util.hs:40 on our stream */
 static uint32_t bounded(uint32_t x, uint32_t L) { return (uint32_t)(((uint64_t)x * L) >> 32); }
@@ -335,8 +337,10 @@ static void tick_node(oracle_t *o, uint32_t l, uint64_t *ctr) {
   for (uint32_t s = 0; s < o->cap; ++s)
     if (st[s] == SWIM_ALIVE) cand[L++] = s; /* filter isAlive over Map.elems */
   if (L == 0) return;
-  uint32_t draws[1 + SWIM_MAX_K];
-  draws_for(o, o->round, self, P_SELECT, 1 + o->k, draws);
+  uint32_t draws[1 + SWIM_MAX_K], grp[4];
+  draws_for(o, o->round, self >> 2, P_TARGET, 4, grp);
+  draws[0] = grp[self & 3];
+  draws_for(o, o->round, self, P_PROXY, o->k, draws + 1);
   uint32_t t, prox[SWIM_MAX_K], tmp[SWIM_MAX_VIEW];
   memcpy(tmp, cand, L * 4);
   shuffle_take(tmp, L, 1, draws, &t);
@@ -345,7 +349,11 @@ static void tick_node(oracle_t *o, uint32_t l, uint64_t *ctr) {
 
   /* T3 probe: Ping (Core.hs:246), unlessAck -> IndirectPings (250), unlessAck -> suspect (253) */
   uint32_t lossw[1 + SWIM_MAX_K];
-  if (o->loss_ppm) draws_for(o, o->round, self, P_LOSS, 1 + o->k, lossw);
+  if (o->loss_ppm) {
+    draws_for(o, o->round, self >> 2, P_LOSS0, 4, grp);
+    lossw[0] = grp[self & 3];
+    draws_for(o, o->round, self, P_LOSS, o->k, lossw + 1);
+  }
 #define LOST(leg) (o->loss_ppm && bounded(lossw[leg], 1000000u) < o->loss_ppm)
   uint32_t tn = ids[t], tinc = inc[t]; /* `m` is captured when the probe starts (Core.hs:243) */
   ctr[SWIM_CTR_PINGS]++;

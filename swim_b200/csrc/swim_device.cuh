@@ -30,8 +30,9 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 #define SWIM_MAX_WORLD 8
 
-// Philox counter purposes
-enum : uint32_t { P_SELECT = 0, P_LOSS = 1, P_SCALAR = 2, P_TOPO = 3 };
+// Philox counter purposes. TARGET and LOSS0 blocks are shared by the four nodes
+// 4g..4g+3 (counter word 1 = node >> 2, draw = word node & 3): one Philox call serves four probes.
+enum : uint32_t { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5 };
 
 struct SimDev {
   uint32_t N, first, n, cap;
@@ -306,54 +307,92 @@ struct Ctr {
 // SWAR helper: bit0 of each of 4 bytes -> 4-bit nibble
 __device__ __forceinline__ uint32_t gather4(uint32_t a) { return (a * 0x01020408u) >> 24 & 0xFu; }
 
+// seeded Bernoulli loss of one probe leg: leg 0 = the direct Ping/Ack round trip (group stream),
+// leg 1+j = the round trip through proxy j (per-node stream)
 __device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t self, uint32_t leg) {
   if (!d.loss_ppm) return false;
-  uint4 y = philox4x32_10(make_uint4(d.round, self, P_LOSS, leg >> 2), d.key0, d.key1);
-  return bounded(word_of(y, leg & 3), 1000000u) < d.loss_ppm;
+  uint4 y;
+  uint32_t w;
+  if (leg == 0) { y = philox4x32_10(make_uint4(d.round, self >> 2, P_LOSS0, 0), d.key0, d.key1); w = self & 3; }
+  else { y = philox4x32_10(make_uint4(d.round, self, P_LOSS, (leg - 1) >> 2), d.key0, d.key1); w = (leg - 1) & 3; }
+  return bounded(word_of(y, w), 1000000u) < d.loss_ppm;
 }
 
-// K1a — lane-per-node streaming pass over every node of the shard: ONE 16-byte load per node
-// (per 32 slots): the alive / suspect / crashed-member bitmaps and the flags word. Draws the probe
-// target with Philox4x32-10 (kRandomMembers store 1 [], Core.hs:239), picks the r-th alive slot
-// (shuffle, Util.hs:36-42) and tests it against the crashed-member bitmap (Ping/Ack, Core.hs:246).
-// Nodes that need more — a Suspect slot to count down, a failed probe, a non-empty piggyback
-// buffer — are appended to the round's work list (warp-aggregated atomicAdd) for K1b.
+// K1a — streaming pass over every node of the shard, FOUR nodes per lane: the four nodes 4g..4g+3
+// share one Philox4x32-10 block (one 32-bit draw each), so a lane issues four independent 16-byte
+// loads (the nodes' meta records: alive / suspect / crashed-member bitmaps + flags), one Philox
+// call, and four r-th-set-bit picks (kRandomMembers store 1 [], Core.hs:239; shuffle, Util.hs:36-42)
+// tested against the crashed-member bitmap (Ping/Ack, Core.hs:246). A warp covers 128 consecutive
+// nodes = 2 KB contiguous. Nodes that need more — a Suspect slot to count down, a failed probe, a
+// non-empty piggyback buffer — are appended to the round's work list for K1b.
+constexpr int kScanGroups = 2; // Philox groups (of 4 nodes) per lane per iteration: 8 nodes, 8 loads in flight
+
 template <int W>
-__global__ void __launch_bounds__(kThreads, 8) tick_scan_kernel(SimDev d) {
+__global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
+  constexpr int U = kScanGroups;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t *wl_cnt = d.wl_cnt + (d.round & 1);
   uint32_t pings = 0;
-  for (uint32_t base = warp * 32; base < d.n; base += nwarps * 32) {
-    const uint32_t l = base + lane;
-    bool work = false;
-    if (l < d.n) {
-      uint32_t am[W], td[W], sus = 0, L = 0, flags = 0;
+  const uint32_t g0 = d.first >> 2, g1 = (d.first + d.n + 3) >> 2; // Philox groups touching this shard
+  for (uint32_t gb = g0 + warp * (32 * U); gb < g1; gb += nwarps * (32 * U)) {
+    uint4 m[U][4];
+    uint32_t valid = 0; // bit u*4+j
 #pragma unroll
-      for (int w = 0; w < W; ++w) {
-        const uint4 m = d.meta[(size_t)l * W + w];
-        am[w] = m.x; sus |= m.y; td[w] = m.z;
-        if (w == 0) flags = m.w;
-        L += __popc(m.x);
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { // 4*U independent 16-byte loads in flight
+        const uint32_t node = 4 * (gb + u * 32 + lane) + j;
+        const bool ok = node >= d.first && node < d.first + d.n;
+        valid |= (uint32_t)ok << (u * 4 + j);
+        m[u][j] = ok ? d.meta[(size_t)(node - d.first) * W] : make_uint4(0, 0, 0, 0);
       }
-      if (flags & 0xFFu) { // a crashed process does nothing
-        work = (flags & 0xFF00u) != 0 || sus != 0; // piggyback to send, or a countdown to run [Q8]
+    uint32_t work = 0; // bit u*4+j: that node needs K1b
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t g = gb + u * 32 + lane;
+      if ((valid >> (u * 4) & 0xFu) == 0) continue;
+      const uint4 x = philox4x32_10(make_uint4(d.round, g, P_TARGET, 0), d.key0, d.key1);
+      uint4 y = make_uint4(0, 0, 0, 0);
+      if (d.loss_ppm) y = philox4x32_10(make_uint4(d.round, g, P_LOSS0, 0), d.key0, d.key1);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!(valid >> (u * 4 + j) & 1u) || (m[u][j].w & 0xFFu) == 0) continue; // a crashed process does nothing
+        uint32_t am[W], td[W], sus = m[u][j].y, L;
+        am[0] = m[u][j].x; td[0] = m[u][j].z; L = __popc(m[u][j].x);
+        if (W > 1) {
+          const uint32_t l = 4 * g + j - d.first;
+#pragma unroll
+          for (int w = 1; w < W; ++w) {
+            const uint4 mw = d.meta[(size_t)l * W + w];
+            am[w] = mw.x; sus |= mw.y; td[w] = mw.z; L += __popc(mw.x);
+          }
+        }
+        bool need = (m[u][j].w & 0xFF00u) != 0 || sus != 0; // piggyback to send, or a countdown to run [Q8]
         if (L) {
-          const uint4 x = philox4x32_10(make_uint4(d.round, d.first + l, P_SELECT, 0), d.key0, d.key1);
-          const uint32_t tslot = pick_remove<W>(am, bounded(x.x, L));
+          const uint32_t tslot = pick_remove<W>(am, bounded(word_of(x, j), L));
           ++pings;                                                          // Ping (Core.hs:246)
           bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;          // Ack iff the target is up
-          if (acked && d.loss_ppm) acked = !leg_lost(d, d.first + l, 0);
-          work |= !acked;
+          if (acked && d.loss_ppm) acked = !(bounded(word_of(y, j), 1000000u) < d.loss_ppm);
+          need |= !acked;
         }
+        work |= (uint32_t)need << (u * 4 + j);
       }
     }
-    const unsigned todo = __ballot_sync(kFull, work);
-    if (todo) {
+    // warp-aggregated append of up to 4*U x 32 nodes
+    if (__any_sync(kFull, work != 0)) {
+      unsigned b[4 * U];
+      uint32_t total = 0;
+#pragma unroll
+      for (int q = 0; q < 4 * U; ++q) { b[q] = __ballot_sync(kFull, work >> q & 1u); total += __popc(b[q]); }
       uint32_t pos = 0;
-      if (lane == 0) pos = atomicAdd(wl_cnt, (uint32_t)__popc(todo));
+      if (lane == 0) pos = atomicAdd(wl_cnt, total);
       pos = __shfl_sync(kFull, pos, 0);
-      if (work) d.wl[pos + __popc(todo & ((1u << lane) - 1))] = l;
+#pragma unroll
+      for (int q = 0; q < 4 * U; ++q) {
+        if (work >> q & 1u) d.wl[pos + __popc(b[q] & ((1u << lane) - 1))] = 4 * (gb + (q >> 2) * 32 + lane) + (q & 3) - d.first;
+        pos += __popc(b[q]);
+      }
     }
   }
   pings = __reduce_add_sync(kFull, pings);
@@ -404,19 +443,18 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
     uint32_t tslot = 0, np = 0, prox[SWIM_MAX_K];
     if (L) {
       // target: draw 0; proxies: kRandomMembers store k [] (Core.hs:249), a fresh shuffle over the
-      // same alive list (neither self nor the target excluded), draws 1..k of the SELECT stream
-      uint4 blk = philox4x32_10(make_uint4(d.round, self, P_SELECT, 0), d.key0, d.key1);
+      // same alive list (neither self nor the target excluded), draws of the node's PROXY stream
+      uint4 blk = philox4x32_10(make_uint4(d.round, self >> 2, P_TARGET, 0), d.key0, d.key1);
       uint32_t tmp[W];
 #pragma unroll
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
-      tslot = pick_remove<W>(tmp, bounded(blk.x, L));
+      tslot = pick_remove<W>(tmp, bounded(word_of(blk, self & 3), L));
 #pragma unroll
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
       np = d.k < L ? d.k : L;
       for (uint32_t j = 0; j < np; ++j) {
-        const uint32_t dr = 1 + j;
-        if (dr == 4) blk = philox4x32_10(make_uint4(d.round, self, P_SELECT, 1), d.key0, d.key1);
-        prox[j] = pick_remove<W>(tmp, bounded(word_of(blk, dr & 3), L - j));
+        if ((j & 3) == 0) blk = philox4x32_10(make_uint4(d.round, self, P_PROXY, j >> 2), d.key0, d.key1);
+        prox[j] = pick_remove<W>(tmp, bounded(word_of(blk, j & 3), L - j));
       }
       // T3: Ping (Core.hs:246); unlessAck -> IndirectPings (247-250); unlessAck -> suspectNode (251-254)
       const bool t_up = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;

@@ -362,7 +362,7 @@ static int wave_grid(const swim_sim *sim, K kernel, size_t warps_needed) {
 template <int W>
 static int run_rounds(swim_sim *sim, uint32_t rounds) {
   SimDev &d = sim->dev;
-  const int grid = wave_grid(sim, tick_scan_kernel<W>, ((size_t)d.n + 31) / 32);
+  const int grid = wave_grid(sim, tick_scan_kernel<W>, ((size_t)d.n + 128 * kScanGroups) / (128 * kScanGroups) + 1);
   const int wgrid = wave_grid(sim, tick_work_kernel<W>, (size_t)d.n);
   const int rgrid = wave_grid(sim, recv_kernel<W>, (size_t)d.n);
   if (sim->tdead_dirty) {
