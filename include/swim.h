@@ -293,7 +293,8 @@ int swim_sim_connect(swim_sim_t *sim, const uint8_t id[SWIM_NCCL_ID_BYTES]);
 /* Fused exchange over peer memory (preferred when all ranks share one NVLink/NVSwitch box):
  * instead of staging envelopes for NCCL, K1b raises the in-edge flag and appends the receiver
  * directly in the owner GPU's memory, and K2 pulls the sender's snapshot from the sender GPU's
- * memory; two device-side cross-GPU barriers per round replace the collective. Call after
+ * memory (plain NVLink stores and loads, nothing staged); one device-side cross-GPU barrier per round
+ * replaces the collective (everything senders write is double-buffered by round parity). Call after
  * swim_sim_set_view: every rank exports a blob (CUDA IPC handles of its mail arrays), the host
  * side all-gathers the blobs in rank order, every rank connects. Without this call (only
  * swim_sim_connect) the staged NCCL all-to-all is used. */

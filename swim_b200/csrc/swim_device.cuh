@@ -62,16 +62,24 @@ struct SimDev {
   uint32_t *obs_slot;        // [n*cap] ... as linear slot indices l*cap + s
   uint32_t *wl, *wl_cnt;     // work list of K1b [n], its round-parity counters [2]
   uint32_t *rl, *rl_cnt;     // receiver list of K2 [n], its round-parity counters [2]
-  // cross-shard delivery over peer memory (NVLink): the same arrays of every rank, mapped here
-  // with CUDA IPC; entry [rank] is this rank's own array. Filled for world == 1 too (one entry).
-  uint8_t *eflag_p[SWIM_MAX_WORLD];
-  uint32_t *mail_p[SWIM_MAX_WORLD];
-  uint32_t *rl_p[SWIM_MAX_WORLD];
-  uint32_t *rl_cnt_p[SWIM_MAX_WORLD];
-  const uint4 *out_p[SWIM_MAX_WORLD];
-  const uint8_t *out_cnt_p[SWIM_MAX_WORLD];
-  uint32_t *bar_p[SWIM_MAX_WORLD]; // cross-GPU barrier words [world] of every rank
-  uint32_t p2p;                    // 1 = fused peer-memory exchange, 0 = staged NCCL all-to-all
+  // Round-parity double buffering: everything a round's senders write for its receivers exists twice
+  // (index = round & 1), so round r+1's senders never touch what round r's receivers still read and ONE
+  // cross-GPU barrier per round (between K1b and K2) is enough.
+  uint32_t estride;          // eflag parity stride of this rank (>= E)
+  uint32_t *claim;           // [n] round stamp: a receiver is processed by exactly one warp per round
+  // cross-shard delivery over peer memory (NVLink): the same arrays of every rank, mapped here with CUDA
+  // IPC; entry [rank] is this rank's own array. Remote traffic is fire-and-forget stores only.
+  uint8_t *eflag_p[SWIM_MAX_WORLD];      // [2][estride_p[r]] in-edge mail flags
+  uint32_t estride_p[SWIM_MAX_WORLD];
+  const uint4 *out_p[SWIM_MAX_WORLD];    // [2][per*B] sender snapshots
+  const uint8_t *out_cnt_p[SWIM_MAX_WORLD]; // [2][per]
+  uint32_t *rlr_p[SWIM_MAX_WORLD];       // [2][world][rcap] receiver ids appended by each source rank
+  uint32_t *rcnt_p[SWIM_MAX_WORLD];      // [2][world] their counts, published by the barrier kernel
+  uint32_t *bar_p[SWIM_MAX_WORLD];       // [world] cross-GPU barrier words
+  uint32_t *rlr, *rcnt;                  // this rank's own receive-side arrays
+  uint32_t *xcnt;                        // [world] envelopes sent to each rank this round (sender side)
+  uint32_t rcap;                         // capacity of one (parity, source) remote list
+  uint32_t p2p;                          // 1 = fused peer-memory exchange, 0 = staged NCCL all-to-all
   // staged exchange through NCCL (baseline path)
   uint4 *xsend;              // [world][xcap] envelopes {ridx, cnt, src, -} + B records, bucketed by rank
   uint32_t *xsend_cnt;       // [world + 1]; the last word is the bucket-overflow flag
@@ -81,6 +89,13 @@ struct SimDev {
   unsigned long long *ctr;   // [SWIM_CTR__COUNT]
 };
 
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// The per-round kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the
+// next kernel's CTAs may be scheduled while this one drains; pdl_wait() blocks until the previous
+// grid has completed and its writes are visible, pdl_launch() lets the following grid start early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -330,6 +345,8 @@ constexpr int kScanGroups = 2; // Philox groups (of 4 nodes) per lane per iterat
 template <int W>
 __global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
   constexpr int U = kScanGroups;
+  pdl_launch();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t *wl_cnt = d.wl_cnt + (d.round & 1);
@@ -407,11 +424,14 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  pdl_launch();
+  pdl_wait();
   const uint32_t n_work = d.wl_cnt[d.round & 1];
   if (warp == 0 && lane == 0) { d.wl_cnt[(d.round + 1) & 1] = 0; }
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  uint32_t *rl_cnt = d.rl_cnt + (d.round & 1);
+  const uint32_t par = d.round & 1;
+  uint32_t *rl_cnt = d.rl_cnt + par;
 
   for (uint32_t item = warp; item < n_work; item += nwarps) {
     const uint32_t ln = d.wl[item], self = d.first + ln;
@@ -498,19 +518,14 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
         const uint32_t owner = d.world == 1 ? 0u : dst / d.per;
         const uint32_t dl = dst - owner * d.per;
         if (owner == d.rank) {
-          d.eflag[ridx] = 1; // raise the in-edge flag (i -> dst)
-          if (d.p2p && d.world > 1) {
-            if (atomicExch_system(&d.mail[dl], d.round) != d.round) d.rl[atomicAdd_system(rl_cnt, 1u)] = dl;
-          } else if (atomicExch(&d.mail[dl], d.round) != d.round) {
-            d.rl[atomicAdd(rl_cnt, 1u)] = dl;
-          }
+          d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
+          if (atomicExch(&d.mail[dl], d.round) != d.round) d.rl[atomicAdd(rl_cnt, 1u)] = dl;
         } else if (d.p2p) {
-          // fused exchange: the flag and the receiver-list entry are written straight into the
-          // owner GPU's memory over NVLink; the receiver will pull our snapshot from ours
-          d.eflag_p[owner][ridx] = 1;
-          if (atomicExch_system(&d.mail_p[owner][dl], d.round) != d.round)
-            d.rl_p[owner][atomicAdd_system(&d.rl_cnt_p[owner][d.round & 1], 1u)] = dl;
-          __threadfence_system(); // peer-memory stores are ordered before this kernel's end + the barrier flag
+          // fused exchange: flag and receiver-list entry go straight into the owner GPU's memory over
+          // NVLink (plain stores, nothing comes back); the receiver pulls our snapshot from our memory
+          d.eflag_p[owner][(size_t)par * d.estride_p[owner] + ridx] = 1;
+          const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
+          d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
         } else {
           const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
           if (k < d.xcap) {
@@ -522,14 +537,14 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
         }
       }
       if (lane == 0) {
-        d.out_cnt[ln] = (uint8_t)pbs.cnt;
+        d.out_cnt[(size_t)par * d.per + ln] = (uint8_t)pbs.cnt;
         c.v[SWIM_CTR_MSGS] += nr;
         c.v[SWIM_CTR_RECS_SENT] += nr * pbs.cnt;
       }
       // snapshot, then one transmission is spent on every record
       uint4 mine = make_uint4(0, 0, 0, 0);
       const bool have = (uint32_t)lane < pbs.cnt;
-      if (have) { mine = pbs.s[lane]; d.out[(size_t)ln * d.B + lane] = mine; }
+      if (have) { mine = pbs.s[lane]; d.out[((size_t)par * d.per + ln) * d.B + lane] = mine; }
       unsigned xm = __ballot_sync(kFull, xs != 0xFFFFFFFFu);
       while (xm) { // cross-shard envelopes carry the records themselves
         const int f = __ffs(xm) - 1;
@@ -561,14 +576,40 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
-  const uint32_t n_recv = d.rl_cnt[d.round & 1];
-  if (warp == 0 && lane == 0) d.rl_cnt[(d.round + 1) & 1] = 0;
+  const uint32_t par = d.round & 1;
+  pdl_launch();
+  pdl_wait();
+  // receivers of this round: the local list, then one list per source rank (fused exchange)
+  uint32_t seg_end[SWIM_MAX_WORLD + 1];
+  uint32_t n_recv = d.rl_cnt[par];
+  seg_end[0] = n_recv;
+  const bool remote_lists = d.world > 1 && d.p2p;
+  if (remote_lists)
+    for (uint32_t a = 0; a < d.world; ++a) {
+      if (a != d.rank) n_recv += d.rcnt[par * d.world + a];
+      seg_end[1 + a] = n_recv;
+    }
+  if (warp == 0 && lane == 0) d.rl_cnt[par ^ 1] = 0;
   if (n_recv == 0) return;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
+  const size_t ebase = (size_t)par * d.estride;
 
   for (uint32_t item = warp; item < n_recv; item += nwarps) {
-    const uint32_t ln = d.rl[item], self = d.first + ln;
+    uint32_t ln;
+    if (item < seg_end[0]) {
+      ln = d.rl[item];
+    } else {
+      uint32_t a = 0;
+      while (item >= seg_end[1 + a]) ++a;
+      ln = d.rlr[((size_t)par * d.world + a) * d.rcap + (item - seg_end[a])];
+    }
+    if (remote_lists) { // a receiver may be listed by several ranks: exactly one warp takes it
+      uint32_t old = 0;
+      if (lane == 0) old = atomicExch(&d.claim[ln], d.round);
+      if (__shfl_sync(kFull, old, 0) == d.round) continue;
+    }
+    const uint32_t self = d.first + ln;
     const bool up = d.alive[self] != 0; // datagrams to a crashed process are lost
     const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
     Row<W> row;
@@ -581,8 +622,8 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
     for (uint32_t eb = e0; eb < e1; eb += 32) {
       const uint32_t e = eb + lane;
       uint32_t f = 0, src = 0;
-      if (e < e1) { f = d.eflag[e]; src = d.in_src[e]; }
-      if (f) d.eflag[e] = 0;
+      if (e < e1) { f = d.eflag[ebase + e]; src = d.in_src[e]; }
+      if (f) d.eflag[ebase + e] = 0;
       unsigned fm = __ballot_sync(kFull, f != 0);
       if (!up) continue;
       while (fm) { // ascending sender id: the in-list is sorted
@@ -593,8 +634,8 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
         uint4 mine = make_uint4(0, 0, 0, 0);
         if (s_kind == 1) { // pull the sender's snapshot (from a peer GPU's memory if it lives there)
           const uint32_t s_rank = d.world == 1 ? 0u : s_id / d.per, sl = s_id - s_rank * d.per;
-          if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][(size_t)sl * d.B + lane];
-          cnt = d.out_cnt_p[s_rank][sl];
+          if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][((size_t)par * d.per + sl) * d.B + lane];
+          cnt = d.out_cnt_p[s_rank][(size_t)par * d.per + sl];
         } else {           // sender on another shard: the envelope arrived in the exchange buffer
           const uint32_t slot = d.eslot[eb + q];
           const uint4 *env = d.xrecv + (size_t)slot * (1 + d.B);
@@ -632,13 +673,19 @@ static __global__ void peer_barrier_kernel(SimDev d, uint32_t stamp, uint32_t *e
   const uint32_t q = threadIdx.x;
   if (q >= d.world) return;
   __threadfence_system();
+  if (q != d.rank) { // tell peer q how many receivers we appended to its list this round
+    volatile uint32_t *cnt = d.rcnt_p[q] + (d.round & 1) * d.world + d.rank;
+    *cnt = d.xcnt[q];
+    d.xcnt[q] = 0;
+    __threadfence_system();
+  }
   volatile uint32_t *theirs = d.bar_p[q] + d.rank;
   *theirs = stamp;
   volatile uint32_t *mine = d.bar_p[d.rank] + q;
   const long long t0 = clock64();
   while ((int32_t)(*mine - stamp) < 0) {
     if (clock64() - t0 > 6000000000ll) { *err = 1; break; } // ~3 s at 2 GHz
-    __nanosleep(100);
+    __nanosleep(40);
   }
   __threadfence_system();
 }

@@ -94,7 +94,7 @@ __global__ void deliver_kernel(SimDev d, uint32_t total) {
   uint32_t *rl_cnt = d.rl_cnt + (d.round & 1);
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
     const uint4 hdr = d.xrecv[(size_t)k * (1 + d.B)]; // {in-edge index, count, sender id, receiver (local)}
-    d.eflag[hdr.x] = 2;
+    d.eflag[(size_t)(d.round & 1) * d.estride + hdr.x] = 2;
     d.eslot[hdr.x] = k;
     if (atomicExch(&d.mail[hdr.w], d.round) != d.round) d.rl[atomicAdd(rl_cnt, 1u)] = hdr.w;
   }
@@ -150,8 +150,8 @@ extern "C" int swim_sim_connect(swim_sim_t *sim, const uint8_t *id) {
 // ------------------------------------------------------------------ fused exchange over peer memory
 namespace {
 struct IpcBlob {
-  uint32_t magic, rank, n, n_edges_lo;
-  cudaIpcMemHandle_t h[7]; // eflag, mail, rl, rl_cnt, out, out_cnt, bar
+  uint32_t magic, rank, n, estride;
+  cudaIpcMemHandle_t h[6]; // eflag, out, out_cnt, rlr, rcnt, bar
 };
 static_assert(sizeof(IpcBlob) <= SWIM_IPC_BLOB_BYTES, "blob too small");
 constexpr uint32_t kBlobMagic = 0x53574D49u; // "SWMI"
@@ -164,9 +164,9 @@ extern "C" int swim_sim_ipc_export(swim_sim_t *sim, uint8_t *blob) {
   SimDev &d = sim->dev;
   IpcBlob b;
   memset(&b, 0, sizeof b);
-  b.magic = kBlobMagic; b.rank = d.rank; b.n = d.n; b.n_edges_lo = (uint32_t)sim->n_edges;
-  void *ptrs[7] = {d.eflag, d.mail, d.rl, d.rl_cnt, d.out, d.out_cnt, sim->d_bar};
-  for (int x = 0; x < 7; ++x) CUDA_TRY(sim, cudaIpcGetMemHandle(&b.h[x], ptrs[x]));
+  b.magic = kBlobMagic; b.rank = d.rank; b.n = d.n; b.estride = d.estride;
+  void *ptrs[6] = {d.eflag, d.out, d.out_cnt, d.rlr, d.rcnt, sim->d_bar};
+  for (int x = 0; x < 6; ++x) CUDA_TRY(sim, cudaIpcGetMemHandle(&b.h[x], ptrs[x]));
   memset(blob, 0, SWIM_IPC_BLOB_BYTES);
   memcpy(blob, &b, sizeof b);
   return SWIM_OK;
@@ -183,14 +183,14 @@ extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
     memcpy(&b, blobs + (size_t)r * SWIM_IPC_BLOB_BYTES, sizeof b);
     if (b.magic != kBlobMagic || b.rank != r) { set_error(sim, "swim_sim_ipc_connect: blob %u is not rank %u's export", r, r); return SWIM_EINVAL; }
     if (r == d.rank) continue;
-    void *p[7];
-    for (int x = 0; x < 7; ++x) {
+    void *p[6];
+    for (int x = 0; x < 6; ++x) {
       CUDA_TRY(sim, cudaIpcOpenMemHandle(&p[x], b.h[x], cudaIpcMemLazyEnablePeerAccess));
       sim->ipc_opened.push_back(p[x]);
     }
-    d.eflag_p[r] = (uint8_t *)p[0]; d.mail_p[r] = (uint32_t *)p[1]; d.rl_p[r] = (uint32_t *)p[2];
-    d.rl_cnt_p[r] = (uint32_t *)p[3]; d.out_p[r] = (const uint4 *)p[4]; d.out_cnt_p[r] = (const uint8_t *)p[5];
-    d.bar_p[r] = (uint32_t *)p[6];
+    d.eflag_p[r] = (uint8_t *)p[0]; d.estride_p[r] = b.estride;
+    d.out_p[r] = (const uint4 *)p[1]; d.out_cnt_p[r] = (const uint8_t *)p[2];
+    d.rlr_p[r] = (uint32_t *)p[3]; d.rcnt_p[r] = (uint32_t *)p[4]; d.bar_p[r] = (uint32_t *)p[5];
   }
   d.p2p = 1;
   sim->connected = true;
@@ -202,8 +202,8 @@ namespace swim {
 void refresh_peer_tables(swim_sim *sim) { // entry [rank] always aliases this rank's own arrays
   SimDev &d = sim->dev;
   const uint32_t r = d.rank;
-  d.eflag_p[r] = d.eflag; d.mail_p[r] = d.mail; d.rl_p[r] = d.rl; d.rl_cnt_p[r] = d.rl_cnt;
-  d.out_p[r] = d.out; d.out_cnt_p[r] = d.out_cnt; d.bar_p[r] = sim->d_bar;
+  d.eflag_p[r] = d.eflag; d.estride_p[r] = d.estride; d.out_p[r] = d.out; d.out_cnt_p[r] = d.out_cnt;
+  d.rlr_p[r] = d.rlr; d.rcnt_p[r] = d.rcnt; d.bar_p[r] = sim->d_bar;
 }
 
 int dist_barrier(swim_sim *sim) {

@@ -155,8 +155,15 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.vlast, slots, 0))) return r;
     if ((r = dalloc(sim, &d.pb, n * d.B, 0))) return r;
     if ((r = dalloc(sim, &d.pb_cnt, n, 0))) return r;
-    if ((r = dalloc(sim, &d.out, n * d.B, 0))) return r;
-    if ((r = dalloc(sim, &d.out_cnt, n, 0))) return r;
+    if ((r = dalloc(sim, &d.out, 2 * (size_t)d.per * d.B, 0))) return r; // [parity][per*B]
+    if ((r = dalloc(sim, &d.out_cnt, 2 * (size_t)d.per, 0))) return r;
+    if ((r = dalloc(sim, &d.claim, n, 0))) return r;
+    if ((r = dalloc(sim, &d.xcnt, SWIM_MAX_WORLD, 0))) return r;
+    d.rcap = d.per * d.fanout; // a source rank can list at most per*fanout receivers per round
+    if (d.world > 1) {
+      if ((r = dalloc(sim, &d.rlr, 2 * (size_t)d.world * d.rcap, 0))) return r;
+      if ((r = dalloc(sim, &d.rcnt, 2 * (size_t)d.world, 0))) return r;
+    }
     if ((r = dalloc(sim, &d.ridx, slots, 0))) return r;
     if ((r = dalloc(sim, &d.in_off, n + 1, 0))) return r;
     if ((r = dalloc(sim, &d.mail, n, 0))) return r;
@@ -254,9 +261,11 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
   if (sim->d_in_src) { cudaFree(sim->d_in_src); sim->d_in_src = nullptr; }
   if (sim->d_eflag) { cudaFree(sim->d_eflag); sim->d_eflag = nullptr; }
   const size_t Ea = E ? (size_t)E : 1;
+  const size_t estride = (Ea + 255) & ~(size_t)255; // parity stride of the mail flags
+  d.estride = (uint32_t)estride;
   CUDA_TRY(sim, cudaMalloc((void **)&sim->d_in_src, Ea * 4));
-  CUDA_TRY(sim, cudaMalloc((void **)&sim->d_eflag, Ea));
-  CUDA_TRY(sim, cudaMemset(sim->d_eflag, 0, Ea));
+  CUDA_TRY(sim, cudaMalloc((void **)&sim->d_eflag, 2 * estride));
+  CUDA_TRY(sim, cudaMemset(sim->d_eflag, 0, 2 * estride));
   CUDA_TRY(sim, cudaMemcpy(sim->d_in_src, in_src.data(), Ea * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(sim, cudaMemcpy(d.in_off, in_off.data(), ((size_t)d.n + 1) * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(sim, cudaMemcpy(d.ridx, ridx.data(), ridx.size() * 4, cudaMemcpyHostToDevice));
@@ -359,6 +368,22 @@ static int wave_grid(const swim_sim *sim, K kernel, size_t warps_needed) {
   return (int)std::min(blocks, (size_t)sim->sm_count * per_sm);
 }
 
+// launch with programmatic stream serialization (see pdl_wait / pdl_launch in swim_device.cuh)
+template <typename K>
+static cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, const SimDev &d) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, d);
+}
+
 template <int W>
 static int run_rounds(swim_sim *sim, uint32_t rounds) {
   SimDev &d = sim->dev;
@@ -406,16 +431,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       ev_pos = ev_end;
     }
     int mk = prof_begin(sim, 1);
-    tick_scan_kernel<W><<<grid, kThreads, 0, sim->stream>>>(d);
+    CUDA_TRY(sim, launch_pdl(tick_scan_kernel<W>, grid, sim->stream, d));
     prof_end(sim, mk);
-    if (d.world > 1 && d.p2p) { // every peer is done pulling last round's snapshots from this rank
-      mk = prof_begin(sim, 2);
-      int rc = swim::dist_barrier(sim);
-      if (rc) return rc;
-      prof_end(sim, mk);
-    }
     mk = prof_begin(sim, 4);
-    tick_work_kernel<W><<<wgrid, kThreads, 0, sim->stream>>>(d);
+    CUDA_TRY(sim, launch_pdl(tick_work_kernel<W>, wgrid, sim->stream, d));
     prof_end(sim, mk);
     if (d.world > 1) { // the exchange step: flags raised on every rank (p2p) / envelopes moved (NCCL)
       mk = prof_begin(sim, 2);
@@ -424,7 +443,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       prof_end(sim, mk);
     }
     mk = prof_begin(sim, 3);
-    recv_kernel<W><<<rgrid, kThreads, 0, sim->stream>>>(d);
+    CUDA_TRY(sim, launch_pdl(recv_kernel<W>, rgrid, sim->stream, d));
     prof_end(sim, mk);
     sim->launches += 3;
     if (sim->profile) sim->prof_ms[5] += 1;
