@@ -55,13 +55,12 @@ struct SimDev {
   uint32_t *in_off;          // [n+1]
   uint32_t *in_src;          // [E] sender ids, ascending per receiver
   uint8_t *eflag;            // [E] 1 = sender mailed this round
-  uint32_t *mail;            // [n] round of the receiver's latest mail (dedupes the receiver list)
   uint4 *meta;               // [n*W] per 32 slots: {alive bitmap, suspect bitmap, crashed-member bitmap,
                              //        flags: byte0 = process up, byte1 = piggyback count (word 0 only)}
   uint32_t *obs_off;         // [N+1] observers of member m among this shard's rows ...
   uint32_t *obs_slot;        // [n*cap] ... as linear slot indices l*cap + s
   uint32_t *wl, *wl_cnt;     // work list of K1b [n], its round-parity counters [2]
-  uint32_t *rl, *rl_cnt;     // receiver list of K2 [n], its round-parity counters [2]
+  uint32_t *rl;              // [n*fanout] receiver candidates: slot item*fanout + f of work item `item`
   // Round-parity double buffering: everything a round's senders write for its receivers exists twice
   // (index = round & 1), so round r+1's senders never touch what round r's receivers still read and ONE
   // cross-GPU barrier per round (between K1b and K2) is enough.
@@ -309,12 +308,19 @@ struct Ctr {
 #pragma unroll
     for (int i = 0; i < SWIM_CTR__COUNT; ++i) v[i] = 0;
   }
+  // block-level flush: warps add into shared memory, then one global atomic per counter per CTA.
+  // Every thread of the CTA must call it (it contains __syncthreads).
   __device__ __forceinline__ void flush(unsigned long long *g, int lane) {
+    __shared__ uint32_t s_ctr[SWIM_CTR__COUNT];
+    if (threadIdx.x < SWIM_CTR__COUNT) s_ctr[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < SWIM_CTR__COUNT; ++i) {
       uint32_t x = __reduce_add_sync(kFull, v[i]);
-      if (lane == 0 && x) atomicAdd(&g[i], (unsigned long long)x);
+      if (lane == 0 && x) atomicAdd(&s_ctr[i], x);
     }
+    __syncthreads();
+    if (threadIdx.x < SWIM_CTR__COUNT && s_ctr[threadIdx.x]) atomicAdd(&g[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
   }
 };
 
@@ -431,7 +437,6 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   const uint32_t par = d.round & 1;
-  uint32_t *rl_cnt = d.rl_cnt + par;
 
   for (uint32_t item = warp; item < n_work; item += nwarps) {
     const uint32_t ln = d.wl[item], self = d.first + ln;
@@ -507,6 +512,7 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
     }
     row_store<W>(row, d, ln, lane);
     // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
+    uint32_t cand = 0xFFFFFFFFu; // lane f < fanout: local receiver of recipient f (K2's candidate slot)
     if (L && pbs.cnt) {
       uint32_t nr = 1, rslot = tslot; // lane f carries recipient f
       for (uint32_t j = 0; j < np && nr < d.fanout; ++j)
@@ -519,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
         const uint32_t dl = dst - owner * d.per;
         if (owner == d.rank) {
           d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
-          if (atomicExch(&d.mail[dl], d.round) != d.round) d.rl[atomicAdd(rl_cnt, 1u)] = dl;
+          cand = dl;
         } else if (d.p2p) {
           // fused exchange: flag and receiver-list entry go straight into the owner GPU's memory over
           // NVLink (plain stores, nothing comes back); the receiver pulls our snapshot from our memory
@@ -564,6 +570,7 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
       __syncwarp();
     }
     pb_store(pbs, d, ln, lane);
+    if ((uint32_t)lane < d.fanout) d.rl[(size_t)item * d.fanout + lane] = cand; // no atomics, no shared counter
   }
   c.flush(d.ctr, lane);
 }
@@ -579,18 +586,18 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
   const uint32_t par = d.round & 1;
   pdl_launch();
   pdl_wait();
-  // receivers of this round: the local list, then one list per source rank (fused exchange)
+  // receivers of this round: the candidate slots written by K1b (fanout per work item, some empty),
+  // then one list per source rank (cross-shard senders). A receiver can appear many times: the claim
+  // stamp lets exactly one warp process it.
   uint32_t seg_end[SWIM_MAX_WORLD + 1];
-  uint32_t n_recv = d.rl_cnt[par];
+  uint32_t n_recv = d.wl_cnt[par] * d.fanout;
   seg_end[0] = n_recv;
-  const bool remote_lists = d.world > 1 && d.p2p;
+  const bool remote_lists = d.world > 1;
   if (remote_lists)
     for (uint32_t a = 0; a < d.world; ++a) {
       if (a != d.rank) n_recv += d.rcnt[par * d.world + a];
       seg_end[1 + a] = n_recv;
     }
-  if (warp == 0 && lane == 0) d.rl_cnt[par ^ 1] = 0;
-  if (n_recv == 0) return;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   const size_t ebase = (size_t)par * d.estride;
@@ -599,16 +606,15 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
     uint32_t ln;
     if (item < seg_end[0]) {
       ln = d.rl[item];
+      if (ln == 0xFFFFFFFFu) continue; // empty candidate slot
     } else {
       uint32_t a = 0;
       while (item >= seg_end[1 + a]) ++a;
       ln = d.rlr[((size_t)par * d.world + a) * d.rcap + (item - seg_end[a])];
     }
-    if (remote_lists) { // a receiver may be listed by several ranks: exactly one warp takes it
-      uint32_t old = 0;
-      if (lane == 0) old = atomicExch(&d.claim[ln], d.round);
-      if (__shfl_sync(kFull, old, 0) == d.round) continue;
-    }
+    uint32_t old = 0;
+    if (lane == 0) old = atomicExch(&d.claim[ln], d.round);
+    if (__shfl_sync(kFull, old, 0) == d.round) continue; // another warp has this receiver
     const uint32_t self = d.first + ln;
     const bool up = d.alive[self] != 0; // datagrams to a crashed process are lost
     const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];

@@ -89,14 +89,23 @@ struct Dist {
   size_t xrecv_cap = 0;         // envelopes
 };
 
-// Received envelopes -> in-edge flags + receiver list. One thread per envelope.
-__global__ void deliver_kernel(SimDev d, uint32_t total) {
-  uint32_t *rl_cnt = d.rl_cnt + (d.round & 1);
+// Received envelopes -> in-edge flags + per-source receiver lists. One thread per envelope; the
+// position of an envelope inside its source's block is its slot in that source's list, so no atomics.
+struct DeliverArgs {
+  uint32_t off[SWIM_MAX_WORLD + 1]; // prefix offsets of the source ranks' blocks inside xrecv
+};
+
+__global__ void deliver_kernel(SimDev d, DeliverArgs a, uint32_t total) {
+  const uint32_t par = d.round & 1;
+  if (blockIdx.x == 0 && threadIdx.x < d.world)
+    d.rcnt[par * d.world + threadIdx.x] = a.off[threadIdx.x + 1] - a.off[threadIdx.x];
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < total; k += gridDim.x * blockDim.x) {
     const uint4 hdr = d.xrecv[(size_t)k * (1 + d.B)]; // {in-edge index, count, sender id, receiver (local)}
-    d.eflag[(size_t)(d.round & 1) * d.estride + hdr.x] = 2;
+    uint32_t src = 0;
+    while (k >= a.off[src + 1]) ++src;
+    d.eflag[(size_t)par * d.estride + hdr.x] = 2;
     d.eslot[hdr.x] = k;
-    if (atomicExch(&d.mail[hdr.w], d.round) != d.round) d.rl[atomicAdd(rl_cnt, 1u)] = hdr.w;
+    d.rlr[((size_t)par * d.world + src) * d.rcap + (k - a.off[src])] = hdr.w;
   }
 }
 
@@ -238,6 +247,8 @@ int dist_exchange(swim_sim *sim) {
   // 2. move exactly the filled part of every bucket
   const size_t env_bytes = (size_t)(1 + d.B) * sizeof(uint4);
   size_t total_recv = 0, any = 0;
+  DeliverArgs da;
+  memset(&da, 0, sizeof da);
   for (uint32_t a = 0; a < G; ++a)
     for (uint32_t b = 0; b < G; ++b) any += x->h_matrix[a * row + b];
   if (any) {
@@ -248,19 +259,21 @@ int dist_exchange(swim_sim *sim) {
       if (n_send)
         NCCL_TRY(sim, g_nccl.Send((const uint8_t *)d.xsend + (size_t)p * d.xcap * env_bytes, n_send * env_bytes, ncclUint8, (int)p, x->comm, sim->stream));
       if (n_recv) {
-        if (total_recv + n_recv > x->xrecv_cap) { g_nccl.GroupEnd(); set_error(sim, "exchange receive buffer overflow"); return SWIM_ECAP; }
+        if (total_recv + n_recv > x->xrecv_cap || n_recv > d.rcap) { g_nccl.GroupEnd(); set_error(sim, "exchange receive buffer overflow"); return SWIM_ECAP; }
         NCCL_TRY(sim, g_nccl.Recv((uint8_t *)d.xrecv + total_recv * env_bytes, n_recv * env_bytes, ncclUint8, (int)p, x->comm, sim->stream));
         total_recv += n_recv;
       }
+      da.off[p + 1] = (uint32_t)total_recv;
     }
     NCCL_TRY(sim, g_nccl.GroupEnd());
-    if (total_recv) {
-      const int grid = (int)std::min<size_t>((total_recv + 255) / 256, (size_t)sim->sm_count * 8);
-      deliver_kernel<<<grid, 256, 0, sim->stream>>>(d, (uint32_t)total_recv);
-      ++sim->launches;
-    }
     CUDA_TRY(sim, cudaMemsetAsync(d.xsend_cnt, 0, row * sizeof(uint32_t), sim->stream));
   }
+  for (uint32_t p = 0; p < G; ++p) // ranks skipped above (self, or nothing exchanged at all) keep their prefix
+    if (da.off[p + 1] < da.off[p]) da.off[p + 1] = da.off[p];
+  // always launched: it also publishes this round's per-source counts (zeros when nothing arrived)
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((total_recv + 255) / 256, (size_t)sim->sm_count * 8));
+  deliver_kernel<<<grid, 256, 0, sim->stream>>>(d, da, (uint32_t)total_recv);
+  ++sim->launches;
   return SWIM_OK;
 }
 

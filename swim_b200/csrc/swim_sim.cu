@@ -166,14 +166,12 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     }
     if ((r = dalloc(sim, &d.ridx, slots, 0))) return r;
     if ((r = dalloc(sim, &d.in_off, n + 1, 0))) return r;
-    if ((r = dalloc(sim, &d.mail, n, 0))) return r;
     if ((r = dalloc(sim, &d.meta, slots / 32, 0))) return r;
     if ((r = dalloc(sim, &d.obs_off, (size_t)d.N + 1, 0))) return r;
     if ((r = dalloc(sim, &d.obs_slot, slots, 0))) return r;
     if ((r = dalloc(sim, &d.wl, n, 0))) return r;
     if ((r = dalloc(sim, &d.wl_cnt, 2, 0))) return r;
-    if ((r = dalloc(sim, &d.rl, n, 0))) return r;
-    if ((r = dalloc(sim, &d.rl_cnt, 2, 0))) return r;
+    if ((r = dalloc(sim, &d.rl, n * d.fanout, 0xFF))) return r; // candidate slots, empty = 0xFFFFFFFF
     if ((r = dalloc(sim, &d.ctr, SWIM_CTR__COUNT, 0))) return r;
     if ((r = dalloc(sim, &sim->d_scratch, 8, 0))) return r;
     if ((r = dalloc(sim, &sim->d_bar, SWIM_MAX_WORLD, 0))) return r;
@@ -269,7 +267,6 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
   CUDA_TRY(sim, cudaMemcpy(sim->d_in_src, in_src.data(), Ea * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(sim, cudaMemcpy(d.in_off, in_off.data(), ((size_t)d.n + 1) * 4, cudaMemcpyHostToDevice));
   CUDA_TRY(sim, cudaMemcpy(d.ridx, ridx.data(), ridx.size() * 4, cudaMemcpyHostToDevice));
-  CUDA_TRY(sim, cudaMemset(d.mail, 0, (d.n ? d.n : 1) * sizeof(uint32_t)));
   d.in_src = sim->d_in_src;
   d.eflag = sim->d_eflag;
   sim->n_edges = E;
