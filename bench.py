@@ -257,6 +257,8 @@ def run_cuda(args):
                 "frac": achieved / peak if achieved else None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
                 "traffic": traffic,
+                "dram_gbs": (traffic / (tick_ms * 1e-3) / 1e9) if traffic and tick_ms > 0 else None,
+                "dram_frac": (traffic / (tick_ms * 1e-3) / 1e9 / peak) if traffic and tick_ms > 0 else None,
                 "algorithmic_bytes_per_launch": ab_tick * n_local,
                 "ab_per_node_round": {"round": ab_round, "tick": ab_tick, "m_bar": m_bar, "b_bar": b_bar},
                 "tick_ms_per_launch": tick_ms, "tick_work_ms_per_launch": prof["tick_work"] / max(1.0, prof["rounds"]),
