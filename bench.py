@@ -264,9 +264,10 @@ def run_cuda(args):
                 "tick_ms_per_launch": tick_ms, "tick_work_ms_per_launch": prof["tick_work"] / max(1.0, prof["rounds"]),
                 "recv_ms_per_launch": prof["recv"] / max(1.0, prof["rounds"]),
                 "exchange_ms_per_round": prof["exchange"] / max(1.0, prof["rounds"]),
-                "note": "achieved uses SURVEY §8(d)'s canonical bytes; the kernel packs liveness+timer into one "
-                        "byte per slot and reads incarnations/buffers only on events, so real DRAM traffic "
-                        "(`traffic`, ncu) is far below the canonical bytes and frac can exceed 1"}
+                "note": "achieved/frac use SURVEY 8(d)'s canonical bytes (376 B/node-round); K1a really moves 16 B/node-round "
+                        "(one uint4 meta record: alive/suspect/crashed-member bitmaps + flags), so frac > 1 means 'faster "
+                        "than streaming the canonical arrays could be', while dram_gbs/dram_frac (ncu traffic / measured "
+                        "launch time) are the real HBM utilisation"}
 
     # ------------------------------------------------ end to end through the C ABI, host buffers
     e2e = None
