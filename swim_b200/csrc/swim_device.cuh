@@ -38,7 +38,8 @@ struct SimDev {
   uint32_t N, first, n, cap;
   uint32_t k, fanout, B, S, T, loss_ppm;
   uint32_t key0, key1;
-  uint32_t round;
+  uint32_t round;            // round number, or the offset from *round_base inside a captured graph
+  const uint32_t *round_base; // null outside CUDA graphs
   uint32_t world, rank, per; // per = nodes per shard
   uint8_t *alive;            // [N]
   uint32_t *self_inc;        // [n]
@@ -95,6 +96,9 @@ struct SimDev {
 // grid has completed and its writes are visible, pdl_launch() lets the following grid start early.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// the round a per-round kernel works on (graph replays read the base from device memory)
+__device__ __forceinline__ uint32_t current_round(const SimDev &d) { return d.round_base ? d.round + *d.round_base : d.round; }
 
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -222,14 +226,14 @@ __device__ __forceinline__ void row_load(Row<W> &r, const SimDev &d, uint32_t l,
 }
 
 template <int W>
-__device__ __forceinline__ void row_store(const Row<W> &r, const SimDev &d, uint32_t l, int lane) {
+__device__ __forceinline__ void row_store(const Row<W> &r, const SimDev &d, uint32_t l, int lane, uint32_t round) {
   size_t base = (size_t)l * d.cap + lane;
 #pragma unroll
   for (int w = 0; w < W; ++w) {
     if (r.touched & (1u << w)) {
       d.vst[base + w * 32] = (uint8_t)r.st[w];
       d.vinc[base + w * 32] = r.inc[w];
-      d.vlast[base + w * 32] = d.round;
+      d.vlast[base + w * 32] = round;
     } else if (r.ticked & (1u << w)) {
       d.vst[base + w * 32] = (uint8_t)r.st[w];
     }
@@ -330,12 +334,12 @@ __device__ __forceinline__ uint32_t gather4(uint32_t a) { return (a * 0x01020408
 
 // seeded Bernoulli loss of one probe leg: leg 0 = the direct Ping/Ack round trip (group stream),
 // leg 1+j = the round trip through proxy j (per-node stream)
-__device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t self, uint32_t leg) {
+__device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t round, uint32_t self, uint32_t leg) {
   if (!d.loss_ppm) return false;
   uint4 y;
   uint32_t w;
-  if (leg == 0) { y = philox4x32_10(make_uint4(d.round, self >> 2, P_LOSS0, 0), d.key0, d.key1); w = self & 3; }
-  else { y = philox4x32_10(make_uint4(d.round, self, P_LOSS, (leg - 1) >> 2), d.key0, d.key1); w = (leg - 1) & 3; }
+  if (leg == 0) { y = philox4x32_10(make_uint4(round, self >> 2, P_LOSS0, 0), d.key0, d.key1); w = self & 3; }
+  else { y = philox4x32_10(make_uint4(round, self, P_LOSS, (leg - 1) >> 2), d.key0, d.key1); w = (leg - 1) & 3; }
   return bounded(word_of(y, w), 1000000u) < d.loss_ppm;
 }
 
@@ -353,9 +357,10 @@ __global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
   constexpr int U = kScanGroups;
   pdl_launch();
   pdl_wait();
+  const uint32_t round = current_round(d);
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  uint32_t *wl_cnt = d.wl_cnt + (d.round & 1);
+  uint32_t *wl_cnt = d.wl_cnt + (round & 1);
   uint32_t pings = 0;
   const uint32_t g0 = d.first >> 2, g1 = (d.first + d.n + 3) >> 2; // Philox groups touching this shard
   for (uint32_t gb = g0 + warp * (32 * U); gb < g1; gb += nwarps * (32 * U)) {
@@ -375,9 +380,9 @@ __global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
     for (int u = 0; u < U; ++u) {
       const uint32_t g = gb + u * 32 + lane;
       if ((valid >> (u * 4) & 0xFu) == 0) continue;
-      const uint4 x = philox4x32_10(make_uint4(d.round, g, P_TARGET, 0), d.key0, d.key1);
+      const uint4 x = philox4x32_10(make_uint4(round, g, P_TARGET, 0), d.key0, d.key1);
       uint4 y = make_uint4(0, 0, 0, 0);
-      if (d.loss_ppm) y = philox4x32_10(make_uint4(d.round, g, P_LOSS0, 0), d.key0, d.key1);
+      if (d.loss_ppm) y = philox4x32_10(make_uint4(round, g, P_LOSS0, 0), d.key0, d.key1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (!(valid >> (u * 4 + j) & 1u) || (m[u][j].w & 0xFFu) == 0) continue; // a crashed process does nothing
@@ -432,11 +437,12 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
   pdl_wait();
-  const uint32_t n_work = d.wl_cnt[d.round & 1];
-  if (warp == 0 && lane == 0) { d.wl_cnt[(d.round + 1) & 1] = 0; }
+  const uint32_t round = current_round(d);
+  const uint32_t n_work = d.wl_cnt[round & 1];
+  if (warp == 0 && lane == 0) { d.wl_cnt[(round + 1) & 1] = 0; }
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  const uint32_t par = d.round & 1;
+  const uint32_t par = round & 1;
 
   for (uint32_t item = warp; item < n_work; item += nwarps) {
     const uint32_t ln = d.wl[item], self = d.first + ln;
@@ -469,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
     if (L) {
       // target: draw 0; proxies: kRandomMembers store k [] (Core.hs:249), a fresh shuffle over the
       // same alive list (neither self nor the target excluded), draws of the node's PROXY stream
-      uint4 blk = philox4x32_10(make_uint4(d.round, self >> 2, P_TARGET, 0), d.key0, d.key1);
+      uint4 blk = philox4x32_10(make_uint4(round, self >> 2, P_TARGET, 0), d.key0, d.key1);
       uint32_t tmp[W];
 #pragma unroll
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
@@ -478,18 +484,18 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
       np = d.k < L ? d.k : L;
       for (uint32_t j = 0; j < np; ++j) {
-        if ((j & 3) == 0) blk = philox4x32_10(make_uint4(d.round, self, P_PROXY, j >> 2), d.key0, d.key1);
+        if ((j & 3) == 0) blk = philox4x32_10(make_uint4(round, self, P_PROXY, j >> 2), d.key0, d.key1);
         prox[j] = pick_remove<W>(tmp, bounded(word_of(blk, j & 3), L - j));
       }
       // T3: Ping (Core.hs:246); unlessAck -> IndirectPings (247-250); unlessAck -> suspectNode (251-254)
       const bool t_up = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;
-      const bool acked = t_up && !leg_lost(d, self, 0);
+      const bool acked = t_up && !leg_lost(d, round, self, 0);
       if (!acked) {
         if (lane == 0) { ++c.v[SWIM_CTR_DIRECT_FAIL]; c.v[SWIM_CTR_INDIRECT_PINGS] += np; }
         bool ok = false;
         if ((uint32_t)lane < np && t_up) {
           const uint32_t ps = prox[lane];
-          ok = (td[ps >> 5] >> (ps & 31) & 1u) == 0 && !leg_lost(d, self, 1 + lane);
+          ok = (td[ps >> 5] >> (ps & 31) & 1u) == 0 && !leg_lost(d, round, self, 1 + lane);
         }
         if (!__any_sync(kFull, ok)) {
           // Suspect (memberIncarnation m) (memberName m) with m captured at probe start
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
         }
       }
     }
-    row_store<W>(row, d, ln, lane);
+    row_store<W>(row, d, ln, lane, round);
     // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
     uint32_t cand = 0xFFFFFFFFu; // lane f < fanout: local receiver of recipient f (K2's candidate slot)
     if (L && pbs.cnt) {
@@ -583,9 +589,10 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
-  const uint32_t par = d.round & 1;
   pdl_launch();
   pdl_wait();
+  const uint32_t round = current_round(d);
+  const uint32_t par = round & 1;
   // receivers of this round: the candidate slots written by K1b (fanout per work item, some empty),
   // then one list per source rank (cross-shard senders). A receiver can appear many times: the claim
   // stamp lets exactly one warp process it.
@@ -613,8 +620,8 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
       ln = d.rlr[((size_t)par * d.world + a) * d.rcap + (item - seg_end[a])];
     }
     uint32_t old = 0;
-    if (lane == 0) old = atomicExch(&d.claim[ln], d.round);
-    if (__shfl_sync(kFull, old, 0) == d.round) continue; // another warp has this receiver
+    if (lane == 0) old = atomicExch(&d.claim[ln], round);
+    if (__shfl_sync(kFull, old, 0) == round) continue; // another warp has this receiver
     const uint32_t self = d.first + ln;
     const bool up = d.alive[self] != 0; // datagrams to a crashed process are lost
     const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
@@ -662,7 +669,7 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
       }
     }
     if (up) {
-      row_store<W>(row, d, ln, lane);
+      row_store<W>(row, d, ln, lane, round);
       pb_store(pbs, d, ln, lane);
       if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
     }
@@ -675,12 +682,13 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
 // waits until all words of its own array reached `stamp`. Runs as a one-warp kernel in stream order,
 // so everything the previous kernel wrote to peer memory is ordered before the flag. The wait is
 // bounded: a missing peer sets *err instead of hanging the GPU.
-static __global__ void peer_barrier_kernel(SimDev d, uint32_t stamp, uint32_t *err) {
+static __global__ void peer_barrier_kernel(SimDev d, uint32_t *err) {
   const uint32_t q = threadIdx.x;
   if (q >= d.world) return;
+  const uint32_t round = current_round(d), stamp = round; // rounds only grow: the round is the barrier stamp
   __threadfence_system();
   if (q != d.rank) { // tell peer q how many receivers we appended to its list this round
-    volatile uint32_t *cnt = d.rcnt_p[q] + (d.round & 1) * d.world + d.rank;
+    volatile uint32_t *cnt = d.rcnt_p[q] + (round & 1) * d.world + d.rank;
     *cnt = d.xcnt[q];
     d.xcnt[q] = 0;
     __threadfence_system();
@@ -741,6 +749,7 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
+  const uint32_t round = d.round; // events run outside captured graphs
   // same-node events stay in list order: a node's events all belong to one warp
   for (uint32_t x = 0; x < n_ev; ++x) {
     const uint32_t node = ev[x].node;
@@ -783,7 +792,7 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
         pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]);
         if (lane == 0) ++c.v[SWIM_CTR_RECS_APPLIED];
       }
-      row_store<W>(row, d, ln, lane);
+      row_store<W>(row, d, ln, lane, round);
       pb_store(pbs, d, ln, lane);
       if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
     }

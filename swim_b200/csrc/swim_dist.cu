@@ -202,6 +202,7 @@ extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
     d.rlr_p[r] = (uint32_t *)p[3]; d.rcnt_p[r] = (uint32_t *)p[4]; d.bar_p[r] = (uint32_t *)p[5];
   }
   d.p2p = 1;
+  sim->graph_dirty = true;
   sim->connected = true;
   return SWIM_OK;
 }
@@ -216,7 +217,7 @@ void refresh_peer_tables(swim_sim *sim) { // entry [rank] always aliases this ra
 }
 
 int dist_barrier(swim_sim *sim) {
-  peer_barrier_kernel<<<1, 32, 0, sim->stream>>>(sim->dev, ++sim->bar_stamp, sim->d_bar_err);
+  peer_barrier_kernel<<<1, 32, 0, sim->stream>>>(sim->dev, sim->d_bar_err);
   ++sim->launches;
   return SWIM_OK;
 }

@@ -42,7 +42,10 @@ struct swim_sim {
   double prof_ms[SWIM_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0};
   uint32_t *d_bar = nullptr;     // [world] cross-GPU barrier words of this rank
   uint32_t *d_bar_err = nullptr; // set by a barrier that timed out
-  uint32_t bar_stamp = 0;
+  uint32_t *d_round_base = nullptr;   // round base read by graph replays
+  cudaGraphExec_t graph_exec = nullptr; // kGraphRounds rounds of (scan, work, [barrier], recv)
+  bool graph_dirty = true;              // device pointers changed: re-capture
+  bool graph_off = false;               // capture failed once: stay on plain launches
   std::vector<void *> ipc_opened; // peer mappings to close
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };

@@ -57,7 +57,7 @@ __global__ void scalar_kernel(SimDev d, ScalarArgs *a) {
       const uint32_t self_inc0 = self_inc;
       uint4 rb = make_uint4(0, 0, 0, 0);
       int v = row_apply<W>(row, d, a->node, self_inc, a->rec, rb, lane, dummy);
-      row_store<W>(row, d, ln, lane);
+      row_store<W>(row, d, ln, lane, d.round);
       __syncwarp();
       if (lane == 0) {
         if (self_inc != self_inc0) d.self_inc[ln] = self_inc;
