@@ -454,7 +454,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   }
   size_t ev_pos = 0;
-  const bool graphable = !sim->profile && !sim->graph_off && (d.world == 1 || d.p2p) && getenv("SWIM_NO_GRAPH") == nullptr;
+  const bool graphable = !sim->profile && !sim->graph_off && (d.world == 1 || d.p2p) && getenv("SWIM_GRAPH") != nullptr; // opt-in: measured slower than PDL launches on B200 (22.9 vs 21.0 us/round at C3)
   for (uint32_t r = 0; r < rounds; ++r) {
     if (graphable && rounds - r >= kGraphRounds &&
         (ev_pos >= n_ev || sim->events[ev_pos].round > sim->round + kGraphRounds)) {
