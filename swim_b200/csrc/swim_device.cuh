@@ -60,8 +60,11 @@ struct SimDev {
                              //        flags: byte0 = process up, byte1 = piggyback count (word 0 only)}
   uint32_t *obs_off;         // [N+1] observers of member m among this shard's rows ...
   uint32_t *obs_slot;        // [n*cap] ... as linear slot indices l*cap + s
-  uint32_t *wl, *wl_cnt;     // work list of K1b [n], its round-parity counters [2]
-  uint32_t *rl;              // [n*fanout] receiver candidates: slot item*fanout + f of work item `item`
+  uint32_t *wl, *wl_cnt;     // work list of K1b [n]; counters indexed by round % 3
+  uint32_t *xtra;            // [3] (round % 3) work items K1b added itself (re-scanned receivers)
+  uint32_t *rl;              // [2][n*fanout] receiver candidates (round parity): slot*fanout + f
+  uint32_t *claim2;          // [n] round stamp: a receiver of round r-1 is re-scanned once in round r
+  uint32_t pipe;             // bit0: this round's K1a skipped last round's receivers; K1b re-scans them
   // Round-parity double buffering: everything a round's senders write for its receivers exists twice
   // (index = round & 1), so round r+1's senders never touch what round r's receivers still read and ONE
   // cross-GPU barrier per round (between K1b and K2) is enough.
@@ -73,6 +76,8 @@ struct SimDev {
   uint32_t estride_p[SWIM_MAX_WORLD];
   const uint4 *out_p[SWIM_MAX_WORLD];    // [2][per*B] sender snapshots
   const uint8_t *out_cnt_p[SWIM_MAX_WORLD]; // [2][per]
+  uint4 *meta_p[SWIM_MAX_WORLD];         // receivers' meta records (mail stamps are written by senders)
+  uint32_t *bar_err;                     // set by a cross-GPU wait that timed out
   uint32_t *rlr_p[SWIM_MAX_WORLD];       // [2][world][rcap] receiver ids appended by each source rank
   uint32_t *rcnt_p[SWIM_MAX_WORLD];      // [2][world] their counts, published by the barrier kernel
   uint32_t *bar_p[SWIM_MAX_WORLD];       // [world] cross-GPU barrier words
@@ -352,16 +357,46 @@ __device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t round, uint32
 // non-empty piggyback buffer — are appended to the round's work list for K1b.
 constexpr int kScanGroups = 2; // Philox groups (of 4 nodes) per lane per iteration: 8 nodes, 8 loads in flight
 
+// Pipelining of consecutive rounds: the receive phase of round r-1 (latency bound) runs in the same
+// kernel as the scan of round r (throughput bound). Senders stamp their receivers' meta records with
+// stamp_of(round); the scan of the next round skips stamped nodes, and K1b re-scans exactly those
+// (after their mail has been applied) and clears the stamp.
+__device__ __forceinline__ uint32_t stamp_of(uint32_t round) { return round % 65535u + 1u; } // 16 bit, never 0
+__device__ __forceinline__ uint32_t ci(uint32_t round) { return round % 3u; }                 // counter slot
+__device__ __forceinline__ uint16_t *stamp_ptr(uint4 *meta) { return reinterpret_cast<uint16_t *>(meta) + 7; }
+
+// One node's tick decision from its meta words (what K1a does per node): counts the Ping and tells
+// whether the node needs K1b. Shared by the scan and by K1b's re-scan of last round's receivers.
 template <int W>
-__global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
+__device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags, uint32_t (&am)[W], const uint32_t (&td)[W],
+                                                uint32_t sus, uint32_t tdraw, uint32_t ldraw, uint32_t &pings) {
+  if ((flags & 0xFFu) == 0) return false;              // a crashed process does nothing
+  bool need = (flags & 0xFF00u) != 0 || sus != 0;       // piggyback to send, or a countdown to run [Q8]
+  uint32_t L = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) L += __popc(am[w]);
+  if (L) {
+    const uint32_t tslot = pick_remove<W>(am, bounded(tdraw, L)); // kRandomMembers store 1 [] (Core.hs:239)
+    ++pings;                                                       // Ping (Core.hs:246)
+    bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;       // Ack iff the target process is up
+    if (acked && d.loss_ppm) acked = !(bounded(ldraw, 1000000u) < d.loss_ppm);
+    need |= !acked;
+  }
+  return need;
+}
+
+// K1a — streaming pass over every node of the shard, EIGHT nodes per lane: the four nodes 4g..4g+3
+// share one Philox4x32-10 block (one 32-bit draw each), so a lane issues eight independent 16-byte
+// loads (the nodes' meta records: alive / suspect / crashed-member bitmaps + flags), two Philox
+// calls, and eight r-th-set-bit picks (shuffle, Util.hs:36-42) tested against the crashed-member
+// bitmap. A warp covers 256 consecutive nodes = 4 KB contiguous. Nodes that need more — a Suspect
+// slot to count down, a failed probe, a non-empty piggyback buffer — are appended to the round's
+// work list for K1b. skip_stamp != 0: nodes carrying that mail stamp are left to K1b's re-scan.
+template <int W>
+__device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint32_t skip_stamp, uint32_t warp, uint32_t nwarps,
+                                          int lane, uint32_t &pings) {
   constexpr int U = kScanGroups;
-  pdl_launch();
-  pdl_wait();
-  const uint32_t round = current_round(d);
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-  uint32_t *wl_cnt = d.wl_cnt + (round & 1);
-  uint32_t pings = 0;
+  uint32_t *wl_cnt = d.wl_cnt + ci(round);
   const uint32_t g0 = d.first >> 2, g1 = (d.first + d.n + 3) >> 2; // Philox groups touching this shard
   for (uint32_t gb = g0 + warp * (32 * U); gb < g1; gb += nwarps * (32 * U)) {
     uint4 m[U][4];
@@ -385,25 +420,19 @@ __global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
       if (d.loss_ppm) y = philox4x32_10(make_uint4(round, g, P_LOSS0, 0), d.key0, d.key1);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        if (!(valid >> (u * 4 + j) & 1u) || (m[u][j].w & 0xFFu) == 0) continue; // a crashed process does nothing
-        uint32_t am[W], td[W], sus = m[u][j].y, L;
-        am[0] = m[u][j].x; td[0] = m[u][j].z; L = __popc(m[u][j].x);
+        if (!(valid >> (u * 4 + j) & 1u)) continue;
+        if (skip_stamp && (m[u][j].w >> 16) == skip_stamp) continue; // has mail from last round: K1b re-scans it
+        uint32_t am[W], td[W], sus = m[u][j].y;
+        am[0] = m[u][j].x; td[0] = m[u][j].z;
         if (W > 1) {
           const uint32_t l = 4 * g + j - d.first;
 #pragma unroll
           for (int w = 1; w < W; ++w) {
             const uint4 mw = d.meta[(size_t)l * W + w];
-            am[w] = mw.x; sus |= mw.y; td[w] = mw.z; L += __popc(mw.x);
+            am[w] = mw.x; sus |= mw.y; td[w] = mw.z;
           }
         }
-        bool need = (m[u][j].w & 0xFF00u) != 0 || sus != 0; // piggyback to send, or a countdown to run [Q8]
-        if (L) {
-          const uint32_t tslot = pick_remove<W>(am, bounded(word_of(x, j), L));
-          ++pings;                                                          // Ping (Core.hs:246)
-          bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;          // Ack iff the target is up
-          if (acked && d.loss_ppm) acked = !(bounded(word_of(y, j), 1000000u) < d.loss_ppm);
-          need |= !acked;
-        }
+        const bool need = node_needs_work<W>(d, m[u][j].w, am, td, sus, word_of(x, j), word_of(y, j), pings);
         work |= (uint32_t)need << (u * 4 + j);
       }
     }
@@ -423,13 +452,25 @@ __global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
       }
     }
   }
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
+  pdl_launch();
+  pdl_wait();
+  const uint32_t round = current_round(d);
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t pings = 0;
+  scan_pass<W>(d, round, 0, warp, nwarps, lane, pings);
   pings = __reduce_add_sync(kFull, pings);
   if (lane == 0 && pings) atomicAdd(&d.ctr[SWIM_CTR_PINGS], (unsigned long long)pings);
 }
 
-// K1b — warp-per-node over the work list: timer expiry -> Dead, probe escalation (k proxies),
-// local suspicion, piggyback send. Lane s owns view slot s; the piggyback buffer is staged in
-// shared memory. Everything K1a derived is recomputed from the row with warp ballots.
+// K1b — warp-per-node over the work list (plus, when pipelined, last round's receivers): countdown
+// and expiry -> Dead, probe escalation (k proxies), local suspicion, piggyback send. Lane s owns view
+// slot s; the piggyback buffer is staged in shared memory. Everything K1a derived is recomputed
+// from the row with warp ballots.
 template <int W>
 __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
@@ -438,14 +479,68 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
   pdl_launch();
   pdl_wait();
   const uint32_t round = current_round(d);
-  const uint32_t n_work = d.wl_cnt[round & 1];
-  if (warp == 0 && lane == 0) { d.wl_cnt[(round + 1) & 1] = 0; }
+  const uint32_t n_work = d.wl_cnt[ci(round)];
+  if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   const uint32_t par = round & 1;
+  uint32_t *rl_out = d.rl + (size_t)par * d.n * d.fanout;
+  const uint32_t my_stamp = stamp_of(round);
+  // pipelined rounds: last round's receivers were skipped by K1a; their mail has been applied by now
+  uint32_t seg_end[SWIM_MAX_WORLD + 1];
+  uint32_t n_rescan = 0;
+  const uint32_t ppar = par ^ 1;
+  if (d.pipe & 1u) {
+    n_rescan = (d.wl_cnt[ci(round - 1)] + d.xtra[ci(round - 1)]) * d.fanout;
+    seg_end[0] = n_rescan;
+    if (d.world > 1)
+      for (uint32_t a = 0; a < d.world; ++a) {
+        if (a != d.rank) n_rescan += d.rcnt[ppar * d.world + a];
+        seg_end[1 + a] = n_rescan;
+      }
+  }
 
-  for (uint32_t item = warp; item < n_work; item += nwarps) {
-    const uint32_t ln = d.wl[item], self = d.first + ln;
+  for (uint32_t idx = warp; idx < n_work + n_rescan; idx += nwarps) {
+    uint32_t ln, slot;
+    if (idx < n_work) {
+      ln = d.wl[idx];
+      slot = idx;
+    } else {
+      const uint32_t cidx = idx - n_work;
+      if (cidx < seg_end[0]) {
+        ln = d.rl[(size_t)ppar * d.n * d.fanout + cidx];
+        if (ln == 0xFFFFFFFFu) continue; // empty candidate slot
+      } else {
+        uint32_t a = 0;
+        while (cidx >= seg_end[1 + a]) ++a;
+        ln = d.rlr[((size_t)ppar * d.world + a) * d.rcap + (cidx - seg_end[a])];
+      }
+      uint32_t old = 0;
+      if (lane == 0) old = atomicExch(&d.claim2[ln], round);
+      if (__shfl_sync(kFull, old, 0) == round) continue; // this receiver is already being re-scanned
+      // the scan step K1a skipped for this node
+      uint32_t am[W], td[W], sus = 0, flags = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint4 mw = d.meta[(size_t)ln * W + w];
+        am[w] = mw.x; sus |= mw.y; td[w] = mw.z;
+        if (w == 0) flags = mw.w;
+      }
+      // retire last round's mail stamp — unless a sender of THIS round has already re-stamped the node
+      if (lane == 0) atomicCAS(reinterpret_cast<unsigned short *>(stamp_ptr(d.meta + (size_t)ln * W)), (unsigned short)stamp_of(round - 1), (unsigned short)0);
+      const uint32_t self = d.first + ln;
+      const uint4 x = philox4x32_10(make_uint4(round, self >> 2, P_TARGET, 0), d.key0, d.key1);
+      uint4 y = make_uint4(0, 0, 0, 0);
+      if (d.loss_ppm) y = philox4x32_10(make_uint4(round, self >> 2, P_LOSS0, 0), d.key0, d.key1);
+      uint32_t pings = 0;
+      const bool need = node_needs_work<W>(d, flags, am, td, sus, word_of(x, self & 3), word_of(y, self & 3), pings);
+      if (lane == 0) c.v[SWIM_CTR_PINGS] += pings;
+      if (!need) continue;
+      uint32_t k = 0;
+      if (lane == 0) k = atomicAdd(&d.xtra[ci(round)], 1u);
+      slot = n_work + __shfl_sync(kFull, k, 0);
+    }
+    const uint32_t self = d.first + ln;
     Row<W> row;
     row_load<W>(row, d, ln, lane);
     pb_load(pbs, d, ln, lane);
@@ -473,8 +568,8 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
     }
     uint32_t tslot = 0, np = 0, prox[SWIM_MAX_K];
     if (L) {
-      // target: draw 0; proxies: kRandomMembers store k [] (Core.hs:249), a fresh shuffle over the
-      // same alive list (neither self nor the target excluded), draws of the node's PROXY stream
+      // target: the node's TARGET draw; proxies: kRandomMembers store k [] (Core.hs:249), a fresh shuffle
+      // over the same alive list (neither self nor the target excluded), draws of the PROXY stream
       uint4 blk = philox4x32_10(make_uint4(round, self >> 2, P_TARGET, 0), d.key0, d.key1);
       uint32_t tmp[W];
 #pragma unroll
@@ -531,11 +626,13 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
         const uint32_t dl = dst - owner * d.per;
         if (owner == d.rank) {
           d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
+          *stamp_ptr(d.meta + (size_t)dl * W) = (uint16_t)my_stamp; // "has mail from this round"
           cand = dl;
         } else if (d.p2p) {
-          // fused exchange: flag and receiver-list entry go straight into the owner GPU's memory over
-          // NVLink (plain stores, nothing comes back); the receiver pulls our snapshot from our memory
+          // fused exchange: flag, mail stamp and receiver-list entry go straight into the owner GPU's
+          // memory over NVLink (plain stores, nothing comes back); the receiver pulls our snapshot
           d.eflag_p[owner][(size_t)par * d.estride_p[owner] + ridx] = 1;
+          *stamp_ptr(d.meta_p[owner] + (size_t)dl * W) = (uint16_t)my_stamp;
           const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
           d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
         } else {
@@ -558,11 +655,11 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
       const bool have = (uint32_t)lane < pbs.cnt;
       if (have) { mine = pbs.s[lane]; d.out[((size_t)par * d.per + ln) * d.B + lane] = mine; }
       unsigned xm = __ballot_sync(kFull, xs != 0xFFFFFFFFu);
-      while (xm) { // cross-shard envelopes carry the records themselves
+      while (xm) { // cross-shard envelopes carry the records themselves (staged NCCL path)
         const int f = __ffs(xm) - 1;
         xm &= xm - 1;
-        const uint32_t slot = __shfl_sync(kFull, xs, f);
-        if (have) d.xsend[(size_t)slot * (1 + d.B) + 1 + lane] = mine;
+        const uint32_t xslot = __shfl_sync(kFull, xs, f);
+        if (have) d.xsend[(size_t)xslot * (1 + d.B) + 1 + lane] = mine;
       }
       const bool keep = have && rec_ttl(mine) > 1;
       const unsigned km = __ballot_sync(kFull, keep);
@@ -576,43 +673,72 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
       __syncwarp();
     }
     pb_store(pbs, d, ln, lane);
-    if ((uint32_t)lane < d.fanout) d.rl[(size_t)item * d.fanout + lane] = cand; // no atomics, no shared counter
+    if ((uint32_t)lane < d.fanout) rl_out[(size_t)slot * d.fanout + lane] = cand; // no atomics, no shared counter
   }
+  if (d.world > 1 && d.p2p) __threadfence_system(); // peer-memory stores are ordered before the grid's completion
   c.flush(d.ctr, lane);
 }
 
+// =================================================================== cross-GPU synchronisation
+// Fused exchange: before a rank applies round `mail_round`'s mail it must know that every peer has
+// finished K1b of that round (all flags / stamps / list entries have landed in its memory) and how
+// many receivers each peer listed. CTA 0 publishes (after griddepcontrol.wait, i.e. after this rank's
+// own K1b completed): per-peer counts, then the round number into word [rank] of every peer's barrier
+// array. Every warp that is about to receive waits until all words of its own array reached the round.
+// The wait is bounded: a missing peer sets *bar_err instead of hanging the GPU.
+__device__ __forceinline__ void peer_publish(const SimDev &d, uint32_t mail_round) {
+  const uint32_t q = threadIdx.x;
+  if (blockIdx.x != 0 || q >= d.world) return;
+  __threadfence_system();
+  if (q != d.rank) {
+    volatile uint32_t *cnt = d.rcnt_p[q] + (mail_round & 1) * d.world + d.rank;
+    *cnt = d.xcnt[q];
+    d.xcnt[q] = 0;
+    __threadfence_system();
+  }
+  volatile uint32_t *theirs = d.bar_p[q] + d.rank;
+  *theirs = mail_round;
+}
+
+__device__ __forceinline__ void peer_wait(const SimDev &d, uint32_t mail_round, int lane) {
+  if ((uint32_t)lane < d.world) {
+    volatile uint32_t *mine = d.bar_p[d.rank] + lane;
+    const long long t0 = clock64();
+    while ((int32_t)(*mine - mail_round) < 0) {
+      if (clock64() - t0 > 6000000000ll) { *d.bar_err = 1; break; } // ~3 s at 2 GHz
+      __nanosleep(40);
+    }
+  }
+  __threadfence_system();
+  __syncwarp();
+}
+
 // =================================================================== K2: receive
-// warp-per-receiver over the round's receiver list. Loads that do not depend on each other are
-// issued together: (row, buffer, in-list bounds) -> (edge flags, sender ids) -> (sender snapshots).
+// warp-per-candidate over the receivers of `round`: claim, in-edge flags -> sender snapshots (local
+// or peer-GPU memory) -> row_apply per record, re-broadcast enqueue. Loads that do not depend on each
+// other are issued together: (row, buffer, in-list bounds) -> (edge flags, sender ids) -> (snapshots).
 template <int W>
-__global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
-  __shared__ uint4 s_pb[kWarpsPerBlock][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
-  pdl_launch();
-  pdl_wait();
-  const uint32_t round = current_round(d);
+__device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool clear_stamp, uint32_t warp, uint32_t nwarps,
+                                          int lane, PbStage &pbs, Ctr &c) {
   const uint32_t par = round & 1;
   // receivers of this round: the candidate slots written by K1b (fanout per work item, some empty),
   // then one list per source rank (cross-shard senders). A receiver can appear many times: the claim
   // stamp lets exactly one warp process it.
   uint32_t seg_end[SWIM_MAX_WORLD + 1];
-  uint32_t n_recv = d.wl_cnt[par] * d.fanout;
+  uint32_t n_recv = (d.wl_cnt[ci(round)] + d.xtra[ci(round)]) * d.fanout;
   seg_end[0] = n_recv;
-  const bool remote_lists = d.world > 1;
-  if (remote_lists)
+  if (d.world > 1)
     for (uint32_t a = 0; a < d.world; ++a) {
       if (a != d.rank) n_recv += d.rcnt[par * d.world + a];
       seg_end[1 + a] = n_recv;
     }
-  Ctr c; c.clear();
-  PbStage pbs; pbs.s = s_pb[wib];
   const size_t ebase = (size_t)par * d.estride;
+  const uint32_t *rl_in = d.rl + (size_t)par * d.n * d.fanout;
 
   for (uint32_t item = warp; item < n_recv; item += nwarps) {
     uint32_t ln;
     if (item < seg_end[0]) {
-      ln = d.rl[item];
+      ln = rl_in[item];
       if (ln == 0xFFFFFFFFu) continue; // empty candidate slot
     } else {
       uint32_t a = 0;
@@ -649,9 +775,9 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
           const uint32_t s_rank = d.world == 1 ? 0u : s_id / d.per, sl = s_id - s_rank * d.per;
           if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][((size_t)par * d.per + sl) * d.B + lane];
           cnt = d.out_cnt_p[s_rank][(size_t)par * d.per + sl];
-        } else {           // sender on another shard: the envelope arrived in the exchange buffer
-          const uint32_t slot = d.eslot[eb + q];
-          const uint4 *env = d.xrecv + (size_t)slot * (1 + d.B);
+        } else {           // staged NCCL path: the envelope arrived in the exchange buffer
+          const uint32_t xslot = d.eslot[eb + q];
+          const uint4 *env = d.xrecv + (size_t)xslot * (1 + d.B);
           if ((uint32_t)lane < d.B) mine = env[1 + lane];
           cnt = env[0].y;
         }
@@ -673,35 +799,52 @@ __global__ void __launch_bounds__(kThreads) recv_kernel(SimDev d) {
       pb_store(pbs, d, ln, lane);
       if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
     }
+    if (clear_stamp && lane == 0) *stamp_ptr(d.meta + (size_t)ln * W) = 0;
   }
+}
+
+// stand-alone K2 (last round of a call, rounds next to events, profiling, staged NCCL exchange)
+template <int W>
+__global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
+  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  pdl_launch();
+  pdl_wait();
+  const uint32_t round = current_round(d);
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+  if (d.world > 1 && d.p2p) { peer_publish(d, round); peer_wait(d, round, lane); }
+  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);
   c.flush(d.ctr, lane);
 }
 
-// =================================================================== cross-GPU barrier
-// Every rank stores `stamp` into word [rank] of every peer's barrier array (NVLink store), then
-// waits until all words of its own array reached `stamp`. Runs as a one-warp kernel in stream order,
-// so everything the previous kernel wrote to peer memory is ordered before the flag. The wait is
-// bounded: a missing peer sets *err instead of hanging the GPU.
-static __global__ void peer_barrier_kernel(SimDev d, uint32_t *err) {
-  const uint32_t q = threadIdx.x;
-  if (q >= d.world) return;
-  const uint32_t round = current_round(d), stamp = round; // rounds only grow: the round is the barrier stamp
-  __threadfence_system();
-  if (q != d.rank) { // tell peer q how many receivers we appended to its list this round
-    volatile uint32_t *cnt = d.rcnt_p[q] + (round & 1) * d.world + d.rank;
-    *cnt = d.xcnt[q];
-    d.xcnt[q] = 0;
-    __threadfence_system();
+// pipelined K2(r-1) + K1a(r): odd warps receive first and scan second, even warps the other way
+// round, so at any moment half the warps wait on dependent loads while the other half issue the scan.
+template <int W>
+__global__ void __launch_bounds__(kThreads, 4) recv_scan_kernel(SimDev d) {
+  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  pdl_launch();
+  pdl_wait();
+  const uint32_t round = current_round(d); // the round being scanned; mail of round - 1 is applied
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+  const bool sync_peers = d.world > 1 && d.p2p;
+  if (sync_peers) peer_publish(d, round - 1);
+  uint32_t pings = 0;
+  if (warp & 1u) {
+    if (sync_peers) peer_wait(d, round - 1, lane);
+    recv_pass<W>(d, round - 1, false, warp, nwarps, lane, pbs, c);
+    scan_pass<W>(d, round, stamp_of(round - 1), warp, nwarps, lane, pings);
+  } else {
+    scan_pass<W>(d, round, stamp_of(round - 1), warp, nwarps, lane, pings);
+    if (sync_peers) peer_wait(d, round - 1, lane);
+    recv_pass<W>(d, round - 1, false, warp, nwarps, lane, pbs, c);
   }
-  volatile uint32_t *theirs = d.bar_p[q] + d.rank;
-  *theirs = stamp;
-  volatile uint32_t *mine = d.bar_p[d.rank] + q;
-  const long long t0 = clock64();
-  while ((int32_t)(*mine - stamp) < 0) {
-    if (clock64() - t0 > 6000000000ll) { *err = 1; break; } // ~3 s at 2 GHz
-    __nanosleep(40);
-  }
-  __threadfence_system();
+  c.v[SWIM_CTR_PINGS] += pings;
+  c.flush(d.ctr, lane);
 }
 
 // =================================================================== events (phase E)

@@ -42,10 +42,8 @@ struct swim_sim {
   double prof_ms[SWIM_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0};
   uint32_t *d_bar = nullptr;     // [world] cross-GPU barrier words of this rank
   uint32_t *d_bar_err = nullptr; // set by a barrier that timed out
-  uint32_t *d_round_base = nullptr;   // round base read by graph replays
-  cudaGraphExec_t graph_exec = nullptr; // kGraphRounds rounds of (scan, work, [barrier], recv)
-  bool graph_dirty = true;              // device pointers changed: re-capture
-  bool graph_off = false;               // capture failed once: stay on plain launches
+  uint32_t *d_round_base = nullptr;   // (reserved: round base for graph replays)
+  bool graph_dirty = true;
   std::vector<void *> ipc_opened; // peer mappings to close
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };
@@ -56,7 +54,6 @@ uint32_t shard_first(uint32_t N, uint32_t world, uint32_t rank);
 int rebuild_edges_from_device(swim_sim *sim);
 int dist_exchange(swim_sim *sim);
 int dist_alloc_edges(swim_sim *sim);
-int dist_barrier(swim_sim *sim);
 void refresh_peer_tables(swim_sim *sim);
 int prof_begin(swim_sim *sim, int phase);
 void prof_end(swim_sim *sim, int mark);

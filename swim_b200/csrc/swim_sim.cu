@@ -170,12 +170,15 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.obs_off, (size_t)d.N + 1, 0))) return r;
     if ((r = dalloc(sim, &d.obs_slot, slots, 0))) return r;
     if ((r = dalloc(sim, &d.wl, n, 0))) return r;
-    if ((r = dalloc(sim, &d.wl_cnt, 2, 0))) return r;
-    if ((r = dalloc(sim, &d.rl, n * d.fanout, 0xFF))) return r; // candidate slots, empty = 0xFFFFFFFF
+    if ((r = dalloc(sim, &d.wl_cnt, 4, 0))) return r;
+    if ((r = dalloc(sim, &d.xtra, 4, 0))) return r;
+    if ((r = dalloc(sim, &d.claim2, n, 0))) return r;
+    if ((r = dalloc(sim, &d.rl, 2 * n * d.fanout, 0xFF))) return r; // [parity] candidate slots, empty = 0xFFFFFFFF
     if ((r = dalloc(sim, &d.ctr, SWIM_CTR__COUNT, 0))) return r;
     if ((r = dalloc(sim, &sim->d_scratch, 8, 0))) return r;
     if ((r = dalloc(sim, &sim->d_bar, SWIM_MAX_WORLD, 0))) return r;
     if ((r = dalloc(sim, &sim->d_bar_err, 1, 0))) return r;
+    d.bar_err = sim->d_bar_err;
     if ((r = dalloc(sim, &sim->d_round_base, 1, 0))) return r;
     return SWIM_OK;
   }();
@@ -193,7 +196,6 @@ extern "C" void swim_sim_destroy(swim_sim_t *sim) {
   if (sim->d_in_src) cudaFree(sim->d_in_src);
   if (sim->d_eflag) cudaFree(sim->d_eflag);
   if (sim->d_events) cudaFree(sim->d_events);
-  if (sim->graph_exec) cudaGraphExecDestroy(sim->graph_exec);
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   if (sim->ev_start) cudaEventDestroy(sim->ev_start);
   if (sim->ev_stop) cudaEventDestroy(sim->ev_stop);
@@ -384,43 +386,6 @@ static cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, const Sim
   return cudaLaunchKernelEx(&cfg, kernel, d);
 }
 
-// ---- CUDA graph of kGraphRounds consecutive event-free rounds: one graph launch instead of
-// 3-4 kernel launches per round. Kernel parameters are frozen at capture, so the round number is
-// (offset baked into each node) + (*d_round_base, written by a one-thread kernel before each replay).
-constexpr uint32_t kGraphRounds = 16;
-
-static __global__ void set_round_base_kernel(uint32_t *p, uint32_t v) { *p = v; }
-
-template <int W>
-static int launch_round(swim_sim *sim, const SimDev &d, int grid, int wgrid, int rgrid) {
-  CUDA_TRY(sim, launch_pdl(tick_scan_kernel<W>, grid, sim->stream, d));
-  CUDA_TRY(sim, launch_pdl(tick_work_kernel<W>, wgrid, sim->stream, d));
-  if (d.world > 1) peer_barrier_kernel<<<1, 32, 0, sim->stream>>>(d, sim->d_bar_err);
-  CUDA_TRY(sim, launch_pdl(recv_kernel<W>, rgrid, sim->stream, d));
-  return SWIM_OK;
-}
-
-template <int W>
-static int capture_graph(swim_sim *sim, int grid, int wgrid, int rgrid) {
-  if (sim->graph_exec) { cudaGraphExecDestroy(sim->graph_exec); sim->graph_exec = nullptr; }
-  SimDev d = sim->dev;
-  d.round_base = sim->d_round_base;
-  cudaGraph_t graph = nullptr;
-  if (cudaStreamBeginCapture(sim->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return SWIM_ECUDA; }
-  int rc = SWIM_OK;
-  for (uint32_t j = 1; j <= kGraphRounds && rc == SWIM_OK; ++j) {
-    d.round = j;
-    rc = launch_round<W>(sim, d, grid, wgrid, rgrid);
-  }
-  cudaError_t e = cudaStreamEndCapture(sim->stream, &graph);
-  if (rc != SWIM_OK || e != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); return SWIM_ECUDA; }
-  e = cudaGraphInstantiate(&sim->graph_exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (e != cudaSuccess) { cudaGetLastError(); sim->graph_exec = nullptr; return SWIM_ECUDA; }
-  sim->graph_dirty = false;
-  return SWIM_OK;
-}
-
 template <int W>
 static int run_rounds(swim_sim *sim, uint32_t rounds) {
   SimDev &d = sim->dev;
@@ -454,23 +419,13 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   }
   size_t ev_pos = 0;
-  const bool graphable = !sim->profile && !sim->graph_off && (d.world == 1 || d.p2p) && getenv("SWIM_GRAPH") != nullptr; // opt-in: measured slower than PDL launches on B200 (22.9 vs 21.0 us/round at C3)
+  // Pipelining: inside one call, K2 of round r is deferred and runs fused with K1a of round r+1
+  // (recv_scan_kernel) unless something must observe the finished round in between: the end of the
+  // call, an event at round r+1, per-kernel profiling, or the staged (host-synchronised) NCCL exchange.
+  const bool pipelined = !sim->profile && (d.world == 1 || d.p2p) && getenv("SWIM_NO_PIPELINE") == nullptr;
+  const int fgrid = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
+  bool pending = false; // K2 of the previous round has not run yet
   for (uint32_t r = 0; r < rounds; ++r) {
-    if (graphable && rounds - r >= kGraphRounds &&
-        (ev_pos >= n_ev || sim->events[ev_pos].round > sim->round + kGraphRounds)) {
-      // the next kGraphRounds rounds carry no events: replay the captured graph
-      if (sim->graph_dirty || !sim->graph_exec) {
-        if (capture_graph<W>(sim, grid, wgrid, rgrid) != SWIM_OK) sim->graph_off = true;
-      }
-      if (sim->graph_exec && !sim->graph_off) {
-        set_round_base_kernel<<<1, 1, 0, sim->stream>>>(sim->d_round_base, sim->round);
-        CUDA_TRY(sim, cudaGraphLaunch(sim->graph_exec, sim->stream));
-        sim->round += kGraphRounds;
-        sim->launches += 1 + kGraphRounds * (d.world > 1 ? 4 : 3);
-        r += kGraphRounds - 1;
-        continue;
-      }
-    }
     d.round = ++sim->round;
     size_t ev_end = ev_pos;
     while (ev_end < n_ev && sim->events[ev_end].round == d.round) ++ev_end;
@@ -484,21 +439,29 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       ev_pos = ev_end;
     }
     int mk = prof_begin(sim, 1);
-    CUDA_TRY(sim, launch_pdl(tick_scan_kernel<W>, grid, sim->stream, d));
+    d.pipe = pending ? 1u : 0u;
+    if (pending) CUDA_TRY(sim, launch_pdl(recv_scan_kernel<W>, fgrid, sim->stream, d)); // K2(r-1) + K1a(r)
+    else CUDA_TRY(sim, launch_pdl(tick_scan_kernel<W>, grid, sim->stream, d));
     prof_end(sim, mk);
     mk = prof_begin(sim, 4);
     CUDA_TRY(sim, launch_pdl(tick_work_kernel<W>, wgrid, sim->stream, d));
     prof_end(sim, mk);
-    if (d.world > 1) { // the exchange step: flags raised on every rank (p2p) / envelopes moved (NCCL)
-      mk = prof_begin(sim, 2);
-      int rc = d.p2p ? swim::dist_barrier(sim) : swim::dist_exchange(sim);
-      if (rc) return rc;
+    d.pipe = 0;
+    sim->launches += 2;
+    const bool next_has_events = ev_pos < n_ev && sim->events[ev_pos].round == d.round + 1;
+    pending = pipelined && r + 1 < rounds && !next_has_events;
+    if (!pending) {
+      if (d.world > 1 && !d.p2p) { // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
+        mk = prof_begin(sim, 2);
+        int rc = swim::dist_exchange(sim);
+        if (rc) return rc;
+        prof_end(sim, mk);
+      }
+      mk = prof_begin(sim, 3);
+      CUDA_TRY(sim, launch_pdl(recv_kernel<W>, rgrid, sim->stream, d));
       prof_end(sim, mk);
+      ++sim->launches;
     }
-    mk = prof_begin(sim, 3);
-    CUDA_TRY(sim, launch_pdl(recv_kernel<W>, rgrid, sim->stream, d));
-    prof_end(sim, mk);
-    sim->launches += 3;
     if (sim->profile) sim->prof_ms[5] += 1;
   }
   sim->events.erase(sim->events.begin(), sim->events.begin() + n_ev);

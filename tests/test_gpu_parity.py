@@ -150,3 +150,48 @@ def test_set_array_alive_rebuilds_crash_bitmaps():
     sim.step(10)
     orc.step(10)
     assert_same_state(sim, orc, "after revive")
+
+
+@pytest.mark.parametrize("seed", range(6, 14))
+def test_random_pipelined_chunks(seed):
+    """Multi-round calls run K2 of round r fused with K1a of round r+1 (receivers are skipped by the scan and
+    re-scanned by K1b); single-round calls do not. Both must equal the oracle at every chunk boundary."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(40, 3000))
+    cap = int(rng.choice([32, 32, 64]))
+    deg = int(rng.integers(2, min(n - 1, cap) + 1))
+    k = int(rng.integers(0, 8))
+    cfg = default_config(n_nodes=n, view_cap=cap, k_indirect=k, fanout=int(rng.integers(1, k + 2)),
+                         pb_cap=int(rng.integers(1, 17)), suspicion_rounds=int(rng.integers(1, 9)),
+                         retransmit=int(rng.integers(1, 9)), loss_ppm=int(rng.choice([0, 30000, 200000])),
+                         seed=int(rng.integers(0, 2 ** 63)))
+    kind = str(rng.choice(["random", "ring"])) if deg < n - 1 else "complete"
+    nbr = generate_topology(kind, n, cap, deg, seed=seed + 1)
+    sim, orc = make_pair(cfg, nbr)
+    chunks = [3, 7, 1, 13, 2, 16, 5]
+    rounds = sum(chunks)
+    ev = random_events(rng, n, rounds, n_crash=max(1, n // 10), n_rejoin=max(1, n // 30), n_inject=n // 4)
+    sim.inject(ev)
+    orc.inject(ev)
+    for c in chunks:
+        sim.step(c)
+        orc.step(c)
+        assert_same_state(sim, orc, f"seed {seed} round {sim.round}")
+
+
+def test_dense_gossip_pipelined():
+    """Complete views: almost every receiver applies news and becomes a sender in the next round, so K1b's
+    re-scan path (receivers turned work items) carries most of the traffic."""
+    n = 33
+    cfg = default_config(n_nodes=n, view_cap=32, k_indirect=3, fanout=4, pb_cap=8, suspicion_rounds=3, retransmit=6,
+                         loss_ppm=150000, seed=12345)
+    nbr = generate_topology("complete", n, 32)
+    sim, orc = make_pair(cfg, nbr)
+    ev = crash_events(2, [1, 5, 9, 20])
+    sim.inject(ev)
+    orc.inject(ev)
+    for c in (40, 1, 25, 30):
+        sim.step(c)
+        orc.step(c)
+        assert_same_state(sim, orc, f"dense round {sim.round}")
+    assert sim.counters()[A.CTR_RECS_APPLIED] > 100 and sim.counters()[A.CTR_REFUTES] > 0
