@@ -102,6 +102,10 @@ struct SimDev {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Pull a cache line into L2 one phase before the warp that needs it runs (K1a -> K1b's rows, K1b -> K2's rows):
+// the dependent-load chains of the warp-per-node kernels then hit L2 instead of HBM.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // the round a per-round kernel works on (graph replays read the base from device memory)
 __device__ __forceinline__ uint32_t current_round(const SimDev &d) { return d.round_base ? d.round + *d.round_base : d.round; }
 
@@ -447,7 +451,13 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
       pos = __shfl_sync(kFull, pos, 0);
 #pragma unroll
       for (int q = 0; q < 4 * U; ++q) {
-        if (work >> q & 1u) d.wl[pos + __popc(b[q] & ((1u << lane) - 1))] = 4 * (gb + (q >> 2) * 32 + lane) + (q & 3) - d.first;
+        if (work >> q & 1u) {
+          const uint32_t l = 4 * (gb + (q >> 2) * 32 + lane) + (q & 3) - d.first;
+          d.wl[pos + __popc(b[q] & ((1u << lane) - 1))] = l;
+          const size_t row = (size_t)l * d.cap; // K1b will want this node's row, buffer and edge indices
+          prefetch_l2(d.vst + row); prefetch_l2(d.nbr + row); prefetch_l2(d.vinc + row); prefetch_l2(d.ridx + row);
+          prefetch_l2(d.pb + (size_t)l * d.B);
+        }
         pos += __popc(b[q]);
       }
     }
@@ -628,6 +638,10 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
           d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
           *stamp_ptr(d.meta + (size_t)dl * W) = (uint16_t)my_stamp; // "has mail from this round"
           cand = dl;
+          const size_t rrow = (size_t)dl * d.cap; // K2 will want the receiver's row, buffer and in-list
+          prefetch_l2(d.vst + rrow); prefetch_l2(d.nbr + rrow); prefetch_l2(d.vinc + rrow);
+          prefetch_l2(d.pb + (size_t)dl * d.B); prefetch_l2(d.in_off + dl);
+          prefetch_l2(d.in_src + (ridx & ~31u)); prefetch_l2(d.self_inc + dl);
         } else if (d.p2p) {
           // fused exchange: flag, mail stamp and receiver-list entry go straight into the owner GPU's
           // memory over NVLink (plain stores, nothing comes back); the receiver pulls our snapshot
@@ -706,11 +720,18 @@ __device__ __forceinline__ void peer_wait(const SimDev &d, uint32_t mail_round, 
     const long long t0 = clock64();
     while ((int32_t)(*mine - mail_round) < 0) {
       if (clock64() - t0 > 6000000000ll) { *d.bar_err = 1; break; } // ~3 s at 2 GHz
-      __nanosleep(40);
+      __nanosleep(200);
     }
+    __threadfence_system(); // acquire: the peers' stores that preceded their flag are visible now
   }
-  __threadfence_system();
   __syncwarp();
+}
+
+// stand-alone form of the same synchronisation (default path): one warp, launched between K1b and K2
+static __global__ void peer_barrier_kernel(SimDev d) {
+  const uint32_t round = current_round(d);
+  peer_publish(d, round);
+  peer_wait(d, round, (int)threadIdx.x);
 }
 
 // =================================================================== K2: receive
@@ -745,19 +766,18 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
       while (item >= seg_end[1 + a]) ++a;
       ln = d.rlr[((size_t)par * d.world + a) * d.rcap + (item - seg_end[a])];
     }
+    // the claim and every load that depends only on `ln` are issued together (one memory round trip)
     uint32_t old = 0;
     if (lane == 0) old = atomicExch(&d.claim[ln], round);
-    if (__shfl_sync(kFull, old, 0) == round) continue; // another warp has this receiver
     const uint32_t self = d.first + ln;
     const bool up = d.alive[self] != 0; // datagrams to a crashed process are lost
     const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
     Row<W> row;
-    uint32_t self_inc = 0, self_inc0 = 0;
-    if (up) {
-      row_load<W>(row, d, ln, lane);
-      pb_load(pbs, d, ln, lane);
-      self_inc = self_inc0 = d.self_inc[ln];
-    }
+    row_load<W>(row, d, ln, lane);
+    pb_load(pbs, d, ln, lane);
+    uint32_t self_inc = d.self_inc[ln];
+    const uint32_t self_inc0 = self_inc;
+    if (__shfl_sync(kFull, old, 0) == round) continue; // another warp has this receiver
     for (uint32_t eb = e0; eb < e1; eb += 32) {
       const uint32_t e = eb + lane;
       uint32_t f = 0, src = 0;
@@ -814,8 +834,7 @@ __global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
   const uint32_t round = current_round(d);
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  if (d.world > 1 && d.p2p) { peer_publish(d, round); peer_wait(d, round, lane); }
-  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);
+  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c); // the host ran peer_barrier_kernel before this launch
   c.flush(d.ctr, lane);
 }
 

@@ -422,7 +422,9 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   // Pipelining: inside one call, K2 of round r is deferred and runs fused with K1a of round r+1
   // (recv_scan_kernel) unless something must observe the finished round in between: the end of the
   // call, an event at round r+1, per-kernel profiling, or the staged (host-synchronised) NCCL exchange.
-  const bool pipelined = !sim->profile && (d.world == 1 || d.p2p) && getenv("SWIM_NO_PIPELINE") == nullptr;
+  // Opt-in (SWIM_PIPELINE=1): bit-exact, but on B200 at C3 it measured no faster than the plain sequence
+  // (every warp's own dependent-load chain is the critical path either way).
+  const bool pipelined = !sim->profile && (d.world == 1 || d.p2p) && getenv("SWIM_PIPELINE") != nullptr;
   const int fgrid = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
   bool pending = false; // K2 of the previous round has not run yet
   for (uint32_t r = 0; r < rounds; ++r) {
@@ -451,10 +453,15 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     const bool next_has_events = ev_pos < n_ev && sim->events[ev_pos].round == d.round + 1;
     pending = pipelined && r + 1 < rounds && !next_has_events;
     if (!pending) {
-      if (d.world > 1 && !d.p2p) { // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
+      if (d.world > 1) {
         mk = prof_begin(sim, 2);
-        int rc = swim::dist_exchange(sim);
-        if (rc) return rc;
+        if (d.p2p) { // fused exchange: the data already sits in the peers' memory; synchronise the GPUs
+          peer_barrier_kernel<<<1, 32, 0, sim->stream>>>(d);
+          ++sim->launches;
+        } else {     // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
+          int rc = swim::dist_exchange(sim);
+          if (rc) return rc;
+        }
         prof_end(sim, mk);
       }
       mk = prof_begin(sim, 3);
