@@ -77,7 +77,8 @@ struct SimDev {
   const uint4 *out_p[SWIM_MAX_WORLD];    // [2][per*B] sender snapshots
   const uint8_t *out_cnt_p[SWIM_MAX_WORLD]; // [2][per]
   uint4 *meta_p[SWIM_MAX_WORLD];         // receivers' meta records (mail stamps are written by senders)
-  uint32_t *bar_err;                     // set by a cross-GPU wait that timed out
+  uint32_t *bar_err;                     // set by a cross-GPU / grid wait that timed out
+  uint32_t *gbar;                        // [2] grid barrier of round_kernel: arrival count, generation
   uint32_t *rlr_p[SWIM_MAX_WORLD];       // [2][world][rcap] receiver ids appended by each source rank
   uint32_t *rcnt_p[SWIM_MAX_WORLD];      // [2][world] their counts, published by the barrier kernel
   uint32_t *bar_p[SWIM_MAX_WORLD];       // [world] cross-GPU barrier words
@@ -482,17 +483,9 @@ __global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
 // slot s; the piggyback buffer is staged in shared memory. Everything K1a derived is recomputed
 // from the row with warp ballots.
 template <int W>
-__global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
-  __shared__ uint4 s_pb[kWarpsPerBlock][32];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
-  pdl_launch();
-  pdl_wait();
-  const uint32_t round = current_round(d);
+__device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps, int lane,
+                                          PbStage &pbs, Ctr &c) {
   const uint32_t n_work = d.wl_cnt[ci(round)];
-  if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
-  Ctr c; c.clear();
-  PbStage pbs; pbs.s = s_pb[wib];
   const uint32_t par = round & 1;
   uint32_t *rl_out = d.rl + (size_t)par * d.n * d.fanout;
   const uint32_t my_stamp = stamp_of(round);
@@ -689,7 +682,21 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
     pb_store(pbs, d, ln, lane);
     if ((uint32_t)lane < d.fanout) rl_out[(size_t)slot * d.fanout + lane] = cand; // no atomics, no shared counter
   }
-  if (d.world > 1 && d.p2p) __threadfence_system(); // peer-memory stores are ordered before the grid's completion
+  if (d.world > 1 && d.p2p) __threadfence_system(); // peer-memory stores are ordered before what follows
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
+  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  pdl_launch();
+  pdl_wait();
+  const uint32_t round = current_round(d);
+  if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+  work_pass<W>(d, round, warp, nwarps, lane, pbs, c);
   c.flush(d.ctr, lane);
 }
 
@@ -863,6 +870,60 @@ __global__ void __launch_bounds__(kThreads, 4) recv_scan_kernel(SimDev d) {
     recv_pass<W>(d, round - 1, false, warp, nwarps, lane, pbs, c);
   }
   c.v[SWIM_CTR_PINGS] += pings;
+  c.flush(d.ctr, lane);
+}
+
+// =================================================================== one kernel per round
+// Default path: K1a, K1b and K2 of one round in ONE launch, separated by grid-wide barriers (all CTAs
+// are resident: the grid is one wave). A round in which nobody has anything to do beyond the probe
+// (the steady state of a healthy cluster) ends after the scan: no K1b, no K2, no extra launches.
+__device__ __forceinline__ void grid_barrier(const SimDev &d) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile uint32_t *gen = d.gbar + 1;
+    const uint32_t g = *gen;
+    __threadfence();
+    if (atomicAdd(d.gbar, 1u) == gridDim.x - 1) {
+      d.gbar[0] = 0;
+      __threadfence();
+      atomicAdd(d.gbar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*gen == g) {
+        if (clock64() - t0 > 6000000000ll) { *d.bar_err = 2; break; }
+        __nanosleep(20);
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads, 4) round_kernel(SimDev d) {
+  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  pdl_launch();
+  pdl_wait();
+  const uint32_t round = current_round(d);
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+  uint32_t pings = 0;
+  scan_pass<W>(d, round, 0, warp, nwarps, lane, pings);                 // K1a
+  c.v[SWIM_CTR_PINGS] += pings;
+  grid_barrier(d);                                                       // the work list is complete
+  const uint32_t n_work = d.wl_cnt[ci(round)];
+  if (n_work == 0 && d.world == 1) {                                     // quiescent round: done
+    if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
+    c.flush(d.ctr, lane);
+    return;
+  }
+  if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c);        // K1b
+  grid_barrier(d);                                                       // every flag and snapshot is written
+  if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
+  if (d.world > 1 && d.p2p) { peer_publish(d, round); peer_wait(d, round, lane); }
+  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);              // K2
   c.flush(d.ctr, lane);
 }
 

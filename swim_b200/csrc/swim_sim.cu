@@ -179,6 +179,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &sim->d_bar, SWIM_MAX_WORLD, 0))) return r;
     if ((r = dalloc(sim, &sim->d_bar_err, 1, 0))) return r;
     d.bar_err = sim->d_bar_err;
+    if ((r = dalloc(sim, &d.gbar, 2, 0))) return r;
     if ((r = dalloc(sim, &sim->d_round_base, 1, 0))) return r;
     return SWIM_OK;
   }();
@@ -426,6 +427,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   // (every warp's own dependent-load chain is the critical path either way).
   const bool pipelined = !sim->profile && (d.world == 1 || d.p2p) && getenv("SWIM_PIPELINE") != nullptr;
   const int fgrid = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
+  // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
+  // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
+  const bool single_kernel = !sim->profile && !pipelined && (d.world == 1 || d.p2p) && getenv("SWIM_SPLIT") == nullptr;
+  const int kgrid = wave_grid(sim, round_kernel<W>, (size_t)d.n);
   bool pending = false; // K2 of the previous round has not run yet
   for (uint32_t r = 0; r < rounds; ++r) {
     d.round = ++sim->round;
@@ -439,6 +444,11 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       prof_end(sim, mk);
       ++sim->launches;
       ev_pos = ev_end;
+    }
+    if (single_kernel) { // K1a + K1b + K2 of this round in one launch (grid barriers inside)
+      CUDA_TRY(sim, launch_pdl(round_kernel<W>, kgrid, sim->stream, d));
+      ++sim->launches;
+      continue;
     }
     int mk = prof_begin(sim, 1);
     d.pipe = pending ? 1u : 0u;
@@ -508,6 +518,11 @@ extern "C" int swim_sim_sync(swim_sim_t *sim) {
     uint32_t err = 0;
     CUDA_TRY(sim, cudaMemcpy(&err, sim->d_bar_err, 4, cudaMemcpyDeviceToHost));
     if (err) { set_error(sim, "a cross-GPU barrier timed out (a peer rank stopped stepping)"); return SWIM_ESTATE; }
+  }
+  if (sim->dev.world == 1) { // grid barrier watchdog of round_kernel
+    uint32_t err = 0;
+    CUDA_TRY(sim, cudaMemcpy(&err, sim->d_bar_err, 4, cudaMemcpyDeviceToHost));
+    if (err) { set_error(sim, "an in-kernel grid barrier timed out"); return SWIM_ESTATE; }
   }
   return SWIM_OK;
 }

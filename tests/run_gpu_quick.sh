@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_gpu.txt; tail -4 gpurun_out/pytest_gpu.txt
 python bench.py --no-cpu > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err; tail -3 gpurun_out/bench_q.err
-SWIM_PIPELINE=1 python bench.py --no-cpu > gpurun_out/bench_q_nograph.json 2>> gpurun_out/bench_q.err
+SWIM_SPLIT=1 python bench.py --no-cpu > gpurun_out/bench_q_nograph.json 2>> gpurun_out/bench_q.err
 python bench.py --no-cpu --warmup 600 --steps 448 > gpurun_out/bench_q_quiet.json 2>> gpurun_out/bench_q.err
 python - <<'PY'
 import json
