@@ -429,7 +429,11 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   const int fgrid = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
   // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
   // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
-  const bool single_kernel = !sim->profile && !pipelined && (d.world == 1 || d.p2p) && getenv("SWIM_SPLIT") == nullptr;
+  // Sharded runs use the split sequence + peer_barrier_kernel: with every warp of a resident grid polling the
+  // peers' flags, round_kernel measured far slower at 2 GPUs (136 ms/round against 39 us), so it is single-GPU only
+  // unless SWIM_ROUND_KERNEL=1 forces it.
+  const bool single_kernel = !sim->profile && !pipelined && getenv("SWIM_SPLIT") == nullptr &&
+                             (d.world == 1 || (d.p2p && getenv("SWIM_ROUND_KERNEL") != nullptr));
   const int kgrid = wave_grid(sim, round_kernel<W>, (size_t)d.n);
   bool pending = false; // K2 of the previous round has not run yet
   for (uint32_t r = 0; r < rounds; ++r) {
