@@ -65,6 +65,7 @@ struct SimDev {
   uint32_t *rl;              // [2][n*fanout] receiver candidates (round parity): slot*fanout + f
   uint32_t *claim2;          // [n] round stamp: a receiver of round r-1 is re-scanned once in round r
   uint32_t pipe;             // bit0: this round's K1a skipped last round's receivers; K1b re-scans them
+  uint32_t stamping;         // 1: senders stamp their receivers' meta records (pipelined rounds only)
   // Round-parity double buffering: everything a round's senders write for its receivers exists twice
   // (index = round & 1), so round r+1's senders never touch what round r's receivers still read and ONE
   // cross-GPU barrier per round (between K1b and K2) is enough.
@@ -360,6 +361,8 @@ __device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t round, uint32
 // tested against the crashed-member bitmap (Ping/Ack, Core.hs:246). A warp covers 128 consecutive
 // nodes = 2 KB contiguous. Nodes that need more — a Suspect slot to count down, a failed probe, a
 // non-empty piggyback buffer — are appended to the round's work list for K1b.
+__device__ __forceinline__ void peer_publish_cta(const SimDev &d, uint32_t mail_round); // defined with the cross-GPU sync
+
 constexpr int kScanGroups = 2; // Philox groups (of 4 nodes) per lane per iteration: 8 nodes, 8 loads in flight
 
 // Pipelining of consecutive rounds: the receive phase of round r-1 (latency bound) runs in the same
@@ -629,7 +632,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
         const uint32_t dl = dst - owner * d.per;
         if (owner == d.rank) {
           d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
-          *stamp_ptr(d.meta + (size_t)dl * W) = (uint16_t)my_stamp; // "has mail from this round"
+          if (d.stamping) *stamp_ptr(d.meta + (size_t)dl * W) = (uint16_t)my_stamp; // "has mail from this round"
           cand = dl;
           const size_t rrow = (size_t)dl * d.cap; // K2 will want the receiver's row, buffer and in-list
           prefetch_l2(d.vst + rrow); prefetch_l2(d.nbr + rrow); prefetch_l2(d.vinc + rrow);
@@ -639,9 +642,10 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           // fused exchange: flag, mail stamp and receiver-list entry go straight into the owner GPU's
           // memory over NVLink (plain stores, nothing comes back); the receiver pulls our snapshot
           d.eflag_p[owner][(size_t)par * d.estride_p[owner] + ridx] = 1;
-          *stamp_ptr(d.meta_p[owner] + (size_t)dl * W) = (uint16_t)my_stamp;
+          if (d.stamping) *stamp_ptr(d.meta_p[owner] + (size_t)dl * W) = (uint16_t)my_stamp;
           const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
           d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
+          __threadfence_system(); // these peer-memory stores are performed before this CTA reports completion
         } else {
           const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
           if (k < d.xcap) {
@@ -682,7 +686,6 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
     pb_store(pbs, d, ln, lane);
     if ((uint32_t)lane < d.fanout) rl_out[(size_t)slot * d.fanout + lane] = cand; // no atomics, no shared counter
   }
-  if (d.world > 1 && d.p2p) __threadfence_system(); // peer-memory stores are ordered before what follows
 }
 
 template <int W>
@@ -697,6 +700,18 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   work_pass<W>(d, round, warp, nwarps, lane, pbs, c);
+  if (d.world > 1 && d.p2p) { // the last CTA to finish tells the peers that this rank's K1b is complete
+    __shared__ uint32_t s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const uint32_t t = atomicAdd(d.gbar + 2, 1u);
+      s_last = t == gridDim.x - 1;
+      if (s_last) d.gbar[2] = 0;
+    }
+    __syncthreads();
+    if (s_last) peer_publish_cta(d, round);
+  }
   c.flush(d.ctr, lane);
 }
 
@@ -708,8 +723,14 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
 // array. Every warp that is about to receive waits until all words of its own array reached the round.
 // The wait is bounded: a missing peer sets *bar_err instead of hanging the GPU.
 __device__ __forceinline__ void peer_publish(const SimDev &d, uint32_t mail_round) {
+  if (blockIdx.x != 0) return;
+  peer_publish_cta(d, mail_round);
+}
+
+// threads q < world of the calling CTA publish to peer q
+__device__ __forceinline__ void peer_publish_cta(const SimDev &d, uint32_t mail_round) {
   const uint32_t q = threadIdx.x;
-  if (blockIdx.x != 0 || q >= d.world) return;
+  if (q >= d.world) return;
   __threadfence_system();
   if (q != d.rank) {
     volatile uint32_t *cnt = d.rcnt_p[q] + (mail_round & 1) * d.world + d.rank;
@@ -841,7 +862,11 @@ __global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
   const uint32_t round = current_round(d);
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c); // the host ran peer_barrier_kernel before this launch
+  if (d.world > 1 && d.p2p) { // every peer's K1b of this round is complete (published by its last CTA)
+    if (wib == 0) peer_wait(d, round, lane);
+    __syncthreads();
+  }
+  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);
   c.flush(d.ctr, lane);
 }
 
@@ -858,7 +883,7 @@ __global__ void __launch_bounds__(kThreads, 4) recv_scan_kernel(SimDev d) {
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   const bool sync_peers = d.world > 1 && d.p2p;
-  if (sync_peers) peer_publish(d, round - 1);
+  // (K1b's last CTA already published round - 1 to the peers)
   uint32_t pings = 0;
   if (warp & 1u) {
     if (sync_peers) peer_wait(d, round - 1, lane);

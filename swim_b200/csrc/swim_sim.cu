@@ -179,7 +179,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &sim->d_bar, SWIM_MAX_WORLD, 0))) return r;
     if ((r = dalloc(sim, &sim->d_bar_err, 1, 0))) return r;
     d.bar_err = sim->d_bar_err;
-    if ((r = dalloc(sim, &d.gbar, 2, 0))) return r;
+    if ((r = dalloc(sim, &d.gbar, 4, 0))) return r;
     if ((r = dalloc(sim, &sim->d_round_base, 1, 0))) return r;
     return SWIM_OK;
   }();
@@ -456,6 +456,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     }
     int mk = prof_begin(sim, 1);
     d.pipe = pending ? 1u : 0u;
+    d.stamping = pipelined ? 1u : 0u;
     if (pending) CUDA_TRY(sim, launch_pdl(recv_scan_kernel<W>, fgrid, sim->stream, d)); // K2(r-1) + K1a(r)
     else CUDA_TRY(sim, launch_pdl(tick_scan_kernel<W>, grid, sim->stream, d));
     prof_end(sim, mk);
@@ -469,13 +470,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     if (!pending) {
       if (d.world > 1) {
         mk = prof_begin(sim, 2);
-        if (d.p2p) { // fused exchange: the data already sits in the peers' memory; synchronise the GPUs
-          peer_barrier_kernel<<<1, 32, 0, sim->stream>>>(d);
-          ++sim->launches;
-        } else {     // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
+        if (!d.p2p) { // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
           int rc = swim::dist_exchange(sim);
           if (rc) return rc;
-        }
+        } // fused exchange: K1b's last CTA has published, K2's CTAs wait for the peers' flags themselves
         prof_end(sim, mk);
       }
       mk = prof_begin(sim, 3);
