@@ -104,10 +104,6 @@ struct SimDev {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Pull a cache line into L2 one phase before the warp that needs it runs (K1a -> K1b's rows, K1b -> K2's rows):
-// the dependent-load chains of the warp-per-node kernels then hit L2 instead of HBM.
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 // the round a per-round kernel works on (graph replays read the base from device memory)
 __device__ __forceinline__ uint32_t current_round(const SimDev &d) { return d.round_base ? d.round + *d.round_base : d.round; }
 
@@ -458,9 +454,6 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
         if (work >> q & 1u) {
           const uint32_t l = 4 * (gb + (q >> 2) * 32 + lane) + (q & 3) - d.first;
           d.wl[pos + __popc(b[q] & ((1u << lane) - 1))] = l;
-          const size_t row = (size_t)l * d.cap; // K1b will want this node's row, buffer and edge indices
-          prefetch_l2(d.vst + row); prefetch_l2(d.nbr + row); prefetch_l2(d.vinc + row); prefetch_l2(d.ridx + row);
-          prefetch_l2(d.pb + (size_t)l * d.B);
         }
         pos += __popc(b[q]);
       }
@@ -634,10 +627,6 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
           if (d.stamping) *stamp_ptr(d.meta + (size_t)dl * W) = (uint16_t)my_stamp; // "has mail from this round"
           cand = dl;
-          const size_t rrow = (size_t)dl * d.cap; // K2 will want the receiver's row, buffer and in-list
-          prefetch_l2(d.vst + rrow); prefetch_l2(d.nbr + rrow); prefetch_l2(d.vinc + rrow);
-          prefetch_l2(d.pb + (size_t)dl * d.B); prefetch_l2(d.in_off + dl);
-          prefetch_l2(d.in_src + (ridx & ~31u)); prefetch_l2(d.self_inc + dl);
         } else if (d.p2p) {
           // fused exchange: flag, mail stamp and receiver-list entry go straight into the owner GPU's
           // memory over NVLink (plain stores, nothing comes back); the receiver pulls our snapshot
@@ -645,7 +634,6 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           if (d.stamping) *stamp_ptr(d.meta_p[owner] + (size_t)dl * W) = (uint16_t)my_stamp;
           const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
           d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
-          __threadfence_system(); // these peer-memory stores are performed before this CTA reports completion
         } else {
           const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
           if (k < d.xcap) {
@@ -686,6 +674,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
     pb_store(pbs, d, ln, lane);
     if ((uint32_t)lane < d.fanout) rl_out[(size_t)slot * d.fanout + lane] = cand; // no atomics, no shared counter
   }
+  if (d.world > 1 && d.p2p) __threadfence_system(); // peer-memory stores are ordered before the grid's completion
 }
 
 template <int W>
@@ -700,18 +689,6 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   work_pass<W>(d, round, warp, nwarps, lane, pbs, c);
-  if (d.world > 1 && d.p2p) { // the last CTA to finish tells the peers that this rank's K1b is complete
-    __shared__ uint32_t s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      const uint32_t t = atomicAdd(d.gbar + 2, 1u);
-      s_last = t == gridDim.x - 1;
-      if (s_last) d.gbar[2] = 0;
-    }
-    __syncthreads();
-    if (s_last) peer_publish_cta(d, round);
-  }
   c.flush(d.ctr, lane);
 }
 
@@ -862,11 +839,7 @@ __global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
   const uint32_t round = current_round(d);
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  if (d.world > 1 && d.p2p) { // every peer's K1b of this round is complete (published by its last CTA)
-    if (wib == 0) peer_wait(d, round, lane);
-    __syncthreads();
-  }
-  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);
+  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c); // sharded runs: the host launched peer_barrier_kernel before this
   c.flush(d.ctr, lane);
 }
 
@@ -883,7 +856,7 @@ __global__ void __launch_bounds__(kThreads, 4) recv_scan_kernel(SimDev d) {
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   const bool sync_peers = d.world > 1 && d.p2p;
-  // (K1b's last CTA already published round - 1 to the peers)
+  if (sync_peers) peer_publish(d, round - 1);
   uint32_t pings = 0;
   if (warp & 1u) {
     if (sync_peers) peer_wait(d, round - 1, lane);

@@ -470,10 +470,13 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     if (!pending) {
       if (d.world > 1) {
         mk = prof_begin(sim, 2);
-        if (!d.p2p) { // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
+        if (d.p2p) { // fused exchange: the data already sits in the peers' memory; synchronise the GPUs
+          peer_barrier_kernel<<<1, 32, 0, sim->stream>>>(d);
+          ++sim->launches;
+        } else {     // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
           int rc = swim::dist_exchange(sim);
           if (rc) return rc;
-        } // fused exchange: K1b's last CTA has published, K2's CTAs wait for the peers' flags themselves
+        }
         prof_end(sim, mk);
       }
       mk = prof_begin(sim, 3);
