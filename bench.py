@@ -208,6 +208,7 @@ def run_cuda(args):
     assert stream.cuda_stream != 0
     sim.set_stream(stream.cuda_stream)
     clocks = ClockSampler(local) if rank == 0 else None  # runs until the end of the e2e region
+    barrier()
     sim.step(args.warmup)
     c0, l0 = sim.counters(), sim.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -28,6 +28,8 @@ namespace swim {
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
+// Ranks drift (host-side setup, first-launch module loads): a peer may legitimately be seconds late.
+constexpr long long kPeerWaitCycles = 120000000000ll; // ~60 s at 2 GHz, then the wait gives up and reports
 #define SWIM_MAX_WORLD 8
 
 // Philox counter purposes. TARGET and LOSS0 blocks are shared by the four nodes
@@ -724,7 +726,7 @@ __device__ __forceinline__ void peer_wait(const SimDev &d, uint32_t mail_round, 
     volatile uint32_t *mine = d.bar_p[d.rank] + lane;
     const long long t0 = clock64();
     while ((int32_t)(*mine - mail_round) < 0) {
-      if (clock64() - t0 > 6000000000ll) { *d.bar_err = 1; break; } // ~3 s at 2 GHz
+      if (clock64() - t0 > kPeerWaitCycles) { *d.bar_err = 1; break; } // a peer stopped stepping
       __nanosleep(200);
     }
     __threadfence_system(); // acquire: the peers' stores that preceded their flag are visible now
