@@ -736,6 +736,8 @@ __device__ __forceinline__ void peer_wait(const SimDev &d, uint32_t mail_round, 
 
 // stand-alone form of the same synchronisation (default path): one warp, launched between K1b and K2
 static __global__ void peer_barrier_kernel(SimDev d) {
+  pdl_launch();
+  pdl_wait(); // K1b of this rank is complete and flushed
   const uint32_t round = current_round(d);
   peer_publish(d, round);
   peer_wait(d, round, (int)threadIdx.x);

@@ -471,7 +471,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       if (d.world > 1) {
         mk = prof_begin(sim, 2);
         if (d.p2p) { // fused exchange: the data already sits in the peers' memory; synchronise the GPUs
-          peer_barrier_kernel<<<1, 32, 0, sim->stream>>>(d);
+          CUDA_TRY(sim, launch_pdl(peer_barrier_kernel, 1, sim->stream, d)); // keeps the PDL chain K1b -> barrier -> K2
           ++sim->launches;
         } else {     // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
           int rc = swim::dist_exchange(sim);
