@@ -487,6 +487,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
   const uint32_t par = round & 1;
   uint32_t *rl_out = d.rl + (size_t)par * d.n * d.fanout;
   const uint32_t my_stamp = stamp_of(round);
+  bool did_remote = false; // this lane stored into a peer GPU's memory
   // pipelined rounds: last round's receivers were skipped by K1a; their mail has been applied by now
   uint32_t seg_end[SWIM_MAX_WORLD + 1];
   uint32_t n_rescan = 0;
@@ -636,6 +637,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           if (d.stamping) *stamp_ptr(d.meta_p[owner] + (size_t)dl * W) = (uint16_t)my_stamp;
           const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
           d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
+          did_remote = true;
         } else {
           const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
           if (k < d.xcap) {
@@ -676,7 +678,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
     pb_store(pbs, d, ln, lane);
     if ((uint32_t)lane < d.fanout) rl_out[(size_t)slot * d.fanout + lane] = cand; // no atomics, no shared counter
   }
-  if (d.world > 1 && d.p2p) __threadfence_system(); // peer-memory stores are ordered before the grid's completion
+  if (did_remote) __threadfence_system(); // peer-memory stores are performed before the grid reports completion
 }
 
 template <int W>
