@@ -338,7 +338,7 @@ def run_cuda(args):
     # ------------------------------------------------ CPU baseline (rank 0, N=1 only): bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rounds = 64
+        rounds = 512  # a bounded sample of roughly 10-30 s of CPU work on the box's host cores
         val, dt, threads, _ = cpu_arm(cfg_kw, nbr, events, n, rounds, 3)
         cpu = {"value": val, "unit": "node-rounds/s", "cores": threads, "kind": "port",
                "sample": f"all {n} nodes of C3, rounds 4..{3 + rounds} ({dt:.1f} s of CPU wall time; restated C "

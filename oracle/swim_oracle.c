@@ -623,31 +623,25 @@ static uint64_t fmix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
   return x;
 }
-static uint64_t dg(uint64_t arr, uint64_t idx, uint64_t val) {
-  return fmix64(fmix64(idx + (arr << 56)) ^ val);
+/* digest term of one element group: tag 1 = node scalars, 2 = view slot, 3 = piggyback record */
+static uint64_t dg3(uint64_t tag, uint64_t idx, uint64_t w0, uint64_t w1) {
+  return fmix64(fmix64(fmix64(idx + (tag << 56)) ^ w0) ^ w1);
 }
 
 EXPORT uint64_t oracle_digest(const oracle_t *o) {
   uint64_t d = 0;
   for (uint32_t l = 0; l < o->n; ++l) {
     uint64_t g = o->first + l;
-    d += dg(SWIM_ARR_ALIVE, g, o->alive[g]);
-    d += dg(SWIM_ARR_SELF_INC, g, o->self_inc[l]);
-    d += dg(SWIM_ARR_SEQNO, g, o->seqno[l]);
-    d += dg(SWIM_ARR_PB_CNT, g, o->pb_cnt[l]);
+    d += dg3(1, g, (uint64_t)o->self_inc[l] | ((uint64_t)o->seqno[l] << 32), (uint64_t)o->alive[g] | ((uint64_t)o->pb_cnt[l] << 8));
     for (uint32_t s = 0; s < o->cap; ++s) {
       size_t x = (size_t)l * o->cap + s;
-      uint64_t gi = g * o->cap + s;
-      d += dg(SWIM_ARR_NBR, gi, o->nbr[x]);
-      d += dg(SWIM_ARR_VST, gi, (uint64_t)(o->state[x] | (o->timer[x] << 2)));
-      d += dg(SWIM_ARR_VINC, gi, o->vinc[x]);
-      d += dg(SWIM_ARR_VLAST, gi, o->vlast[x]);
+      uint64_t st = (uint64_t)(o->state[x] | (o->timer[x] << 2));
+      d += dg3(2, g * o->cap + s, (uint64_t)o->nbr[x] | ((uint64_t)o->vinc[x] << 32), st | ((uint64_t)o->vlast[x] << 8));
     }
     for (uint32_t q = 0; q < o->pb_cnt[l]; ++q) {
       const rec_t *r = &o->pb[(size_t)l * o->B + q];
-      uint64_t gi = (g * o->B + q) * 2;
-      d += dg(SWIM_ARR_PB, gi, (uint64_t)r->member | ((uint64_t)r->incarnation << 32));
-      d += dg(SWIM_ARR_PB, gi + 1, (uint64_t)r->from | ((uint64_t)r->kind << 32) | ((uint64_t)r->ttl << 40));
+      d += dg3(3, g * o->B + q, (uint64_t)r->member | ((uint64_t)r->incarnation << 32),
+               (uint64_t)r->from | ((uint64_t)r->kind << 32) | ((uint64_t)r->ttl << 40));
     }
   }
   return d;

@@ -1033,51 +1033,51 @@ __device__ __forceinline__ uint64_t fmix64(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
   return x;
 }
-__device__ __forceinline__ uint64_t dg(uint64_t arr, uint64_t idx, uint64_t val) {
-  return fmix64(fmix64(idx + (arr << 56)) ^ val);
+// digest term of one element group: tag 1 = node scalars, 2 = view slot, 3 = piggyback record
+__device__ __forceinline__ uint64_t dg3(uint64_t tag, uint64_t idx, uint64_t w0, uint64_t w1) {
+  return fmix64(fmix64(fmix64(idx + (tag << 56)) ^ w0) ^ w1);
 }
 
+// One thread per view slot / node / record, grid-stride, fully coalesced; three fmix64 per element group.
 static __global__ void __launch_bounds__(kThreads) digest_kernel(SimDev d, unsigned long long *out) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
   uint64_t acc = 0;
-  for (uint32_t l = warp; l < d.n; l += nwarps) {
+  const size_t slots = (size_t)d.n * d.cap;
+  for (size_t x = tid; x < slots; x += nthr) {
+    const uint64_t gi = (uint64_t)d.first * d.cap + x;
+    acc += dg3(2, gi, (uint64_t)d.nbr[x] | ((uint64_t)d.vinc[x] << 32), (uint64_t)d.vst[x] | ((uint64_t)d.vlast[x] << 8));
+  }
+  for (size_t l = tid; l < d.n; l += nthr) {
     const uint64_t g = d.first + l;
-    const uint32_t cnt = d.pb_cnt[l];
-    if (lane == 0) {
-      acc += dg(SWIM_ARR_ALIVE, g, d.alive[g]);
-      acc += dg(SWIM_ARR_SELF_INC, g, d.self_inc[l]);
-      acc += dg(SWIM_ARR_SEQNO, g, d.seqno[l]);
-      acc += dg(SWIM_ARR_PB_CNT, g, cnt);
-    }
-    for (uint32_t s = lane; s < d.cap; s += 32) {
-      const size_t x = (size_t)l * d.cap + s;
-      const uint64_t gi = g * d.cap + s;
-      acc += dg(SWIM_ARR_NBR, gi, d.nbr[x]);
-      acc += dg(SWIM_ARR_VST, gi, d.vst[x]);
-      acc += dg(SWIM_ARR_VINC, gi, d.vinc[x]);
-      acc += dg(SWIM_ARR_VLAST, gi, d.vlast[x]);
-    }
-    if ((uint32_t)lane < cnt) {
-      const uint4 r = d.pb[(size_t)l * d.B + lane];
-      const uint64_t gi = (g * d.B + lane) * 2;
-      acc += dg(SWIM_ARR_PB, gi, (uint64_t)r.x | ((uint64_t)r.y << 32));
-      acc += dg(SWIM_ARR_PB, gi + 1, (uint64_t)r.z | ((uint64_t)(r.w & 0xFFu) << 32) | ((uint64_t)((r.w >> 8) & 0xFFu) << 40));
-    }
+    acc += dg3(1, g, (uint64_t)d.self_inc[l] | ((uint64_t)d.seqno[l] << 32), (uint64_t)d.alive[g] | ((uint64_t)d.pb_cnt[l] << 8));
+  }
+  const size_t recs = (size_t)d.n * d.B;
+  for (size_t x = tid; x < recs; x += nthr) {
+    const size_t l = x / d.B, q = x % d.B;
+    if (q >= d.pb_cnt[l]) continue;
+    const uint4 r = d.pb[x];
+    acc += dg3(3, (uint64_t)d.first * d.B + x, (uint64_t)r.x | ((uint64_t)r.y << 32),
+               (uint64_t)r.z | ((uint64_t)(r.w & 0xFFu) << 32) | ((uint64_t)((r.w >> 8) & 0xFFu) << 40));
   }
 #pragma unroll
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(kFull, acc, o);
-  if (lane == 0 && acc) atomicAdd(out, (unsigned long long)acc);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, (unsigned long long)acc);
 }
 
+// Convergence detector: view entries of live observers that disagree with the truth. Uses the
+// crashed-member bitmap of the meta record (current: the host rebuilds it first when it is dirty),
+// so a slot costs one state byte and a shared 16-byte record instead of two gathers.
 static __global__ void __launch_bounds__(kThreads) mismatch_kernel(SimDev d, unsigned long long *out) {
   const size_t total = (size_t)d.n * d.cap;
+  const uint32_t W = d.cap >> 5;
   uint32_t bad = 0;
   for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t l = (uint32_t)(x / d.cap);
+    const uint32_t l = (uint32_t)(x / d.cap), s = (uint32_t)(x % d.cap);
     const uint32_t st = d.vst[x] & 3u;
-    if (st == SWIM_VACANT || !d.alive[d.first + l]) continue;
-    bad += d.alive[d.nbr[x]] ? st != SWIM_ALIVE : st != SWIM_DEAD;
+    const uint4 m = d.meta[(size_t)l * W + (s >> 5)];
+    const uint32_t up = W == 1 ? m.w & 0xFFu : d.meta[(size_t)l * W].w & 0xFFu;
+    if (st == SWIM_VACANT || !up) continue;
+    bad += (m.z >> (s & 31) & 1u) ? st != SWIM_DEAD : st != SWIM_ALIVE;
   }
   bad = __reduce_add_sync(kFull, bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, (unsigned long long)bad);

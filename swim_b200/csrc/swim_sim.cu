@@ -676,8 +676,13 @@ static int reduce_u64(swim_sim *sim, int which, uint64_t *out) {
   CUDA_TRY(sim, cudaMemsetAsync(sim->d_scratch, 0, 8, sim->stream));
   const SimDev &d = sim->dev;
   if (which == 0) {
-    digest_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    digest_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
   } else {
+    if (sim->tdead_dirty) { // the detector reads the crashed-member bitmaps
+      derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+      ++sim->launches;
+      sim->tdead_dirty = false;
+    }
     const size_t total = (size_t)d.n * d.cap;
     mismatch_kernel<<<grid_for(sim, (total + 31) / 32 / 4 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
   }
