@@ -1,22 +1,27 @@
 // swim_device.cuh — sm_100a device code of the SWIM bulk simulator.
 //
 // One simulated node == one `Store` (reference Types.hs:53-60). Per round every node runs
-//   tick  : suspicion countdown (Core.hs:141 FIXME) + kRandomMembers/shuffle target and
-//           proxy selection (Core.hs:69-74, Util.hs:36-42) + probeNode' (Core.hs:243-269)
-//           + piggyback send (Core.hs:127-138)
-//   recv  : process / suspectOrDeadNode' / aliveNode (Core.hs:89-121,142-218)
+//   K1a scan : kRandomMembers/shuffle target selection (Core.hs:69-74, Util.hs:36-42) and the direct
+//              Ping/Ack of probeNode' (Core.hs:243-247)
+//   K1b work : suspicion countdown (Core.hs:141 FIXME), k IndirectPings, local suspicion
+//              (Core.hs:247-254), piggyback send (Core.hs:127-138)
+//   K2  recv : process / suspectOrDeadNode' / aliveNode (Core.hs:89-121,142-218)
 //
-// Mapping to the hardware (integer / indexing work, HBM+L2 bound, no tensor cores):
-//   * a warp owns 32 consecutive nodes. Phase A is lane-per-node: each lane streams its
-//     node's packed state row with 128-bit loads (a warp reads 1 KB contiguous), builds the
-//     alive bitmask with SWAR, draws with Philox4x32-10 and picks the r-th alive slot.
-//   * nodes that have work beyond the read-only probe (timer expiry, failed probe,
-//     non-empty piggyback buffer, mail) are found with __ballot_sync and handled
-//     warp-per-node: lane s owns view slot s, the piggyback buffer is staged in shared
-//     memory, membership lookups are a ballot over the id row.
-//   * mail is delivered without atomics or sorting: the sender raises a byte flag on the
-//     static in-edge (i -> j) of the receiver's sorted in-list; the receiver walks its
-//     flags in ascending sender order and pulls the sender's snapshot.
+// Mapping to the hardware (integer / indexing work, no tensor cores by design):
+//   * K1a streams ONE 16-byte `meta` record per node (alive / suspect / crashed-member bitmaps +
+//     flags); a lane handles 8 nodes (8 independent 128-bit loads, two Philox4x32-10 calls — four
+//     nodes share a block —, eight r-th-set-bit picks); a warp covers 4 KB contiguous.
+//   * nodes that need more than the read-only probe (a countdown to run, a failed probe, a non-empty
+//     piggyback buffer) go to a work list (warp-aggregated append) and are handled warp-per-node:
+//     lane s owns view slot s, the piggyback buffer is staged in shared memory, membership lookups
+//     are a ballot over the id row.
+//   * mail is delivered without sorting or contended atomics: the sender raises a byte flag on the
+//     static in-edge (i -> j) of the receiver's sorted in-list and records j in its own candidate
+//     slot; a receiver is claimed once (per-receiver stamp), walks its flags in ascending sender
+//     order and pulls the sender's snapshot — from local HBM or, across shards, from the peer GPU's
+//     HBM over NVLink.
+//   * default launch: round_kernel = K1a | grid barrier | K1b | grid barrier | K2 in one resident wave;
+//     the same passes exist as separate kernels for profiling and the staged NCCL exchange.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,8 +45,7 @@ struct SimDev {
   uint32_t N, first, n, cap;
   uint32_t k, fanout, B, S, T, loss_ppm;
   uint32_t key0, key1;
-  uint32_t round;            // round number, or the offset from *round_base inside a captured graph
-  const uint32_t *round_base; // null outside CUDA graphs
+  uint32_t round;
   uint32_t world, rank, per; // per = nodes per shard
   uint8_t *alive;            // [N]
   uint32_t *self_inc;        // [n]
@@ -105,9 +109,6 @@ struct SimDev {
 // grid has completed and its writes are visible, pdl_launch() lets the following grid start early.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-// the round a per-round kernel works on (graph replays read the base from device memory)
-__device__ __forceinline__ uint32_t current_round(const SimDev &d) { return d.round_base ? d.round + *d.round_base : d.round; }
 
 // ------------------------------------------------------------------ Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -338,9 +339,6 @@ struct Ctr {
 };
 
 // =================================================================== K1: tick
-// SWAR helper: bit0 of each of 4 bytes -> 4-bit nibble
-__device__ __forceinline__ uint32_t gather4(uint32_t a) { return (a * 0x01020408u) >> 24 & 0xFu; }
-
 // seeded Bernoulli loss of one probe leg: leg 0 = the direct Ping/Ack round trip (group stream),
 // leg 1+j = the round trip through proxy j (per-node stream)
 __device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t round, uint32_t self, uint32_t leg) {
@@ -467,7 +465,7 @@ template <int W>
 __global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
   pdl_launch();
   pdl_wait();
-  const uint32_t round = current_round(d);
+  const uint32_t round = d.round;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t pings = 0;
@@ -688,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
   pdl_wait();
-  const uint32_t round = current_round(d);
+  const uint32_t round = d.round;
   if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
@@ -740,7 +738,7 @@ __device__ __forceinline__ void peer_wait(const SimDev &d, uint32_t mail_round, 
 static __global__ void peer_barrier_kernel(SimDev d) {
   pdl_launch();
   pdl_wait(); // K1b of this rank is complete and flushed
-  const uint32_t round = current_round(d);
+  const uint32_t round = d.round;
   peer_publish(d, round);
   peer_wait(d, round, (int)threadIdx.x);
 }
@@ -842,7 +840,7 @@ __global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
   pdl_wait();
-  const uint32_t round = current_round(d);
+  const uint32_t round = d.round;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c); // sharded runs: the host launched peer_barrier_kernel before this
@@ -858,7 +856,7 @@ __global__ void __launch_bounds__(kThreads, 4) recv_scan_kernel(SimDev d) {
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
   pdl_wait();
-  const uint32_t round = current_round(d); // the round being scanned; mail of round - 1 is applied
+  const uint32_t round = d.round; // the round being scanned; mail of round - 1 is applied
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   const bool sync_peers = d.world > 1 && d.p2p;
@@ -910,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 4) round_kernel(SimDev d) {
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
   pdl_wait();
-  const uint32_t round = current_round(d);
+  const uint32_t round = d.round;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   uint32_t pings = 0;

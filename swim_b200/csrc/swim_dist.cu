@@ -203,7 +203,6 @@ extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
     d.meta_p[r] = (uint4 *)p[6];
   }
   d.p2p = 1;
-  sim->graph_dirty = true;
   sim->connected = true;
   return SWIM_OK;
 }

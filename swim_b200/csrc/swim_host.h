@@ -42,8 +42,6 @@ struct swim_sim {
   double prof_ms[SWIM_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0};
   uint32_t *d_bar = nullptr;     // [world] cross-GPU barrier words of this rank
   uint32_t *d_bar_err = nullptr; // set by a barrier that timed out
-  uint32_t *d_round_base = nullptr;   // (reserved: round base for graph replays)
-  bool graph_dirty = true;
   std::vector<void *> ipc_opened; // peer mappings to close
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };

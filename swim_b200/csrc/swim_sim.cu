@@ -180,7 +180,6 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &sim->d_bar_err, 1, 0))) return r;
     d.bar_err = sim->d_bar_err;
     if ((r = dalloc(sim, &d.gbar, 4, 0))) return r;
-    if ((r = dalloc(sim, &sim->d_round_base, 1, 0))) return r;
     return SWIM_OK;
   }();
   if (rc) { g_last_error = sim->last_error; swim_sim_destroy(sim); return rc; }
@@ -275,7 +274,6 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
   d.in_src = sim->d_in_src;
   d.eflag = sim->d_eflag;
   sim->n_edges = E;
-  sim->graph_dirty = true;
   return swim::dist_alloc_edges(sim);
 }
 

@@ -63,6 +63,29 @@ def crash_events(round_, nodes):
     return make_events(np.full(len(nodes), round_, np.uint32), nodes, np.full(len(nodes), A.EV_CRASH, np.uint8))
 
 
+def churn_events(n_nodes, rounds, crash_ppm, rejoin_min=10, rejoin_max=50, seed=1, first_round=1):
+    """Seeded churn trace (BASELINE config C5): every round each up node crashes with probability
+    crash_ppm/1e6 and rejoins after U[rejoin_min, rejoin_max] rounds (with incarnation + 1 and an Alive
+    broadcast — that is what SWIM_EV_REJOIN does). Returns events for rounds first_round..first_round+rounds-1."""
+    rng = np.random.default_rng(seed)
+    up = np.ones(n_nodes, dtype=bool)
+    back_at = np.zeros(n_nodes, dtype=np.int64)
+    parts = []
+    for r in range(first_round, first_round + rounds):
+        rejoin = np.flatnonzero(~up & (back_at == r))
+        crash = np.flatnonzero(up & (rng.random(n_nodes) < crash_ppm * 1e-6))
+        if len(rejoin):
+            parts.append(make_events(np.full(len(rejoin), r, np.uint32), rejoin.astype(np.uint32),
+                                     np.full(len(rejoin), A.EV_REJOIN, np.uint8)))
+            up[rejoin] = True
+        if len(crash):
+            parts.append(make_events(np.full(len(crash), r, np.uint32), crash.astype(np.uint32),
+                                     np.full(len(crash), A.EV_CRASH, np.uint8)))
+            up[crash] = False
+            back_at[crash] = r + rng.integers(rejoin_min, rejoin_max + 1, size=len(crash))
+    return concat_events(parts) if parts else np.zeros(0, dtype=A.EVENT_DTYPE)
+
+
 class Simulator:
     def __init__(self, cfg: A.Config = None, **kw):
         self.cfg = cfg if cfg is not None else default_config(**kw)

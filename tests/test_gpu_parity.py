@@ -195,3 +195,22 @@ def test_dense_gossip_pipelined():
         orc.step(c)
         assert_same_state(sim, orc, f"dense round {sim.round}")
     assert sim.counters()[A.CTR_RECS_APPLIED] > 100 and sim.counters()[A.CTR_REFUTES] > 0
+
+
+def test_c5_churn_parity():
+    """BASELINE config C5 at test size: continuous churn (crash / rejoin with incarnation + 1), ring views so
+    gossip carries, a few suspicion timeouts; every array equal to the oracle at every chunk boundary."""
+    from swim_b200.sim import churn_events
+    n = 4096
+    nbr = generate_topology("ring", n, 32, 16)
+    ev = churn_events(n, 120, crash_ppm=3000, rejoin_min=10, rejoin_max=40, seed=3)
+    for S in (2, 8):
+        cfg = default_config(n_nodes=n, suspicion_rounds=S, retransmit=6, loss_ppm=5000, seed=21 + S)
+        sim, orc = make_pair(cfg, nbr)
+        sim.inject(ev)
+        orc.inject(ev)
+        for c in (1, 30, 9, 80):
+            sim.step(c)
+            orc.step(c)
+            assert_same_state(sim, orc, f"churn S={S} round {sim.round}")
+        assert sim.counters()[A.CTR_RECS_APPLIED] > 0

@@ -223,3 +223,29 @@ def test_suspicion_timer_counts_rounds():
     # the Dead record names the declaring node in deadFrom and is now in node 0's piggyback buffer
     pb = o.get_array(A.ARR_PB).reshape(8, -1)[0]
     assert (pb[0]["member"], pb[0]["kind"], pb[0]["from"]) == (2, A.MSG_DEAD, 0)
+
+
+def test_c5_churn_suspicion_sweep_small():
+    """BASELINE config C5 in miniature (10 % of the nodes down at any time, suspicion-timeout sweep): with a
+    long suspicion timeout fewer entries die by their own timer (the Dead gossip or the rejoin arrives first); refutations stay zero
+    without loss; rejoined nodes are re-admitted through their Alive(incarnation + 1) broadcast."""
+    from swim_b200.sim import churn_events, generate_topology
+    n, rounds = 256, 300
+    nbr = generate_topology("ring", n, 32, 16)  # neighbours share views, so gossip carries
+    ev = churn_events(n, rounds, crash_ppm=3300, rejoin_min=10, rejoin_max=50, seed=5)
+    assert len(ev) > 100
+    dead_declared = []
+    for S in (2, 5, 13):
+        o = Oracle(default_config(n_nodes=n, suspicion_rounds=S, retransmit=6, seed=9))
+        o.set_view(nbr)
+        o.inject(ev)
+        o.step(rounds)
+        c = o.counters()
+        dead_declared.append(int(c[A.CTR_DEAD_TIMEOUT]))
+        assert c[A.CTR_REFUTES] == 0 and c[A.CTR_SUSPECT_LOCAL] > 0
+        inc = o.get_array(A.ARR_SELF_INC)
+        assert inc.max() >= 1  # somebody rejoined with a bumped incarnation
+        # a rejoined node's higher incarnation has reached at least one of its observers
+        vinc = o.get_array(A.ARR_VINC)
+        assert vinc.max() >= 1
+    assert min(dead_declared) > 0 and dead_declared[2] < dead_declared[0]  # fewer timer-declared deaths with a long timeout
