@@ -344,6 +344,13 @@ int swim_handle_message(swim_sim_t *sim, uint32_t node, uint32_t sender_addr,
                         uint16_t sender_port, const swim_message_t *msg,
                         swim_gossip_t *out, size_t cap, size_t *n_out);
 
+/* disseminate's `Broadcast msg -> enqueue msg` branch (Core.hs:131,136-138; a FIXME no-op in the reference):
+ * put a Suspect/Alive/Dead message into the node's piggyback buffer, from where the bulk rounds send
+ * it `retransmit` times. swim_get_broadcasts reads the buffer back, newest first (what the next
+ * compound Envelope to a ping target would carry). */
+int swim_broadcast(swim_sim_t *sim, uint32_t node, const swim_message_t *msg);
+int swim_get_broadcasts(swim_sim_t *sim, uint32_t node, swim_message_t *out, size_t cap, size_t *n_out);
+
 /* ====================== wire codec: Types.hs parity ==================================
  * Envelope framing (Types.hs:96-119) around msgpack-of-aeson-generic bodies
  * (Types.hs:147-155). Names travel as strings on the wire. */

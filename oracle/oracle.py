@@ -66,6 +66,8 @@ def lib():
                                            C.POINTER(C.c_int)]
         L.oracle_handle_message.argtypes = [vp, u32, u32, C.c_uint16, C.POINTER(A.Message), vp, sz,
                                             C.POINTER(sz)]
+        L.oracle_broadcast.argtypes = [vp, u32, C.POINTER(A.Message)]
+        L.oracle_get_broadcasts.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
         L.oracle_philox.argtypes = [vp, vp, vp]
         L.oracle_num_threads.restype = C.c_int
         _lib = L
@@ -216,6 +218,15 @@ class Oracle:
 
     def alive_node(self, node, msg):
         return self._apply(node, A.MSG_ALIVE, msg)
+
+    def broadcast(self, node, msg):
+        _chk(lib().oracle_broadcast(self._h, node, C.byref(msg)), "broadcast")
+
+    def get_broadcasts(self, node):
+        buf = (A.Message * A.MAX_PB)()
+        n = C.c_size_t()
+        _chk(lib().oracle_get_broadcasts(self._h, node, buf, A.MAX_PB, C.byref(n)), "get_broadcasts")
+        return [_copy(buf[i]) for i in range(n.value)]
 
     def handle_message(self, node, sender_addr, sender_port, msg):
         out = (A.Gossip * 4)()

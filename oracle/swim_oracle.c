@@ -797,6 +797,25 @@ EXPORT int oracle_apply_message(oracle_t *o, uint32_t node, int want, const swim
   return SWIM_OK;
 }
 
+/* disseminate, Broadcast branch (Core.hs:131,136-138) */
+EXPORT int oracle_broadcast(oracle_t *o, uint32_t node, const swim_message_t *msg) {
+  if (node < o->first || node >= o->first + o->n) return SWIM_EINVAL;
+  if (msg->kind != SWIM_MSG_SUSPECT && msg->kind != SWIM_MSG_ALIVE && msg->kind != SWIM_MSG_DEAD) return SWIM_EINVAL;
+  if (msg->incarnation < 0 || msg->incarnation > 0xFFFFFFFFll) return SWIM_ERANGE;
+  uint64_t sink[SWIM_CTR__COUNT] = {0};
+  pb_enqueue(o, node - o->first, rec_of_msg(msg), sink);
+  return SWIM_OK;
+}
+
+EXPORT int oracle_get_broadcasts(const oracle_t *o, uint32_t node, swim_message_t *out, size_t cap, size_t *n_out) {
+  if (node < o->first || node >= o->first + o->n) return SWIM_EINVAL;
+  uint32_t l = node - o->first;
+  if (o->pb_cnt[l] > cap) return SWIM_ECAP;
+  for (uint32_t q = 0; q < o->pb_cnt[l]; ++q) msg_of_rec(o, &o->pb[(size_t)l * o->B + q], &out[q]);
+  *n_out = o->pb_cnt[l];
+  return SWIM_OK;
+}
+
 /* process (Core.hs:89-117) */
 EXPORT int oracle_handle_message(oracle_t *o, uint32_t node, uint32_t sender_addr, uint16_t sender_port,
                                  const swim_message_t *msg, swim_gossip_t *out, size_t cap, size_t *n_out) {

@@ -239,6 +239,42 @@ def process(store: Store, sender: SockAddrInet, msg: Message) -> List[Gossip]:
     return res
 
 
+def _msg_from_c(store: Store, c: A.Message) -> Message:
+    name = store._name(c.node) if c.node == store._self or c.node < len(store._names) else f"#{c.node}"
+    if c.kind == A.MSG_SUSPECT:
+        return Suspect(int(c.incarnation), name)
+    if c.kind == A.MSG_DEAD:
+        frm = store._name(c.dead_from) if c.dead_from == store._self or c.dead_from < len(store._names) else f"#{c.dead_from}"
+        return Dead(int(c.incarnation), name, frm)
+    host, addr = store._meta.get(name, ("", SockAddrInet(c.port, c.target)))
+    return Alive(int(c.incarnation), name, addr.host, addr.port)
+
+
+def pending_broadcasts(store: Store) -> List[Message]:
+    """The store's piggyback buffer, newest first (what the next compound Envelope would carry)."""
+    buf = (A.Message * A.MAX_PB)()
+    n = C.c_size_t()
+    check(lib().swim_get_broadcasts(store._h(), store._self, buf, A.MAX_PB, C.byref(n)), "swim_get_broadcasts", store._h())
+    return [_msg_from_c(store, buf[i]) for i in range(n.value)]
+
+
+def disseminate(store: Store, gossip: Iterable[Gossip]):
+    """disseminate (Core.hs:127-138): `Direct msg addr` -> a datagram to send now (framed as an Envelope — the
+    reference sends a bare `encode msg` that its own receiver cannot decode); `Broadcast msg` ->
+    the piggyback buffer (the reference's `enqueue _msg = return ()` FIXME). Returns [(bytes, addr)]."""
+    from .types import encode
+    out = []
+    for g in gossip:
+        if isinstance(g, Direct):
+            out.append((encode(Envelope((g.msg,))), g.addr))
+        else:
+            if isinstance(g.msg, Alive) and g.msg.node != store.storeSelf.memberName and store._id(g.msg.node) == _UNKNOWN:
+                store._intern(g.msg.node, "", SockAddrInet(g.msg.port, g.msg.addr))
+            c = _msg_to_c(store, g.msg)
+            check(lib().swim_broadcast(store._h(), store._self, C.byref(c)), "swim_broadcast", store._h())
+    return out
+
+
 def handleUDPMessage(store: Store, datagrams) -> List[Gossip]:
     """handleUDPMessage (Core.hs:79-121) over a list of (bytes, sender) datagrams: decode the
     Envelope, process every message, concatenate the Gossip. A decode failure raises (the

@@ -22,7 +22,7 @@ using namespace swim;
 
 namespace {
 
-enum : uint32_t { OP_APPLY = 0, OP_KRANDOM = 1, OP_REMOVE_DEAD = 2, OP_NEXT_SEQNO = 3, OP_NEXT_INC = 4 };
+enum : uint32_t { OP_APPLY = 0, OP_KRANDOM = 1, OP_REMOVE_DEAD = 2, OP_NEXT_SEQNO = 3, OP_NEXT_INC = 4, OP_ENQUEUE = 5 };
 
 struct ScalarArgs {
   uint32_t op, node, n, allow_insert;
@@ -38,6 +38,7 @@ struct ScalarArgs {
 
 template <int W>
 __global__ void scalar_kernel(SimDev d, ScalarArgs *a) {
+  __shared__ uint4 s_pb[32];
   const int lane = threadIdx.x;
   const uint32_t ln = a->node - d.first;
   uint32_t dummy = 0;
@@ -107,6 +108,15 @@ __global__ void scalar_kernel(SimDev d, ScalarArgs *a) {
         }
         a->n_out = want;
       }
+      break;
+    }
+    case OP_ENQUEUE: { // disseminate: Broadcast msg -> enqueue (Core.hs:131,136-138), same buffer code as the bulk kernels
+      PbStage pbs;
+      pbs.s = s_pb;
+      pb_load(pbs, d, ln, lane);
+      pb_enqueue(pbs, d, a->rec, lane, dummy);
+      pb_store(pbs, d, ln, lane);
+      if (lane == 0) a->value = dummy; // 1 = the oldest record fell off a full buffer
       break;
     }
     case OP_REMOVE_DEAD: // removeDeadNodes (Core.hs:65-67): Map.filter (not . isDead)
@@ -341,6 +351,41 @@ extern "C" int swim_dead_node(swim_sim_t *sim, uint32_t node, const swim_message
 }
 extern "C" int swim_alive_node(swim_sim_t *sim, uint32_t node, const swim_message_t *msg, swim_message_t *out, int *has_out) {
   return apply_message(sim, node, SWIM_MSG_ALIVE, msg, out, has_out);
+}
+
+// disseminate, Broadcast branch (Core.hs:131,136-138)
+extern "C" int swim_broadcast(swim_sim_t *sim, uint32_t node, const swim_message_t *msg) {
+  int rc = check_node(sim, node);
+  if (rc) return rc;
+  if (!msg) return SWIM_EINVAL;
+  if (msg->kind != SWIM_MSG_SUSPECT && msg->kind != SWIM_MSG_ALIVE && msg->kind != SWIM_MSG_DEAD) {
+    set_error(sim, "swim_broadcast: Ping / IndirectPing / Ack are sent directly, never enqueued (Core.hs:124-126)");
+    return SWIM_EINVAL;
+  }
+  if (msg->incarnation < 0 || msg->incarnation > 0xFFFFFFFFll) { set_error(sim, "incarnation does not fit u32"); return SWIM_ERANGE; }
+  ScalarArgs a;
+  memset(&a, 0, sizeof a);
+  a.op = OP_ENQUEUE; a.node = node;
+  a.rec = make_uint4(msg->node, (uint32_t)msg->incarnation, msg->kind == SWIM_MSG_DEAD ? msg->dead_from : 0u, msg->kind);
+  return run_scalar(sim, a);
+}
+
+extern "C" int swim_get_broadcasts(swim_sim_t *sim, uint32_t node, swim_message_t *out, size_t cap, size_t *n_out) {
+  int rc = check_node(sim, node);
+  if (rc) return rc;
+  if (!out || !n_out) return SWIM_EINVAL;
+  const SimDev &d = sim->dev;
+  const uint32_t l = node - d.first;
+  uint8_t cnt = 0;
+  std::vector<uint4> recs(d.B);
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  CUDA_TRY(sim, cudaMemcpy(&cnt, d.pb_cnt + l, 1, cudaMemcpyDeviceToHost));
+  CUDA_TRY(sim, cudaMemcpy(recs.data(), d.pb + (size_t)l * d.B, d.B * sizeof(uint4), cudaMemcpyDeviceToHost));
+  if (cnt > cap) return SWIM_ECAP;
+  for (uint32_t q = 0; q < cnt; ++q) msg_of_rec(sim, recs[q], &out[q]);
+  *n_out = cnt;
+  return SWIM_OK;
 }
 
 // `process` (Core.hs:89-117)

@@ -168,3 +168,30 @@ def _members(sim, node, cap):
     n = C.c_size_t()
     check(lib().swim_get_members(sim._h, node, buf, cap, C.byref(n)), "get", sim._h)
     return [buf[i] for i in range(n.value)]
+
+
+def test_disseminate(store):
+    """disseminate (Core.hs:127-138) on the device: Direct -> datagram, Broadcast -> piggyback buffer, which a
+    bulk round then carries to the ping target."""
+    from oracle.oracle import Oracle
+    from swim_b200 import core
+    from swim_b200.types import Ack, Broadcast, Dead, Direct, Envelope, Ping, Suspect, decode
+    store.set_members(make_members())
+    wire = core.disseminate(store, [Direct(Ack(7, ()), addr()), Broadcast(Suspect(0, "alive")), Broadcast(Dead(2, "dead", "suspect")),
+                                    Broadcast(Suspect(1, "alive"))])
+    assert len(wire) == 1 and wire[0][1] == addr() and decode(wire[0][0]) == Envelope((Ack(7, ()),))
+    assert core.pending_broadcasts(store) == [Suspect(1, "alive"), Dead(2, "dead", "suspect")]  # newest first, replaced
+    # the same queue semantics as the oracle's
+    import ctypes as C
+    from swim_b200._lib import check, lib
+    from swim_b200.sim import Simulator, default_config
+    cfg = default_config(n_nodes=N_NODES, pb_cap=4)
+    sim, orc = Simulator(cfg), Oracle(cfg)
+    rng = np.random.default_rng(4)
+    for _ in range(60):
+        m = msg(int(rng.choice([A.MSG_SUSPECT, A.MSG_ALIVE, A.MSG_DEAD])), int(rng.integers(0, 9)), int(rng.integers(0, 5)),
+                dead_from=int(rng.integers(0, 9)))
+        check(lib().swim_broadcast(sim._h, SELF, C.byref(m)), "swim_broadcast", sim._h)
+        orc.broadcast(SELF, m)
+        assert np.array_equal(sim.get_array(A.ARR_PB), orc.get_array(A.ARR_PB))
+        assert np.array_equal(sim.get_array(A.ARR_PB_CNT), orc.get_array(A.ARR_PB_CNT))

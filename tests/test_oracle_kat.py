@@ -249,3 +249,22 @@ def test_c5_churn_suspicion_sweep_small():
         vinc = o.get_array(A.ARR_VINC)
         assert vinc.max() >= 1
     assert min(dead_declared) > 0 and dead_declared[2] < dead_declared[0]  # fewer timer-declared deaths with a long timeout
+
+
+def test_broadcast_queue(store):
+    """[Q5] disseminate's Broadcast branch: newest first, a newer record about the same member replaces the older
+    one, a full buffer drops its oldest record, Ping/Ack are never enqueued."""
+    B = store.cfg.pb_cap
+    for i in range(B):
+        store.broadcast(SELF, msg(A.MSG_SUSPECT, i, inc=i))
+    got = store.get_broadcasts(SELF)
+    assert [m.node for m in got] == list(range(B - 1, -1, -1))
+    store.broadcast(SELF, msg(A.MSG_DEAD, 3, inc=9, dead_from=7))      # replaces Suspect(3)
+    got = store.get_broadcasts(SELF)
+    assert len(got) == B and (got[0].kind, got[0].node, got[0].incarnation, got[0].dead_from) == (A.MSG_DEAD, 3, 9, 7)
+    assert [m.node for m in got].count(3) == 1
+    store.broadcast(SELF, msg(A.MSG_ALIVE, 50, inc=1))                  # full: the oldest (member 0) falls off
+    got = store.get_broadcasts(SELF)
+    assert len(got) == B and got[0].node == 50 and 0 not in [m.node for m in got]
+    with pytest.raises(OracleError):
+        store.broadcast(SELF, msg(A.MSG_PING, 1))
