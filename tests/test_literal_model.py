@@ -130,7 +130,8 @@ def test_c_oracle_equals_literal_model(seed):
     # kRandomMembers: the literal shuffle fed with the oracle's Philox draws picks the same members
     for n_take in (1, 4, 18):
         key = [cfg.seed & 0xFFFFFFFF, cfg.seed >> 32]
-        draws = iter(w for blk in range(8) for w in philox([orc_calls(orc), self_id, 2, blk], key))
+        call = orc_calls(orc)
+        draws = iter(w for blk in range(8) for w in philox([call, self_id, 2, blk], key))
         rand = lambda lo, hi: (next(draws) * (hi - lo + 1)) >> 32
         want = [ids[m.name] for m in M.k_random_members(lit, n_take, [lit.members[self_name]], rand)]
         got = [m.id for m in orc.k_random_members(self_id, n_take, [])]
