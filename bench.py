@@ -13,7 +13,8 @@ piggyback envelopes per round.
 Prints ONE JSON line (rank 0). `value` = node·rounds/s with state resident in HBM, timed with
 CUDA events on the stream the kernels run on, max over ranks. `e2e` = the same metric through
 the C ABI one round per call with host buffers: every step uploads that round's event trace,
-runs one round and reads the counters, the state digest and the convergence count back.
+runs one round and reads the counters, the state digest and the convergence count back
+(swim_sim_inject + swim_sim_step(1) + swim_sim_observe).
 """
 import argparse
 import json
@@ -287,9 +288,7 @@ def run_cuda(args):
                 sim.inject(arr)  # host buffer -> library -> device (uploaded by the step below)
                 h2d += arr.nbytes
             sim.step(1)
-            c = sim.counters()
-            dg = sim.digest()
-            mm = sim.mismatches()
+            c, dg, mm = sim.observe()  # counters + digest + convergence count, one read-back
             d2h += c.nbytes + 16
             return c, dg, mm
 
@@ -308,8 +307,8 @@ def run_cuda(args):
             dt = float(t.item())
         e2e = {"value": n * args.steps / dt, "unit": "node-rounds/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps,
-               "what": "per round: swim_sim_inject(host events) + swim_sim_step(1) + swim_sim_counters + "
-                       "swim_sim_digest + swim_sim_mismatches (host wall clock, max over ranks)"}
+               "what": "per round: swim_sim_inject(host events) + swim_sim_step(1) + swim_sim_observe (counters, digest, "
+                       "convergence count) — host wall clock, max over ranks"}
         sim.close()
     clk = clocks.stop() if clocks else None
 

@@ -262,6 +262,10 @@ int swim_sim_digest(swim_sim_t *sim, uint64_t *digest);
 /* Copy min(n, SWIM_CTR__COUNT) cumulative counters of this rank. */
 int swim_sim_counters(swim_sim_t *sim, uint64_t *out, size_t n);
 
+/* counters + digest + convergence count in one call and ONE synchronisation (any output may be NULL): the
+ * per-round read-back of a convergence-study loop. */
+int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_counters, uint64_t *digest, uint64_t *mismatches);
+
 /* Convergence detector: number of (live observer, member) view entries on this rank that
  * disagree with the truth (crashed member not Dead, or live member not Alive). */
 int swim_sim_mismatches(swim_sim_t *sim, uint64_t *count);

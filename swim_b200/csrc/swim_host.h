@@ -41,7 +41,8 @@ struct swim_sim {
   size_t prof_used = 0;
   double prof_ms[SWIM_PROFILE_SLOTS] = {0, 0, 0, 0, 0, 0};
   uint32_t *d_bar = nullptr;     // [world] cross-GPU barrier words of this rank
-  uint32_t *d_bar_err = nullptr; // set by a barrier that timed out
+  uint32_t *h_bar_err = nullptr;            // pinned + device-mapped watchdog word of the in-kernel waits
+  unsigned long long *h_observe = nullptr;  // pinned staging of swim_sim_observe
   std::vector<void *> ipc_opened; // peer mappings to close
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };

@@ -175,10 +175,14 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.claim2, n, 0))) return r;
     if ((r = dalloc(sim, &d.rl, 2 * n * d.fanout, 0xFF))) return r; // [parity] candidate slots, empty = 0xFFFFFFFF
     if ((r = dalloc(sim, &d.ctr, SWIM_CTR__COUNT, 0))) return r;
-    if ((r = dalloc(sim, &sim->d_scratch, 8, 0))) return r;
+    if ((r = dalloc(sim, &sim->d_scratch, 2, 0))) return r;
     if ((r = dalloc(sim, &sim->d_bar, SWIM_MAX_WORLD, 0))) return r;
-    if ((r = dalloc(sim, &sim->d_bar_err, 1, 0))) return r;
-    d.bar_err = sim->d_bar_err;
+    // watchdog word of the in-kernel waits: pinned host memory mapped into the device, so swim_sim_sync reads it
+    // without a copy (it is written only when a wait gives up)
+    CUDA_TRY(sim, cudaHostAlloc((void **)&sim->h_bar_err, sizeof(uint32_t), cudaHostAllocMapped));
+    *sim->h_bar_err = 0;
+    CUDA_TRY(sim, cudaHostGetDevicePointer((void **)&d.bar_err, sim->h_bar_err, 0));
+    CUDA_TRY(sim, cudaHostAlloc((void **)&sim->h_observe, (SWIM_CTR__COUNT + 2) * sizeof(unsigned long long), cudaHostAllocDefault));
     if ((r = dalloc(sim, &d.gbar, 4, 0))) return r;
     return SWIM_OK;
   }();
@@ -197,6 +201,8 @@ extern "C" void swim_sim_destroy(swim_sim_t *sim) {
   if (sim->d_eflag) cudaFree(sim->d_eflag);
   if (sim->d_events) cudaFree(sim->d_events);
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
+  if (sim->h_bar_err) cudaFreeHost(sim->h_bar_err);
+  if (sim->h_observe) cudaFreeHost(sim->h_observe);
   if (sim->ev_start) cudaEventDestroy(sim->ev_start);
   if (sim->ev_stop) cudaEventDestroy(sim->ev_stop);
   if (sim->own_stream) cudaStreamDestroy(sim->own_stream);
@@ -517,15 +523,10 @@ extern "C" int swim_sim_sync(swim_sim_t *sim) {
   if (!sim) return SWIM_EINVAL;
   cudaSetDevice(sim->device);
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
-  if (sim->dev.world > 1 && sim->dev.p2p) {
-    uint32_t err = 0;
-    CUDA_TRY(sim, cudaMemcpy(&err, sim->d_bar_err, 4, cudaMemcpyDeviceToHost));
-    if (err) { set_error(sim, "a cross-GPU barrier timed out (a peer rank stopped stepping)"); return SWIM_ESTATE; }
-  }
-  if (sim->dev.world == 1) { // grid barrier watchdog of round_kernel
-    uint32_t err = 0;
-    CUDA_TRY(sim, cudaMemcpy(&err, sim->d_bar_err, 4, cudaMemcpyDeviceToHost));
-    if (err) { set_error(sim, "an in-kernel grid barrier timed out"); return SWIM_ESTATE; }
+  const uint32_t err = *(volatile uint32_t *)sim->h_bar_err;
+  if (err) {
+    set_error(sim, err == 1 ? "a cross-GPU wait timed out (a peer rank stopped stepping)" : "an in-kernel grid barrier timed out");
+    return SWIM_ESTATE;
   }
   return SWIM_OK;
 }
@@ -701,6 +702,35 @@ extern "C" int swim_sim_digest(swim_sim_t *sim, uint64_t *digest) {
 extern "C" int swim_sim_mismatches(swim_sim_t *sim, uint64_t *count) {
   if (!sim || !count) return SWIM_EINVAL;
   return reduce_u64(sim, 1, count);
+}
+
+extern "C" int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_counters, uint64_t *digest, uint64_t *mismatches) {
+  if (!sim) return SWIM_EINVAL;
+  cudaSetDevice(sim->device);
+  const SimDev &d = sim->dev;
+  CUDA_TRY(sim, cudaMemsetAsync(sim->d_scratch, 0, 16, sim->stream));
+  if (digest) {
+    digest_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    ++sim->launches;
+  }
+  if (mismatches) {
+    if (sim->tdead_dirty) {
+      derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+      ++sim->launches;
+      sim->tdead_dirty = false;
+    }
+    mismatch_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 4 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch + 1);
+    ++sim->launches;
+  }
+  CUDA_TRY(sim, cudaGetLastError());
+  unsigned long long *h = sim->h_observe;
+  CUDA_TRY(sim, cudaMemcpyAsync(h, sim->d_scratch, 16, cudaMemcpyDeviceToHost, sim->stream));
+  CUDA_TRY(sim, cudaMemcpyAsync(h + 2, d.ctr, SWIM_CTR__COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  if (digest) *digest = h[0];
+  if (mismatches) *mismatches = h[1];
+  for (size_t i = 0; counters && i < n_counters && i < SWIM_CTR__COUNT; ++i) counters[i] = h[2 + i];
+  return SWIM_OK;
 }
 
 extern "C" int swim_sim_counters(swim_sim_t *sim, uint64_t *out, size_t n) {

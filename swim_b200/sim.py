@@ -189,6 +189,14 @@ class Simulator:
         check(lib().swim_sim_profile_ms(self._h, out, 6), "swim_sim_profile_ms", self._h)
         return dict(zip(["events", "tick_scan", "exchange", "recv", "tick_work", "rounds"], list(out)))
 
+    def observe(self):
+        """(counters, digest, mismatches) with one device synchronisation."""
+        out = np.zeros(A.CTR_COUNT, dtype=np.uint64)
+        dg, mm = C.c_uint64(), C.c_uint64()
+        check(lib().swim_sim_observe(self._h, out.ctypes.data, A.CTR_COUNT, C.byref(dg), C.byref(mm)), "swim_sim_observe",
+              self._h)
+        return out, dg.value, mm.value
+
     def state(self):
         """All bulk arrays as a dict (the checkable form of dumpStore, Util.hs:64-74)."""
         return {A.ARRAY_NAMES[a]: self.get_array(a) for a in range(A.ARR_COUNT)}

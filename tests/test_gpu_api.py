@@ -54,6 +54,8 @@ def test_state_round_trip_and_counters():
         if arr != A.ARR_NBR:
             b.set_array(arr, a.get_array(arr))
     assert a.digest() == b.digest()
+    c, dg, mm = a.observe()
+    assert c.tolist() == a.counters().tolist() and dg == a.digest() and mm == a.mismatches()
     assert a.round == 12 and b.round == 0
     st = a.state()
     assert set(st) == set(A.ARRAY_NAMES.values()) and st["vst"].shape == (n * 32,)
