@@ -46,6 +46,7 @@ struct SimDev {
   uint32_t k, fanout, B, S, T, loss_ppm;
   uint32_t key0, key1;
   uint32_t round;
+  uint32_t nrounds;          // round_kernel: consecutive rounds in this launch (>= 1)
   uint32_t world, rank, per; // per = nodes per shard
   uint8_t *alive;            // [N]
   uint32_t *self_inc;        // [n]
@@ -908,24 +909,26 @@ __global__ void __launch_bounds__(kThreads, 4) round_kernel(SimDev d) {
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
   pdl_wait();
-  const uint32_t round = d.round;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  uint32_t pings = 0;
-  scan_pass<W>(d, round, 0, warp, nwarps, lane, pings);                 // K1a
-  c.v[SWIM_CTR_PINGS] += pings;
-  grid_barrier(d);                                                       // the work list is complete
-  const uint32_t n_work = d.wl_cnt[ci(round)];
-  if (n_work == 0 && d.world == 1) {                                     // quiescent round: done
+  // d.nrounds consecutive event-free rounds in this launch (the host splits calls at rounds that carry events)
+  for (uint32_t it = 0; it < d.nrounds; ++it) {
+    const uint32_t round = d.round + it;
+    // slot (round + 1) % 3 of the list counters was last used two rounds ago: clear it now, well before the
+    // next round's scan (which starts after this round's first barrier) appends to it
     if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
-    c.flush(d.ctr, lane);
-    return;
+    uint32_t pings = 0;
+    scan_pass<W>(d, round, 0, warp, nwarps, lane, pings);                // K1a
+    c.v[SWIM_CTR_PINGS] += pings;
+    grid_barrier(d);                                                      // the work list is complete
+    const uint32_t n_work = d.wl_cnt[ci(round)];
+    if (n_work == 0 && d.world == 1) continue;                            // quiescent round: nothing was written
+    if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c);       // K1b
+    grid_barrier(d);                                                      // every flag and snapshot is written
+    if (d.world > 1 && d.p2p) { peer_publish(d, round); peer_wait(d, round, lane); }
+    recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);             // K2
+    if (it + 1 < d.nrounds) grid_barrier(d);                              // views and buffers settled before the next scan
   }
-  if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c);        // K1b
-  grid_barrier(d);                                                       // every flag and snapshot is written
-  if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
-  if (d.world > 1 && d.p2p) { peer_publish(d, round); peer_wait(d, round, lane); }
-  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);              // K2
   c.flush(d.ctr, lane);
 }
 

@@ -439,6 +439,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   const bool single_kernel = !sim->profile && !pipelined && getenv("SWIM_SPLIT") == nullptr &&
                              (d.world == 1 || (d.p2p && getenv("SWIM_ROUND_KERNEL") != nullptr));
   const int kgrid = wave_grid(sim, round_kernel<W>, (size_t)d.n);
+  const bool multi_round_off = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
   bool pending = false; // K2 of the previous round has not run yet
   for (uint32_t r = 0; r < rounds; ++r) {
     d.round = ++sim->round;
@@ -453,9 +454,15 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       ++sim->launches;
       ev_pos = ev_end;
     }
-    if (single_kernel) { // K1a + K1b + K2 of this round in one launch (grid barriers inside)
+    if (single_kernel) { // K1a + K1b + K2 in one launch (grid barriers inside), for every round up to the next event
+      uint32_t nr = rounds - r;
+      if (ev_pos < n_ev) nr = std::min<uint32_t>(nr, sim->events[ev_pos].round - d.round);
+      if (d.world > 1 || multi_round_off) nr = 1;
+      d.nrounds = nr;
       CUDA_TRY(sim, launch_pdl(round_kernel<W>, kgrid, sim->stream, d));
       ++sim->launches;
+      sim->round += nr - 1;
+      r += nr - 1;
       continue;
     }
     int mk = prof_begin(sim, 1);
