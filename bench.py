@@ -348,7 +348,11 @@ def run_cuda(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
                 "data": "synthetic", "config": config_dict(cfg_kw, n, world, exchange["mode"]), "clocks": clk, "e2e": e2e,
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "convergence": conv,
+                "gpu_launches": launches,
+                "gpu_launches_note": "round_kernel<1> runs K1a, K1b and K2 of every consecutive event-free round of a call "
+                                     "in ONE launch (grid barriers between phases), so the timed region of K rounds is a "
+                                     "handful of launches, not 3K",
+                "roofline": roofline, "cpu_baseline": cpu, "convergence": conv,
                 "counters_timed_region": dict(zip(A.CTR_NAMES, [int(x) for x in ctr_delta]))}
         print(json.dumps(line))
     if world > 1:

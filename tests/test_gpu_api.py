@@ -59,7 +59,7 @@ def test_state_round_trip_and_counters():
     assert a.round == 12 and b.round == 0
     st = a.state()
     assert set(st) == set(A.ARRAY_NAMES.values()) and st["vst"].shape == (n * 32,)
-    assert a.launch_count() >= 12  # at least one kernel per round
+    assert a.launch_count() >= 2  # round_kernel covers every event-free stretch of a call in one launch
 
 
 def test_profile_hooks_and_caller_stream():
