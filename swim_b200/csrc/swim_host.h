@@ -34,6 +34,7 @@ struct swim_sim {
   void *d_sargs = nullptr; // scalar-call argument block (swim_scalar.cu)
   std::vector<swim_event_t> events; // pending, sorted by round (stable)
   std::string last_error;
+  int grids[5] = {0, 0, 0, 0, 0}; // one-wave grid sizes of the per-round kernels (filled on first use)
   uint64_t launches = 0;
   bool profile = false;
   std::vector<cudaEvent_t> prof_events; // pool, reused

@@ -394,9 +394,14 @@ static cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, const Sim
 template <int W>
 static int run_rounds(swim_sim *sim, uint32_t rounds) {
   SimDev &d = sim->dev;
-  const int grid = wave_grid(sim, tick_scan_kernel<W>, ((size_t)d.n + 128 * kScanGroups) / (128 * kScanGroups) + 1);
-  const int wgrid = wave_grid(sim, tick_work_kernel<W>, (size_t)d.n);
-  const int rgrid = wave_grid(sim, recv_kernel<W>, (size_t)d.n);
+  if (!sim->grids[0]) { // occupancy queries once per handle, not once per call
+    sim->grids[0] = wave_grid(sim, tick_scan_kernel<W>, ((size_t)d.n + 128 * kScanGroups) / (128 * kScanGroups) + 1);
+    sim->grids[1] = wave_grid(sim, tick_work_kernel<W>, (size_t)d.n);
+    sim->grids[2] = wave_grid(sim, recv_kernel<W>, (size_t)d.n);
+    sim->grids[3] = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
+    sim->grids[4] = wave_grid(sim, round_kernel<W>, (size_t)d.n);
+  }
+  const int grid = sim->grids[0], wgrid = sim->grids[1], rgrid = sim->grids[2];
   if (sim->tdead_dirty) {
     derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
     ++sim->launches;
@@ -430,7 +435,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   // Opt-in (SWIM_PIPELINE=1): bit-exact, but on B200 at C3 it measured no faster than the plain sequence
   // (every warp's own dependent-load chain is the critical path either way).
   const bool pipelined = !sim->profile && (d.world == 1 || d.p2p) && getenv("SWIM_PIPELINE") != nullptr;
-  const int fgrid = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
+  const int fgrid = sim->grids[3];
   // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
   // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
   // Sharded runs use the split sequence + peer_barrier_kernel: with every warp of a resident grid polling the
@@ -438,7 +443,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   // unless SWIM_ROUND_KERNEL=1 forces it.
   const bool single_kernel = !sim->profile && !pipelined && getenv("SWIM_SPLIT") == nullptr &&
                              (d.world == 1 || (d.p2p && getenv("SWIM_ROUND_KERNEL") != nullptr));
-  const int kgrid = wave_grid(sim, round_kernel<W>, (size_t)d.n);
+  const int kgrid = sim->grids[4];
   const bool multi_round_off = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
   bool pending = false; // K2 of the previous round has not run yet
   for (uint32_t r = 0; r < rounds; ++r) {
