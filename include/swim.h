@@ -379,6 +379,27 @@ int swim_envelope_encode(const swim_wire_message_t *msgs, size_t n, uint8_t *buf
 int swim_envelope_decode(const uint8_t *buf, size_t len, swim_wire_message_t *msgs,
                          size_t cap, size_t *n_out);
 
+/* ====================== simulated traffic as real datagrams ===========
+ * The piggyback envelopes of the LAST executed round, encoded exactly as the reference would put them
+ * on the wire (Types.hs:96-119,151-155): one datagram per (sender, receiver), a single message or a
+ * compound Envelope of the sender's buffered Suspect/Alive/Dead records. Simulated nodes have no
+ * names; on the wire node i is called "n<i>" (decimal), Alive carries addr = i and port = base_port.
+ * Host-side encoder (the codec above, one sender per OpenMP thread) over device snapshots; single
+ * shard only. Datagram k occupies buf[index[k].offset .. +index[k].length). */
+typedef struct swim_datagram {
+  uint32_t src, dst;   /* simulated sender and receiver */
+  uint32_t length;     /* bytes */
+  uint32_t n_messages; /* records in the envelope */
+  uint64_t offset;     /* into buf */
+} swim_datagram_t;
+int swim_sim_export_round(swim_sim_t *sim, uint8_t *buf, size_t cap, swim_datagram_t *index, size_t index_cap,
+                          size_t *n_datagrams, size_t *n_bytes);
+
+/* The reverse direction: decode one captured datagram (names "n<i>") addressed to `node` and queue its
+ * Suspect/Alive/Dead messages as SWIM_EV_INJECT events for `round` (Ping/IndirectPing/Ack carry no state
+ * and are skipped). A decode failure returns SWIM_EDECODE (Core.hs:86-87). */
+int swim_sim_inject_datagram(swim_sim_t *sim, uint32_t round, uint32_t node, const uint8_t *data, size_t len);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -48,6 +48,9 @@ def lib():
         L.oracle_outbox_count.argtypes = [vp, u32]
         L.oracle_outbox_read.argtypes = [vp, u32, vp]
         L.oracle_inbox_add.argtypes = [vp, vp, sz]
+        L.oracle_sent_count.restype = sz
+        L.oracle_sent_count.argtypes = [vp]
+        L.oracle_sent_read.argtypes = [vp, vp]
         L.oracle_array_bytes.restype = sz
         L.oracle_array_bytes.argtypes = [vp, C.c_int]
         L.oracle_get_array.argtypes = [vp, C.c_int, vp, sz]
@@ -137,6 +140,19 @@ class Oracle:
         if c:
             lib().oracle_outbox_read(self._h, dst_rank, buf.ctypes.data)
         return buf
+
+    def sent(self):
+        """Envelopes sent in the last round: [(src, dst, records)] with records as RECORD_DTYPE rows."""
+        c = lib().oracle_sent_count(self._h)
+        w = lib().oracle_env_words(self._h)
+        buf = np.zeros((c, w), dtype=np.uint32)
+        if c:
+            lib().oracle_sent_read(self._h, buf.ctypes.data)
+        out = []
+        for row in buf:
+            recs = row[4:4 + 4 * int(row[2])].copy().view(A.RECORD_DTYPE)
+            out.append((int(row[1]), int(row[0]), recs))
+        return out
 
     def inbox_add(self, words):
         words = np.ascontiguousarray(words, dtype=np.uint32)

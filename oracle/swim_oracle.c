@@ -525,6 +525,30 @@ EXPORT void oracle_inbox_add(oracle_t *o, const uint32_t *words, size_t count) {
   }
 }
 
+/* every envelope sent in the last round (local and cross-shard), ascending sender, recipient order as chosen:
+ * what the reference's `disseminate` would have put on the wire had it had its piggyback queue */
+EXPORT size_t oracle_sent_count(const oracle_t *o) {
+  size_t c = 0;
+  for (uint32_t l = 0; l < o->n; ++l)
+    if (o->out_cnt[l])
+      for (uint32_t f = 0; f <= o->k; ++f) c += o->send_to[(size_t)l * (1 + o->k) + f] != SWIM_NO_MEMBER;
+  return c;
+}
+EXPORT void oracle_sent_read(const oracle_t *o, uint32_t *words) {
+  size_t W = oracle_env_words(o), c = 0;
+  for (uint32_t l = 0; l < o->n; ++l) {
+    if (!o->out_cnt[l]) continue;
+    for (uint32_t f = 0; f <= o->k; ++f) {
+      uint32_t dst = o->send_to[(size_t)l * (1 + o->k) + f];
+      if (dst == SWIM_NO_MEMBER) continue;
+      uint32_t *w = words + c++ * W;
+      memset(w, 0, W * 4);
+      w[0] = dst; w[1] = o->first + l; w[2] = o->out_cnt[l];
+      memcpy(w + 4, o->out + (size_t)l * o->B, o->out_cnt[l] * sizeof(rec_t));
+    }
+  }
+}
+
 static int env_cmp(const void *a, const void *b) {
   const env_t *x = (const env_t *)a, *y = (const env_t *)b;
   if (x->dst != y->dst) return x->dst < y->dst ? -1 : 1;

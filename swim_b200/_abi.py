@@ -64,6 +64,11 @@ class Event(C.Structure):
                 ("msg", Message)]
 
 
+class Datagram(C.Structure):
+    _fields_ = [("src", C.c_uint32), ("dst", C.c_uint32), ("length", C.c_uint32), ("n_messages", C.c_uint32),
+                ("offset", C.c_uint64)]
+
+
 class WireMessage(C.Structure):
     _fields_ = [("kind", C.c_uint8), ("payload_len", C.c_uint8), ("port", C.c_uint16), ("seq_no", C.c_uint32),
                 ("target", C.c_uint32), ("incarnation", C.c_int64), ("payload", C.c_uint8 * ACK_PAYLOAD_MAX),

@@ -62,6 +62,8 @@ def lib():
     sig("swim_sim_launch_count", i, vp, P(u64))
     sig("swim_sim_set_profile", i, vp, i)
     sig("swim_sim_profile_ms", i, vp, vp, sz)
+    sig("swim_sim_export_round", i, vp, vp, sz, vp, sz, P(sz), P(sz))
+    sig("swim_sim_inject_datagram", i, vp, u32, u32, vp, sz)
     sig("swim_nccl_unique_id", i, vp)
     sig("swim_sim_connect", i, vp, vp)
     sig("swim_sim_ipc_export", i, vp, vp)

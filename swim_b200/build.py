@@ -12,7 +12,7 @@ OBJ = os.path.join(HERE, "csrc", "build")
 SO = os.path.join(HERE, "libswim_b200.so")
 INCLUDE = os.path.join(HERE, "..", "include")
 
-SOURCES = ["swim_sim.cu", "swim_scalar.cu", "swim_dist.cu", "swim_topology.cpp", "swim_codec.cpp"]
+SOURCES = ["swim_sim.cu", "swim_scalar.cu", "swim_dist.cu", "swim_export.cu", "swim_topology.cpp", "swim_codec.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden,-fopenmp,-Wall", "-I", INCLUDE]
 

@@ -279,7 +279,6 @@ void dist_teardown(swim_sim *sim) {
   if (!x) return;
   if (x->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(x->comm);
   if (x->h_matrix) cudaFreeHost(x->h_matrix);
-  if (sim->d_eslot) cudaFree(sim->d_eslot);
   delete x;
   sim->dist = nullptr;
 }

@@ -200,6 +200,7 @@ extern "C" void swim_sim_destroy(swim_sim_t *sim) {
   if (sim->d_in_src) cudaFree(sim->d_in_src);
   if (sim->d_eflag) cudaFree(sim->d_eflag);
   if (sim->d_events) cudaFree(sim->d_events);
+  if (sim->d_eslot) { cudaFree(sim->d_eslot); sim->d_eslot = nullptr; }
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   if (sim->h_bar_err) cudaFreeHost(sim->h_bar_err);
   if (sim->h_observe) cudaFreeHost(sim->h_observe);
@@ -225,7 +226,13 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
   // global in-degree, then per-shard exclusive offsets
   std::vector<uint32_t> deg((size_t)N + 1, 0);
   for (size_t x = 0, tot = (size_t)N * cap; x < tot; ++x)
-    if (nbr[x] != SWIM_NO_MEMBER) deg[nbr[x]]++;
+    if (nbr[x] != SWIM_NO_MEMBER) {
+      if (nbr[x] >= N) { // rows of other shards are not validated by swim_sim_set_view: keep the index build in bounds
+        set_error(sim, "view matrix entry %zu holds id %u >= N (%u)", x, nbr[x], N);
+        return SWIM_EINVAL;
+      }
+      deg[nbr[x]]++;
+    }
   std::vector<uint64_t> goff((size_t)N + 1);
   uint64_t acc = 0;
   for (uint32_t j = 0; j <= N; ++j) {

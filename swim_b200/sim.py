@@ -197,6 +197,27 @@ class Simulator:
               self._h)
         return out, dg.value, mm.value
 
+    def export_round(self):
+        """The last round's piggyback envelopes as real datagrams in the reference's wire format:
+        [(src, dst, bytes)] — node i is called "n<i>" on the wire (swim_sim_export_round)."""
+        nd, nb = C.c_size_t(), C.c_size_t()
+        rc = lib().swim_sim_export_round(self._h, None, 0, None, 0, C.byref(nd), C.byref(nb))
+        if rc not in (0, A.ECAP):
+            check(rc, "swim_sim_export_round", self._h)
+        if nd.value == 0:
+            return []
+        buf = (C.c_uint8 * max(1, nb.value))()
+        idx = (A.Datagram * nd.value)()
+        check(lib().swim_sim_export_round(self._h, buf, nb.value, idx, nd.value, C.byref(nd), C.byref(nb)),
+              "swim_sim_export_round", self._h)
+        raw = bytes(buf)
+        return [(d.src, d.dst, raw[d.offset:d.offset + d.length]) for d in idx]
+
+    def inject_datagram(self, round_, node, data: bytes):
+        """Queue a captured datagram (names "n<id>") for delivery to `node` at `round_`."""
+        buf = (C.c_uint8 * max(1, len(data))).from_buffer_copy(data if data else b"\0")
+        check(lib().swim_sim_inject_datagram(self._h, round_, node, buf, len(data)), "swim_sim_inject_datagram", self._h)
+
     def state(self):
         """All bulk arrays as a dict (the checkable form of dumpStore, Util.hs:64-74)."""
         return {A.ARRAY_NAMES[a]: self.get_array(a) for a in range(A.ARR_COUNT)}
