@@ -139,7 +139,7 @@ def cpu_arm(cfg_kw, nbr, events, n_nodes, steps, warmup):
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return None
     cfg_kw, nbr, events, n = workload(1)
     val, dt, threads, _ = cpu_arm(cfg_kw, nbr, events, n, args.steps, args.warmup)
     line = {
@@ -152,7 +152,7 @@ def run_reference(args):
                                    "(restated C oracle, OpenMP; the Haskell reference cannot be built here)"},
         "e2e": {"value": val, "unit": "node-rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    return line
 
 
 def config_dict(cfg_kw, n, n_gpus, exchange_mode="single"):
@@ -354,9 +354,27 @@ def run_cuda(args):
                                      "handful of launches, not 3K",
                 "roofline": roofline, "cpu_baseline": cpu, "convergence": conv,
                 "counters_timed_region": dict(zip(A.CTR_NAMES, [int(x) for x in ctr_delta]))}
-        print(json.dumps(line))
+    else:
+        line = None
     if world > 1:
         dist.destroy_process_group()
+    return line
+
+
+class StdoutToStderr:
+    """Everything third parties print on fd 1 during the run (e.g. NCCL's version banner) goes to stderr, so that
+    stdout carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -373,10 +391,10 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_cuda(args)
+    with StdoutToStderr():
+        line = run_reference(args) if args.impl == "reference" else run_cuda(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
