@@ -125,9 +125,9 @@ class ClockSampler:
 def cpu_arm(cfg_kw, nbr, events, n_nodes, steps, warmup):
     """The CPU arm: the restated oracle (oracle/swim_oracle.c, OpenMP over nodes) on the same config, with all the
     host threads this process may use (torchrun exports OMP_NUM_THREADS=1 to its workers: override it before the
-    oracle's OpenMP runtime starts; SWIM_CPU_THREADS pins a number)."""
-    os.environ["OMP_NUM_THREADS"] = os.environ.get("SWIM_CPU_THREADS", str(usable_cpus()))
-    from oracle.oracle import Oracle, num_threads
+    default through omp_set_num_threads; SWIM_CPU_THREADS pins a number)."""
+    from oracle.oracle import Oracle, num_threads, set_num_threads
+    set_num_threads(int(os.environ.get("SWIM_CPU_THREADS", usable_cpus())))
     from swim_b200.sim import default_config
     orc = Oracle(default_config(**cfg_kw))
     orc.set_view(nbr)

@@ -73,6 +73,7 @@ def lib():
         L.oracle_get_broadcasts.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
         L.oracle_philox.argtypes = [vp, vp, vp]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -260,3 +261,7 @@ def _copy(s):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))

@@ -872,6 +872,14 @@ EXPORT int oracle_handle_message(oracle_t *o, uint32_t node, uint32_t sender_add
   return SWIM_EINVAL;
 }
 
+EXPORT void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 EXPORT int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
