@@ -254,9 +254,9 @@ int swim_sim_get_array(swim_sim_t *sim, int arr, void *host_buf, size_t bytes);
 int swim_sim_set_array(swim_sim_t *sim, int arr, const void *host_buf, size_t bytes);
 int swim_sim_array_bytes(const swim_sim_t *sim, int arr, size_t *bytes);
 
-/* Order-independent 64-bit digest of this rank's state (sum over elements of a mixed
- * (array, global index, value) hash); the digests of all ranks add up (mod 2^64) to the
- * single-GPU digest. dumpStore's content (Util.hs:64-74) in checkable form. */
+/* Order-independent 64-bit digest of this rank's state (sum mod 2^64 of a mixed hash per node, per view
+ * slot and per buffered record, keyed by global indices: DESIGN.md 2.4); the digests of all ranks add up
+ * to the single-GPU digest. dumpStore's content (Util.hs:64-74) in checkable form. */
 int swim_sim_digest(swim_sim_t *sim, uint64_t *digest);
 
 /* Copy min(n, SWIM_CTR__COUNT) cumulative counters of this rank. */
