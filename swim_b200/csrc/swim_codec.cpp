@@ -57,10 +57,30 @@ void put_str(Out &o, const char *s, size_t n) {
 }
 void put_key(Out &o, const char *s) { put_str(o, s, strlen(s)); }
 
+// Names are Haskell `String`s carried as msgpack str = UTF-8 text (Types.hs:70,122-145): a byte string that is
+// not well-formed UTF-8 (overlong forms, surrogates, > U+10FFFF included) has no `String` and fails to decode.
+bool utf8_ok(const char *p, size_t n) {
+  const unsigned char *s = (const unsigned char *)p;
+  for (size_t i = 0; i < n;) {
+    const unsigned c = s[i];
+    size_t len; unsigned cp, lo;
+    if (c < 0x80) { ++i; continue; }
+    else if ((c & 0xE0) == 0xC0) { len = 2; cp = c & 0x1F; lo = 0x80; }
+    else if ((c & 0xF0) == 0xE0) { len = 3; cp = c & 0x0F; lo = 0x800; }
+    else if ((c & 0xF8) == 0xF0) { len = 4; cp = c & 0x07; lo = 0x10000; }
+    else return false;
+    if (i + len > n) return false;
+    for (size_t k = 1; k < len; ++k) { if ((s[i + k] & 0xC0) != 0x80) return false; cp = (cp << 6) | (s[i + k] & 0x3F); }
+    if (cp < lo || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+    i += len;
+  }
+  return true;
+}
+
 // Message body (Types.hs:151-152 `put = putLazyByteString . packAeson`)
 bool put_body(Out &o, const swim_wire_message_t &m) {
   const size_t nn = strnlen(m.node, SWIM_NAME_MAX + 1), nf = strnlen(m.dead_from, SWIM_NAME_MAX + 1);
-  if (nn > SWIM_NAME_MAX || nf > SWIM_NAME_MAX) return false;
+  if (nn > SWIM_NAME_MAX || nf > SWIM_NAME_MAX || !utf8_ok(m.node, nn) || !utf8_ok(m.dead_from, nf)) return false;
   switch (m.kind) {
     case SWIM_MSG_PING:
       o.u8(0x83); put_key(o, "tag"); put_key(o, "Ping");
@@ -211,7 +231,7 @@ bool get_body(const uint8_t *p, size_t len, swim_wire_message_t &m) {
   auto u32ok = [](int64_t v) { return v >= 0 && v <= 0xFFFFFFFFll; }; // Word32 fields
   auto u16ok = [](int64_t v) { return v >= 0 && v <= 0xFFFF; };       // Word16 fields
   auto name = [](char *dst, const std::string &s) {
-    if (s.size() > SWIM_NAME_MAX || memchr(s.data(), 0, s.size())) return false;
+    if (s.size() > SWIM_NAME_MAX || memchr(s.data(), 0, s.size()) || !utf8_ok(s.data(), s.size())) return false;
     memcpy(dst, s.data(), s.size());
     return true;
   };

@@ -128,3 +128,42 @@ def test_cross_check_with_python_msgpack_random():
             assert d.pop("tag") == type(m).__name__
             exp = {k: (list(v) if isinstance(v, tuple) else v) for k, v in m.__dict__.items()}
             assert d == exp
+
+
+def ping_with_raw_name(name: bytes) -> bytes:
+    n = len(name)
+    hdr = bytes([0xA0 | n]) if n < 32 else bytes([0xD9, n])
+    return bytes([0]) + b"\x83" + msgpack.packb("tag") + msgpack.packb("Ping") + msgpack.packb("seqNo") + b"\x01" \
+        + msgpack.packb("node") + hdr + name
+
+
+def test_names_must_be_utf8():
+    """A name is a Haskell `String` (Types.hs:70) carried as msgpack str: bytes that are not well-formed UTF-8 have
+    no String, so the datagram fails to parse — never a name the host side cannot represent."""
+    assert decode(ping_with_raw_name("nœud-é-東京-🜁".encode())) == Envelope((Ping(1, "nœud-é-東京-🜁"),))
+    for bad in (b"\x80", b"a\xc3", b"\xc0\x80", b"\xe0\x80\x80", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xf8\x88\x80\x80\x80",
+                b"\xff", b"ab\xe2\x82"):
+        with pytest.raises(SwimError) as e:
+            decode(ping_with_raw_name(bad))
+        assert e.value.code == A.EDECODE and "Could not parse" in str(e.value)
+
+
+def test_utf8_validation_agrees_with_python():
+    hyp = pytest.importorskip("hypothesis")
+    st = hyp.strategies
+    pieces = st.one_of(st.binary(min_size=1, max_size=4), st.text(min_size=1, max_size=2).map(str.encode),
+                       st.sampled_from([b"\xc0\xaf", b"\xed\xbf\xbf", b"\xf4\x8f\xbf\xbf", b"\xf0\x90\x80\x80", b"\xef\xbf\xbf"]))
+
+    @hyp.settings(max_examples=600, deadline=None)
+    @hyp.given(st.lists(pieces, max_size=6).map(b"".join).filter(lambda b: len(b) <= 200 and b"\0" not in b))
+    def check(raw):
+        try:
+            want = raw.decode("utf-8")
+        except UnicodeDecodeError:
+            want = None
+        try:
+            got = decode(ping_with_raw_name(raw)).unEnvelope[0].node
+        except SwimError:
+            got = None
+        assert got == want
+    check()
