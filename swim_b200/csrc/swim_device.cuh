@@ -902,6 +902,52 @@ __device__ __forceinline__ void grid_barrier(const SimDev &d) {
   __syncthreads();
 }
 
+// The same barrier for sharded runs with the fused exchange, placed between K1b and K2: it also synchronises the
+// GPUs, and only ONE thread per GPU talks to the peers. The last CTA to arrive — by then every CTA of this rank has
+// finished K1b and fenced its peer-memory stores — publishes the per-peer receiver counts and this rank's round word
+// into every peer's memory, waits until every peer's word for this round has landed here, and only then releases the
+// local grid. Everybody else spins on the local generation word, exactly as in grid_barrier.
+__device__ __forceinline__ void grid_peer_barrier(const SimDev &d, uint32_t mail_round) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile uint32_t *gen = d.gbar + 1;
+    const uint32_t g = *gen;
+    __threadfence_system(); // this CTA's stores into peer memory are performed before it reports arrival
+    if (atomicAdd(d.gbar, 1u) == gridDim.x - 1) {
+      for (uint32_t q = 0; q < d.world; ++q) {
+        if (q == d.rank) continue;
+        volatile uint32_t *cnt = d.rcnt_p[q] + (mail_round & 1) * d.world + d.rank;
+        *cnt = atomicExch(&d.xcnt[q], 0u);
+      }
+      __threadfence_system();
+      for (uint32_t q = 0; q < d.world; ++q) {
+        volatile uint32_t *theirs = d.bar_p[q] + d.rank;
+        *theirs = mail_round;
+      }
+      const long long t0 = clock64();
+      for (uint32_t q = 0; q < d.world; ++q) {
+        volatile uint32_t *mine = d.bar_p[d.rank] + q;
+        while ((int32_t)(*mine - mail_round) < 0) {
+          if (clock64() - t0 > kPeerWaitCycles) { *d.bar_err = 1; break; } // a peer stopped stepping
+          __nanosleep(100);
+        }
+      }
+      __threadfence_system(); // acquire: what the peers stored before their round word is visible from here on
+      d.gbar[0] = 0;
+      __threadfence();
+      atomicAdd(d.gbar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      while (*gen == g) {
+        if (clock64() - t0 > kPeerWaitCycles + 6000000000ll) { *d.bar_err = 2; break; }
+        __nanosleep(20);
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
 template <int W>
 __global__ void __launch_bounds__(kThreads, 4) round_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
@@ -924,8 +970,8 @@ __global__ void __launch_bounds__(kThreads, 4) round_kernel(SimDev d) {
     const uint32_t n_work = d.wl_cnt[ci(round)];
     if (n_work == 0 && d.world == 1) continue;                            // quiescent round: nothing was written
     if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c);       // K1b
-    grid_barrier(d);                                                      // every flag and snapshot is written
-    if (d.world > 1 && d.p2p) { peer_publish(d, round); peer_wait(d, round, lane); }
+    if (d.world > 1 && d.p2p) grid_peer_barrier(d, round);                // ... on every rank (one thread per GPU polls)
+    else grid_barrier(d);                                                 // every flag and snapshot is written
     recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);             // K2
     if (it + 1 < d.nrounds) grid_barrier(d);                              // views and buffers settled before the next scan
   }

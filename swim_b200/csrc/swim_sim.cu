@@ -445,11 +445,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   const int fgrid = sim->grids[3];
   // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
   // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
-  // Sharded runs use the split sequence + peer_barrier_kernel: with every warp of a resident grid polling the
-  // peers' flags, round_kernel measured far slower at 2 GPUs (136 ms/round against 39 us), so it is single-GPU only
-  // unless SWIM_ROUND_KERNEL=1 forces it.
-  const bool single_kernel = !sim->profile && !pipelined && getenv("SWIM_SPLIT") == nullptr &&
-                             (d.world == 1 || (d.p2p && getenv("SWIM_ROUND_KERNEL") != nullptr));
+  // Sharded runs with the fused exchange use the same kernel: its K1b/K2 barrier is grid_peer_barrier (the last CTA
+  // to arrive talks to the peers, one thread per GPU). [r2-prep: UNVALIDATED on hardware — an earlier form in which
+  // every warp polled the peers' flags measured 136 ms/round at 2 GPUs; SWIM_SPLIT=1 restores the three-launch path.]
+  const bool single_kernel = !sim->profile && !pipelined && getenv("SWIM_SPLIT") == nullptr && (d.world == 1 || d.p2p);
   const int kgrid = sim->grids[4];
   const bool multi_round_off = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
   bool pending = false; // K2 of the previous round has not run yet
@@ -469,7 +468,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     if (single_kernel) { // K1a + K1b + K2 in one launch (grid barriers inside), for every round up to the next event
       uint32_t nr = rounds - r;
       if (ev_pos < n_ev) nr = std::min<uint32_t>(nr, sim->events[ev_pos].round - d.round);
-      if (d.world > 1 || multi_round_off) nr = 1;
+      if (multi_round_off) nr = 1;
       d.nrounds = nr;
       CUDA_TRY(sim, launch_pdl(round_kernel<W>, kgrid, sim->stream, d));
       ++sim->launches;
