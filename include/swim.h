@@ -95,6 +95,16 @@ typedef struct swim_config {
 } swim_config_t;
 
 #define SWIM_F_NONE 0u
+/* Protocol variants. Off = the reference's rules as written / as completed in DESIGN.md §2.
+ * SWIM_F_STRICT_OVERRIDE: the SWIM paper's §4.2 override order instead of the guards of suspectOrDeadNode'
+ *   (Core.hs:151-152,182-184): Suspect(i) also overrides Suspect(j) for i > j (and re-arms the
+ *   countdown); Dead(i) ("Confirm") overrides Alive(j)/Suspect(j) for ANY i, j and keeps max(i, j).
+ * SWIM_F_ROUND_ROBIN: the "robust scheme" the reference asks for (`-- FIXME: move from random to robust scheme`,
+ *   Core.hs:232; SWIM paper §4.3): ping targets are taken in a per-node, per-epoch pseudo-random ORDER of the view
+ *   instead of uniformly at random, so every Alive member is probed at least once per view_cap rounds. */
+#define SWIM_F_STRICT_OVERRIDE 1u
+#define SWIM_F_ROUND_ROBIN 2u
+#define SWIM_F__ALL 3u
 
 /* ---- Member (Types.hs:62-68). name -> id; memberHost/memberHostNew -> (addr, port);
  * memberLastChange (UTCTime) -> the round at which the entry last changed. */

@@ -80,7 +80,7 @@ EXPORT void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 /* counter layout: (a, id, purpose, block); key = seed lo, hi. The target draw and the
  * direct-leg loss draw of node i are word (i & 3) of the block with id = i >> 2 (four nodes share a
  * block); proxy draws and indirect-leg loss draws use per-node blocks. */
-enum { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5 };
+enum { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6 };
 
 /* bounded draw: floor(x * L / 2^32) — `randomR (0, L-1)` of Util.hs:40 on our stream */
 static uint32_t bounded(uint32_t x, uint32_t L) { return (uint32_t)(((uint64_t)x * L) >> 32); }
@@ -140,6 +140,8 @@ EXPORT oracle_t *oracle_create(const swim_config_t *cfg) {
   if (cfg->pb_cap < 1 || cfg->pb_cap > SWIM_MAX_PB) return NULL;
   if (cfg->suspicion_rounds < 1 || cfg->suspicion_rounds > SWIM_MAX_TIMER) return NULL;
   if (cfg->retransmit < 1 || cfg->retransmit > 255 || cfg->loss_ppm > 1000000u) return NULL;
+  if (cfg->flags & ~SWIM_F__ALL) return NULL;
+  if ((cfg->flags & SWIM_F_ROUND_ROBIN) && (cfg->view_cap & (cfg->view_cap - 1))) return NULL; /* xor order */
   oracle_t *o = (oracle_t *)calloc(1, sizeof *o);
   o->cfg = *cfg;
   o->N = cfg->n_nodes; o->cap = cfg->view_cap; o->k = cfg->k_indirect; o->fanout = cfg->fanout;
@@ -229,12 +231,14 @@ static int apply_record(oracle_t *o, uint32_t l, rec_t r, int allow_insert, rec_
   uint8_t *tm = o->timer + (size_t)l * o->cap;
   uint32_t *inc = o->vinc + (size_t)l * o->cap;
   uint32_t *last = o->vlast + (size_t)l * o->cap;
+  const int strict = (o->cfg.flags & SWIM_F_STRICT_OVERRIDE) != 0;
   if (err) *err = 0;
   if (r.member == self) {
     /* own entry is virtual (Alive, storeIncarnation) */
     if (r.kind == SWIM_MSG_ALIVE) return 0; /* our own refutation coming back */
-    /* Core.hs:151: `i < memberIncarnation m || livenessCheck m` -> ignore (self is Alive) */
-    if (r.incarnation < o->self_inc[l]) return 0;
+    /* Core.hs:151: `i < memberIncarnation m || livenessCheck m` -> ignore (self is Alive).
+     * STRICT_OVERRIDE: a Confirm overrides whatever the others hold, so even a stale one must be refuted. */
+    if (r.incarnation < o->self_inc[l] && !(strict && r.kind == SWIM_MSG_DEAD)) return 0;
     /* Core.hs:155-166 refute; [Q9] terminating nextIncarnation' */
     uint32_t base = o->self_inc[l] > r.incarnation ? o->self_inc[l] : r.incarnation;
     o->self_inc[l] = base + 1;
@@ -261,6 +265,32 @@ static int apply_record(oracle_t *o, uint32_t l, rec_t r, int allow_insert, rec_
     ids[pos] = r.member; st[pos] = SWIM_ALIVE; tm[pos] = 0; inc[pos] = r.incarnation; last[pos] = o->round;
     *rb = r;
     return 1;
+  }
+  if (strict) {
+    /* SWIM paper §4.2 (SWIM_F_STRICT_OVERRIDE):
+     *   {Suspect Mj, i} overrides {Suspect Mj, j} i > j and {Alive Mj, j} i >= j
+     *   {Confirm Mj, i} overrides {Alive Mj, j} and {Suspect Mj, j}, any i and j
+     *   {Alive Mj, i}   overrides {Suspect Mj, j} and {Alive Mj, j}, i > j (and Dead, so that a rejoin is seen: [Q7]) */
+    switch (r.kind) {
+      case SWIM_MSG_SUSPECT:
+        if (st[s] == SWIM_DEAD) return 0;
+        if (st[s] == SWIM_ALIVE ? r.incarnation < inc[s] : r.incarnation <= inc[s]) return 0;
+        inc[s] = r.incarnation; st[s] = SWIM_SUSPECT; tm[s] = (uint8_t)o->S; last[s] = o->round;
+        *rb = r;
+        return 1;
+      case SWIM_MSG_DEAD:
+        if (st[s] == SWIM_DEAD) return 0;
+        if (r.incarnation > inc[s]) inc[s] = r.incarnation; /* keeps max(i, j) */
+        st[s] = SWIM_DEAD; tm[s] = 0; last[s] = o->round;
+        *rb = r;
+        return 1;
+      case SWIM_MSG_ALIVE:
+        if (r.incarnation <= inc[s]) return 0;
+        inc[s] = r.incarnation; st[s] = SWIM_ALIVE; tm[s] = 0; last[s] = o->round;
+        *rb = r;
+        return 1;
+    }
+    return 0;
   }
   switch (r.kind) {
     case SWIM_MSG_SUSPECT:
@@ -342,8 +372,23 @@ static void tick_node(oracle_t *o, uint32_t l, uint64_t *ctr) {
   draws[0] = grp[self & 3];
   draws_for(o, o->round, self, P_PROXY, o->k, draws + 1);
   uint32_t t, prox[SWIM_MAX_K], tmp[SWIM_MAX_VIEW];
-  memcpy(tmp, cand, L * 4);
-  shuffle_take(tmp, L, 1, draws, &t);
+  if (o->cfg.flags & SWIM_F_ROUND_ROBIN) {
+    /* `-- FIXME: move from random to robust scheme` (Core.hs:232), SWIM paper §4.3. Rounds are grouped in epochs of
+     * `cap` rounds; within epoch e node i walks its view in the order  slot(p) = p xor b,  p = (round + r) mod cap,
+     * (b, r) drawn once per (epoch, node); the target is the first Alive slot at or after p in that order (cyclic).
+     * Every slot position comes up exactly once per epoch, so an Alive member waits < 2 cap rounds for a probe. */
+    draws_for(o, o->round / o->cap, self >> 2, P_RR, 4, grp);
+    const uint32_t word = grp[self & 3], b = word & (o->cap - 1), r = (word >> 16) & (o->cap - 1);
+    const uint32_t p = (o->round + r) & (o->cap - 1);
+    t = SWIM_NO_MEMBER;
+    for (uint32_t x = 0; x < o->cap && t == SWIM_NO_MEMBER; ++x) {
+      const uint32_t slot = ((p + x) & (o->cap - 1)) ^ b;
+      if (st[slot] == SWIM_ALIVE) t = slot;
+    }
+  } else {
+    memcpy(tmp, cand, L * 4);
+    shuffle_take(tmp, L, 1, draws, &t);
+  }
   memcpy(tmp, cand, L * 4); /* a fresh shuffle: target and self are not excluded (Core.hs:249) */
   uint32_t np = shuffle_take(tmp, L, o->k, draws + 1, prox);
 

@@ -19,6 +19,7 @@ NCCL_ID_BYTES = 128
 IPC_BLOB_BYTES = 512
 
 EV_CRASH, EV_REJOIN, EV_INJECT = 0, 1, 2
+F_NONE, F_STRICT_OVERRIDE, F_ROUND_ROBIN = 0, 1, 2  # SWIM_F_*: protocol variants
 TOPO_COMPLETE, TOPO_RANDOM, TOPO_RING = 0, 1, 2
 
 (ARR_ALIVE, ARR_SELF_INC, ARR_SEQNO, ARR_NBR, ARR_VST, ARR_VINC, ARR_VLAST, ARR_PB, ARR_PB_CNT) = range(9)

@@ -39,11 +39,12 @@ constexpr long long kPeerWaitCycles = 120000000000ll; // ~60 s at 2 GHz, then th
 
 // Philox counter purposes. TARGET and LOSS0 blocks are shared by the four nodes
 // 4g..4g+3 (counter word 1 = node >> 2, draw = word node & 3): one Philox call serves four probes.
-enum : uint32_t { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5 };
+enum : uint32_t { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6 };
 
 struct SimDev {
   uint32_t N, first, n, cap;
   uint32_t k, fanout, B, S, T, loss_ppm;
+  uint32_t flags;            // SWIM_F_* protocol variants
   uint32_t key0, key1;
   uint32_t round;
   uint32_t nrounds;          // round_kernel: consecutive rounds in this launch (>= 1)
@@ -111,31 +112,47 @@ struct SimDev {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ------------------------------------------------------------------ pure integer helpers
+// Philox and the slot-selection arithmetic are host+device so that tests/device_helpers_harness.cu can run the very
+// same functions on the CPU (no GPU in the build container) against the oracle's independent statements.
+#ifdef __CUDA_ARCH__
+#define SWIM_UMULHI(a, b) __umulhi((a), (b))
+#define SWIM_POPC(x) __popc(x)
+#define SWIM_FFS(x) __ffs(x)
+#define SWIM_ROTR(x, n) __funnelshift_r((x), (x), (n))
+#else
+#define SWIM_UMULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
+#define SWIM_POPC(x) __builtin_popcount(x)
+#define SWIM_FFS(x) __builtin_ffs((int)(x))
+#define SWIM_ROTR(x, n) (((n) & 31u) ? (((x) >> ((n) & 31u)) | ((x) << (32u - ((n) & 31u)))) : (x))
+#endif
+#define SWIM_HD __host__ __device__ __forceinline__
+
 // ------------------------------------------------------------------ Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+SWIM_HD uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    uint32_t hi0 = SWIM_UMULHI(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = SWIM_UMULHI(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
   return c;
 }
-__device__ __forceinline__ uint32_t word_of(uint4 v, int i) {
+SWIM_HD uint32_t word_of(uint4 v, int i) {
   return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
 }
 // randomR (0, L-1) (Util.hs:40) on the Philox stream
-__device__ __forceinline__ uint32_t bounded(uint32_t x, uint32_t L) { return __umulhi(x, L); }
+SWIM_HD uint32_t bounded(uint32_t x, uint32_t L) { return SWIM_UMULHI(x, L); }
 
 // position of the r-th (0-based) set bit of m; requires r < popc(m)
-__device__ __forceinline__ uint32_t nth_set(uint32_t m, uint32_t r) {
+SWIM_HD uint32_t nth_set(uint32_t m, uint32_t r) {
   uint32_t pos = 0, c;
-  c = __popc(m & 0xFFFFu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
-  c = __popc(m & 0xFFu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
-  c = __popc(m & 0xFu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
-  c = __popc(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
+  c = SWIM_POPC(m & 0xFFFFu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
+  c = SWIM_POPC(m & 0xFFu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
+  c = SWIM_POPC(m & 0xFu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
+  c = SWIM_POPC(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
   if (r >= (m & 1u)) pos += 1;
   return pos;
 }
@@ -143,10 +160,10 @@ __device__ __forceinline__ uint32_t nth_set(uint32_t m, uint32_t r) {
 // `shuffle` (Util.hs:36-42) on a W-word bitmask of candidate slots: pick the r-th remaining
 // candidate in ascending slot order and remove it (order preserved by construction).
 template <int W>
-__device__ __forceinline__ uint32_t pick_remove(uint32_t (&m)[W], uint32_t r) {
+SWIM_HD uint32_t pick_remove(uint32_t (&m)[W], uint32_t r) {
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    uint32_t c = __popc(m[w]);
+    uint32_t c = SWIM_POPC(m[w]);
     if (r < c) {
       uint32_t b = nth_set(m[w], r);
       m[w] &= ~(1u << b);
@@ -155,6 +172,55 @@ __device__ __forceinline__ uint32_t pick_remove(uint32_t (&m)[W], uint32_t r) {
     r -= c;
   }
   return 0; // unreachable when r < total
+}
+
+// ---- SWIM_F_ROUND_ROBIN (`-- FIXME: move from random to robust scheme`, Core.hs:232; SWIM paper 4.3) ----------------
+// Rounds are grouped in epochs of cap = 32 W rounds; in epoch e a node walks its view in the order slot(p) = p xor b,
+// p = (round + r) mod cap, with (b, r) drawn once per (epoch, node); the target is the first Alive slot at or after p in
+// that order (cyclic). Stateless — nothing to store or write back — and every position comes up once per epoch.
+// bit i of the result = bit (i xor b) of m (b < 32): five conditional butterfly stages
+SWIM_HD uint32_t xor_permute(uint32_t m, uint32_t b) {
+  if (b & 1u)  m = ((m & 0x55555555u) << 1) | ((m >> 1) & 0x55555555u);
+  if (b & 2u)  m = ((m & 0x33333333u) << 2) | ((m >> 2) & 0x33333333u);
+  if (b & 4u)  m = ((m & 0x0F0F0F0Fu) << 4) | ((m >> 4) & 0x0F0F0F0Fu);
+  if (b & 8u)  m = ((m & 0x00FF00FFu) << 8) | ((m >> 8) & 0x00FF00FFu);
+  if (b & 16u) m = (m << 16) | (m >> 16);
+  return m;
+}
+
+// requires at least one bit set in am[]
+template <int W>
+SWIM_HD uint32_t rr_pick(const uint32_t (&am)[W], uint32_t word, uint32_t round) {
+  constexpr uint32_t capm = 32u * W - 1u;
+  const uint32_t b = word & capm, r = (word >> 16) & capm, p = (round + r) & capm;
+  if constexpr (W == 1) {
+    const uint32_t pm = xor_permute(am[0], b);
+    const uint32_t x = SWIM_ROTR(pm, p); // rotate position p to bit 0
+    return ((p + (uint32_t)SWIM_FFS(x) - 1u) & 31u) ^ b;
+  } else {
+    uint32_t pm[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      uint32_t src = 0;
+#pragma unroll
+      for (int v = 0; v < W; ++v)
+        if ((uint32_t)v == ((uint32_t)w ^ (b >> 5))) src = am[v];
+      pm[w] = xor_permute(src, b & 31u);
+    }
+    const uint32_t pw = p >> 5, po = p & 31u;
+#pragma unroll
+    for (int t = 0; t <= W; ++t) {
+      const uint32_t w = (pw + t) & (W - 1);
+      uint32_t m = 0;
+#pragma unroll
+      for (int v = 0; v < W; ++v)
+        if ((uint32_t)v == w) m = pm[v];
+      if (t == 0) m &= ~0u << po;
+      if (t == W) m &= (1u << po) - 1u;
+      if (m) return (w * 32u + (uint32_t)SWIM_FFS(m) - 1u) ^ b;
+    }
+    return 0; // unreachable when a bit is set
+  }
 }
 
 // ------------------------------------------------------------------ records
@@ -274,7 +340,8 @@ __device__ __forceinline__ int row_apply(Row<W> &r, const SimDev &d, uint32_t se
   if (rec.x == self) {
     // own entry is virtual: (Alive, storeIncarnation)
     if (kind == SWIM_MSG_ALIVE) return 0;
-    if (rec.y < self_inc) return 0;                 // Core.hs:151 stale incarnation
+    // Core.hs:151 stale incarnation; STRICT_OVERRIDE: a Confirm overrides whatever the others hold -> always refuted
+    if (rec.y < self_inc && !((d.flags & SWIM_F_STRICT_OVERRIDE) && kind == SWIM_MSG_DEAD)) return 0;
     uint32_t base = self_inc > rec.y ? self_inc : rec.y;
     self_inc = base + 1;                            // Core.hs:155-166; [Q9] terminating bump
     if (lane == 0) ++refutes;
@@ -296,8 +363,20 @@ __device__ __forceinline__ int row_apply(Row<W> &r, const SimDev &d, uint32_t se
     if (w == hw) { st_s = a; inc_s = b; }
   }
   const uint32_t live = st_s & 3u;
-  uint32_t nst;
-  if (kind == SWIM_MSG_SUSPECT) {
+  uint32_t nst, ninc = rec.y;
+  if (d.flags & SWIM_F_STRICT_OVERRIDE) { // SWIM paper 4.2 instead of the reference's guards (include/swim.h)
+    if (kind == SWIM_MSG_SUSPECT) {
+      if (live == SWIM_DEAD || (live == SWIM_ALIVE ? rec.y < inc_s : rec.y <= inc_s)) return 0;
+      nst = SWIM_SUSPECT | (d.S << 2);
+    } else if (kind == SWIM_MSG_DEAD) {
+      if (live == SWIM_DEAD) return 0;
+      ninc = rec.y > inc_s ? rec.y : inc_s;
+      nst = SWIM_DEAD;
+    } else {
+      if (rec.y <= inc_s) return 0;
+      nst = SWIM_ALIVE;
+    }
+  } else if (kind == SWIM_MSG_SUSPECT) {
     if (rec.y < inc_s || live != SWIM_ALIVE) return 0; // Core.hs:151,183
     nst = SWIM_SUSPECT | (d.S << 2);                   // [Q8] arm the countdown
   } else if (kind == SWIM_MSG_DEAD) {
@@ -310,7 +389,7 @@ __device__ __forceinline__ int row_apply(Row<W> &r, const SimDev &d, uint32_t se
   if (lane == hl) {
 #pragma unroll
     for (int w = 0; w < W; ++w)
-      if (w == hw) { r.st[w] = nst; r.inc[w] = rec.y; r.touched |= 1u << w; } // Core.hs:171-177
+      if (w == hw) { r.st[w] = nst; r.inc[w] = ninc; r.touched |= 1u << w; } // Core.hs:171-177
   }
   rb = rec; // Core.hs:179 `return $ Just msg`: the identical message (deadFrom intact)
   return 1;
@@ -370,18 +449,31 @@ __device__ __forceinline__ uint32_t stamp_of(uint32_t round) { return round % 65
 __device__ __forceinline__ uint32_t ci(uint32_t round) { return round % 3u; }                 // counter slot
 __device__ __forceinline__ uint16_t *stamp_ptr(uint4 *meta) { return reinterpret_cast<uint16_t *>(meta) + 7; }
 
+// The Philox block holding the target draws of the four nodes 4g..4g+3, and the pick itself (random: kRandomMembers
+// store 1 [], Core.hs:239 over shuffle, Util.hs:36-42; round-robin: see rr_pick). `am` is consumed.
+template <int W>
+__device__ __forceinline__ uint4 target_block(const SimDev &d, uint32_t round, uint32_t g) {
+  if (d.flags & SWIM_F_ROUND_ROBIN) return philox4x32_10(make_uint4(round / (32u * W), g, P_RR, 0), d.key0, d.key1);
+  return philox4x32_10(make_uint4(round, g, P_TARGET, 0), d.key0, d.key1);
+}
+template <int W>
+__device__ __forceinline__ uint32_t pick_target(const SimDev &d, uint32_t (&am)[W], uint32_t word, uint32_t L, uint32_t round) {
+  if (d.flags & SWIM_F_ROUND_ROBIN) return rr_pick<W>(am, word, round);
+  return pick_remove<W>(am, bounded(word, L));
+}
+
 // One node's tick decision from its meta words (what K1a does per node): counts the Ping and tells
 // whether the node needs K1b. Shared by the scan and by K1b's re-scan of last round's receivers.
 template <int W>
 __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags, uint32_t (&am)[W], const uint32_t (&td)[W],
-                                                uint32_t sus, uint32_t tdraw, uint32_t ldraw, uint32_t &pings) {
+                                                uint32_t sus, uint32_t tdraw, uint32_t ldraw, uint32_t round, uint32_t &pings) {
   if ((flags & 0xFFu) == 0) return false;              // a crashed process does nothing
   bool need = (flags & 0xFF00u) != 0 || sus != 0;       // piggyback to send, or a countdown to run [Q8]
   uint32_t L = 0;
 #pragma unroll
   for (int w = 0; w < W; ++w) L += __popc(am[w]);
   if (L) {
-    const uint32_t tslot = pick_remove<W>(am, bounded(tdraw, L)); // kRandomMembers store 1 [] (Core.hs:239)
+    const uint32_t tslot = pick_target<W>(d, am, tdraw, L, round); // kRandomMembers store 1 [] (Core.hs:239)
     ++pings;                                                       // Ping (Core.hs:246)
     bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;       // Ack iff the target process is up
     if (acked && d.loss_ppm) acked = !(bounded(ldraw, 1000000u) < d.loss_ppm);
@@ -420,7 +512,7 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
     for (int u = 0; u < U; ++u) {
       const uint32_t g = gb + u * 32 + lane;
       if ((valid >> (u * 4) & 0xFu) == 0) continue;
-      const uint4 x = philox4x32_10(make_uint4(round, g, P_TARGET, 0), d.key0, d.key1);
+      const uint4 x = target_block<W>(d, round, g);
       uint4 y = make_uint4(0, 0, 0, 0);
       if (d.loss_ppm) y = philox4x32_10(make_uint4(round, g, P_LOSS0, 0), d.key0, d.key1);
 #pragma unroll
@@ -437,7 +529,7 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
             am[w] = mw.x; sus |= mw.y; td[w] = mw.z;
           }
         }
-        const bool need = node_needs_work<W>(d, m[u][j].w, am, td, sus, word_of(x, j), word_of(y, j), pings);
+        const bool need = node_needs_work<W>(d, m[u][j].w, am, td, sus, word_of(x, j), word_of(y, j), round, pings);
         work |= (uint32_t)need << (u * 4 + j);
       }
     }
@@ -530,11 +622,11 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
       // retire last round's mail stamp — unless a sender of THIS round has already re-stamped the node
       if (lane == 0) atomicCAS(reinterpret_cast<unsigned short *>(stamp_ptr(d.meta + (size_t)ln * W)), (unsigned short)stamp_of(round - 1), (unsigned short)0);
       const uint32_t self = d.first + ln;
-      const uint4 x = philox4x32_10(make_uint4(round, self >> 2, P_TARGET, 0), d.key0, d.key1);
+      const uint4 x = target_block<W>(d, round, self >> 2);
       uint4 y = make_uint4(0, 0, 0, 0);
       if (d.loss_ppm) y = philox4x32_10(make_uint4(round, self >> 2, P_LOSS0, 0), d.key0, d.key1);
       uint32_t pings = 0;
-      const bool need = node_needs_work<W>(d, flags, am, td, sus, word_of(x, self & 3), word_of(y, self & 3), pings);
+      const bool need = node_needs_work<W>(d, flags, am, td, sus, word_of(x, self & 3), word_of(y, self & 3), round, pings);
       if (lane == 0) c.v[SWIM_CTR_PINGS] += pings;
       if (!need) continue;
       uint32_t k = 0;
@@ -571,11 +663,11 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
     if (L) {
       // target: the node's TARGET draw; proxies: kRandomMembers store k [] (Core.hs:249), a fresh shuffle
       // over the same alive list (neither self nor the target excluded), draws of the PROXY stream
-      uint4 blk = philox4x32_10(make_uint4(round, self >> 2, P_TARGET, 0), d.key0, d.key1);
+      uint4 blk = target_block<W>(d, round, self >> 2);
       uint32_t tmp[W];
 #pragma unroll
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
-      tslot = pick_remove<W>(tmp, bounded(word_of(blk, self & 3), L));
+      tslot = pick_target<W>(d, tmp, word_of(blk, self & 3), L, round);
 #pragma unroll
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
       np = d.k < L ? d.k : L;

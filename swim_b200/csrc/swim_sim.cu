@@ -87,6 +87,7 @@ static int validate(const swim_config_t *c) {
   if (c->pb_cap < 1 || c->pb_cap > SWIM_MAX_PB) return SWIM_EINVAL;
   if (c->suspicion_rounds < 1 || c->suspicion_rounds > SWIM_MAX_TIMER) return SWIM_EINVAL;
   if (c->retransmit < 1 || c->retransmit > 255 || c->loss_ppm > 1000000u) return SWIM_EINVAL;
+  if (c->flags & ~SWIM_F__ALL) return SWIM_EINVAL;
   return SWIM_OK;
 }
 
@@ -133,6 +134,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   memset(&d, 0, sizeof d);
   d.N = cfg->n_nodes; d.cap = cfg->view_cap; d.k = cfg->k_indirect; d.fanout = cfg->fanout;
   d.B = cfg->pb_cap; d.S = cfg->suspicion_rounds; d.T = cfg->retransmit; d.loss_ppm = cfg->loss_ppm;
+  d.flags = cfg->flags;
   d.key0 = (uint32_t)cfg->seed; d.key1 = (uint32_t)(cfg->seed >> 32);
   d.world = cfg->world; d.rank = cfg->rank;
   d.per = (uint32_t)(((uint64_t)d.N + d.world - 1) / d.world);
