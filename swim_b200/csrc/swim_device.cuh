@@ -111,31 +111,43 @@ struct SimDev {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ------------------------------------------------------------------ pure integer helpers
+// Philox and the slot-selection arithmetic are host+device so that tests/device_helpers_harness.cu can run the very
+// same functions on the CPU (no GPU in the build container) against the oracle's independent statements.
+#ifdef __CUDA_ARCH__
+#define SWIM_UMULHI(a, b) __umulhi((a), (b))
+#define SWIM_POPC(x) __popc(x)
+#else
+#define SWIM_UMULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
+#define SWIM_POPC(x) __builtin_popcount(x)
+#endif
+#define SWIM_HD __host__ __device__ __forceinline__
+
 // ------------------------------------------------------------------ Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+SWIM_HD uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    uint32_t hi0 = SWIM_UMULHI(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = SWIM_UMULHI(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
     c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
   return c;
 }
-__device__ __forceinline__ uint32_t word_of(uint4 v, int i) {
+SWIM_HD uint32_t word_of(uint4 v, int i) {
   return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
 }
 // randomR (0, L-1) (Util.hs:40) on the Philox stream
-__device__ __forceinline__ uint32_t bounded(uint32_t x, uint32_t L) { return __umulhi(x, L); }
+SWIM_HD uint32_t bounded(uint32_t x, uint32_t L) { return SWIM_UMULHI(x, L); }
 
 // position of the r-th (0-based) set bit of m; requires r < popc(m)
-__device__ __forceinline__ uint32_t nth_set(uint32_t m, uint32_t r) {
+SWIM_HD uint32_t nth_set(uint32_t m, uint32_t r) {
   uint32_t pos = 0, c;
-  c = __popc(m & 0xFFFFu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
-  c = __popc(m & 0xFFu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
-  c = __popc(m & 0xFu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
-  c = __popc(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
+  c = SWIM_POPC(m & 0xFFFFu); if (r >= c) { r -= c; pos += 16; m >>= 16; }
+  c = SWIM_POPC(m & 0xFFu);   if (r >= c) { r -= c; pos += 8;  m >>= 8; }
+  c = SWIM_POPC(m & 0xFu);    if (r >= c) { r -= c; pos += 4;  m >>= 4; }
+  c = SWIM_POPC(m & 0x3u);    if (r >= c) { r -= c; pos += 2;  m >>= 2; }
   if (r >= (m & 1u)) pos += 1;
   return pos;
 }
@@ -143,10 +155,10 @@ __device__ __forceinline__ uint32_t nth_set(uint32_t m, uint32_t r) {
 // `shuffle` (Util.hs:36-42) on a W-word bitmask of candidate slots: pick the r-th remaining
 // candidate in ascending slot order and remove it (order preserved by construction).
 template <int W>
-__device__ __forceinline__ uint32_t pick_remove(uint32_t (&m)[W], uint32_t r) {
+SWIM_HD uint32_t pick_remove(uint32_t (&m)[W], uint32_t r) {
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    uint32_t c = __popc(m[w]);
+    uint32_t c = SWIM_POPC(m[w]);
     if (r < c) {
       uint32_t b = nth_set(m[w], r);
       m[w] &= ~(1u << b);
