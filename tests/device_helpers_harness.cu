@@ -24,6 +24,7 @@ void h_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
   uint4 r = philox4x32_10(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), key[0], key[1]);
   out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
+uint32_t h_bounded(uint32_t x, uint32_t L) { return bounded(x, L); }
 uint32_t h_nth_set(uint32_t m, uint32_t r) { return nth_set(m, r); }
 uint32_t h_xor_permute(uint32_t m, uint32_t b) { return xor_permute(m, b); }
 

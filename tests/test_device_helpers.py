@@ -4,6 +4,7 @@ and this file checks it against the oracle's Philox and against plain-Python sta
 No GPU needed (nvcc compiles the host side)."""
 import ctypes as C
 import os
+import shutil
 import subprocess
 
 import numpy as np
@@ -16,14 +17,16 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.fixture(scope="module")
 def dh(tmp_path_factory):
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
     so = tmp_path_factory.mktemp("dh") / "libdevice_helpers.so"
     r = subprocess.run(["nvcc", "-O1", "-std=c++17", "-arch=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", str(so),
                         os.path.join(HERE, "device_helpers_harness.cu")], capture_output=True, text=True)
     if r.returncode != 0:
         pytest.fail("host build of the device helpers failed:\n" + r.stderr[-2000:])
     L = C.CDLL(str(so))
-    L.h_nth_set.restype = L.h_xor_permute.restype = L.h_pick_remove.restype = L.h_rr_pick.restype = C.c_uint32
-    L.h_nth_set.argtypes = L.h_xor_permute.argtypes = [C.c_uint32, C.c_uint32]
+    L.h_nth_set.restype = L.h_xor_permute.restype = L.h_pick_remove.restype = L.h_rr_pick.restype = L.h_bounded.restype = C.c_uint32
+    L.h_nth_set.argtypes = L.h_xor_permute.argtypes = L.h_bounded.argtypes = [C.c_uint32, C.c_uint32]
     L.h_pick_remove.argtypes = [C.c_int, C.c_void_p, C.c_uint32]
     L.h_rr_pick.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32]
     L.h_philox.argtypes = [C.c_void_p] * 3
@@ -42,6 +45,14 @@ def test_philox_matches_oracle_and_random123(dh):
     c, k, o = (C.c_uint32 * 4)(0, 0, 0, 0), (C.c_uint32 * 2)(0, 0), (C.c_uint32 * 4)()
     dh.h_philox(c, k, o)
     assert list(o) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]  # Random123 known answer
+
+
+def test_bounded_draw(dh):  # randomR (0, L-1) (Util.hs:40) as mulhi(x, L)
+    rng = np.random.default_rng(4)
+    for _ in range(2000):
+        x, L = int(rng.integers(0, 2 ** 32)), int(rng.integers(1, 300))
+        got = dh.h_bounded(x, L)
+        assert got == (x * L) >> 32 and 0 <= got < L
 
 
 def bits(words):
