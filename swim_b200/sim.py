@@ -189,13 +189,14 @@ class Simulator:
         check(lib().swim_sim_profile_ms(self._h, out, 6), "swim_sim_profile_ms", self._h)
         return dict(zip(["events", "tick_scan", "exchange", "recv", "tick_work", "rounds"], list(out)))
 
-    def observe(self):
-        """(counters, digest, mismatches) with one device synchronisation."""
+    def observe(self, digest=True, mismatches=True):
+        """(counters, digest, mismatches) with one device synchronisation; a part that is switched off is not
+        computed (its kernel is not launched) and comes back as None."""
         out = np.zeros(A.CTR_COUNT, dtype=np.uint64)
         dg, mm = C.c_uint64(), C.c_uint64()
-        check(lib().swim_sim_observe(self._h, out.ctypes.data, A.CTR_COUNT, C.byref(dg), C.byref(mm)), "swim_sim_observe",
-              self._h)
-        return out, dg.value, mm.value
+        check(lib().swim_sim_observe(self._h, out.ctypes.data, A.CTR_COUNT, C.byref(dg) if digest else None,
+                                     C.byref(mm) if mismatches else None), "swim_sim_observe", self._h)
+        return out, dg.value if digest else None, mm.value if mismatches else None
 
     def export_round(self):
         """The last round's piggyback envelopes as real datagrams in the reference's wire format:
