@@ -1220,17 +1220,26 @@ static __global__ void __launch_bounds__(kThreads) digest_kernel(SimDev d, unsig
 // Convergence detector: view entries of live observers that disagree with the truth. Uses the
 // crashed-member bitmap of the meta record (current: the host rebuilds it first when it is dirty),
 // so a slot costs one state byte and a shared 16-byte record instead of two gathers.
+// Convergence count from the per-node meta records alone (16 B per node; the kernels keep them in step with the rows):
+// a view entry of a live observer is wrong when the member is down and the entry is not Dead, or the member is up and
+// the entry is not Alive. Only entries that are neither Alive nor Suspect of members that are up need the state byte
+// (Dead is wrong, vacant is not counted) — none on a full row in steady state.
 static __global__ void __launch_bounds__(kThreads) mismatch_kernel(SimDev d, unsigned long long *out) {
-  const size_t total = (size_t)d.n * d.cap;
   const uint32_t W = d.cap >> 5;
   uint32_t bad = 0;
-  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x) {
-    const uint32_t l = (uint32_t)(x / d.cap), s = (uint32_t)(x % d.cap);
-    const uint32_t st = d.vst[x] & 3u;
-    const uint4 m = d.meta[(size_t)l * W + (s >> 5)];
-    const uint32_t up = W == 1 ? m.w & 0xFFu : d.meta[(size_t)l * W].w & 0xFFu;
-    if (st == SWIM_VACANT || !up) continue;
-    bad += (m.z >> (s & 31) & 1u) ? st != SWIM_DEAD : st != SWIM_ALIVE;
+  for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < d.n; l += (size_t)gridDim.x * blockDim.x) {
+    const uint4 m0 = d.meta[l * W];
+    if ((m0.w & 0xFFu) == 0) continue; // a crashed observer's view does not count
+    for (uint32_t w = 0; w < W; ++w) {
+      const uint4 m = w ? d.meta[l * W + w] : m0;
+      bad += __popc(m.z & (m.x | m.y)) + __popc(m.y & ~m.z);
+      uint32_t rest = ~(m.x | m.y | m.z);
+      while (rest) {
+        const uint32_t s = __ffs(rest) - 1;
+        rest &= rest - 1;
+        bad += (d.vst[l * d.cap + w * 32 + s] & 3u) == SWIM_DEAD;
+      }
+    }
   }
   bad = __reduce_add_sync(kFull, bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, (unsigned long long)bad);

@@ -702,8 +702,7 @@ static int reduce_u64(swim_sim *sim, int which, uint64_t *out) {
       ++sim->launches;
       sim->tdead_dirty = false;
     }
-    const size_t total = (size_t)d.n * d.cap;
-    mismatch_kernel<<<grid_for(sim, (total + 31) / 32 / 4 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    mismatch_kernel<<<grid_for(sim, ((size_t)d.n + 31) / 32), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
   }
   CUDA_TRY(sim, cudaGetLastError());
   ++sim->launches;
@@ -739,7 +738,7 @@ extern "C" int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_co
       ++sim->launches;
       sim->tdead_dirty = false;
     }
-    mismatch_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 4 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch + 1);
+    mismatch_kernel<<<grid_for(sim, ((size_t)d.n + 31) / 32), kThreads, 0, sim->stream>>>(d, sim->d_scratch + 1);
     ++sim->launches;
   }
   CUDA_TRY(sim, cudaGetLastError());
