@@ -34,6 +34,11 @@ def _stale(target, srcs):
 
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "nvcc")
+    global NVCC_FLAGS
+    wpb = os.environ.get("SWIM_WPB")  # experiment: CTA size of the per-round kernels (8, 16 or 32 warps)
+    if wpb and not any(f.startswith("-DSWIM_WARPS_PER_BLOCK") for f in NVCC_FLAGS):
+        NVCC_FLAGS = NVCC_FLAGS + ["-DSWIM_WARPS_PER_BLOCK=" + wpb]
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     deps = _deps()
     jobs = []

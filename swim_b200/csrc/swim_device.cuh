@@ -30,7 +30,14 @@
 
 namespace swim {
 
-constexpr int kWarpsPerBlock = 8;
+// CTA shape of the per-round kernels: 8 warps x 4 CTAs per SM by default. -DSWIM_WARPS_PER_BLOCK=16|32 (build.py: env
+// SWIM_WPB) keeps 32 resident warps per SM at 64 registers with fewer, larger CTAs: fewer arrivals on the grid barrier.
+#ifndef SWIM_WARPS_PER_BLOCK
+#define SWIM_WARPS_PER_BLOCK 8
+#endif
+constexpr int kWarpsPerBlock = SWIM_WARPS_PER_BLOCK;
+constexpr int kMinBlocks = 32 / kWarpsPerBlock;
+static_assert(kWarpsPerBlock == 8 || kWarpsPerBlock == 16 || kWarpsPerBlock == 32, "SWIM_WARPS_PER_BLOCK");
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 // Ranks drift (host-side setup, first-launch module loads): a peer may legitimately be seconds late.
@@ -556,7 +563,7 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
 }
 
 template <int W>
-__global__ void __launch_bounds__(kThreads, 4) tick_scan_kernel(SimDev d) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) tick_scan_kernel(SimDev d) {
   pdl_launch();
   pdl_wait();
   const uint32_t round = d.round;
@@ -787,7 +794,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
 }
 
 template <int W>
-__global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) tick_work_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
@@ -941,7 +948,7 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
 
 // stand-alone K2 (last round of a call, rounds next to events, profiling, staged NCCL exchange)
 template <int W>
-__global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) recv_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
@@ -957,7 +964,7 @@ __global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
 // pipelined K2(r-1) + K1a(r): odd warps receive first and scan second, even warps the other way
 // round, so at any moment half the warps wait on dependent loads while the other half issue the scan.
 template <int W>
-__global__ void __launch_bounds__(kThreads, 4) recv_scan_kernel(SimDev d) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) recv_scan_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
@@ -1055,7 +1062,7 @@ __device__ __forceinline__ void grid_peer_barrier(const SimDev &d, uint32_t mail
 }
 
 template <int W>
-__global__ void __launch_bounds__(kThreads, 4) round_kernel(SimDev d) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
   __shared__ uint4 s_pb[kWarpsPerBlock][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
