@@ -1,0 +1,79 @@
+#!/usr/bin/env python
+"""BASELINE config C5 — churn and a suspicion-timeout sweep: detection latency, false positives and
+convergence against S, on 1..8 GPUs.
+
+    python studies/c5_suspicion_sweep.py --nodes-per-gpu 65536 --rounds 300
+    torchrun --nproc-per-node 8 studies/c5_suspicion_sweep.py --nodes-per-gpu 2097152 --rounds 1000   # C5 itself
+
+Per round every up node crashes with probability --crash-ppm / 1e6 and rejoins after U[10, 50] rounds with its
+incarnation + 1 and an Alive broadcast (SWIM_EV_REJOIN). One JSON line per S on rank 0:
+  detection latency (rounds from the crash to the observer's Dead mark: mean / p50 / p99 / max over all entries whose
+  member is down at the end), undetected / stale entries, false positives (entries Dead while the member was up;
+  refutations), the mismatch time series, device time per round.
+The CUDA library does the stepping; this file and swim_b200/study.py only read arrays back."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nodes-per-gpu", type=int, default=65536)
+    ap.add_argument("--rounds", type=int, default=300)
+    ap.add_argument("--suspicion", type=int, nargs="+", default=[2, 3, 5, 8, 13])
+    ap.add_argument("--crash-ppm", type=int, default=1000)
+    ap.add_argument("--loss-ppm", type=int, default=0)
+    ap.add_argument("--flags", type=int, default=0, help="SWIM_F_* protocol variants")
+    ap.add_argument("--sample-every", type=int, default=10)
+    ap.add_argument("--seed", type=int, default=0x5EED0001 + 5)
+    args = ap.parse_args()
+
+    import torch
+    from swim_b200 import dist as sd
+    from swim_b200.sim import Simulator, churn_events, default_config, generate_topology
+    from swim_b200.study import run_sweep_point
+
+    rank, world, local = sd.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("c5_suspicion_sweep needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    n = args.nodes_per_gpu * world
+    nbr = generate_topology("random", n, 32, 32, seed=args.seed & 0xFFFF)
+    events = churn_events(n, args.rounds, args.crash_ppm, 10, 50, seed=args.seed & 0xFFFF)
+    red = (lambda xs: [int(v) for v in sd.global_sum(xs)]) if world > 1 else None
+    for S in args.suspicion:
+        cfg = default_config(n_nodes=n, suspicion_rounds=S, loss_ppm=args.loss_ppm, seed=args.seed, rank=rank, world=world,
+                             device=local, flags=args.flags)
+        sim = Simulator(cfg)
+        sim.set_view(nbr)
+        mode = sd.connect(sim)
+        sim.inject(events)
+        t0 = time.perf_counter()
+        res = run_sweep_point(sim, events, args.rounds, args.sample_every, red)
+        wall = time.perf_counter() - t0
+        sim.close()
+        if rank == 0:
+            rep = res["report"]
+            line = {"config": {"workload": "C5", "n_nodes": n, "n_gpus": world, "rounds": args.rounds, "S": S,
+                               "crash_ppm": args.crash_ppm, "loss_ppm": args.loss_ppm, "flags": args.flags, "exchange": mode,
+                               "events": int(len(events))},
+                    "detection_latency_rounds": rep.pop("latency"),
+                    "entries": rep, "counters": res["counters"],
+                    "false_positive_rate": (rep["false_dead"] + res["counters"]["refutes"]) / max(1, res["counters"]["pings"]),
+                    "mismatch_series": res["mismatch_series"], "wall_s": wall,
+                    "node_rounds_per_s_wall": n * args.rounds / wall}
+            print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
