@@ -191,8 +191,8 @@ def run_cuda(args):
 
     exchange = {"mode": "single"}
 
-    def fresh(inject=True):
-        sim = Simulator(default_config(rank=rank, world=world, device=local, **cfg_kw))
+    def fresh(inject=True, flags=0):
+        sim = Simulator(default_config(rank=rank, world=world, device=local, flags=flags, **cfg_kw))
         sim.set_view(nbr)
         exchange["mode"] = sdist.connect(sim, args.exchange)
         if inject:
@@ -321,24 +321,30 @@ def run_cuda(args):
     # ------------------------------------------------ convergence metric (second half of BASELINE's metric)
     conv = None
     if rank == 0 or world > 1:
-        sim = fresh()
-        sim.step(CRASH_ROUND)
-        r = CRASH_ROUND
-        limit = args.converge_limit
-        mm = None
-        while r < limit:
-            sim.step(8)
-            r += 8
-            mm = sim.mismatches()
-            if world > 1:
-                t = torch.tensor([mm], device="cuda", dtype=torch.int64)
-                dist.all_reduce(t)
-                mm = int(t.item())
-            if mm == 0:
-                break
-        conv = {"rounds_to_convergence": r if mm == 0 else None, "checked_every": 8, "limit": limit,
-                "mismatches_at_end": mm, "crash_round": CRASH_ROUND}
-        sim.close()
+        def rounds_to_convergence(flags):
+            sim = fresh(flags=flags)
+            sim.step(CRASH_ROUND)
+            r = CRASH_ROUND
+            mm = None
+            while r < args.converge_limit:
+                sim.step(8)
+                r += 8
+                mm = sim.mismatches()
+                if world > 1:
+                    t = torch.tensor([mm], device="cuda", dtype=torch.int64)
+                    dist.all_reduce(t)
+                    mm = int(t.item())
+                if mm == 0:
+                    break
+            sim.close()
+            return (r if mm == 0 else None), mm
+
+        r0, mm0 = rounds_to_convergence(0)
+        # the same workload with the paper's round-robin probe order (SWIM_F_ROUND_ROBIN, `-- FIXME: move from random to
+        # robust scheme`, Core.hs:232): every observer reaches the crashed member within 2 view_cap - 1 rounds
+        r1, mm1 = rounds_to_convergence(A.F_ROUND_ROBIN)
+        conv = {"rounds_to_convergence": r0, "checked_every": 8, "limit": args.converge_limit, "mismatches_at_end": mm0,
+                "crash_round": CRASH_ROUND, "rounds_to_convergence_round_robin": r1, "mismatches_at_end_round_robin": mm1}
 
     # ------------------------------------------------ CPU baseline (rank 0, N=1 only): bounded sample
     cpu = None
