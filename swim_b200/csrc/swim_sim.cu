@@ -412,7 +412,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   }
   const int grid = sim->grids[0], wgrid = sim->grids[1], rgrid = sim->grids[2];
   if (sim->tdead_dirty) {
-    derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+    SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
     ++sim->launches;
     sim->tdead_dirty = false;
   }
@@ -462,7 +462,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       const uint32_t cnt = (uint32_t)(ev_end - ev_pos);
       const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count);
       int mk = prof_begin(sim, 0);
-      event_kernel<W><<<eg, kThreads, 0, sim->stream>>>(d, (const DevEvent *)sim->d_events + ev_pos, cnt);
+      SWIM_LAUNCH(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt);
       prof_end(sim, mk);
       ++sim->launches;
       ev_pos = ev_end;
@@ -695,14 +695,14 @@ static int reduce_u64(swim_sim *sim, int which, uint64_t *out) {
   CUDA_TRY(sim, cudaMemsetAsync(sim->d_scratch, 0, 8, sim->stream));
   const SimDev &d = sim->dev;
   if (which == 0) {
-    digest_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    SWIM_LAUNCH(digest_kernel, grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, sim->stream, d, sim->d_scratch);
   } else {
     if (sim->tdead_dirty) { // the detector reads the crashed-member bitmaps
-      derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+      SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
       ++sim->launches;
       sim->tdead_dirty = false;
     }
-    mismatch_kernel<<<grid_for(sim, ((size_t)d.n + 31) / 32), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    SWIM_LAUNCH(mismatch_kernel, grid_for(sim, ((size_t)d.n + 31) / 32), kThreads, sim->stream, d, sim->d_scratch);
   }
   CUDA_TRY(sim, cudaGetLastError());
   ++sim->launches;
@@ -729,16 +729,16 @@ extern "C" int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_co
   const SimDev &d = sim->dev;
   CUDA_TRY(sim, cudaMemsetAsync(sim->d_scratch, 0, 16, sim->stream));
   if (digest) {
-    digest_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    SWIM_LAUNCH(digest_kernel, grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, sim->stream, d, sim->d_scratch);
     ++sim->launches;
   }
   if (mismatches) {
     if (sim->tdead_dirty) {
-      derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+      SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
       ++sim->launches;
       sim->tdead_dirty = false;
     }
-    mismatch_kernel<<<grid_for(sim, ((size_t)d.n + 31) / 32), kThreads, 0, sim->stream>>>(d, sim->d_scratch + 1);
+    SWIM_LAUNCH(mismatch_kernel, grid_for(sim, ((size_t)d.n + 31) / 32), kThreads, sim->stream, d, sim->d_scratch + 1);
     ++sim->launches;
   }
   CUDA_TRY(sim, cudaGetLastError());
