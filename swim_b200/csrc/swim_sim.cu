@@ -447,10 +447,13 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   const int fgrid = sim->grids[3];
   // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
   // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
-  // Sharded runs with the fused exchange use the same kernel: its K1b/K2 barrier is grid_peer_barrier (the last CTA
-  // to arrive talks to the peers, one thread per GPU). [r2-prep: UNVALIDATED on hardware — an earlier form in which
-  // every warp polled the peers' flags measured 136 ms/round at 2 GPUs; SWIM_SPLIT=1 restores the three-launch path.]
-  const bool single_kernel = !sim->profile && !pipelined && getenv("SWIM_SPLIT") == nullptr && (d.world == 1 || d.p2p);
+  // Sharded runs use the split sequence + peer_barrier_kernel (the path measured on hardware in round 1: 41-52 us per
+  // round at 2-8 GPUs). SWIM_ROUND_KERNEL=1 selects round_kernel for them too: its K1b/K2 barrier is then
+  // grid_peer_barrier (the last CTA to arrive talks to the peers, ONE thread per GPU — an earlier form in which every
+  // warp polled the peers' flags measured 136 ms/round) and consecutive event-free rounds share one launch. Bit-exact in
+  // the emulated multi-rank runs (tests/test_emu_parity.py); not yet timed on NVLink hardware, hence opt-in.
+  const bool single_kernel = !sim->profile && !pipelined && getenv("SWIM_SPLIT") == nullptr &&
+                             (d.world == 1 || (d.p2p && getenv("SWIM_ROUND_KERNEL") != nullptr));
   const int kgrid = sim->grids[4];
   const bool multi_round_off = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
   bool pending = false; // K2 of the previous round has not run yet
