@@ -28,6 +28,18 @@
 
 #include "../../include/swim.h"
 
+// Kernel launches and CTA-shared arrays go through two macros so that tests/emu (a SIMT emulator + CUDA runtime stubs,
+// test infrastructure) can compile these very sources for the CPU. In a CUDA build they expand to the plain syntax.
+#ifdef SWIM_EMU
+#define SWIM_LAUNCH(kernel, grid, block, stream, ...) swim_emu::launch((grid), (block), [=] { kernel(__VA_ARGS__); })
+#define SWIM_SHARED_1D(T, name, n) static char name##_tag; T *name = (T *)swim_emu::shared(&name##_tag, sizeof(T) * (n))
+#define SWIM_SHARED_2D(T, name, n0, n1) static char name##_tag; T (*name)[n1] = (T (*)[n1])swim_emu::shared(&name##_tag, sizeof(T) * (n0) * (n1))
+#else
+#define SWIM_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define SWIM_SHARED_1D(T, name, n) __shared__ T name[n]
+#define SWIM_SHARED_2D(T, name, n0, n1) __shared__ T name[n0][n1]
+#endif
+
 namespace swim {
 
 constexpr int kWarpsPerBlock = 8;
@@ -108,8 +120,13 @@ struct SimDev {
 // The per-round kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the
 // next kernel's CTAs may be scheduled while this one drains; pdl_wait() blocks until the previous
 // grid has completed and its writes are visible, pdl_launch() lets the following grid start early.
+#ifdef SWIM_EMU
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_launch() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ------------------------------------------------------------------ pure integer helpers
 // Philox and the slot-selection arithmetic are host+device so that tests/device_helpers_harness.cu can run the very
@@ -338,7 +355,7 @@ struct Ctr {
   // block-level flush: warps add into shared memory, then one global atomic per counter per CTA.
   // Every thread of the CTA must call it (it contains __syncthreads).
   __device__ __forceinline__ void flush(unsigned long long *g, int lane) {
-    __shared__ uint32_t s_ctr[SWIM_CTR__COUNT];
+    SWIM_SHARED_1D(uint32_t, s_ctr, SWIM_CTR__COUNT);
     if (threadIdx.x < SWIM_CTR__COUNT) s_ctr[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
@@ -694,7 +711,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
 
 template <int W>
 __global__ void __launch_bounds__(kThreads, 4) tick_work_kernel(SimDev d) {
-  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
@@ -848,7 +865,7 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
 // stand-alone K2 (last round of a call, rounds next to events, profiling, staged NCCL exchange)
 template <int W>
 __global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
-  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
@@ -864,7 +881,7 @@ __global__ void __launch_bounds__(kThreads, 4) recv_kernel(SimDev d) {
 // round, so at any moment half the warps wait on dependent loads while the other half issue the scan.
 template <int W>
 __global__ void __launch_bounds__(kThreads, 4) recv_scan_kernel(SimDev d) {
-  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
@@ -916,7 +933,7 @@ __device__ __forceinline__ void grid_barrier(const SimDev &d) {
 
 template <int W>
 __global__ void __launch_bounds__(kThreads, 4) round_kernel(SimDev d) {
-  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
@@ -984,7 +1001,7 @@ struct DevEvent {
 
 template <int W>
 __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEvent *ev, uint32_t n_ev) {
-  __shared__ uint4 s_pb[kWarpsPerBlock][32];
+  SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   Ctr c; c.clear();

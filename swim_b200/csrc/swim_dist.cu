@@ -267,7 +267,7 @@ int dist_exchange(swim_sim *sim) {
     if (da.off[p + 1] < da.off[p]) da.off[p + 1] = da.off[p];
   // always launched: it also publishes this round's per-source counts (zeros when nothing arrived)
   const int grid = (int)std::max<size_t>(1, std::min<size_t>((total_recv + 255) / 256, (size_t)sim->sm_count * 8));
-  deliver_kernel<<<grid, 256, 0, sim->stream>>>(d, da, (uint32_t)total_recv);
+  SWIM_LAUNCH(deliver_kernel, grid, 256, sim->stream, d, da, (uint32_t)total_recv);
   ++sim->launches;
   return SWIM_OK;
 }

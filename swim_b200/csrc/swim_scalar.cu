@@ -38,7 +38,7 @@ struct ScalarArgs {
 
 template <int W>
 __global__ void scalar_kernel(SimDev d, ScalarArgs *a) {
-  __shared__ uint4 s_pb[32];
+  SWIM_SHARED_1D(uint4, s_pb, 32);
   const int lane = threadIdx.x;
   const uint32_t ln = a->node - d.first;
   uint32_t dummy = 0;
@@ -150,10 +150,10 @@ int run_scalar(swim_sim *sim, ScalarArgs &h) {
   ScalarArgs *da = (ScalarArgs *)sim->d_sargs;
   CUDA_TRY(sim, cudaMemcpyAsync(da, &h, sizeof h, cudaMemcpyHostToDevice, sim->stream));
   switch (d.cap / 32) {
-    case 1: scalar_kernel<1><<<1, 32, 0, sim->stream>>>(d, da); break;
-    case 2: scalar_kernel<2><<<1, 32, 0, sim->stream>>>(d, da); break;
-    case 4: scalar_kernel<4><<<1, 32, 0, sim->stream>>>(d, da); break;
-    default: scalar_kernel<8><<<1, 32, 0, sim->stream>>>(d, da); break;
+    case 1: SWIM_LAUNCH(scalar_kernel<1>, 1, 32, sim->stream, d, da); break;
+    case 2: SWIM_LAUNCH(scalar_kernel<2>, 1, 32, sim->stream, d, da); break;
+    case 4: SWIM_LAUNCH(scalar_kernel<4>, 1, 32, sim->stream, d, da); break;
+    default: SWIM_LAUNCH(scalar_kernel<8>, 1, 32, sim->stream, d, da); break;
   }
   CUDA_TRY(sim, cudaGetLastError());
   ++sim->launches;

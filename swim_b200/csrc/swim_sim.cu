@@ -410,7 +410,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   }
   const int grid = sim->grids[0], wgrid = sim->grids[1], rgrid = sim->grids[2];
   if (sim->tdead_dirty) {
-    derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+    SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
     ++sim->launches;
     sim->tdead_dirty = false;
   }
@@ -440,8 +440,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   // (recv_scan_kernel) unless something must observe the finished round in between: the end of the
   // call, an event at round r+1, per-kernel profiling, or the staged (host-synchronised) NCCL exchange.
   // Opt-in (SWIM_PIPELINE=1): bit-exact, but on B200 at C3 it measured no faster than the plain sequence
-  // (every warp's own dependent-load chain is the critical path either way).
-  const bool pipelined = !sim->profile && (d.world == 1 || d.p2p) && getenv("SWIM_PIPELINE") != nullptr;
+  // (every warp's own dependent-load chain is the critical path either way). Single shard only: the scan of round
+  // r+1 skips nodes by the mail stamps of round r, and a peer GPU's stamps may still be in flight when it starts
+  // (the emulated two-rank run of tests/test_emu_parity.py diverges from the oracle with it).
+  const bool pipelined = !sim->profile && d.world == 1 && getenv("SWIM_PIPELINE") != nullptr;
   const int fgrid = sim->grids[3];
   // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
   // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
@@ -461,7 +463,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       const uint32_t cnt = (uint32_t)(ev_end - ev_pos);
       const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count);
       int mk = prof_begin(sim, 0);
-      event_kernel<W><<<eg, kThreads, 0, sim->stream>>>(d, (const DevEvent *)sim->d_events + ev_pos, cnt);
+      SWIM_LAUNCH(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt);
       prof_end(sim, mk);
       ++sim->launches;
       ev_pos = ev_end;
@@ -694,15 +696,15 @@ static int reduce_u64(swim_sim *sim, int which, uint64_t *out) {
   CUDA_TRY(sim, cudaMemsetAsync(sim->d_scratch, 0, 8, sim->stream));
   const SimDev &d = sim->dev;
   if (which == 0) {
-    digest_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    SWIM_LAUNCH(digest_kernel, grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, sim->stream, d, sim->d_scratch);
   } else {
     if (sim->tdead_dirty) { // the detector reads the crashed-member bitmaps
-      derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+      SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
       ++sim->launches;
       sim->tdead_dirty = false;
     }
     const size_t total = (size_t)d.n * d.cap;
-    mismatch_kernel<<<grid_for(sim, (total + 31) / 32 / 4 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    SWIM_LAUNCH(mismatch_kernel, grid_for(sim, (total + 31) / 32 / 4 + 1), kThreads, sim->stream, d, sim->d_scratch);
   }
   CUDA_TRY(sim, cudaGetLastError());
   ++sim->launches;
@@ -729,16 +731,16 @@ extern "C" int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_co
   const SimDev &d = sim->dev;
   CUDA_TRY(sim, cudaMemsetAsync(sim->d_scratch, 0, 16, sim->stream));
   if (digest) {
-    digest_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch);
+    SWIM_LAUNCH(digest_kernel, grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 8 + 1), kThreads, sim->stream, d, sim->d_scratch);
     ++sim->launches;
   }
   if (mismatches) {
     if (sim->tdead_dirty) {
-      derive_meta_kernel<<<grid_for(sim, d.n), kThreads, 0, sim->stream>>>(d);
+      SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
       ++sim->launches;
       sim->tdead_dirty = false;
     }
-    mismatch_kernel<<<grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 4 + 1), kThreads, 0, sim->stream>>>(d, sim->d_scratch + 1);
+    SWIM_LAUNCH(mismatch_kernel, grid_for(sim, ((size_t)d.n * d.cap + 31) / 32 / 4 + 1), kThreads, sim->stream, d, sim->d_scratch + 1);
     ++sim->launches;
   }
   CUDA_TRY(sim, cudaGetLastError());

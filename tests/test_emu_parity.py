@@ -1,0 +1,198 @@
+"""The device code on the CPU. tests/emu compiles the library's own CUDA sources (swim_b200/csrc/*.cu, swim_device.cuh)
+with g++ against a SIMT emulator (a warp = one OS thread, a lane = one fiber; see tests/emu/include/cuda_runtime.h) into
+tests/emu/libswim_emu.so, which exports the same C ABI. These tests point the ctypes loader at it — a test-only switch —
+and repeat the parity scenarios of the `-m gpu` suite at small sizes against the oracle: the same kernels (grid barriers,
+warp ballots, candidate slots, claim stamps, peer-memory exchange with several ranks in one process) without a GPU.
+What the emulator cannot show: real memory-model effects, occupancy, performance."""
+import ctypes as C
+import threading
+
+import numpy as np
+import pytest
+
+from helpers import assert_same_state, crash_events, default_config, generate_topology, make_pair, random_events
+from spec_fixture import member, msg
+from swim_b200 import _abi as A
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emu_library():
+    import os
+    import sys
+    import swim_b200._lib as L
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "emu"))
+    import build_emu
+    so = build_emu.build()
+    saved = (L.SO_PATH, L._lib)
+    L.SO_PATH, L._lib = so, None
+    assert L.lib().swim_abi_version() == A.ABI_VERSION
+    yield
+    L.SO_PATH, L._lib = saved
+
+
+def test_c1_every_round():
+    cfg = default_config(n_nodes=32, seed=0x5EED0001 + 1)
+    nbr = generate_topology("complete", 32, 32)
+    sim, orc = make_pair(cfg, nbr)
+    ev = crash_events(10, [7, 19])
+    sim.inject(ev)
+    orc.inject(ev)
+    for r in range(100):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"round {r + 1}")
+    assert sim.mismatches() == 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_small(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 160))
+    deg = int(rng.integers(1, min(n - 1, 32) + 1))
+    k = int(rng.integers(0, 8))
+    cfg = default_config(n_nodes=n, view_cap=32, k_indirect=k, fanout=int(rng.integers(1, k + 2)),
+                         pb_cap=int(rng.integers(1, 33)), suspicion_rounds=int(rng.integers(1, 12)),
+                         retransmit=int(rng.integers(1, 12)), loss_ppm=int(rng.choice([0, 0, 50000, 300000])),
+                         seed=int(rng.integers(0, 2 ** 63)))
+    kind = rng.choice(["random", "ring"]) if deg < n - 1 else "complete"
+    nbr = generate_topology(str(kind), n, 32, deg, seed=seed + 1)
+    sim, orc = make_pair(cfg, nbr)
+    rounds = 40
+    ev = random_events(rng, n, rounds, n_crash=max(1, n // 10), n_rejoin=max(1, n // 30), n_inject=n // 4)
+    sim.inject(ev)
+    orc.inject(ev)
+    for r in range(rounds):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"seed {seed} round {r + 1}")
+
+
+@pytest.mark.parametrize("cap", [64, 128, 256])
+def test_wide_rows(cap):
+    rng = np.random.default_rng(cap)
+    n = 120
+    cfg = default_config(n_nodes=n, view_cap=cap, k_indirect=5, fanout=4, pb_cap=16, suspicion_rounds=3, retransmit=5,
+                         loss_ppm=20000, seed=cap)
+    nbr = generate_topology("random", n, cap, min(cap - 7, n - 1), seed=3)
+    sim, orc = make_pair(cfg, nbr)
+    ev = random_events(rng, n, 30, n_crash=12, n_rejoin=5, n_inject=20)
+    sim.inject(ev)
+    orc.inject(ev)
+    for r in range(30):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"cap {cap} round {r + 1}")
+
+
+def test_multi_round_launches_equal_single_steps():
+    """round_kernel runs every event-free stretch of a call in one launch (grid barriers inside)."""
+    rng = np.random.default_rng(9)
+    n = 300
+    cfg = default_config(n_nodes=n, seed=77)
+    nbr = generate_topology("random", n, 32, 20, seed=2)
+    ev = random_events(rng, n, 60, n_crash=20, n_rejoin=6, n_inject=10)
+    a, orc = make_pair(cfg, nbr)
+    a.inject(ev)
+    orc.inject(ev)
+    for chunk in (1, 7, 2, 30, 20):
+        a.step(chunk)
+        orc.step(chunk)
+        assert_same_state(a, orc, f"after a chunk of {chunk}")
+
+
+def test_scalar_calls_match_oracle():
+    from oracle.oracle import Oracle, OracleError
+    from swim_b200._lib import check, lib
+    from swim_b200.sim import Simulator
+    rng = np.random.default_rng(11)
+    for flags in (0,):
+        cfg = default_config(n_nodes=256, view_cap=32, suspicion_rounds=7)
+        sim, orc = Simulator(cfg), Oracle(cfg)
+        node = 100
+        ms = [member(int(i), int(rng.integers(0, 3)), int(rng.integers(0, 4))) for i in rng.choice(90, 20, replace=False)]
+        for m in ms:
+            m.timer = 3 if m.liveness == A.SUSPECT else 0
+        check(lib().swim_set_members(sim._h, node, (A.Member * len(ms))(*ms), len(ms)), "set", sim._h)
+        orc.set_members(node, ms)
+        fns = {A.MSG_SUSPECT: (lib().swim_suspect_node, orc.suspect_node), A.MSG_DEAD: (lib().swim_dead_node, orc.dead_node),
+               A.MSG_ALIVE: (lib().swim_alive_node, orc.alive_node)}
+        for step in range(150):
+            kind = int(rng.choice([A.MSG_SUSPECT, A.MSG_DEAD, A.MSG_ALIVE]))
+            who = int(rng.choice([node, int(rng.integers(0, 90)), int(rng.integers(0, 90))]))
+            if who == node and kind == A.MSG_ALIVE:
+                who = int(rng.integers(0, 90))
+            m = msg(kind, who, int(rng.integers(0, 6)), dead_from=int(rng.integers(0, 90)))
+            out, has = A.Message(), C.c_int()
+            rc = fns[kind][0](sim._h, node, C.byref(m), C.byref(out), C.byref(has))
+            try:
+                exp = fns[kind][1](node, m)
+            except OracleError as e:
+                assert (rc, e.code) == (A.ECAP, A.ECAP)
+                continue
+            assert rc == 0 and bool(has.value) == (exp is not None), (flags, step, kind, who)
+            if exp is not None:
+                assert (out.kind, out.node, out.incarnation, out.dead_from) == (exp.kind, exp.node, exp.incarnation, exp.dead_from)
+            buf, cnt = (A.Member * 32)(), C.c_size_t()
+            check(lib().swim_get_members(sim._h, node, buf, 32, C.byref(cnt)), "get", sim._h)
+            got = [(buf[i].id, buf[i].liveness, buf[i].timer, buf[i].incarnation) for i in range(cnt.value)]
+            assert got == [(x.id, x.liveness, x.timer, x.incarnation) for x in orc.get_members(node)], step
+        for n_pick in (0, 1, 5, 64):
+            buf, cnt = (A.Member * 32)(), C.c_size_t()
+            check(lib().swim_k_random_members(sim._h, node, n_pick, None, 0, buf, 32, C.byref(cnt)), "krm", sim._h)
+            assert [buf[i].id for i in range(cnt.value)] == [x.id for x in orc.k_random_members(node, n_pick, [])]
+        sim.step(3)
+        orc.step(3)
+        assert sim.digest() == orc.digest()
+
+
+# ---------------------------------------------------------------- several ranks in one process (fused exchange)
+def run_sharded(world, n, chunks, loss, deg):
+    """`world` handles = `world` emulated GPUs; CUDA IPC is the identity in one process, so the peers' arrays are mapped
+    exactly as on an NVLink box. Each rank steps on its own host thread (its kernel waits for the others in-kernel)."""
+    from oracle.oracle import Oracle
+    from swim_b200.sim import Simulator
+    rng = np.random.default_rng(world * 100 + n)
+    nbr = generate_topology("random", n, 32, deg, seed=6)
+    total = sum(chunks)
+    events = random_events(rng, n, total, n_crash=max(2, n // 12), n_rejoin=max(1, n // 40), n_inject=n // 10)
+    kw = dict(n_nodes=n, k_indirect=3, fanout=4, pb_cap=6, suspicion_rounds=4, retransmit=5, loss_ppm=loss, seed=4242)
+    sims = [Simulator(default_config(rank=r, world=world, **kw)) for r in range(world)]
+    for s in sims:
+        s.set_view(nbr)
+    blobs = [s.ipc_export() for s in sims]
+    for s in sims:
+        s.ipc_connect(blobs)
+        s.inject(events)
+    ref = Oracle(default_config(**kw))
+    ref.set_view(nbr)
+    ref.inject(events)
+    for c in chunks:
+        errs = []
+
+        def work(s):
+            try:
+                s.step(c)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=work, args=(s,)) for s in sims]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errs, errs
+        ref.step(c)
+        assert sum(s.digest() for s in sims) % 2 ** 64 == ref.digest(), f"digest differs at round {ref.round}"
+        assert sum(s.mismatches() for s in sims) == ref.mismatches()
+    assert np.sum([s.counters() for s in sims], axis=0).tolist() == ref.counters().tolist()
+    for a in range(A.ARR_COUNT):
+        got = sims[0].get_array(a) if a == A.ARR_ALIVE else np.concatenate([s.get_array(a) for s in sims])
+        assert np.array_equal(got, ref.get_array(a)), A.ARRAY_NAMES[a]
+    assert ref.counters()[A.CTR_MSGS_RECV] > 0
+    for s in sims:
+        s.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_fused_exchange_equals_oracle(world):
+    run_sharded(world, n=403, chunks=[1] * 6 + [12], loss=20000, deg=24)
