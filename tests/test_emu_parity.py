@@ -194,10 +194,16 @@ def run_sharded(world, n, chunks, loss, deg, flags=0):
         s.close()
 
 
+@pytest.mark.parametrize("path", ["split", "round_kernel"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_fused_exchange_equals_oracle(world):
+def test_sharded_fused_exchange_equals_oracle(world, path, monkeypatch):
+    """split: K1a / K1b / peer_barrier_kernel / K2 as separate launches (the default for shards); round_kernel
+    (SWIM_ROUND_KERNEL=1): one launch per event-free stretch, grid_peer_barrier between K1b and K2."""
+    if path == "round_kernel":
+        monkeypatch.setenv("SWIM_ROUND_KERNEL", "1")
     run_sharded(world, n=403, chunks=[1] * 6 + [12], loss=20000, deg=24)
 
 
-def test_sharded_variants():
+def test_sharded_variants(monkeypatch):
+    monkeypatch.setenv("SWIM_ROUND_KERNEL", "1")
     run_sharded(2, n=200, chunks=[1, 1, 40], loss=0, deg=20, flags=A.F_STRICT_OVERRIDE | A.F_ROUND_ROBIN)
