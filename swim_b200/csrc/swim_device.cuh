@@ -18,8 +18,8 @@
 //   * mail is delivered without sorting or contended atomics: the sender raises a byte flag on the
 //     static in-edge (i -> j) of the receiver's sorted in-list and records j in its own candidate
 //     slot; a receiver is claimed once (per-receiver stamp), walks its flags in ascending sender
-//     order and reads the sender's snapshot from local HBM — a sender on another GPU has pushed it there
-//     over NVLink.
+//     order and pulls the sender's snapshot — from local HBM or, across shards, from the peer GPU's
+//     HBM over NVLink.
 //   * default launch: round_kernel = K1a | grid barrier | K1b | grid barrier | K2 in one resident wave;
 //     the same passes exist as separate kernels for profiling and the staged NCCL exchange.
 #pragma once
@@ -77,9 +77,8 @@ struct SimDev {
   uint32_t *vlast;           // [n*cap]
   uint4 *pb;                 // [n*B] {member, inc, from, kind | ttl<<8}
   uint8_t *pb_cnt;           // [n]
-  uint4 *out;                // [2][N*B] snapshots sent this round (parity), indexed by GLOBAL sender id: a sender's own
-                             //   rank and every rank that owns one of its recipients hold a copy (pushed over NVLink)
-  uint8_t *out_cnt;          // [2][N]
+  uint4 *out;                // [n*B] snapshot sent this round
+  uint8_t *out_cnt;          // [n]
   uint32_t *ridx;            // [n*cap] index of edge (i,s) in the receiver's in-list
   uint32_t *in_off;          // [n+1]
   uint32_t *in_src;          // [E] sender ids, ascending per receiver
@@ -103,8 +102,8 @@ struct SimDev {
   // IPC; entry [rank] is this rank's own array. Remote traffic is fire-and-forget stores only.
   uint8_t *eflag_p[SWIM_MAX_WORLD];      // [2][estride_p[r]] in-edge mail flags
   uint32_t estride_p[SWIM_MAX_WORLD];
-  uint4 *out_p[SWIM_MAX_WORLD];          // the peers' snapshot arrays (K1b pushes into them; K2 reads only its own)
-  uint8_t *out_cnt_p[SWIM_MAX_WORLD];
+  const uint4 *out_p[SWIM_MAX_WORLD];    // [2][per*B] sender snapshots
+  const uint8_t *out_cnt_p[SWIM_MAX_WORLD]; // [2][per]
   uint4 *meta_p[SWIM_MAX_WORLD];         // receivers' meta records (mail stamps are written by senders)
   uint32_t *bar_err;                     // set by a cross-GPU / grid wait that timed out
   uint32_t *gbar;                        // [2] grid barrier of round_kernel: arrival count, generation
@@ -737,7 +736,6 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
       for (uint32_t j = 0; j < np && nr < d.fanout; ++j)
         if (prox[j] != tslot) { if ((uint32_t)lane == nr) rslot = prox[j]; ++nr; }
       uint32_t xs = 0xFFFFFFFFu; // exchange-bucket slot when lane f's recipient lives on another shard
-      uint32_t push_to = 0;      // fused exchange: bit q = lane f's recipient lives on GPU q
       if ((uint32_t)lane < nr) {
         const size_t e = (size_t)ln * d.cap + rslot;
         const uint32_t dst = d.nbr[e], ridx = d.ridx[e];
@@ -754,7 +752,6 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           if (d.stamping) *stamp_ptr(d.meta_p[owner] + (size_t)dl * W) = (uint16_t)my_stamp;
           const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
           d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
-          push_to = 1u << owner;
           did_remote = true;
         } else {
           const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
@@ -766,26 +763,15 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           }
         }
       }
-      const size_t oi = (size_t)par * d.N + self; // snapshots are indexed by global sender id on every rank
       if (lane == 0) {
-        d.out_cnt[oi] = (uint8_t)pbs.cnt;
+        d.out_cnt[(size_t)par * d.per + ln] = (uint8_t)pbs.cnt;
         c.v[SWIM_CTR_MSGS] += nr;
         c.v[SWIM_CTR_RECS_SENT] += nr * pbs.cnt;
       }
       // snapshot, then one transmission is spent on every record
       uint4 mine = make_uint4(0, 0, 0, 0);
       const bool have = (uint32_t)lane < pbs.cnt;
-      if (have) { mine = pbs.s[lane]; d.out[oi * d.B + lane] = mine; }
-      // fused exchange: the snapshot is pushed ONCE into every other GPU that owns a recipient (plain NVLink stores), so
-      // the receive pass reads local memory only
-      push_to = __reduce_or_sync(kFull, push_to);
-      if (push_to) did_remote = true;
-      while (push_to) {
-        const int q = __ffs(push_to) - 1;
-        push_to &= push_to - 1;
-        if (have) d.out_p[q][oi * d.B + lane] = mine;
-        if (lane == 0) d.out_cnt_p[q][oi] = (uint8_t)pbs.cnt;
-      }
+      if (have) { mine = pbs.s[lane]; d.out[((size_t)par * d.per + ln) * d.B + lane] = mine; }
       unsigned xm = __ballot_sync(kFull, xs != 0xFFFFFFFFu);
       while (xm) { // cross-shard envelopes carry the records themselves (staged NCCL path)
         const int f = __ffs(xm) - 1;
@@ -931,10 +917,10 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
         const uint32_t s_id = __shfl_sync(kFull, src, q), s_kind = __shfl_sync(kFull, f, q);
         uint32_t cnt;
         uint4 mine = make_uint4(0, 0, 0, 0);
-        if (s_kind == 1) { // the sender's snapshot: written here by a local sender, pushed here by a remote one
-          const size_t oi = (size_t)par * d.N + s_id;
-          if ((uint32_t)lane < d.B) mine = d.out[oi * d.B + lane];
-          cnt = d.out_cnt[oi];
+        if (s_kind == 1) { // pull the sender's snapshot (from a peer GPU's memory if it lives there)
+          const uint32_t s_rank = d.world == 1 ? 0u : s_id / d.per, sl = s_id - s_rank * d.per;
+          if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][((size_t)par * d.per + sl) * d.B + lane];
+          cnt = d.out_cnt_p[s_rank][(size_t)par * d.per + sl];
         } else {           // staged NCCL path: the envelope arrived in the exchange buffer
           const uint32_t xslot = d.eslot[eb + q];
           const uint4 *env = d.xrecv + (size_t)xslot * (1 + d.B);

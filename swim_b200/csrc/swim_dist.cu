@@ -198,7 +198,7 @@ extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
       sim->ipc_opened.push_back(p[x]);
     }
     d.eflag_p[r] = (uint8_t *)p[0]; d.estride_p[r] = b.estride;
-    d.out_p[r] = (uint4 *)p[1]; d.out_cnt_p[r] = (uint8_t *)p[2];
+    d.out_p[r] = (const uint4 *)p[1]; d.out_cnt_p[r] = (const uint8_t *)p[2];
     d.rlr_p[r] = (uint32_t *)p[3]; d.rcnt_p[r] = (uint32_t *)p[4]; d.bar_p[r] = (uint32_t *)p[5];
     d.meta_p[r] = (uint4 *)p[6];
   }

@@ -72,13 +72,13 @@ extern "C" int swim_sim_export_round(swim_sim_t *sim, uint8_t *buf, size_t cap, 
   std::vector<swim_record_t> recs((size_t)n_work * B);
   {
     std::vector<uint8_t> all_cnt(d.n);
-    CUDA_TRY(sim, cudaMemcpy(all_cnt.data(), d.out_cnt + (size_t)par * d.N + d.first, d.n, cudaMemcpyDeviceToHost));
+    CUDA_TRY(sim, cudaMemcpy(all_cnt.data(), d.out_cnt + (size_t)par * d.per, d.n, cudaMemcpyDeviceToHost));
     for (uint32_t k = 0; k < n_work; ++k) cnt[k] = all_cnt[wl[k]];
     for (uint32_t k = 0; k < n_work; ++k) {
       bool sends = false;
       for (uint32_t f = 0; f < F; ++f) sends |= rl[(size_t)k * F + f] != 0xFFFFFFFFu;
       if (!sends) { cnt[k] = 0; continue; }
-      CUDA_TRY(sim, cudaMemcpy(&recs[(size_t)k * B], d.out + ((size_t)par * d.N + d.first + wl[k]) * B, cnt[k] * sizeof(swim_record_t),
+      CUDA_TRY(sim, cudaMemcpy(&recs[(size_t)k * B], d.out + ((size_t)par * d.per + wl[k]) * B, cnt[k] * sizeof(swim_record_t),
                                cudaMemcpyDeviceToHost));
     }
   }

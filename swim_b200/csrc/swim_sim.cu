@@ -157,8 +157,8 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.vlast, slots, 0))) return r;
     if ((r = dalloc(sim, &d.pb, n * d.B, 0))) return r;
     if ((r = dalloc(sim, &d.pb_cnt, n, 0))) return r;
-    if ((r = dalloc(sim, &d.out, 2 * (size_t)d.N * d.B, 0))) return r; // [parity][N*B]: global sender ids (swim_device.cuh)
-    if ((r = dalloc(sim, &d.out_cnt, 2 * (size_t)d.N, 0))) return r;
+    if ((r = dalloc(sim, &d.out, 2 * (size_t)d.per * d.B, 0))) return r; // [parity][per*B]
+    if ((r = dalloc(sim, &d.out_cnt, 2 * (size_t)d.per, 0))) return r;
     if ((r = dalloc(sim, &d.claim, n, 0))) return r;
     if ((r = dalloc(sim, &d.xcnt, SWIM_MAX_WORLD, 0))) return r;
     d.rcap = d.per * d.fanout; // a source rank can list at most per*fanout receivers per round
