@@ -365,6 +365,17 @@ int swim_handle_message(swim_sim_t *sim, uint32_t node, uint32_t sender_addr,
 int swim_broadcast(swim_sim_t *sim, uint32_t node, const swim_message_t *msg);
 int swim_get_broadcasts(swim_sim_t *sim, uint32_t node, swim_message_t *out, size_t cap, size_t *n_out);
 
+/* The two per-period steps a real-time node runs besides the probe (`failureDetector`, Core.hs:233-241), for ONE store:
+ * swim_tick_timers — the suspicion countdown the reference leaves as a FIXME (`need a timer to mark this node as dead
+ *   after suspect timeout`, Core.hs:141): every Suspect entry's timer - 1; an entry reaching 0 becomes Dead and
+ *   Dead(incarnation, member, from = node) is enqueued for dissemination. *n_expired (may be NULL) = entries that died.
+ * swim_take_broadcasts — the piggyback payload of the next outgoing message (the compound Envelope of Types.hs:96-119
+ *   that `disseminate`'s FIXME, Core.hs:136, never builds): the buffer as swim_get_broadcasts returns it, after which
+ *   one of each record's `retransmit` transmissions is spent; records at 0 leave the buffer.
+ * Both run the same device code as phases T1 / T4 of the bulk rounds. */
+int swim_tick_timers(swim_sim_t *sim, uint32_t node, uint32_t *n_expired);
+int swim_take_broadcasts(swim_sim_t *sim, uint32_t node, swim_message_t *out, size_t cap, size_t *n_out);
+
 /* ====================== wire codec: Types.hs parity ==================================
  * Envelope framing (Types.hs:96-119) around msgpack-of-aeson-generic bodies
  * (Types.hs:147-155). Names travel as strings on the wire. */

@@ -71,6 +71,8 @@ def lib():
                                             C.POINTER(sz)]
         L.oracle_broadcast.argtypes = [vp, u32, C.POINTER(A.Message)]
         L.oracle_get_broadcasts.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
+        L.oracle_take_broadcasts.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
+        L.oracle_tick_timers.argtypes = [vp, u32, C.POINTER(u32)]
         L.oracle_philox.argtypes = [vp, vp, vp]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
@@ -244,6 +246,17 @@ class Oracle:
         n = C.c_size_t()
         _chk(lib().oracle_get_broadcasts(self._h, node, buf, A.MAX_PB, C.byref(n)), "get_broadcasts")
         return [_copy(buf[i]) for i in range(n.value)]
+
+    def take_broadcasts(self, node):
+        buf = (A.Message * A.MAX_PB)()
+        n = C.c_size_t()
+        _chk(lib().oracle_take_broadcasts(self._h, node, buf, A.MAX_PB, C.byref(n)), "take_broadcasts")
+        return [_copy(buf[i]) for i in range(n.value)]
+
+    def tick_timers(self, node):
+        e = C.c_uint32()
+        _chk(lib().oracle_tick_timers(self._h, node, C.byref(e)), "tick_timers")
+        return e.value
 
     def handle_message(self, node, sender_addr, sender_port, msg):
         out = (A.Gossip * 4)()

@@ -339,6 +339,26 @@ static void draws_for(const oracle_t *o, uint32_t a, uint32_t node, uint32_t pur
   }
 }
 
+/* T1 [Q8] suspicion countdown of node `l`, ascending slot order (`-- FIXME: need a timer to mark this node as dead
+ * after suspect timeout`, Core.hs:141). Returns the number of entries that expired. */
+static uint32_t tick_timers(oracle_t *o, uint32_t l, uint64_t *ctr) {
+  uint32_t self = o->first + l, expired = 0;
+  uint32_t *ids = o->nbr + (size_t)l * o->cap;
+  uint8_t *st = o->state + (size_t)l * o->cap;
+  uint8_t *tm = o->timer + (size_t)l * o->cap;
+  uint32_t *inc = o->vinc + (size_t)l * o->cap;
+  uint32_t *last = o->vlast + (size_t)l * o->cap;
+  for (uint32_t s = 0; s < o->cap; ++s)
+    if (st[s] == SWIM_SUSPECT && --tm[s] == 0) {
+      st[s] = SWIM_DEAD; last[s] = o->round;
+      rec_t d = {ids[s], inc[s], self, SWIM_MSG_DEAD, 0, 0};
+      pb_enqueue(o, l, d, ctr);
+      ctr[SWIM_CTR_DEAD_TIMEOUT]++;
+      ++expired;
+    }
+  return expired;
+}
+
 /* ------------------------------------------------------------------ phase T: one tick
  * failureDetector (Core.hs:233-241) + probeNode' (Core.hs:243-269) for node `l`. */
 static void tick_node(oracle_t *o, uint32_t l, uint64_t *ctr) {
@@ -349,18 +369,9 @@ static void tick_node(oracle_t *o, uint32_t l, uint64_t *ctr) {
   if (!o->alive[self]) return; /* a crashed process does nothing */
   uint32_t *ids = o->nbr + (size_t)l * o->cap;
   uint8_t *st = o->state + (size_t)l * o->cap;
-  uint8_t *tm = o->timer + (size_t)l * o->cap;
   uint32_t *inc = o->vinc + (size_t)l * o->cap;
-  uint32_t *last = o->vlast + (size_t)l * o->cap;
 
-  /* T1 [Q8] suspicion countdown, ascending slot order */
-  for (uint32_t s = 0; s < o->cap; ++s)
-    if (st[s] == SWIM_SUSPECT && --tm[s] == 0) {
-      st[s] = SWIM_DEAD; last[s] = o->round;
-      rec_t d = {ids[s], inc[s], self, SWIM_MSG_DEAD, 0, 0};
-      pb_enqueue(o, l, d, ctr);
-      ctr[SWIM_CTR_DEAD_TIMEOUT]++;
-    }
+  tick_timers(o, l, ctr); /* T1 */
 
   /* T2 kRandomMembers store 1 [] (Core.hs:239, [Q11]) and kRandomMembers store k [] (Core.hs:249) */
   uint32_t cand[SWIM_MAX_VIEW], L = 0;
@@ -882,6 +893,28 @@ EXPORT int oracle_get_broadcasts(const oracle_t *o, uint32_t node, swim_message_
   if (o->pb_cnt[l] > cap) return SWIM_ECAP;
   for (uint32_t q = 0; q < o->pb_cnt[l]; ++q) msg_of_rec(o, &o->pb[(size_t)l * o->B + q], &out[q]);
   *n_out = o->pb_cnt[l];
+  return SWIM_OK;
+}
+
+/* one protocol period's suspicion countdown of one store (phase T1; counters untouched, like every scalar call) */
+EXPORT int oracle_tick_timers(oracle_t *o, uint32_t node, uint32_t *n_expired) {
+  if (node < o->first || node >= o->first + o->n) return SWIM_EINVAL;
+  uint64_t sink[SWIM_CTR__COUNT] = {0};
+  uint32_t e = tick_timers(o, node - o->first, sink);
+  if (n_expired) *n_expired = e;
+  return SWIM_OK;
+}
+
+/* the piggyback payload of the next outgoing message (phase T4): the buffer, then one transmission spent on every record */
+EXPORT int oracle_take_broadcasts(oracle_t *o, uint32_t node, swim_message_t *out, size_t cap, size_t *n_out) {
+  int rc = oracle_get_broadcasts(o, node, out, cap, n_out);
+  if (rc) return rc;
+  uint32_t l = node - o->first, cnt = o->pb_cnt[l], w = 0;
+  rec_t *q = o->pb + (size_t)l * o->B;
+  for (uint32_t x = 0; x < cnt; ++x)
+    if (q[x].ttl > 1) { q[w] = q[x]; q[w].ttl--; ++w; }
+  memset(q + w, 0, (o->B - w) * sizeof(rec_t));
+  o->pb_cnt[l] = (uint8_t)w;
   return SWIM_OK;
 }
 

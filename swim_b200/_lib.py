@@ -81,6 +81,8 @@ def lib():
         "swim_handle_message": (vp, u32, u32, C.c_uint16, P(A.Message), vp, sz, P(sz)),
         "swim_broadcast": (vp, u32, P(A.Message)),
         "swim_get_broadcasts": (vp, u32, vp, sz, P(sz)),
+        "swim_take_broadcasts": (vp, u32, vp, sz, P(sz)),
+        "swim_tick_timers": (vp, u32, P(u32)),
         "swim_envelope_encode": (vp, sz, vp, sz, P(sz)),
         "swim_envelope_decode": (vp, sz, vp, sz, P(sz)),
     }.items():

@@ -258,6 +258,25 @@ def pending_broadcasts(store: Store) -> List[Message]:
     return [_msg_from_c(store, buf[i]) for i in range(n.value)]
 
 
+def take_broadcasts(store: Store) -> List[Message]:
+    """The piggyback payload of the next outgoing message: the buffer (newest first), after which one of each record's
+    `retransmit` transmissions is spent (phase T4 of DESIGN.md 2.2; the compound Envelope `disseminate`'s FIXME,
+    Core.hs:136, never builds)."""
+    buf = (A.Message * A.MAX_PB)()
+    n = C.c_size_t()
+    check(lib().swim_take_broadcasts(store._h(), store._self, buf, A.MAX_PB, C.byref(n)), "swim_take_broadcasts", store._h())
+    return [_msg_from_c(store, buf[i]) for i in range(n.value)]
+
+
+def tickTimers(store: Store) -> int:
+    """One protocol period of the suspicion countdown (`-- FIXME: need a timer to mark this node as dead after suspect
+    timeout`, Core.hs:141): expired Suspect entries become Dead and their Dead(inc, member, from = self) is enqueued.
+    Returns how many expired."""
+    e = C.c_uint32()
+    check(lib().swim_tick_timers(store._h(), store._self, C.byref(e)), "swim_tick_timers", store._h())
+    return e.value
+
+
 def disseminate(store: Store, gossip: Iterable[Gossip]):
     """disseminate (Core.hs:127-138): `Direct msg addr` -> a datagram to send now (framed as an Envelope — the
     reference sends a bare `encode msg` that its own receiver cannot decode); `Broadcast msg` ->

@@ -22,7 +22,7 @@ using namespace swim;
 
 namespace {
 
-enum : uint32_t { OP_APPLY = 0, OP_KRANDOM = 1, OP_REMOVE_DEAD = 2, OP_NEXT_SEQNO = 3, OP_NEXT_INC = 4, OP_ENQUEUE = 5 };
+enum : uint32_t { OP_APPLY = 0, OP_KRANDOM = 1, OP_REMOVE_DEAD = 2, OP_NEXT_SEQNO = 3, OP_NEXT_INC = 4, OP_ENQUEUE = 5, OP_TICK_TIMERS = 6, OP_SPEND = 7 };
 
 struct ScalarArgs {
   uint32_t op, node, n, allow_insert;
@@ -117,6 +117,51 @@ __global__ void scalar_kernel(SimDev d, ScalarArgs *a) {
       pb_enqueue(pbs, d, a->rec, lane, dummy);
       pb_store(pbs, d, ln, lane);
       if (lane == 0) a->value = dummy; // 1 = the oldest record fell off a full buffer
+      break;
+    }
+    case OP_TICK_TIMERS: { // phase T1 for one store: the same countdown / expiry code as work_pass
+      Row<W> row;
+      row_load<W>(row, d, ln, lane);
+      PbStage pbs;
+      pbs.s = s_pb;
+      pb_load(pbs, d, ln, lane);
+      uint32_t expired = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        if ((row.st[w] & 3u) == SWIM_SUSPECT) { row.st[w] -= 4u; row.ticked |= 1u << w; }
+        unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && (row.st[w] >> 2) == 0);
+        if (em >> lane & 1u) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
+        while (em) {
+          const int s = __ffs(em) - 1;
+          em &= em - 1;
+          const uint32_t m = __shfl_sync(kFull, row.nb[w], s), i = __shfl_sync(kFull, row.inc[w], s);
+          pb_enqueue(pbs, d, make_rec(m, i, a->node, SWIM_MSG_DEAD), lane, dummy);
+          ++expired;
+        }
+      }
+      row_store<W>(row, d, ln, lane, d.round);
+      pb_store(pbs, d, ln, lane);
+      if (lane == 0) a->value = expired;
+      break;
+    }
+    case OP_SPEND: { // phase T4's "one transmission is spent on every record" for one store
+      PbStage pbs;
+      pbs.s = s_pb;
+      pb_load(pbs, d, ln, lane);
+      uint4 mine = make_uint4(0, 0, 0, 0);
+      const bool have = (uint32_t)lane < pbs.cnt;
+      if (have) mine = pbs.s[lane];
+      const bool keep = have && rec_ttl(mine) > 1;
+      const unsigned km = __ballot_sync(kFull, keep);
+      __syncwarp();
+      if (keep) {
+        mine.w -= 1u << 8;
+        pbs.s[__popc(km & ((1u << lane) - 1))] = mine;
+      }
+      pbs.cnt = __popc(km);
+      pbs.dirty = true;
+      __syncwarp();
+      pb_store(pbs, d, ln, lane);
       break;
     }
     case OP_REMOVE_DEAD: // removeDeadNodes (Core.hs:65-67): Map.filter (not . isDead)
@@ -386,6 +431,27 @@ extern "C" int swim_get_broadcasts(swim_sim_t *sim, uint32_t node, swim_message_
   for (uint32_t q = 0; q < cnt; ++q) msg_of_rec(sim, recs[q], &out[q]);
   *n_out = cnt;
   return SWIM_OK;
+}
+
+extern "C" int swim_tick_timers(swim_sim_t *sim, uint32_t node, uint32_t *n_expired) {
+  int rc = check_node(sim, node);
+  if (rc) return rc;
+  ScalarArgs a;
+  memset(&a, 0, sizeof a);
+  a.op = OP_TICK_TIMERS; a.node = node;
+  rc = run_scalar(sim, a);
+  if (rc) return rc;
+  if (n_expired) *n_expired = a.value;
+  return SWIM_OK;
+}
+
+extern "C" int swim_take_broadcasts(swim_sim_t *sim, uint32_t node, swim_message_t *out, size_t cap, size_t *n_out) {
+  int rc = swim_get_broadcasts(sim, node, out, cap, n_out);
+  if (rc) return rc;
+  ScalarArgs a;
+  memset(&a, 0, sizeof a);
+  a.op = OP_SPEND; a.node = node;
+  return run_scalar(sim, a);
 }
 
 // `process` (Core.hs:89-117)

@@ -138,6 +138,17 @@ def test_scalar_calls_match_oracle():
             check(lib().swim_get_members(sim._h, node, buf, 32, C.byref(cnt)), "get", sim._h)
             got = [(buf[i].id, buf[i].liveness, buf[i].timer, buf[i].incarnation) for i in range(cnt.value)]
             assert got == [(x.id, x.liveness, x.timer, x.incarnation) for x in orc.get_members(node)], step
+            if step % 7 == 3:  # the per-period steps of a real-time node: countdown, piggyback payload
+                e = C.c_uint32()
+                check(lib().swim_tick_timers(sim._h, node, C.byref(e)), "tick", sim._h)
+                assert e.value == orc.tick_timers(node), step
+                mb, mc = (A.Message * A.MAX_PB)(), C.c_size_t()
+                check(lib().swim_take_broadcasts(sim._h, node, mb, A.MAX_PB, C.byref(mc)), "take", sim._h)
+                assert [(mb[i].kind, mb[i].node, mb[i].incarnation, mb[i].dead_from) for i in range(mc.value)] == \
+                    [(x.kind, x.node, x.incarnation, x.dead_from) for x in orc.take_broadcasts(node)], step
+            elif exp is not None:
+                check(lib().swim_broadcast(sim._h, node, C.byref(out)), "bc", sim._h)
+                orc.broadcast(node, exp)
         for n_pick in (0, 1, 5, 64):
             buf, cnt = (A.Member * 32)(), C.c_size_t()
             check(lib().swim_k_random_members(sim._h, node, n_pick, None, 0, buf, 32, C.byref(cnt)), "krm", sim._h)

@@ -145,6 +145,17 @@ def test_scalar_api_matches_oracle_on_random_sequences():
             if step % 50 == 49:
                 check(lib().swim_remove_dead_nodes(sim._h, node), "rm", sim._h)
                 orc.remove_dead_nodes(node)
+            if step % 7 == 3:  # the per-period steps of a real-time node: countdown, piggyback payload (spends a transmission)
+                e = C.c_uint32()
+                check(lib().swim_tick_timers(sim._h, node, C.byref(e)), "tick", sim._h)
+                assert e.value == orc.tick_timers(node), step
+                mb, mc = (A.Message * A.MAX_PB)(), C.c_size_t()
+                check(lib().swim_take_broadcasts(sim._h, node, mb, A.MAX_PB, C.byref(mc)), "take", sim._h)
+                assert [(mb[i].kind, mb[i].node, mb[i].incarnation, mb[i].dead_from) for i in range(mc.value)] == \
+                    [(x.kind, x.node, x.incarnation, x.dead_from) for x in orc.take_broadcasts(node)], step
+            elif exp is not None:
+                check(lib().swim_broadcast(sim._h, node, C.byref(out)), "bc", sim._h)
+                orc.broadcast(node, exp)
             got = [(x.id, x.liveness, x.timer, x.incarnation, x.last_change) for x in _members(sim, node, cap)]
             want = [(x.id, x.liveness, x.timer, x.incarnation, x.last_change) for x in orc.get_members(node)]
             assert got == want, step

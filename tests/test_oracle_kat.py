@@ -268,3 +268,29 @@ def test_broadcast_queue(store):
     assert len(got) == B and got[0].node == 50 and 0 not in [m.node for m in got]
     with pytest.raises(OracleError):
         store.broadcast(SELF, msg(A.MSG_PING, 1))
+
+
+def test_scalar_period_steps_tick_timers_and_take_broadcasts(store):
+    """The two per-period steps of a real-time node besides the probe: the suspicion countdown (Core.hs:141 FIXME, [Q8]) and
+    the piggyback payload with its transmission budget (Core.hs:136 FIXME, [Q5])."""
+    # fixture: "suspect" is Suspect with 5 periods left
+    for left in (4, 3, 2, 1):
+        assert store.tick_timers(SELF) == 0
+        assert [m.timer for m in store.get_members(SELF) if m.id == SUSPECT_ID] == [left]
+    assert store.get_broadcasts(SELF) == []
+    assert store.tick_timers(SELF) == 1                                   # expires: Dead, and the Dead is gossiped
+    assert view(store)[SUSPECT_ID] == (A.DEAD, 0)
+    got = store.get_broadcasts(SELF)
+    assert [(m.kind, m.node, m.incarnation, m.dead_from) for m in got] == [(A.MSG_DEAD, SUSPECT_ID, 0, SELF)]
+    assert store.tick_timers(SELF) == 0                                   # nothing left to count down
+    # a fresh suspicion arms S = 5 periods
+    assert store.suspect_node(SELF, msg(A.MSG_SUSPECT, ALIVE_ID, 0)) is not None
+    store.broadcast(SELF, msg(A.MSG_SUSPECT, ALIVE_ID, 0))
+    # default retransmit T = 8: each take returns the buffer (newest first) and spends one transmission of every record
+    for _ in range(8):
+        got = store.take_broadcasts(SELF)
+        assert [(m.kind, m.node) for m in got] == [(A.MSG_SUSPECT, ALIVE_ID), (A.MSG_DEAD, SUSPECT_ID)]
+    assert store.take_broadcasts(SELF) == [] and store.get_broadcasts(SELF) == []
+    # a record enqueued later has its own budget
+    store.broadcast(SELF, msg(A.MSG_ALIVE, ALIVE_ID, 3))
+    assert len(store.take_broadcasts(SELF)) == 1 and len(store.get_broadcasts(SELF)) == 1
