@@ -17,7 +17,7 @@ module SwimFFI
   , msgPing, msgIndirectPing, msgAck, msgSuspect, msgAlive, msgDead
     -- raw imports of the bulk / codec / replay entry points (marshalled by the caller)
   , c_simInject, c_simGetArray, c_simSetArray, c_simCounters, c_simObserve, c_simExportRound
-  , c_simInjectDatagram, c_getBroadcasts, c_envEncode, c_envDecode, simCounters
+  , c_simInjectDatagram, c_getBroadcasts, c_takeBroadcasts, c_tickTimers, c_envEncode, c_envDecode, simCounters
   ) where
 
 import Control.Monad (when)
@@ -127,6 +127,8 @@ foreign import ccall safe   "swim_sim_observe"         c_simObserve        :: Si
 foreign import ccall safe   "swim_sim_export_round"    c_simExportRound    :: Sim -> Ptr Word8 -> CSize -> Ptr () -> CSize -> Ptr CSize -> Ptr CSize -> IO CInt
 foreign import ccall safe   "swim_sim_inject_datagram" c_simInjectDatagram :: Sim -> Word32 -> Word32 -> Ptr Word8 -> CSize -> IO CInt
 foreign import ccall safe   "swim_get_broadcasts"      c_getBroadcasts     :: Sim -> Word32 -> Ptr CMessage -> CSize -> Ptr CSize -> IO CInt
+foreign import ccall safe   "swim_take_broadcasts"     c_takeBroadcasts    :: Sim -> Word32 -> Ptr CMessage -> CSize -> Ptr CSize -> IO CInt
+foreign import ccall safe   "swim_tick_timers"         c_tickTimers        :: Sim -> Word32 -> Ptr Word32 -> IO CInt
 foreign import ccall unsafe "swim_envelope_encode"     c_envEncode         :: Ptr () -> CSize -> Ptr Word8 -> CSize -> Ptr CSize -> IO CInt
 foreign import ccall unsafe "swim_envelope_decode"     c_envDecode         :: Ptr Word8 -> CSize -> Ptr () -> CSize -> Ptr CSize -> IO CInt
 

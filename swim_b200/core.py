@@ -112,6 +112,16 @@ class Store:
         self._meta[name] = (host, addr)
         arr = (A.Member * max(1, len(raw)))(*raw)
         check(lib().swim_set_members(self._h(), self._self, arr, len(raw)), "swim_set_members", self._h())
+        # records waiting in the piggyback buffer name members by id as well
+        B = self.sim.cfg.pb_cap
+        cnt = int(self.sim.get_array(A.ARR_PB_CNT)[self._self])
+        if cnt:
+            pb = self.sim.get_array(A.ARR_PB)
+            mine = pb[self._self * B:self._self * B + cnt]
+            for f in ("member", "from"):
+                shift = (mine[f] >= pos) & (mine[f] < self._self)
+                mine[f][shift] += 1
+            self.sim.set_array(A.ARR_PB, pb)
         return pos
 
     # ---- counters -----------------------------------------------------------------------
@@ -246,7 +256,10 @@ def _msg_from_c(store: Store, c: A.Message) -> Message:
     if c.kind == A.MSG_DEAD:
         frm = store._name(c.dead_from) if c.dead_from == store._self or c.dead_from < len(store._names) else f"#{c.dead_from}"
         return Dead(int(c.incarnation), name, frm)
-    host, addr = store._meta.get(name, ("", SockAddrInet(c.port, c.target)))
+    if name == store.storeSelf.memberName:  # our own announcement / refutation carries our real address (Core.hs:160-166)
+        addr = store.storeSelf.memberHostNew
+    else:
+        addr = store._meta.get(name, ("", SockAddrInet(c.port, c.target)))[1]
     return Alive(int(c.incarnation), name, addr.host, addr.port)
 
 
