@@ -1,5 +1,5 @@
 """swim_b200/daemon.py — the real-time single-node daemon (Core.main completed) — on loopback UDP, with the
-library's scalar calls running on the SIMT emulator (tests/emu; the same test on hardware is tests/test_gpu_daemon.py)."""
+library's scalar calls running on the SIMT emulator (tests/emu; the same test on hardware is tests/test_gpu_zz_daemon.py)."""
 import socket
 import time
 
