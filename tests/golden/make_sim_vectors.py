@@ -22,6 +22,15 @@ SCENARIOS = {
     # sparse random views with loss, churn-like events and injected messages
     "mixed": dict(cfg=dict(n_nodes=200, k_indirect=5, fanout=3, pb_cap=5, suspicion_rounds=4, retransmit=6, loss_ppm=60000,
                            seed=424242), topo=("random", 200, 32, 14, 9), rounds=60, events="random"),
+    # the protocol variants of DESIGN.md 2.5 on the same kind of workload: SWIM 4.2 override order, round-robin probe order
+    # (more than two epochs of 32 rounds), and both together on 64-slot rows
+    "mixed_strict": dict(cfg=dict(n_nodes=200, k_indirect=5, fanout=3, pb_cap=5, suspicion_rounds=4, retransmit=6, loss_ppm=60000,
+                                  seed=424243, flags=1), topo=("random", 200, 32, 14, 9), rounds=60, events="random"),
+    "mixed_round_robin": dict(cfg=dict(n_nodes=200, k_indirect=5, fanout=3, pb_cap=5, suspicion_rounds=4, retransmit=6,
+                                       loss_ppm=60000, seed=424244, flags=2), topo=("random", 200, 32, 14, 9), rounds=80,
+                              events="random"),
+    "wide_both": dict(cfg=dict(n_nodes=150, view_cap=64, k_indirect=4, fanout=4, pb_cap=9, suspicion_rounds=3, retransmit=5,
+                               loss_ppm=20000, seed=424245, flags=3), topo=("random", 150, 64, 50, 4), rounds=140, events="random"),
 }
 
 
