@@ -477,8 +477,8 @@ __device__ __forceinline__ uint16_t *stamp_ptr(uint4 *meta) { return reinterpret
 // store 1 [], Core.hs:239 over shuffle, Util.hs:36-42; round-robin: see rr_pick). `am` is consumed.
 template <int W>
 __device__ __forceinline__ uint4 target_block(const SimDev &d, uint32_t round, uint32_t g) {
-  if (d.flags & SWIM_F_ROUND_ROBIN) return philox4x32_10(make_uint4(round / (32u * W), g, P_RR, 0), d.key0, d.key1);
-  return philox4x32_10(make_uint4(round, g, P_TARGET, 0), d.key0, d.key1);
+  const bool rr = (d.flags & SWIM_F_ROUND_ROBIN) != 0; // one Philox call either way: only the counter words differ
+  return philox4x32_10(make_uint4(rr ? round / (32u * W) : round, g, rr ? P_RR : P_TARGET, 0), d.key0, d.key1);
 }
 template <int W>
 __device__ __forceinline__ uint32_t pick_target(const SimDev &d, uint32_t (&am)[W], uint32_t word, uint32_t L, uint32_t round) {
