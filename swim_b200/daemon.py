@@ -44,8 +44,12 @@ class Node:
         me = Member(name, host, self.addr, Liveness.IsAliveC, 0, 0)
         self.store = core.Store(me, self.cfg, capacity=capacity, **sim_kw)
         self.lock = threading.RLock()
-        self.acks: Dict[int, threading.Event] = {}                      # storeAckHandler (Types.hs:58)
-        self.relays: Dict[int, Tuple[SockAddrInet, int]] = {}           # proxy: my ping's seqNo -> (requester, its seqNo)
+        # storeAckHandler (Types.hs:58): seqNo -> (event, senders whose Ack counts: the target, later the proxies). Own probes
+        # take their seqNo from storeSeqNo, relayed ones from storeIncarnation (Q4), so the two number spaces overlap: an Ack
+        # is matched by sequence number AND sender
+        self.acks: Dict[int, Tuple[threading.Event, set]] = {}
+        # proxy side: my ping's seqNo -> (requester, its seqNo, the target I pinged, when)
+        self.relays: Dict[int, Tuple[SockAddrInet, int, SockAddrInet, float]] = {}
         self.stop_flag = threading.Event()
         self.threads: List[threading.Thread] = []
         self.stats = {"pings": 0, "acks": 0, "indirect": 0, "suspected": 0, "relayed": 0, "datagrams": 0, "decode_errors": 0, "send_errors": 0}
@@ -99,10 +103,14 @@ class Node:
             if isinstance(m, Ack):
                 self.stats["acks"] += 1
                 with self.lock:  # invokeAckHandler (Core.hs:220-221) ... and the relay promised at Core.hs:103-104
-                    ev = self.acks.get(m.seqNo)
-                    relay = self.relays.pop(m.seqNo, None)
-                if ev:
-                    ev.set()
+                    mine = self.acks.get(m.seqNo)
+                    relay = self.relays.get(m.seqNo)
+                    if relay is not None and relay[2] == sender:
+                        del self.relays[m.seqNo]
+                    else:
+                        relay = None
+                if mine and sender in mine[1]:
+                    mine[0].set()
                 if relay:
                     self.stats["relayed"] += 1
                     self._send([Ack(relay[1], ())], relay[0])
@@ -113,7 +121,7 @@ class Node:
                 for g in out:  # the forwarded Ping carries OUR sequence number (Q4): remember whom to answer
                     if isinstance(g, Direct) and isinstance(g.msg, Ping):
                         with self.lock:
-                            self.relays[g.msg.seqNo] = (sender, m.seqNo)
+                            self.relays[g.msg.seqNo] = (sender, m.seqNo, g.addr, time.monotonic())
             gossip.extend(out)
         self._flush(gossip)
 
@@ -138,7 +146,12 @@ class Node:
             seq = core.nextSeqNo(self.store)                              # Core.hs:238
             targets = core.kRandomMembers(self.store, 1, [])              # Core.hs:239
             payload = core.take_broadcasts(self.store)                    # Core.hs:136 FIXME: the compound message
-            ev = self.acks[seq] = threading.Event()
+            ev = threading.Event()
+            allowed = {targets[0].memberHostNew} if targets else set()
+            self.acks[seq] = (ev, allowed)
+            now = time.monotonic()                                        # relays nobody answered are forgotten
+            for k in [k for k, v in self.relays.items() if now - v[3] > 4 * self.period]:
+                del self.relays[k]
         try:
             if not targets:
                 return None
@@ -153,6 +166,8 @@ class Node:
             for p in proxies:
                 if p.memberName != m.memberName:
                     self.stats["indirect"] += 1
+                    with self.lock:
+                        allowed.add(p.memberHostNew)                                            # its relayed Ack counts
                     self._send([ip] + payload, p.memberHostNew)                                 # Core.hs:250
             if self._wait_ack(seq, ev, self.period / 3):
                 return m.memberName, "indirect-ack"

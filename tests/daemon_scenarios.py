@@ -52,7 +52,16 @@ def scenario_probe_escalation_and_relay():
         b.handle_datagram(raw, c.addr)
         msgs, frm, raw = recv_msgs(c)
         assert msgs == [Ack(proxy_seq, ())] and frm == b.addr
+        # own probes count storeSeqNo, relayed ones storeIncarnation (Q4): the same number can be in flight twice. An own probe
+        # of `a` with that very sequence number must not take b's Ack for its own
+        import threading
+        own = threading.Event()
+        with c.lock:
+            c.acks[proxy_seq] = (own, {a.addr})
         c.handle_datagram(raw, b.addr)
+        assert not own.is_set()
+        with c.lock:
+            del c.acks[proxy_seq]
         msgs, frm, _ = recv_msgs(a)
         assert msgs == [Ack(7, ())] and frm == c.addr                       # the requester gets its own sequence number back
         assert c.stats["relayed"] == 1
