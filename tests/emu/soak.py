@@ -1,6 +1,6 @@
 """Developer tool: fuzz the device code on the emulator against the oracle — random sizes, view widths, fan-outs, buffer
 capacities, loss, crashes / rejoins / injected messages, protocol variants, single- and multi-round launches.
-    python tests/emu/soak.py FIRST_SEED N_SEEDS        (prints one line per failing seed; exit code 1 if any)"""
+    python tests/emu/soak.py FIRST_SEED N_SEEDS [sharded]   (prints one line per failing seed; exit code 1 if any)"""
 import os
 import sys
 import traceback
@@ -47,12 +47,71 @@ def one(seed):
     sim.close()
 
 
+def one_sharded(seed):
+    """Several ranks in one process (fused exchange), stepped by one host thread each, against the single-shard oracle."""
+    import threading
+    from oracle.oracle import Oracle
+    from swim_b200 import _abi as A
+    from swim_b200.sim import Simulator
+    rng = np.random.default_rng(seed)
+    world = int(rng.integers(2, 5))
+    n = int(rng.integers(world * 2, 400))
+    deg = int(rng.integers(1, min(n - 1, 32) + 1))
+    k = int(rng.integers(0, 8))
+    kw = dict(n_nodes=n, k_indirect=k, fanout=int(rng.integers(1, k + 2)), pb_cap=int(rng.integers(1, 17)),
+              suspicion_rounds=int(rng.integers(1, 9)), retransmit=int(rng.integers(1, 9)),
+              loss_ppm=int(rng.choice([0, 20000, 200000])), seed=int(rng.integers(0, 2 ** 63)), flags=int(rng.integers(0, 4)))
+    if rng.random() < 0.5:
+        os.environ["SWIM_ROUND_KERNEL"] = "1"
+    else:
+        os.environ.pop("SWIM_ROUND_KERNEL", None)
+    nbr = generate_topology("random" if deg < n - 1 else "complete", n, 32, deg, seed=int(rng.integers(1, 1000)))
+    rounds = int(rng.integers(10, 50))
+    ev = random_events(rng, n, rounds, n_crash=max(1, n // 8), n_rejoin=max(1, n // 30), n_inject=n // 5)
+    sims = [Simulator(default_config(rank=r, world=world, **kw)) for r in range(world)]
+    for s_ in sims:
+        s_.set_view(nbr)
+    blobs = [s_.ipc_export() for s_ in sims]
+    for s_ in sims:
+        s_.ipc_connect(blobs)
+        s_.inject(ev)
+    ref = Oracle(default_config(**kw))
+    ref.set_view(nbr)
+    ref.inject(ev)
+    done = 0
+    while done < rounds:
+        chunk = min(int(rng.choice([1, 1, 3, 11])), rounds - done)
+        errs = []
+
+        def work(x):
+            try:
+                x.step(chunk)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=work, args=(x,)) for x in sims]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert not errs, errs
+        ref.step(chunk)
+        done += chunk
+        where = f"seed {seed} round {done} (world={world} n={n} flags={kw['flags']} rk={os.environ.get('SWIM_ROUND_KERNEL')})"
+        assert sum(x.digest() for x in sims) % 2 ** 64 == ref.digest(), where
+        assert sum(x.mismatches() for x in sims) == ref.mismatches(), where
+    assert np.sum([x.counters() for x in sims], axis=0).tolist() == ref.counters().tolist()
+    for a in range(A.ARR_COUNT):
+        got = sims[0].get_array(a) if a == A.ARR_ALIVE else np.concatenate([x.get_array(a) for x in sims])
+        assert np.array_equal(got, ref.get_array(a)), A.ARRAY_NAMES[a]
+    for x in sims:
+        x.close()
+
+
 def main():
     first, count = int(sys.argv[1]), int(sys.argv[2])
+    sharded = len(sys.argv) > 3 and sys.argv[3] == "sharded"
     bad = 0
     for seed in range(first, first + count):
         try:
-            one(seed)
+            (one_sharded if sharded else one)(seed)
         except Exception as e:  # noqa: BLE001
             bad += 1
             print(f"FAIL seed {seed}: {e}", flush=True)
