@@ -175,3 +175,44 @@ def test_codec_under_asan_ubsan(tmp_path):
     assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr
     _, n_ok, n_bad = r.stdout.split()
     assert int(n_ok) > 300 and int(n_bad) > 300
+
+
+EMU_ASAN_DRIVER = r'''
+import sys
+root, so = sys.argv[1], sys.argv[2]
+sys.path[:0] = [root, root + "/tests", root + "/tests/emu"]
+import swim_b200._lib as L
+import soak                      # scenario generators (builds / selects the plain emulator library on import) ...
+L.SO_PATH, L._lib = so, None     # ... but this process runs the AddressSanitizer build
+for seed in (31001, 31002, 31003):
+    soak.one(seed)
+soak.one_sharded(32001)
+print("ok")
+'''
+
+
+def test_device_code_under_asan_on_the_emulator(tmp_path):
+    """The CUDA sources compiled for the CPU (tests/emu) WITH AddressSanitizer: every cudaMalloc is an instrumented heap
+    block, so an out-of-bounds access of a kernel — e.g. the speculative loads K2 issues before it knows an in-list's
+    length — aborts here. Random scenarios against the oracle, one of them sharded over several ranks."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    libasan = subprocess.run(["g++", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(libasan):
+        pytest.skip("libasan.so not found")
+    saved = (build_emu.OBJ, build_emu.SO)
+    try:
+        build_emu.OBJ, build_emu.SO = str(tmp_path / "build"), str(tmp_path / "libswim_emu_asan.so")
+        try:
+            so = build_emu.build(force=True, extra=("-fsanitize=address", "-fno-omit-frame-pointer"))
+        except RuntimeError as e:
+            pytest.skip(f"cannot build the sanitizer variant: {e}")
+    finally:
+        build_emu.OBJ, build_emu.SO = saved
+    script = tmp_path / "drive.py"
+    script.write_text(EMU_ASAN_DRIVER)
+    env = dict(os.environ, LD_PRELOAD=libasan,
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:abort_on_error=1")
+    r = subprocess.run([sys.executable, str(script), ROOT, so], capture_output=True, text=True, env=env, timeout=1200)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), (r.stdout[-500:], r.stderr[-3000:])
+    assert "ERROR: AddressSanitizer" not in r.stderr
