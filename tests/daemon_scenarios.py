@@ -118,12 +118,14 @@ def scenario_live_cluster_detects_a_crash(period=0.25, deadline=60.0):
         t0 = time.monotonic()
         while time.monotonic() - t0 < deadline:
             va, vb = a.members(), b.members()
-            if va["c"].memberAlive == Liveness.IsDeadC and vb["c"].memberAlive == Liveness.IsDeadC:
+            # ... and the survivors hold each other Alive (on a loaded machine an Ack can miss its deadline: the false
+            # suspicion is then refuted with a higher incarnation, which takes a few more periods)
+            if va["c"].memberAlive == Liveness.IsDeadC and vb["c"].memberAlive == Liveness.IsDeadC and \
+                    va["b"].memberAlive == Liveness.IsAliveC and vb["a"].memberAlive == Liveness.IsAliveC:
                 break
             time.sleep(period)
         else:
             raise AssertionError("the crash was not detected: " + repr((a.members(), b.members())))
-        assert a.members()["b"].memberAlive == Liveness.IsAliveC and b.members()["a"].memberAlive == Liveness.IsAliveC
         assert a.stats["acks"] > 0 and b.stats["acks"] > 0
         assert a.stats["decode_errors"] == b.stats["decode_errors"] == 0
     finally:
