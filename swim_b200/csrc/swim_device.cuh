@@ -454,13 +454,6 @@ __device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t round, uint32
   return bounded(word_of(y, w), 1000000u) < d.loss_ppm;
 }
 
-// K1a — streaming pass over every node of the shard, FOUR nodes per lane: the four nodes 4g..4g+3
-// share one Philox4x32-10 block (one 32-bit draw each), so a lane issues four independent 16-byte
-// loads (the nodes' meta records: alive / suspect / crashed-member bitmaps + flags), one Philox
-// call, and four r-th-set-bit picks (kRandomMembers store 1 [], Core.hs:239; shuffle, Util.hs:36-42)
-// tested against the crashed-member bitmap (Ping/Ack, Core.hs:246). A warp covers 128 consecutive
-// nodes = 2 KB contiguous. Nodes that need more — a Suspect slot to count down, a failed probe, a
-// non-empty piggyback buffer — are appended to the round's work list for K1b.
 __device__ __forceinline__ void peer_publish_cta(const SimDev &d, uint32_t mail_round); // defined with the cross-GPU sync
 
 constexpr int kScanGroups = 2; // Philox groups (of 4 nodes) per lane per iteration: 8 nodes, 8 loads in flight
