@@ -77,8 +77,8 @@ struct SimDev {
   uint32_t *vlast;           // [n*cap]
   uint4 *pb;                 // [n*B] {member, inc, from, kind | ttl<<8}
   uint8_t *pb_cnt;           // [n]
-  uint4 *out;                // [n*B] snapshot sent this round
-  uint8_t *out_cnt;          // [n]
+  uint4 *out;                // [2][per*B] snapshot sent this round (round parity)
+  uint8_t *out_cnt;          // [2][per]
   uint32_t *ridx;            // [n*cap] index of edge (i,s) in the receiver's in-list
   uint32_t *in_off;          // [n+1]
   uint32_t *in_src;          // [E] sender ids, ascending per receiver
