@@ -37,6 +37,8 @@ struct swim_sim {
   int grids[5] = {0, 0, 0, 0, 0}; // one-wave grid sizes of the per-round kernels (filled on first use)
   uint64_t launches = 0;
   bool profile = false;
+  // launch-path switches, read from the environment once per handle (swim_sim_create), not once per call
+  bool opt_pipeline = false, opt_split = false, opt_round_kernel = false, opt_one_round = false;
   std::vector<cudaEvent_t> prof_events; // pool, reused
   std::vector<std::pair<int, int>> prof_marks; // (phase, index of start event); stop = start + 1
   size_t prof_used = 0;

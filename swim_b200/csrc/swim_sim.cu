@@ -122,6 +122,10 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   swim_sim *sim = new (std::nothrow) swim_sim();
   if (!sim) return SWIM_ENOMEM;
   sim->cfg = *cfg;
+  sim->opt_pipeline = getenv("SWIM_PIPELINE") != nullptr;
+  sim->opt_split = getenv("SWIM_SPLIT") != nullptr;
+  sim->opt_round_kernel = getenv("SWIM_ROUND_KERNEL") != nullptr;
+  sim->opt_one_round = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
   if (cfg->device >= 0) {
     rc = [&]() { CUDA_TRY(sim, cudaSetDevice(cfg->device)); return SWIM_OK; }();
     if (rc) { g_last_error = sim->last_error; delete sim; return rc; }
@@ -445,7 +449,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   // (every warp's own dependent-load chain is the critical path either way). Single shard only: the scan of round
   // r+1 skips nodes by the mail stamps of round r, and a peer GPU's stamps may still be in flight when it starts
   // (the emulated two-rank run of tests/test_emu_parity.py diverges from the oracle with it).
-  const bool pipelined = !sim->profile && d.world == 1 && getenv("SWIM_PIPELINE") != nullptr;
+  const bool pipelined = !sim->profile && d.world == 1 && sim->opt_pipeline;
   const int fgrid = sim->grids[3];
   // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
   // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
@@ -454,10 +458,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   // grid_peer_barrier (the last CTA to arrive talks to the peers, ONE thread per GPU — an earlier form in which every
   // warp polled the peers' flags measured 136 ms/round) and consecutive event-free rounds share one launch. Bit-exact in
   // the emulated multi-rank runs (tests/test_emu_parity.py); not yet timed on NVLink hardware, hence opt-in.
-  const bool single_kernel = !sim->profile && !pipelined && getenv("SWIM_SPLIT") == nullptr &&
-                             (d.world == 1 || (d.p2p && getenv("SWIM_ROUND_KERNEL") != nullptr));
+  const bool single_kernel = !sim->profile && !pipelined && !sim->opt_split &&
+                             (d.world == 1 || (d.p2p && sim->opt_round_kernel));
   const int kgrid = sim->grids[4];
-  const bool multi_round_off = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
+  const bool multi_round_off = sim->opt_one_round;
   bool pending = false; // K2 of the previous round has not run yet
   for (uint32_t r = 0; r < rounds; ++r) {
     d.round = ++sim->round;
