@@ -180,8 +180,9 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.xtra, 4, 0))) return r;
     if ((r = dalloc(sim, &d.claim2, n, 0))) return r;
     if ((r = dalloc(sim, &d.rl, 2 * n * d.fanout, 0xFF))) return r; // [parity] candidate slots, empty = 0xFFFFFFFF
-    if ((r = dalloc(sim, &d.ctr, SWIM_CTR__COUNT, 0))) return r;
-    if ((r = dalloc(sim, &sim->d_scratch, 2, 0))) return r;
+    // {digest, mismatch count} scratch and the counters share one block: swim_sim_observe reads both back in one copy
+    if ((r = dalloc(sim, &sim->d_scratch, 2 + SWIM_CTR__COUNT, 0))) return r;
+    d.ctr = sim->d_scratch + 2;
     if ((r = dalloc(sim, &sim->d_bar, SWIM_MAX_WORLD, 0))) return r;
     // watchdog word of the in-kernel waits: pinned host memory mapped into the device, so swim_sim_sync reads it
     // without a copy (it is written only when a wait gives up)
@@ -752,8 +753,7 @@ extern "C" int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_co
   }
   CUDA_TRY(sim, cudaGetLastError());
   unsigned long long *h = sim->h_observe;
-  CUDA_TRY(sim, cudaMemcpyAsync(h, sim->d_scratch, 16, cudaMemcpyDeviceToHost, sim->stream));
-  CUDA_TRY(sim, cudaMemcpyAsync(h + 2, d.ctr, SWIM_CTR__COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
+  CUDA_TRY(sim, cudaMemcpyAsync(h, sim->d_scratch, (2 + SWIM_CTR__COUNT) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sim->stream));
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   if (digest) *digest = h[0];
   if (mismatches) *mismatches = h[1];
