@@ -90,7 +90,8 @@ class Simulator:
     def __init__(self, cfg: A.Config = None, **kw):
         self.cfg = cfg if cfg is not None else default_config(**kw)
         h = C.c_void_p()
-        check(lib().swim_sim_create(C.byref(self.cfg), C.byref(h)), "swim_sim_create")
+        self._lib = lib()  # the library that owns the handle also destroys it
+        check(self._lib.swim_sim_create(C.byref(self.cfg), C.byref(h)), "swim_sim_create")
         self._h = h
         f, n = C.c_uint32(), C.c_uint32()
         check(lib().swim_sim_local_range(h, C.byref(f), C.byref(n)), "swim_sim_local_range", h)
@@ -98,7 +99,7 @@ class Simulator:
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().swim_sim_destroy(self._h)
+            self._lib.swim_sim_destroy(self._h)
             self._h = None
 
     def __del__(self):
