@@ -45,6 +45,11 @@ def build(force=False, extra=()):
         list(ex.map(run, jobs))
     if force or jobs or _stale(SO, objs):
         run(["g++", "-shared", "-o", SO] + objs + ["-fopenmp", "-pthread", "-ldl"] + list(extra))
+    # the in-process NCCL stand-in the staged exchange binds through SWIM_NCCL_LIB in the emulated tests
+    fake = os.path.join(os.path.dirname(SO), "libfake_nccl.so")
+    src = os.path.join(HERE, "fake_nccl.cpp")
+    if force or _stale(fake, [src] + deps):
+        run(["g++"] + FLAGS + list(extra) + ["-shared", "-o", fake, src])
     return SO
 
 

@@ -159,7 +159,7 @@ def test_scalar_calls_match_oracle():
 
 
 # ---------------------------------------------------------------- several ranks in one process (fused exchange)
-def run_sharded(world, n, chunks, loss, deg, flags=0):
+def run_sharded(world, n, chunks, loss, deg, flags=0, mode="p2p"):
     """`world` handles = `world` emulated GPUs; CUDA IPC is the identity in one process, so the peers' arrays are mapped
     exactly as on an NVLink box. Each rank steps on its own host thread (its kernel waits for the others in-kernel)."""
     from oracle.oracle import Oracle
@@ -172,9 +172,19 @@ def run_sharded(world, n, chunks, loss, deg, flags=0):
     sims = [Simulator(default_config(rank=r, world=world, **kw)) for r in range(world)]
     for s in sims:
         s.set_view(nbr)
-    blobs = [s.ipc_export() for s in sims]
+    if mode == "p2p":
+        blobs = [s.ipc_export() for s in sims]
+        for s in sims:
+            s.ipc_connect(blobs)
+    else:  # staged exchange: NCCL replaced by tests/emu/fake_nccl.cpp (ranks = threads); the rendezvous blocks until all joined
+        from swim_b200.sim import nccl_unique_id
+        uid = nccl_unique_id()
+        ts = [threading.Thread(target=s.connect, args=(uid,)) for s in sims]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
     for s in sims:
-        s.ipc_connect(blobs)
         s.inject(events)
     ref = Oracle(default_config(**kw))
     ref.set_view(nbr)
@@ -218,3 +228,13 @@ def test_sharded_fused_exchange_equals_oracle(world, path, monkeypatch):
 def test_sharded_variants(monkeypatch):
     monkeypatch.setenv("SWIM_ROUND_KERNEL", "1")
     run_sharded(2, n=200, chunks=[1, 1, 40], loss=0, deg=20, flags=A.F_STRICT_OVERRIDE | A.F_ROUND_ROBIN)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_staged_exchange_equals_oracle(world, monkeypatch):
+    """The NCCL baseline path (bucketed envelopes, all-gathered counts, send/recv per peer, deliver_kernel) with an in-process
+    stand-in for the nine NCCL calls the library binds at run time."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    monkeypatch.setenv("SWIM_NCCL_LIB", os.path.join(here, "emu", "libfake_nccl.so"))
+    run_sharded(world, n=403, chunks=[1] * 5 + [9], loss=20000, deg=24, mode="nccl")
