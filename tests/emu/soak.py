@@ -15,6 +15,7 @@ import build_emu  # noqa: E402
 import swim_b200._lib as L  # noqa: E402
 
 L.SO_PATH, L._lib = build_emu.build(), None
+os.environ["SWIM_NCCL_LIB"] = os.path.join(HERE, "libfake_nccl.so")
 
 from helpers import assert_same_state, default_config, generate_topology, make_pair, random_events  # noqa: E402
 
@@ -71,9 +72,18 @@ def one_sharded(seed):
     sims = [Simulator(default_config(rank=r, world=world, **kw)) for r in range(world)]
     for s_ in sims:
         s_.set_view(nbr)
-    blobs = [s_.ipc_export() for s_ in sims]
+    staged = rng.random() < 0.3  # the NCCL baseline path, NCCL replaced by tests/emu/fake_nccl.cpp
+    if staged:
+        from swim_b200.sim import nccl_unique_id
+        uid = nccl_unique_id()
+        ts = [threading.Thread(target=s_.connect, args=(uid,)) for s_ in sims]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    else:
+        blobs = [s_.ipc_export() for s_ in sims]
+        for s_ in sims:
+            s_.ipc_connect(blobs)
     for s_ in sims:
-        s_.ipc_connect(blobs)
         s_.inject(ev)
     ref = Oracle(default_config(**kw))
     ref.set_view(nbr)
@@ -94,7 +104,7 @@ def one_sharded(seed):
         assert not errs, errs
         ref.step(chunk)
         done += chunk
-        where = f"seed {seed} round {done} (world={world} n={n} flags={kw['flags']} rk={os.environ.get('SWIM_ROUND_KERNEL')})"
+        where = f"seed {seed} round {done} (world={world} n={n} flags={kw['flags']} rk={os.environ.get('SWIM_ROUND_KERNEL')} staged={staged})"
         assert sum(x.digest() for x in sims) % 2 ** 64 == ref.digest(), where
         assert sum(x.mismatches() for x in sims) == ref.mismatches(), where
     assert np.sum([x.counters() for x in sims], axis=0).tolist() == ref.counters().tolist()
