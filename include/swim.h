@@ -258,6 +258,11 @@ int swim_sim_inject(swim_sim_t *sim, const swim_event_t *events, size_t n);
 /* Number of rounds executed so far (== the seqNo of the last Ping, Core.hs:238). */
 int swim_sim_round(const swim_sim_t *sim, uint32_t *round);
 
+/* Checkpoint / resume: a run is reproduced exactly by the config, the view (SWIM_ARR_NBR rows -> swim_sim_set_view), the
+ * other state arrays (swim_sim_set_array), the events still pending, and the round counter — the counter of every
+ * Philox draw. swim_sim_set_round puts a fresh handle at `round` (pending events must lie after it). */
+int swim_sim_set_round(swim_sim_t *sim, uint32_t round);
+
 /* Bulk copies of one state array (SWIM_ARR_*) between device and a host buffer of exactly
  * `bytes` bytes. set_array(SWIM_ARR_NBR) is rejected: use swim_sim_set_view. */
 int swim_sim_get_array(swim_sim_t *sim, int arr, void *host_buf, size_t bytes);

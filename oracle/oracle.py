@@ -73,6 +73,7 @@ def lib():
         L.oracle_get_broadcasts.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
         L.oracle_take_broadcasts.argtypes = [vp, u32, vp, sz, C.POINTER(sz)]
         L.oracle_tick_timers.argtypes = [vp, u32, C.POINTER(u32)]
+        L.oracle_set_round.argtypes = [vp, u32]
         L.oracle_philox.argtypes = [vp, vp, vp]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
@@ -169,6 +170,9 @@ class Oracle:
     @property
     def round(self):
         return lib().oracle_round(self._h)
+
+    def set_round(self, r):
+        _chk(lib().oracle_set_round(self._h, r), "set_round")
 
     def counters(self):
         out = np.zeros(A.CTR_COUNT, dtype=np.uint64)

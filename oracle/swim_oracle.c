@@ -644,6 +644,12 @@ EXPORT int oracle_step(oracle_t *o, uint32_t rounds) {
 }
 
 EXPORT uint32_t oracle_round(const oracle_t *o) { return o->round; }
+EXPORT int oracle_set_round(oracle_t *o, uint32_t round) {
+  for (size_t x = 0; x < o->n_ev; ++x)
+    if (o->ev[x].round <= round) return SWIM_EINVAL;
+  o->round = round;
+  return SWIM_OK;
+}
 EXPORT void oracle_counters(const oracle_t *o, uint64_t *out) { memcpy(out, o->ctr, sizeof o->ctr); }
 
 /* ------------------------------------------------------------------ state access */

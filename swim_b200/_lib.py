@@ -45,6 +45,7 @@ def lib():
     sig("swim_sim_local_range", i, vp, P(u32), P(u32))
     sig("swim_sim_set_view", i, vp, vp)
     sig("swim_topology_generate", i, i, u32, u32, u32, u64, vp)
+    sig("swim_sim_set_round", i, vp, u32)
     sig("swim_sim_step", i, vp, u32)
     sig("swim_sim_step_async", i, vp, u32)
     sig("swim_sim_sync", i, vp)

@@ -582,6 +582,18 @@ extern "C" int swim_sim_last_step_ms(const swim_sim_t *sim, float *ms) {
   return e == cudaSuccess ? SWIM_OK : SWIM_ECUDA;
 }
 
+extern "C" int swim_sim_set_round(swim_sim_t *sim, uint32_t round) {
+  if (!sim) return SWIM_EINVAL;
+  if (!sim->events.empty() && sim->events.front().round <= round) {
+    set_error(sim, "swim_sim_set_round: an event is pending at round %u <= %u", sim->events.front().round, round);
+    return SWIM_EINVAL;
+  }
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  sim->round = round;
+  return SWIM_OK;
+}
+
 extern "C" int swim_sim_round(const swim_sim_t *sim, uint32_t *round) {
   if (!sim || !round) return SWIM_EINVAL;
   *round = sim->round;

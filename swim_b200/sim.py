@@ -224,6 +224,27 @@ class Simulator:
         """All bulk arrays as a dict (the checkable form of dumpStore, Util.hs:64-74)."""
         return {A.ARRAY_NAMES[a]: self.get_array(a) for a in range(A.ARR_COUNT)}
 
+    def set_round(self, r):
+        check(lib().swim_sim_set_round(self._h, r), "swim_sim_set_round", self._h)
+
+    def checkpoint(self):
+        """Everything a single-shard run needs to be resumed bit for bit: the state arrays and the round (the counter of
+        every Philox draw). Pending events and the config are the caller's (they are inputs, not state)."""
+        ck = self.state()
+        ck["round"] = self.round
+        return ck
+
+    def restore(self, ck):
+        """Put a FRESH single-shard handle (same config) into a checkpointed state."""
+        if self.cfg.world != 1:
+            raise ValueError("restore() takes the global view matrix: single-shard handles only")
+        by_name = {v: k for k, v in A.ARRAY_NAMES.items()}
+        self.set_view(ck["nbr"].reshape(self.cfg.n_nodes, self.cfg.view_cap))
+        for name, data in ck.items():
+            if name not in ("nbr", "round"):
+                self.set_array(by_name[name], data)
+        self.set_round(int(ck["round"]))
+
     # ---- multi-GPU
     def connect(self, unique_id: bytes):
         """Staged exchange: join the NCCL communicator (swim_sim_connect)."""

@@ -107,3 +107,29 @@ def test_strict_override_scalar_calls_match_oracle():
         got = [(buf[i].id, buf[i].liveness, buf[i].timer, buf[i].incarnation) for i in range(cnt.value)]
         assert got == [(x.id, x.liveness, x.timer, x.incarnation) for x in orc.get_members(node)], step
     assert sim.get_array(A.ARR_SELF_INC)[node] == orc.get_array(A.ARR_SELF_INC)[node]
+
+
+def test_checkpoint_and_resume():
+    """State arrays + round counter reproduce a run exactly (swim_sim_set_round): a fresh handle restored from a checkpoint
+    continues with the digests of the run it was taken from and of the oracle."""
+    from swim_b200.sim import Simulator
+    rng = np.random.default_rng(5)
+    n = 4000
+    kw = dict(n_nodes=n, seed=31, loss_ppm=30000)
+    nbr = generate_topology("random", n, 32, 20, seed=8)
+    ev = random_events(rng, n, 60, n_crash=200, n_rejoin=60, n_inject=300)
+    a, orc = make_pair(default_config(**kw), nbr)
+    a.inject(ev)
+    orc.inject(ev)
+    a.step(25)
+    orc.step(25)
+    ck = a.checkpoint()
+    b = Simulator(default_config(**kw))
+    b.restore(ck)
+    b.inject(ev[ev["round"] > 25])
+    assert b.round == 25 and b.digest() == a.digest()
+    for _ in range(7):
+        a.step(5)
+        b.step(5)
+        orc.step(5)
+        assert a.digest() == b.digest() == orc.digest()
