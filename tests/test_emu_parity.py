@@ -268,3 +268,24 @@ def test_checkpoint_and_resume():
     assert np.array_equal(a.get_array(A.ARR_VLAST), b.get_array(A.ARR_VLAST))
     # counters are cumulative since create: the resumed handle counts from the checkpoint on
     assert (a.counters() - b.counters()).min() >= 0
+
+
+@pytest.mark.parametrize("loss,flags", [(0, 0), (1500, 0), (700, A.F_ROUND_ROBIN), (6000, A.F_STRICT_OVERRIDE)])
+def test_long_launches_through_quiet_and_busy_stretches(loss, flags):
+    """One call = one launch per event-free stretch. Quiescent stretches (a healthy cluster) and rounds with work alternate:
+    rarely lost probes raise a suspicion now and then, a crash lands in the middle. State AND counters (every Ping is
+    counted exactly once) must equal the oracle's wherever the kernel stops batching rounds."""
+    n = 300
+    cfg = default_config(n_nodes=n, seed=1234 + loss, loss_ppm=loss, flags=flags)
+    nbr = generate_topology("random", n, 32, 24, seed=5)
+    sim, orc = make_pair(cfg, nbr)
+    ev = crash_events(57, [17, 200])
+    sim.inject(ev)
+    orc.inject(ev)
+    for chunk in (3, 41, 100, 7, 120):
+        sim.step(chunk)
+        orc.step(chunk)
+        assert_same_state(sim, orc, f"loss {loss} after {sim.round} rounds")
+    import os
+    if not any(os.environ.get(k) for k in ("SWIM_SPLIT", "SWIM_PIPELINE", "SWIM_ONE_ROUND_PER_LAUNCH")):
+        assert sim.launch_count() < 40  # one launch per event-free stretch (+ digests of the comparisons)
