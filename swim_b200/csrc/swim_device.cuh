@@ -486,15 +486,19 @@ __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags,
                                                 uint32_t sus, uint32_t tdraw, uint32_t ldraw, uint32_t round, uint32_t &pings) {
   if ((flags & 0xFFu) == 0) return false;              // a crashed process does nothing
   bool need = (flags & 0xFF00u) != 0 || sus != 0;       // piggyback to send, or a countdown to run [Q8]
-  uint32_t L = 0;
+  uint32_t L = 0, risk = d.loss_ppm;
 #pragma unroll
-  for (int w = 0; w < W; ++w) L += __popc(am[w]);
+  for (int w = 0; w < W; ++w) { L += __popc(am[w]); risk |= am[w] & td[w]; }
   if (L) {
-    const uint32_t tslot = pick_target<W>(d, am, tdraw, L, round); // kRandomMembers store 1 [] (Core.hs:239)
-    ++pings;                                                       // Ping (Core.hs:246)
-    bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;       // Ack iff the target process is up
-    if (acked && d.loss_ppm) acked = !(bounded(ldraw, 1000000u) < d.loss_ppm);
-    need |= !acked;
+    ++pings;                                                         // Ping (Core.hs:246)
+    // No crashed process among the Alive slots and no message loss: whichever slot the draw selects, the Ack comes
+    // back, so the pick (and, in the scan, the Philox block behind `tdraw`) is not needed — the common case.
+    if (risk) {
+      const uint32_t tslot = pick_target<W>(d, am, tdraw, L, round); // kRandomMembers store 1 [] (Core.hs:239)
+      bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;       // Ack iff the target process is up
+      if (acked && d.loss_ppm) acked = !(bounded(ldraw, 1000000u) < d.loss_ppm);
+      need |= !acked;
+    }
   }
   return need;
 }
@@ -529,7 +533,13 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
     for (int u = 0; u < U; ++u) {
       const uint32_t g = gb + u * 32 + lane;
       if ((valid >> (u * 4) & 0xFu) == 0) continue;
-      const uint4 x = target_block<W>(d, round, g);
+      // the four target draws are only looked at by nodes whose probe can fail (node_needs_work: `risk`)
+      bool draws = W > 1 || d.loss_ppm != 0;
+      if (W == 1)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) draws |= (m[u][j].x & m[u][j].z) != 0; // an Alive slot whose process is down
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (draws) x = target_block<W>(d, round, g);
       uint4 y = make_uint4(0, 0, 0, 0);
       if (d.loss_ppm) y = philox4x32_10(make_uint4(round, g, P_LOSS0, 0), d.key0, d.key1);
 #pragma unroll
