@@ -107,6 +107,8 @@ struct SimDev {
   uint4 *meta_p[SWIM_MAX_WORLD];         // receivers' meta records (mail stamps are written by senders)
   uint32_t *bar_err;                     // set by a cross-GPU / grid wait that timed out
   uint32_t *gbar;                        // [2] grid barrier of round_kernel: arrival count, generation
+  uint32_t *qm;                          // [3] busy masks of round_kernel's batched quiet scans (batch number % 3)
+  uint32_t qbatch;                       // rounds per batched quiet scan (<= 8); 0 or 1 = off
   uint32_t *rlr_p[SWIM_MAX_WORLD];       // [2][world][rcap] receiver ids appended by each source rank
   uint32_t *rcnt_p[SWIM_MAX_WORLD];      // [2][world] their counts, published by the barrier kernel
   uint32_t *bar_p[SWIM_MAX_WORLD];       // [world] cross-GPU barrier words
@@ -594,6 +596,71 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tick_scan_kernel(SimDev 
   if (lane == 0 && pings) atomicAdd(&d.ctr[SWIM_CTR_PINGS], (unsigned long long)pings);
 }
 
+// K1a over Q consecutive rounds at once, for stretches in which nothing happens. A round whose scan lists no work
+// writes nothing, so the scan of the round after it reads the same meta records: one pass loads them once and decides
+// rounds round .. round+Q-1 together. Only the probe outcome depends on the round (through the target draw), and only
+// for nodes that have a crashed process in an Alive slot — rare once a cluster has converged; everything else a node
+// can need (a buffered record, a countdown) holds for every round of the batch. Nothing is listed: the result is the
+// lane's mask of rounds that are NOT quiet (bit q: round + q), the caller commits the rounds before the first such bit
+// and runs the ordinary scan from there. `pings` is the Ping count of ONE round (the same for each of them).
+// Requires loss_ppm == 0 (with loss every probe depends on a draw and there are no quiet stretches to speak of).
+template <int W>
+__device__ __forceinline__ uint32_t quiet_scan(const SimDev &d, uint32_t round, uint32_t Q, uint32_t warp, uint32_t nwarps,
+                                               int lane, uint32_t &pings) {
+  constexpr int U = kScanGroups;
+  const uint32_t allq = (1u << Q) - 1u;
+  uint32_t busy = 0;
+  const uint32_t g0 = d.first >> 2, g1 = (d.first + d.n + 3) >> 2;
+  for (uint32_t gb = g0 + warp * (32 * U); gb < g1; gb += nwarps * (32 * U)) {
+    uint4 m[U][4];
+    uint32_t valid = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t node = 4 * (gb + u * 32 + lane) + j;
+        const bool ok = node >= d.first && node < d.first + d.n;
+        valid |= (uint32_t)ok << (u * 4 + j);
+        m[u][j] = ok ? d.meta[(size_t)(node - d.first) * W] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t g = gb + u * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!(valid >> (u * 4 + j) & 1u)) continue;
+        uint32_t am[W], td[W], sus = m[u][j].y, risk = 0;
+        am[0] = m[u][j].x; td[0] = m[u][j].z;
+        if (W > 1) {
+          const uint32_t l = 4 * g + j - d.first;
+#pragma unroll
+          for (int w = 1; w < W; ++w) {
+            const uint4 mw = d.meta[(size_t)l * W + w];
+            am[w] = mw.x; sus |= mw.y; td[w] = mw.z;
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) risk |= am[w] & td[w];
+        if (!risk) { // the draw is never looked at: one decision for the whole batch
+          if (node_needs_work<W>(d, m[u][j].w, am, td, sus, 0, 0, round, pings)) busy = allq;
+          continue;
+        }
+        uint32_t p = 0;
+        for (uint32_t q = 0; q < Q; ++q) {
+          uint32_t amq[W];
+#pragma unroll
+          for (int w = 0; w < W; ++w) amq[w] = am[w];
+          const uint4 x = target_block<W>(d, round + q, g);
+          p = 0;
+          if (node_needs_work<W>(d, m[u][j].w, amq, td, sus, word_of(x, j), 0, round + q, p)) busy |= 1u << q;
+        }
+        pings += p;
+      }
+    }
+  }
+  return busy;
+}
+
 // K1b — warp-per-node over the work list (plus, when pipelined, last round's receivers): countdown
 // and expiry -> Dead, probe escalation (k proxies), local suspicion, piggyback send. Lane s owns view
 // slot s; the piggyback buffer is staged in shared memory. Everything K1a derived is recomputed
@@ -1077,16 +1144,41 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   // d.nrounds consecutive event-free rounds in this launch (the host splits calls at rounds that carry events)
+  // Batched quiet scans (single shard, no loss): after a round that listed no work, the next up to d.qbatch rounds are
+  // decided by ONE pass over the meta records and ONE barrier (quiet_scan). Its busy mask is OR-ed into qm[batch % 3];
+  // a slot is cleared two batches (>= two barriers) before it is used again, slot 0 here, ahead of the first round's
+  // barrier. While rounds are quiet all three list counters stay zero, so the ordinary path resumes at any round.
+  const bool batching = d.qbatch > 1 && d.world == 1 && d.loss_ppm == 0;
+  bool prev_quiet = false;
+  uint32_t nb = 0;
+  if (batching && warp == 0 && lane == 0) d.qm[0] = 0;
   for (uint32_t it = 0; it < d.nrounds; ++it) {
     const uint32_t round = d.round + it;
     // slot (round + 1) % 3 of the list counters was last used two rounds ago: clear it now, well before the
     // next round's scan (which starts after this round's first barrier) appends to it
     if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
+    if (batching && prev_quiet && d.nrounds - it >= 2) {
+      const uint32_t Q = d.qbatch < d.nrounds - it ? d.qbatch : d.nrounds - it;
+      if (warp == 0 && lane == 0) d.qm[(nb + 1) % 3] = 0;
+      uint32_t p1 = 0;
+      uint32_t busy = quiet_scan<W>(d, round, Q, warp, nwarps, lane, p1);
+      busy = __reduce_or_sync(kFull, busy);
+      if (lane == 0 && busy) atomicOr(&d.qm[nb % 3], busy);
+      grid_barrier(d);
+      const uint32_t mask = *(volatile uint32_t *)&d.qm[nb % 3];
+      ++nb;
+      const uint32_t fb = mask ? (uint32_t)__ffs(mask) - 1u : Q; // rounds round .. round+fb-1 are quiet: committed
+      c.v[SWIM_CTR_PINGS] += p1 * fb;
+      prev_quiet = fb == Q;
+      if (fb) { it += fb - 1; continue; }
+      // fb == 0: this very round has work — the ordinary scan below lists it
+    }
     uint32_t pings = 0;
     scan_pass<W>(d, round, 0, warp, nwarps, lane, pings);                // K1a
     c.v[SWIM_CTR_PINGS] += pings;
     grid_barrier(d);                                                      // the work list is complete
     const uint32_t n_work = d.wl_cnt[ci(round)];
+    prev_quiet = n_work == 0;
     if (n_work == 0 && d.world == 1) continue;                            // quiescent round: nothing was written
     if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c);       // K1b
     if (d.world > 1 && d.p2p) grid_peer_barrier(d, round);                // ... on every rank (one thread per GPU polls)

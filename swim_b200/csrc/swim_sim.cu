@@ -126,6 +126,8 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   sim->opt_split = getenv("SWIM_SPLIT") != nullptr;
   sim->opt_round_kernel = getenv("SWIM_ROUND_KERNEL") != nullptr;
   sim->opt_one_round = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
+  // rounds decided per batched quiet scan of round_kernel (1..8; 0 or 1 turns batching off)
+  if (const char *qb = getenv("SWIM_QUIET_BATCH")) sim->opt_quiet_batch = (uint32_t)std::min(8l, std::max(0l, strtol(qb, nullptr, 10)));
   if (cfg->device >= 0) {
     rc = [&]() { CUDA_TRY(sim, cudaSetDevice(cfg->device)); return SWIM_OK; }();
     if (rc) { g_last_error = sim->last_error; delete sim; return rc; }
@@ -191,6 +193,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     CUDA_TRY(sim, cudaHostGetDevicePointer((void **)&d.bar_err, sim->h_bar_err, 0));
     CUDA_TRY(sim, cudaHostAlloc((void **)&sim->h_observe, (SWIM_CTR__COUNT + 2) * sizeof(unsigned long long), cudaHostAllocDefault));
     if ((r = dalloc(sim, &d.gbar, 4, 0))) return r;
+    if ((r = dalloc(sim, &d.qm, 4, 0))) return r;
     return SWIM_OK;
   }();
   if (rc) { g_last_error = sim->last_error; swim_sim_destroy(sim); return rc; }
@@ -482,6 +485,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       if (ev_pos < n_ev) nr = std::min<uint32_t>(nr, sim->events[ev_pos].round - d.round);
       if (multi_round_off) nr = 1;
       d.nrounds = nr;
+      d.qbatch = sim->opt_quiet_batch;
       CUDA_TRY(sim, launch_pdl(round_kernel<W>, kgrid, sim->stream, d));
       ++sim->launches;
       sim->round += nr - 1;
