@@ -165,7 +165,7 @@ def config_dict(cfg_kw, n, n_gpus, exchange_mode="single"):
             "retransmit": 8, "crash_round": CRASH_ROUND, "seed": SEED,
             "parallelism": f"shard{n_gpus}" if n_gpus > 1 else "single", "exchange": exchange_mode,
             "launch_switches": {k: os.environ[k] for k in ("SWIM_PIPELINE", "SWIM_SPLIT", "SWIM_ROUND_KERNEL",
-                                                            "SWIM_ONE_ROUND_PER_LAUNCH", "SWIM_WPB") if k in os.environ},
+                                                            "SWIM_ONE_ROUND_PER_LAUNCH", "SWIM_WPB", "SWIM_QUIET_BATCH") if k in os.environ},
             "l2": "no flush between rounds: consecutive rounds of one simulation share state by definition; "
                   "state arrays total 0.5 GB/GPU (> 126 MB L2), the per-round hot set (packed state rows 32 MB "
                   "+ flags) is L2-resident by design"}

@@ -16,6 +16,15 @@ r = b['roofline']
 print('value %.3e  us/round %.2f  e2e %.3e  conv %s' % (b['value'], b['ms_per_step'] * 1e3, b['e2e']['value'], b['convergence']))
 print({k: round(r[k] * 1e3, 2) for k in r if k.endswith('ms_per_launch')}, 'clocks', b.get('clocks'))
 PY
+# 2b. batched quiet scans A/B (R2_PREP_NOTES.md #11): off and 8 against the default (4) of step 2
+for Q in 0 8; do
+  SWIM_QUIET_BATCH=$Q timeout 300 python bench.py --no-cpu > gpurun_out/r2_bench_qb$Q.json 2> gpurun_out/r2_bench_qb$Q.err
+  python - "$Q" <<'PY'
+import json, sys
+b = json.loads(open('gpurun_out/r2_bench_qb%s.json' % sys.argv[1]).read().strip().splitlines()[-1])
+print('SWIM_QUIET_BATCH', sys.argv[1], 'value %.3e  us/round %.2f' % (b['value'], b['ms_per_step'] * 1e3))
+PY
+done
 # 3. CTA-size A/B (R2_PREP_NOTES.md #5): rebuild on the box, bench without the CPU arm, restore the default build
 for W in 16 32; do
   SWIM_WPB=$W python -m swim_b200.build > /dev/null 2> gpurun_out/r2_build_wpb$W.err

@@ -214,3 +214,23 @@ def test_c5_churn_parity():
             orc.step(c)
             assert_same_state(sim, orc, f"churn S={S} round {sim.round}")
         assert sim.counters()[A.CTR_RECS_APPLIED] > 0
+
+
+@pytest.mark.parametrize("qbatch", ["0", "3", "8"])
+def test_batched_quiet_scans(qbatch, monkeypatch):
+    """round_kernel's batched quiet scans (SWIM_QUIET_BATCH rounds per pass after a round without work):
+    a few crashed nodes, each in 32 views, make quiet and busy rounds alternate inside long launches for a while (a batch
+    ends wherever some observer's draw hits a crashed member), then the cluster converges and whole batches commit.
+    State, digest and counters — every Ping counted exactly once — equal the oracle's; 0 turns batching off."""
+    monkeypatch.setenv("SWIM_QUIET_BATCH", qbatch)
+    n = 6000
+    cfg = default_config(n_nodes=n, seed=777 + int(qbatch), suspicion_rounds=2, retransmit=2)
+    nbr = generate_topology("random", n, 32, 32, seed=13)
+    sim, orc = make_pair(cfg, nbr)
+    ev = crash_events(4, [101, 4000])
+    sim.inject(ev)
+    orc.inject(ev)
+    for chunk in (1, 2, 3, 61, 9, 40, 2, 130, 64, 11):
+        sim.step(chunk)
+        orc.step(chunk)
+        assert_same_state(sim, orc, f"qbatch {qbatch} after {sim.round} rounds")
