@@ -291,16 +291,17 @@ def test_long_launches_through_quiet_and_busy_stretches(loss, flags):
         assert sim.launch_count() < 40  # one launch per event-free stretch (+ digests of the comparisons)
 
 
-@pytest.mark.parametrize("qbatch,flags", [("0", 0), ("2", 0), ("5", A.F_ROUND_ROBIN), ("8", 0), ("8", A.F_STRICT_OVERRIDE)])
-def test_batched_quiet_scans(qbatch, flags, monkeypatch):
+@pytest.mark.parametrize("qbatch,flags,cap", [("0", 0, 32), ("2", 0, 32), ("5", A.F_ROUND_ROBIN, 32), ("8", 0, 32),
+                                              ("8", A.F_STRICT_OVERRIDE, 32), ("4", 0, 64), ("7", A.F_ROUND_ROBIN, 128)])
+def test_batched_quiet_scans(qbatch, flags, cap, monkeypatch):
     """round_kernel decides up to SWIM_QUIET_BATCH rounds per pass once a round listed no work (quiet_scan). Two crashed
     nodes sit in 32 views each: for a long while a round is busy only when some observer's draw hits one of them, so quiet
     and busy rounds alternate inside a launch and batches end early at every position; later the cluster is converged and
     whole batches commit, including the short one at the end of a launch. State and counters equal the oracle's."""
     monkeypatch.setenv("SWIM_QUIET_BATCH", qbatch)
     n = 230
-    cfg = default_config(n_nodes=n, seed=99 + int(qbatch), suspicion_rounds=2, retransmit=2, flags=flags)
-    nbr = generate_topology("random", n, 32, 32, seed=11)
+    cfg = default_config(n_nodes=n, view_cap=cap, seed=99 + int(qbatch), suspicion_rounds=2, retransmit=2, flags=flags)
+    nbr = generate_topology("random", n, cap, cap - 7 if cap > 32 else 32, seed=11)
     sim, orc = make_pair(cfg, nbr)
     ev = concat_events([crash_events(4, [101]), crash_events(90, [7])])
     sim.inject(ev)

@@ -64,6 +64,8 @@ def test_state_round_trip_and_counters():
 
 def test_profile_hooks_and_caller_stream():
     import torch
+    if not torch.cuda.is_available():
+        pytest.skip("torch CUDA streams and events: hardware only (SWIM_TEST_EMU dry run)")
     from swim_b200.sim import Simulator
     n = 20000
     sim = Simulator(default_config(n_nodes=n))
