@@ -164,6 +164,8 @@ def config_dict(cfg_kw, n, n_gpus, exchange_mode="single"):
             "n_nodes": n, "view_degree": 32, "k_indirect": 3, "fanout": 4, "pb_cap": 8, "suspicion_rounds": 5,
             "retransmit": 8, "crash_round": CRASH_ROUND, "seed": SEED,
             "parallelism": f"shard{n_gpus}" if n_gpus > 1 else "single", "exchange": exchange_mode,
+            # rounds decided per batched quiet scan of round_kernel (single shard; 0 = off), DESIGN.md section 5
+            "quiet_batch": (min(8, max(0, int(os.environ.get("SWIM_QUIET_BATCH", "4")))) if n_gpus == 1 else 0),
             "launch_switches": {k: os.environ[k] for k in ("SWIM_PIPELINE", "SWIM_SPLIT", "SWIM_ROUND_KERNEL",
                                                             "SWIM_ONE_ROUND_PER_LAUNCH", "SWIM_WPB", "SWIM_QUIET_BATCH") if k in os.environ},
             "l2": "no flush between rounds: consecutive rounds of one simulation share state by definition; "
