@@ -1066,11 +1066,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) recv_scan_kernel(SimDev 
 // Default path: K1a, K1b and K2 of one round in ONE launch, separated by grid-wide barriers (all CTAs
 // are resident: the grid is one wave). A round in which nobody has anything to do beyond the probe
 // (the steady state of a healthy cluster) ends after the scan: no K1b, no K2, no extra launches.
+// Thread 0 of a CTA keeps its own copy of the generation word in shared memory: read once at kernel start
+// (barrier_begin; no barrier of this launch can complete before every CTA has arrived, and the previous launch is over),
+// then counted — every CTA takes part in every barrier — so arriving costs no global load ahead of the atomic.
+__device__ __forceinline__ uint32_t *barrier_generation() {
+  SWIM_SHARED_1D(uint32_t, s_bar_gen, 1);
+  return s_bar_gen;
+}
+__device__ __forceinline__ void barrier_begin(const SimDev &d) {
+  if (threadIdx.x == 0) *barrier_generation() = *(volatile uint32_t *)(d.gbar + 1);
+}
 __device__ __forceinline__ void grid_barrier(const SimDev &d) {
   __syncthreads();
   if (threadIdx.x == 0) {
     volatile uint32_t *gen = d.gbar + 1;
-    const uint32_t g = *gen;
+    const uint32_t g = (*barrier_generation())++;
     __threadfence();
     if (atomicAdd(d.gbar, 1u) == gridDim.x - 1) {
       d.gbar[0] = 0;
@@ -1097,7 +1107,7 @@ __device__ __forceinline__ void grid_peer_barrier(const SimDev &d, uint32_t mail
   __syncthreads();
   if (threadIdx.x == 0) {
     volatile uint32_t *gen = d.gbar + 1;
-    const uint32_t g = *gen;
+    const uint32_t g = (*barrier_generation())++;
     __threadfence_system(); // this CTA's stores into peer memory are performed before it reports arrival
     if (atomicAdd(d.gbar, 1u) == gridDim.x - 1) {
       for (uint32_t q = 0; q < d.world; ++q) {
@@ -1141,6 +1151,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   pdl_launch();
   pdl_wait();
+  barrier_begin(d);
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   // d.nrounds consecutive event-free rounds in this launch (the host splits calls at rounds that carry events)
