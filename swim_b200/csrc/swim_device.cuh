@@ -669,6 +669,9 @@ template <int W>
 __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps, int lane,
                                           PbStage &pbs, Ctr &c) {
   const uint32_t n_work = d.wl_cnt[ci(round)];
+  // this warp's first list entry is fetched together with the count (one memory round trip instead of two); the entry
+  // is only looked at when warp < n_work
+  const uint32_t first_ln = warp < d.n ? d.wl[warp] : 0u;
   const uint32_t par = round & 1;
   uint32_t *rl_out = d.rl + (size_t)par * d.n * d.fanout;
   const uint32_t my_stamp = stamp_of(round);
@@ -690,7 +693,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
   for (uint32_t idx = warp; idx < n_work + n_rescan; idx += nwarps) {
     uint32_t ln, slot;
     if (idx < n_work) {
-      ln = d.wl[idx];
+      ln = idx == warp ? first_ln : d.wl[idx];
       slot = idx;
     } else {
       const uint32_t cidx = idx - n_work;
@@ -951,11 +954,13 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
     }
   const size_t ebase = (size_t)par * d.estride;
   const uint32_t *rl_in = d.rl + (size_t)par * d.n * d.fanout;
+  // as in K1b: the warp's first candidate is fetched together with the counts
+  const uint32_t first_cand = warp < d.n * d.fanout ? rl_in[warp] : 0xFFFFFFFFu;
 
   for (uint32_t item = warp; item < n_recv; item += nwarps) {
     uint32_t ln;
     if (item < seg_end[0]) {
-      ln = rl_in[item];
+      ln = item == warp ? first_cand : rl_in[item];
       if (ln == 0xFFFFFFFFu) continue; // empty candidate slot
     } else {
       uint32_t a = 0;
