@@ -734,6 +734,13 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
     Row<W> row;
     row_load<W>(row, d, ln, lane);
     pb_load(pbs, d, ln, lane);
+    // the row's edge indices travel with the row (narrow rows): the send step below needs the recipients' in-edge
+    // indices, and loading them there would be one more dependent memory round trip per item
+    constexpr bool kCarry = W <= 2;
+    uint32_t rix[W];
+    if (kCarry)
+#pragma unroll
+      for (int w = 0; w < W; ++w) rix[w] = d.ridx[(size_t)ln * d.cap + w * 32 + lane];
     uint32_t td[W], am[W], L = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -809,9 +816,16 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
       for (uint32_t j = 0; j < np && nr < d.fanout; ++j)
         if (prox[j] != tslot) { if ((uint32_t)lane == nr) rslot = prox[j]; ++nr; }
       uint32_t xs = 0xFFFFFFFFu; // exchange-bucket slot when lane f's recipient lives on another shard
+      uint32_t dst_c = 0, ridx_c = 0; // recipient id and in-edge index of lane f's slot, from the lanes that hold them
+      if (kCarry)
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const uint32_t a = __shfl_sync(kFull, row.nb[w], rslot & 31), b = __shfl_sync(kFull, rix[w], rslot & 31);
+          if ((uint32_t)w == (rslot >> 5)) { dst_c = a; ridx_c = b; }
+        }
       if ((uint32_t)lane < nr) {
         const size_t e = (size_t)ln * d.cap + rslot;
-        const uint32_t dst = d.nbr[e], ridx = d.ridx[e];
+        const uint32_t dst = kCarry ? dst_c : d.nbr[e], ridx = kCarry ? ridx_c : d.ridx[e];
         const uint32_t owner = d.world == 1 ? 0u : dst / d.per;
         const uint32_t dl = dst - owner * d.per;
         if (owner == d.rank) {
