@@ -959,7 +959,8 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
   // then one list per source rank (cross-shard senders). A receiver can appear many times: the claim
   // stamp lets exactly one warp process it.
   uint32_t seg_end[SWIM_MAX_WORLD + 1];
-  uint32_t n_recv = (d.wl_cnt[ci(round)] + d.xtra[ci(round)]) * d.fanout;
+  const uint32_t n_listed = d.wl_cnt[ci(round)]; // candidate slots [0, n_listed * fanout) belong to the senders wl[0..)
+  uint32_t n_recv = (n_listed + d.xtra[ci(round)]) * d.fanout;
   seg_end[0] = n_recv;
   if (d.world > 1)
     for (uint32_t a = 0; a < d.world; ++a) {
@@ -970,11 +971,19 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
   const uint32_t *rl_in = d.rl + (size_t)par * d.n * d.fanout;
   // as in K1b: the warp's first candidate is fetched together with the counts
   const uint32_t first_cand = warp < d.n * d.fanout ? rl_in[warp] : 0xFFFFFFFFu;
+  // A candidate slot also names one sender of its receiver: slot / fanout is that sender's position in the work list.
+  // Its snapshot is fetched together with the receiver's row, ahead of the in-edge flags that will ask for it — for the
+  // usual envelope (one sender per receiver per round) the pass is one dependent round trip shorter. The flags still
+  // decide what is applied and in which order; the early copy only replaces the load of that one sender.
+  const uint32_t first_snd = warp / d.fanout < d.n ? d.wl[warp / d.fanout] : 0u;
 
   for (uint32_t item = warp; item < n_recv; item += nwarps) {
-    uint32_t ln;
+    uint32_t ln, snd = 0;
+    bool early = false;
     if (item < seg_end[0]) {
       ln = item == warp ? first_cand : rl_in[item];
+      const uint32_t si = item / d.fanout;
+      if (si < n_listed) { snd = item == warp ? first_snd : d.wl[si]; early = true; }
       if (ln == 0xFFFFFFFFu) continue; // empty candidate slot
     } else {
       uint32_t a = 0;
@@ -992,6 +1001,12 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
     pb_load(pbs, d, ln, lane);
     uint32_t self_inc = d.self_inc[ln];
     const uint32_t self_inc0 = self_inc;
+    uint4 early_rec = make_uint4(0, 0, 0, 0);
+    uint32_t early_cnt = 0;
+    if (early) {
+      if ((uint32_t)lane < d.B) early_rec = d.out_p[d.rank][((size_t)par * d.per + snd) * d.B + lane];
+      early_cnt = d.out_cnt_p[d.rank][(size_t)par * d.per + snd];
+    }
     if (__shfl_sync(kFull, old, 0) == round) continue; // another warp has this receiver
     for (uint32_t eb = e0; eb < e1; eb += 32) {
       const uint32_t e = eb + lane;
@@ -1006,7 +1021,10 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool 
         const uint32_t s_id = __shfl_sync(kFull, src, q), s_kind = __shfl_sync(kFull, f, q);
         uint32_t cnt;
         uint4 mine = make_uint4(0, 0, 0, 0);
-        if (s_kind == 1) { // pull the sender's snapshot (from a peer GPU's memory if it lives there)
+        if (s_kind == 1 && early && s_id == d.first + snd) { // the sender this candidate slot came from: already here
+          mine = early_rec;
+          cnt = early_cnt;
+        } else if (s_kind == 1) { // pull the sender's snapshot (from a peer GPU's memory if it lives there)
           const uint32_t s_rank = d.world == 1 ? 0u : s_id / d.per, sl = s_id - s_rank * d.per;
           if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][((size_t)par * d.per + sl) * d.B + lane];
           cnt = d.out_cnt_p[s_rank][(size_t)par * d.per + sl];
