@@ -661,17 +661,20 @@ __device__ __forceinline__ uint32_t quiet_scan(const SimDev &d, uint32_t round, 
   return busy;
 }
 
+// This warp's first list entry, to be fetched together with the list count (one memory round trip instead of two); the
+// entry is only looked at when warp < n_work. Volatile: the load stays where it is written, ahead of the branch on the count.
+__device__ __forceinline__ uint32_t first_work_entry(const SimDev &d, uint32_t warp) {
+  return warp < d.n ? *(volatile const uint32_t *)(d.wl + warp) : 0u;
+}
+
 // K1b — warp-per-node over the work list (plus, when pipelined, last round's receivers): countdown
 // and expiry -> Dead, probe escalation (k proxies), local suspicion, piggyback send. Lane s owns view
 // slot s; the piggyback buffer is staged in shared memory. Everything K1a derived is recomputed
 // from the row with warp ballots.
 template <int W>
 __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps, int lane,
-                                          PbStage &pbs, Ctr &c) {
+                                          PbStage &pbs, Ctr &c, uint32_t first_ln) {
   const uint32_t n_work = d.wl_cnt[ci(round)];
-  // this warp's first list entry is fetched together with the count (one memory round trip instead of two); the entry
-  // is only looked at when warp < n_work
-  const uint32_t first_ln = warp < d.n ? d.wl[warp] : 0u;
   const uint32_t par = round & 1;
   uint32_t *rl_out = d.rl + (size_t)par * d.n * d.fanout;
   const uint32_t my_stamp = stamp_of(round);
@@ -894,7 +897,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tick_work_kernel(SimDev 
   if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  work_pass<W>(d, round, warp, nwarps, lane, pbs, c);
+  work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_work_entry(d, warp));
   c.flush(d.ctr, lane);
 }
 
@@ -1226,9 +1229,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     c.v[SWIM_CTR_PINGS] += pings;
     grid_barrier(d);                                                      // the work list is complete
     const uint32_t n_work = d.wl_cnt[ci(round)];
+    const uint32_t first_ln = first_work_entry(d, warp);                  // in flight together with the count
     prev_quiet = n_work == 0;
     if (n_work == 0 && d.world == 1) continue;                            // quiescent round: nothing was written
-    if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c);       // K1b
+    if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_ln); // K1b
     if (d.world > 1 && d.p2p) grid_peer_barrier(d, round);                // ... on every rank (one thread per GPU polls)
     else grid_barrier(d);                                                 // every flag and snapshot is written
     recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);             // K2
