@@ -75,6 +75,93 @@ def algorithmic_bytes(cfg_kw, n_nodes, rounds, ctr_delta):
     return floor + 2 * msg_side, floor + msg_side, m_bar, b_bar
 
 
+def summarize_timeline(tl, warmup):
+    """tl: [rounds, 8] ns stamps of round_kernel's phase boundaries (CTA 0; swim_sim_get_timeline). Per-phase means over
+    the rounds that ran the phase; a round committed by a batched quiet scan shares its batch's stamps."""
+    scan, work, recv, busy_total, quiet_total, bar3 = [], [], [], [], [], []
+    own = {"scan": [], "work": [], "recv": []}  # CTA 0's own share of a phase (the rest is waiting at the barrier)
+    n_busy = n_quiet = 0
+    r = 0
+    R = len(tl)
+    while r < R:
+        t = tl[r]
+        if t[0] == 0:
+            r += 1
+            continue
+        if t[4] == 0:  # ended after the first barrier: a quiescent round, or a committed batch of them
+            span = int(t[7]) if t[7] > 0 else 1
+            quiet_total.append((t[2] - t[0]) / span)
+            n_quiet += span
+            r += span
+            continue
+        n_busy += 1
+        scan.append(t[2] - t[0]); own["scan"].append(t[1] - t[0])
+        work.append(t[4] - t[2]); own["work"].append(t[3] - t[2])
+        end = t[6] if t[6] else t[5]
+        recv.append(end - t[4]); own["recv"].append(t[5] - t[4])
+        busy_total.append(end - t[0])
+        r += 1
+    f = lambda v: float(np.mean(v)) / 1e3 if len(v) else None
+    return {"busy_rounds": n_busy, "quiet_rounds": n_quiet, "busy_us": f(busy_total), "quiet_us": f(quiet_total),
+            "scan_us": f(scan), "work_us": f(work), "recv_us": f(recv),
+            "cta0_scan_us": f(own["scan"]), "cta0_work_us": f(own["work"]), "cta0_recv_us": f(own["recv"]),
+            "busy_us_max": float(np.max(busy_total)) / 1e3 if busy_total else None,
+            "what": "in-kernel %globaltimer stamps of CTA 0 at round_kernel's phase boundaries over the timed rounds; a phase "
+                    "runs from one grid barrier to the next (scan | work = K1b | recv = K2), cta0_* is CTA 0's own part of it"}
+
+
+def make_roofline(cfg_kw, n_local, ms_per_round, ab_round, m_bar, b_bar, peak, measured_peak, prof, rounds_p, timeline,
+                  ctr_delta, steps, world):
+    """SURVEY 8(d) as written: the kernel in the timed path (round_kernel<W>: scan, tick work and receive of every round
+    of a launch), achieved = canonical algorithmic bytes per round / its CUDA-event time per round."""
+    achieved = ab_round * n_local / (ms_per_round * 1e-3) / 1e9
+    traffic = dram_gbs = None
+    tp = os.path.join(ROOT, "profiles", "round_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp))
+        traffic = t.get("dram_bytes_per_round")
+    if traffic:
+        dram_gbs = traffic / (ms_per_round * 1e-3) / 1e9
+    # what the implementation has to move per round: one 16-byte record per node (scan) + the rows it opens
+    msgs = float(ctr_delta[A.CTR_MSGS]) / steps / max(1, world)
+    impl = 16.0 * n_local + 1024.0 * msgs + 900.0 * msgs / max(1.0, cfg_kw["fanout"] * 0.97)
+    calib = None
+    cp = os.path.join(ROOT, "profiles", "calibration.json")
+    if os.path.exists(cp):
+        calib = json.load(open(cp))
+    floor = None
+    if calib and timeline and timeline.get("busy_rounds"):
+        # a busy round: 3 grid barriers + the dependent-load chains (K1b: list entry -> row; K2: candidate -> row -> flags ->
+        # [snapshot]), each warp walking its items one after the other
+        nwarps = calib.get("resident_warps", 4736)
+        items_w = max(1.0, msgs / max(1.0, cfg_kw["fanout"] * 0.97) / nwarps)
+        items_r = max(1.0, msgs / nwarps)
+        hop = calib["hbm_load_ns"] / 1e3
+        floor_busy = 3 * calib["grid_barrier_ns"] / 1e3 + hop * (2 * items_w + 3 * items_r)
+        floor = {"busy_round_us": floor_busy, "measured_busy_round_us": timeline["busy_us"],
+                 "frac_of_floor": floor_busy / timeline["busy_us"] if timeline["busy_us"] else None,
+                 "grid_barrier_us": calib["grid_barrier_ns"] / 1e3, "hbm_dependent_load_us": hop,
+                 "l2_dependent_load_us": calib.get("l2_load_ns", 0) / 1e3,
+                 "model": "3 barriers + hop x (2 x K1b items per warp + 3 x K2 items per warp), mean items of the timed rounds"}
+    return {"bound": "hbm", "kernel": "round_kernel<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if measured_peak else "6650 GB/s (of fallback)",
+            "traffic": traffic, "dram_gbs": dram_gbs, "dram_frac": dram_gbs / peak if dram_gbs else None,
+            "algorithmic_bytes_per_round": ab_round * n_local,
+            "ab_per_node_round": {"round": ab_round, "m_bar": m_bar, "b_bar": b_bar},
+            "impl_bytes_per_round_model": impl,
+            "latency_floor": floor, "timeline": timeline,
+            "split_kernels_us": {"tick_scan": prof["tick_scan"] / rounds_p * 1e3, "tick_work": prof["tick_work"] / rounds_p * 1e3,
+                                 "recv": prof["recv"] / rounds_p * 1e3, "exchange": prof["exchange"] / rounds_p * 1e3,
+                                 "events_total": prof["events"] * 1e3},
+            "note": "achieved = SURVEY 8(d)'s canonical bytes per round (376 B/node quiescent floor + message terms) / the "
+                    "CUDA-event time per round of the kernel in the timed path. The implementation moves far fewer bytes (a "
+                    "16-byte derived record per node in the scan, full rows only for nodes with work): `traffic` (ncu dram "
+                    "bytes per round) and dram_frac say how much of HBM it really uses; at C3's size the round is bound by "
+                    "grid barriers and dependent-load chains (latency_floor), not by bandwidth — the HBM-regime point is "
+                    "profiles/r02_hbm_regime.md"}
+
+
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -143,15 +230,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    cfg_kw, nbr, events, n = workload(1)
+    cfg_kw, nbr, events, n = workload(args.gpus, args.nodes_per_gpu)  # the same N as the CUDA arm at --gpus G (one shard: all on the host)
     val, dt, threads, _ = cpu_arm(cfg_kw, nbr, events, n, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "simulated node-rounds/sec", "value": val, "unit": "node-rounds/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32", "data": "synthetic",
-        "config": config_dict(cfg_kw, n, 1),
+        "config": config_dict(cfg_kw, n, args.gpus),
         "cpu_baseline": {"value": val, "unit": "node-rounds/s", "cores": threads, "kind": "port",
-                         "sample": f"all {n} nodes of C3, rounds {args.warmup + 1}..{args.warmup + args.steps} "
+                         "sample": f"all {n} nodes of C3 x{args.gpus}, rounds {args.warmup + 1}..{args.warmup + args.steps} "
                                    "(restated C oracle, OpenMP; the Haskell reference cannot be built here)"},
         "e2e": {"value": val, "unit": "node-rounds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -209,40 +296,72 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     # ------------------------------------------------ device-resident timing (value)
+    # One handle, one device-resident checkpoint (swim_sim_save at round 0, events pending): every timing window starts
+    # from the same state and runs the same rounds, so the windows differ only by the machine.
     sim = fresh()
     # a non-default torch stream: its handle is what the library launches on, so the torch events
     # below bracket the kernels (handle 0 would mean "the handle's private stream" to the C ABI)
     stream = torch.cuda.Stream()
     assert stream.cuda_stream != 0
     sim.set_stream(stream.cuda_stream)
+    sim.save()
     clocks = ClockSampler(local) if rank == 0 else None  # runs until the end of the e2e region
+    # clock spin-up: a fresh process finds the GPU at its idle clock (~1 GHz on this pool) and a 2 ms window is over
+    # before the governor reacts; run real rounds for a while first, then go back to the checkpoint. (Not part of the
+    # W warm-up rounds: those are rounds 1..W of the workload and precede every window.)
     barrier()
-    sim.step(args.warmup)
-    c0, l0 = sim.counters(), sim.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    sim.step_async(args.steps)
-    ev1.record(stream)
-    barrier()
-    ms = ev0.elapsed_time(ev1)
-    c1, l1 = sim.counters(), sim.launch_count()
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        cd = torch.tensor((c1 - c0).astype(np.int64), device="cuda")
-        dist.all_reduce(cd)
-        ctr_delta = cd.cpu().numpy().astype(np.uint64)
-    else:
-        ctr_delta = c1 - c0
+    t_spin = time.perf_counter()
+    while time.perf_counter() - t_spin < args.spinup:
+        sim.step(256)
+    windows = []
+    ctr_delta, launches = None, 0
+    for w in range(args.windows):
+        barrier()
+        sim.load()
+        barrier()
+        sim.step(args.warmup)
+        c0, l0 = sim.counters(), sim.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        sim.step_async(args.steps)
+        ev1.record(stream)
+        barrier()
+        ms_w = ev0.elapsed_time(ev1)
+        sim.sync()
+        c1, l1 = sim.counters(), sim.launch_count()
+        if world > 1:
+            t = torch.tensor([ms_w], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_w = float(t.item())
+        windows.append(ms_w)
+        if ctr_delta is None:
+            if world > 1:
+                cd = torch.tensor((c1 - c0).astype(np.int64), device="cuda")
+                dist.all_reduce(cd)
+                ctr_delta = cd.cpu().numpy().astype(np.uint64)
+            else:
+                ctr_delta = c1 - c0
+            launches = int(l1 - l0)
+    ms = float(np.median(windows))
     value = n * args.steps / (ms * 1e-3)
-    launches = int(l1 - l0)
 
-    # ------------------------------------------------ per-kernel timing of the same rounds (roofline)
-    sim.close()
-    sim = fresh()
-    sim.set_stream(stream.cuda_stream)
+    # ------------------------------------------------ phase timeline of the same rounds (fused kernel, in-kernel timer)
+    timeline = None
+    if world == 1:
+        barrier()
+        sim.load()
+        sim.step(args.warmup)
+        sim.set_timeline(args.steps)
+        sim.step(args.steps)
+        tl = sim.timeline(args.steps).astype(np.int64)
+        sim.set_timeline(0)
+        timeline = summarize_timeline(tl, args.warmup)
+
+    # ------------------------------------------------ per-kernel timing of the same rounds (split launches)
+    barrier()
+    sim.load()
+    barrier()
     sim.step(args.warmup)
     sim.set_profile(True)
     sim.step(args.steps)
@@ -255,44 +374,27 @@ def run_cuda(args):
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    tick_ms = prof["tick_scan"] / max(1.0, prof["rounds"])
     n_local = n // world
-    achieved = ab_tick * n_local / (tick_ms * 1e-3) / 1e9 if tick_ms > 0 else None
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "tick_traffic.json")
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "tick_scan_kernel<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None,
-                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)",
-                "traffic": traffic,
-                "dram_gbs": (traffic / (tick_ms * 1e-3) / 1e9) if traffic and tick_ms > 0 else None,
-                "dram_frac": (traffic / (tick_ms * 1e-3) / 1e9 / peak) if traffic and tick_ms > 0 else None,
-                "algorithmic_bytes_per_launch": ab_tick * n_local,
-                "ab_per_node_round": {"round": ab_round, "tick": ab_tick, "m_bar": m_bar, "b_bar": b_bar},
-                "tick_ms_per_launch": tick_ms, "tick_work_ms_per_launch": prof["tick_work"] / max(1.0, prof["rounds"]),
-                "recv_ms_per_launch": prof["recv"] / max(1.0, prof["rounds"]),
-                "exchange_ms_per_round": prof["exchange"] / max(1.0, prof["rounds"]),
-                "note": "achieved/frac use SURVEY 8(d)'s canonical bytes (376 B/node-round); K1a really moves 16 B/node-round "
-                        "(one uint4 meta record: alive/suspect/crashed-member bitmaps + flags), so frac > 1 means 'faster "
-                        "than streaming the canonical arrays could be', while dram_gbs/dram_frac (ncu traffic / measured "
-                        "launch time) are the real HBM utilisation"}
+    rounds_p = max(1.0, prof["rounds"])
+    roofline = make_roofline(cfg_kw, n_local, ms / args.steps, ab_round, m_bar, b_bar, peak, bool(peaks), prof, rounds_p,
+                             timeline, ctr_delta, args.steps, world)
 
     # ------------------------------------------------ end to end through the C ABI, host buffers
     e2e = None
     if True:
         sim = fresh(inject=False)
+        sim.save()
         by_round = {}
         for e in events:
             by_round.setdefault(int(e["round"]), []).append(e)
+        by_round = {r: np.array(v, dtype=A.EVENT_DTYPE) for r, v in by_round.items()}
         h2d = d2h = 0
 
         def one_round(r):
             nonlocal h2d, d2h
-            evs = by_round.get(r)
-            if evs:
-                arr = np.array(evs, dtype=A.EVENT_DTYPE)
-                sim.inject(arr)  # host buffer -> library -> device (uploaded by the step below)
+            arr = by_round.get(r)
+            if arr is not None:
+                sim.inject(arr)  # host buffer -> library (pinned staging) -> device, uploaded by the step below
                 h2d += arr.nbytes
             sim.step_async(1)
             # the round's result as a convergence study reads it: counters + convergence count, one read-back and ONE
@@ -301,24 +403,32 @@ def run_cuda(args):
             d2h += c.nbytes + 8
             return c, dg, mm
 
-        for r in range(1, args.warmup + 1):
-            one_round(r)
-        h2d = d2h = 0
-        barrier()
-        t0 = time.perf_counter()
-        for r in range(args.warmup + 1, args.warmup + args.steps + 1):
-            one_round(r)
-        sim.sync()  # surfaces a watchdog report, if any; the stream is already idle
-        barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        e2e_windows = []
+        for w in range(args.windows):
+            barrier()
+            sim.load()
+            barrier()
+            for r in range(1, args.warmup + 1):
+                one_round(r)
+            h2d = d2h = 0
+            barrier()
+            t0 = time.perf_counter()
+            for r in range(args.warmup + 1, args.warmup + args.steps + 1):
+                one_round(r)
+            sim.sync()  # surfaces a watchdog report, if any; the stream is already idle
+            barrier()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e_windows.append(dt)
+        dt = float(np.median(e2e_windows))
         e2e = {"value": n * args.steps / dt, "unit": "node-rounds/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps,
+               "windows_ms": [round(x * 1e3, 4) for x in e2e_windows],
                "what": "per round: swim_sim_inject(host events) + swim_sim_step_async(1) + swim_sim_observe (counters, "
-                       "convergence count; one synchronisation) — host wall clock, max over ranks"}
+                       "convergence count; one synchronisation) — host wall clock, max over ranks, median of the windows"}
         sim.close()
     clk = clocks.stop() if clocks else None
 
@@ -367,6 +477,10 @@ def run_cuda(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32",
                 "data": "synthetic", "config": config_dict(cfg_kw, n, world, exchange["mode"]), "clocks": clk, "e2e": e2e,
+                "timing": {"windows_ms": [round(x, 5) for x in windows], "stat": "median", "min_ms": min(windows),
+                           "max_ms": max(windows), "spinup_s": args.spinup,
+                           "how": "every window: swim_sim_load (device checkpoint of round 0) -> W warm-up rounds -> "
+                                  "K timed rounds between CUDA events on the launching stream, max over ranks"},
                 "gpu_launches": launches,
                 "gpu_launches_note": "round_kernel<1> runs K1a, K1b and K2 of every consecutive event-free round of a call "
                                      "in ONE launch (grid barriers between phases), so the timed region of K rounds is a "
@@ -405,6 +519,8 @@ def main():
     ap.add_argument("--nodes-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--converge-limit", type=int, default=1200)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps rounds each; the median is reported")
+    ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed rounds before the first window (GPU clocks)")
     ap.add_argument("--exchange", default=None, choices=[None, "p2p", "nccl"],
                     help="cross-shard exchange: fused peer-memory (default) or staged NCCL all-to-all")
     args = ap.parse_args()

@@ -263,6 +263,16 @@ int swim_sim_round(const swim_sim_t *sim, uint32_t *round);
  * Philox draw. swim_sim_set_round puts a fresh handle at `round` (pending events must lie after it). */
 int swim_sim_set_round(swim_sim_t *sim, uint32_t round);
 
+/* Device-resident checkpoint, one slot per handle. swim_sim_save copies this rank's mutable state (alive[], incarnations,
+ * the rows' liveness / incarnation / lastChange, the piggyback buffers, the counters), the round counter and the pending
+ * events into a second set of device arrays: stream-ordered device-to-device copies, no host traffic. swim_sim_load puts
+ * the handle back there (and clears every round-stamped scratch array), so the same rounds can be stepped again and
+ * give the same result — what a parameter sweep or a repeated timing window needs. A new view (swim_sim_set_view) or
+ * a membership change through the scalar calls drops the checkpoint. Sharded runs: every rank saves / loads its own
+ * shard while ALL ranks are between steps (host-side barrier before and after). */
+int swim_sim_save(swim_sim_t *sim);
+int swim_sim_load(swim_sim_t *sim);
+
 /* Bulk copies of one state array (SWIM_ARR_*) between device and a host buffer of exactly
  * `bytes` bytes. set_array(SWIM_ARR_NBR) is rejected: use swim_sim_set_view. */
 int swim_sim_get_array(swim_sim_t *sim, int arr, void *host_buf, size_t bytes);
@@ -300,6 +310,19 @@ int swim_sim_launch_count(const swim_sim_t *sim, uint64_t *count);
 #define SWIM_PROFILE_SLOTS 6
 int swim_sim_set_profile(swim_sim_t *sim, int enable);
 int swim_sim_profile_ms(swim_sim_t *sim, double *out, size_t n);
+
+/* Phase timeline of the fused per-round kernel (profiling aid): after swim_sim_set_timeline(sim, R) the next R rounds
+ * record the device's nanosecond timer at their phase boundaries, 8 words per round — [0] round start, [1] scan done
+ * (CTA 0), [2] first grid barrier passed, [3] tick work done (CTA 0), [4] second barrier passed, [5] receive done (CTA 0),
+ * [6] third barrier passed, [7] rounds committed by a batched quiet scan; words of phases a round skipped stay 0.
+ * R = 0 switches it off. Single-kernel launch path only. */
+int swim_sim_set_timeline(swim_sim_t *sim, uint32_t rounds);
+int swim_sim_get_timeline(swim_sim_t *sim, uint64_t *out /* [rounds][8] */, size_t rounds);
+
+/* Latency calibration of this GPU, in nanoseconds: out[0] = one grid barrier of the fused kernel's resident wave,
+ * out[1] = one dependent global load missing L2 (pointer chase over 512 MB), out[2] = the same hitting L2 (1 MB),
+ * out[3] = resident warps of the fused kernel. n >= 4. What bench.py's roofline.latency_floor is built from. */
+int swim_sim_calibrate(swim_sim_t *sim, double *out, size_t n);
 
 /* ---- multi-GPU plumbing (one process per GPU; ranks own contiguous node ranges) ------
  * The per-round exchange is one all-to-all of cross-shard piggyback envelopes (the UDP

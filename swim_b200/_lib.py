@@ -46,6 +46,11 @@ def lib():
     sig("swim_sim_set_view", i, vp, vp)
     sig("swim_topology_generate", i, i, u32, u32, u32, u64, vp)
     sig("swim_sim_set_round", i, vp, u32)
+    sig("swim_sim_save", i, vp)
+    sig("swim_sim_calibrate", i, vp, vp, sz)
+    sig("swim_sim_set_timeline", i, vp, u32)
+    sig("swim_sim_get_timeline", i, vp, vp, sz)
+    sig("swim_sim_load", i, vp)
     sig("swim_sim_step", i, vp, u32)
     sig("swim_sim_step_async", i, vp, u32)
     sig("swim_sim_sync", i, vp)

@@ -123,6 +123,10 @@ struct SimDev {
   uint32_t *eslot;           // [E] exchange-buffer slot of the envelope raised on in-edge e
   uint32_t xcap;             // envelopes per destination bucket
   unsigned long long *ctr;   // [SWIM_CTR__COUNT]
+  // in-kernel phase timeline (swim_sim_set_timeline; null = off): %globaltimer of CTA 0 at the phase boundaries of
+  // round_kernel, 8 words per round starting at round tl_round0
+  unsigned long long *tl;
+  uint32_t tl_cap, tl_round0;
 };
 
 
@@ -137,6 +141,18 @@ __device__ __forceinline__ void pdl_launch() {}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
+
+// Phase timeline of round_kernel: one thread of CTA 0 stores %globaltimer (ns) at each phase boundary. Slots per round:
+// 0 start, 1 scan done (CTA 0), 2 barrier 1 passed (every CTA's scan done), 3 work done (CTA 0), 4 barrier 2 passed,
+// 5 receive done (CTA 0), 6 barrier 3 passed, 7 = number of rounds a batched quiet scan committed at this round.
+__device__ __forceinline__ void tl_mark(const SimDev &d, uint32_t round, int slot, unsigned long long val = ~0ull) {
+#ifndef SWIM_EMU
+  if (d.tl && blockIdx.x == 0 && threadIdx.x == 0 && round - d.tl_round0 < d.tl_cap) {
+    if (val == ~0ull) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(val));
+    d.tl[(size_t)(round - d.tl_round0) * 8 + slot] = val;
+  }
+#endif
+}
 
 // ------------------------------------------------------------------ pure integer helpers
 // Philox and the slot-selection arithmetic are host+device so that tests/device_helpers_harness.cu can run the very
@@ -1205,6 +1221,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
   if (batching && warp == 0 && lane == 0) d.qm[0] = 0;
   for (uint32_t it = 0; it < d.nrounds; ++it) {
     const uint32_t round = d.round + it;
+    tl_mark(d, round, 0);
     // slot (round + 1) % 3 of the list counters was last used two rounds ago: clear it now, well before the
     // next round's scan (which starts after this round's first barrier) appends to it
     if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
@@ -1215,10 +1232,13 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
       uint32_t busy = quiet_scan<W>(d, round, Q, warp, nwarps, lane, p1);
       busy = __reduce_or_sync(kFull, busy);
       if (lane == 0 && busy) atomicOr(&d.qm[nb % 3], busy);
+      tl_mark(d, round, 1);
       grid_barrier(d);
       const uint32_t mask = *(volatile uint32_t *)&d.qm[nb % 3];
       ++nb;
       const uint32_t fb = mask ? (uint32_t)__ffs(mask) - 1u : Q; // rounds round .. round+fb-1 are quiet: committed
+      tl_mark(d, round, 2);
+      tl_mark(d, round, 7, fb);
       c.v[SWIM_CTR_PINGS] += p1 * fb;
       prev_quiet = fb == Q;
       if (fb) { it += fb - 1; continue; }
@@ -1227,16 +1247,22 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     uint32_t pings = 0;
     scan_pass<W>(d, round, 0, warp, nwarps, lane, pings);                // K1a
     c.v[SWIM_CTR_PINGS] += pings;
+    tl_mark(d, round, 1);
     grid_barrier(d);                                                      // the work list is complete
+    tl_mark(d, round, 2);
     const uint32_t n_work = d.wl_cnt[ci(round)];
     const uint32_t first_ln = first_work_entry(d, warp);                  // in flight together with the count
     prev_quiet = n_work == 0;
     if (n_work == 0 && d.world == 1) continue;                            // quiescent round: nothing was written
     if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_ln); // K1b
+    tl_mark(d, round, 3);
     if (d.world > 1 && d.p2p) grid_peer_barrier(d, round);                // ... on every rank (one thread per GPU polls)
     else grid_barrier(d);                                                 // every flag and snapshot is written
+    tl_mark(d, round, 4);
     recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);             // K2
+    tl_mark(d, round, 5);
     if (it + 1 < d.nrounds) grid_barrier(d);                              // views and buffers settled before the next scan
+    tl_mark(d, round, 6);
   }
   c.flush(d.ctr, lane);
 }
@@ -1287,10 +1313,13 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   const uint32_t round = d.round; // events run outside captured graphs
-  // same-node events stay in list order: a node's events all belong to one warp
-  for (uint32_t x = 0; x < n_ev; ++x) {
-    const uint32_t node = ev[x].node;
-    if (node % nwarps != warp) continue;
+  // The host hands over one round's events grouped by node (stable: a node's events keep the order they were given in).
+  // A run of same-node events belongs to the warp whose stride position is the run's first event, so a warp looks at
+  // n_ev / nwarps list entries plus the runs it owns — not at the whole list.
+  for (uint32_t x0 = warp; x0 < n_ev; x0 += nwarps) {
+   const uint32_t node = ev[x0].node;
+   if (x0 && ev[x0 - 1].node == node) continue; // inside somebody else's run
+   for (uint32_t x = x0; x < n_ev && ev[x].node == node; ++x) {
     const uint32_t kind = ev[x].kind;
     const bool local = node >= d.first && node < d.first + d.n;
     const uint32_t ln = node - d.first;
@@ -1334,6 +1363,7 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
       if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
     }
     __syncwarp();
+   }
   }
   c.flush(d.ctr, lane);
 }

@@ -30,6 +30,16 @@ struct swim_sim {
   uint32_t *d_eslot = nullptr; // exchange-buffer slot per in-edge (world > 1)
   void *d_events = nullptr;
   size_t d_events_cap = 0;
+  void *h_events = nullptr;          // pinned staging of the events of one swim_sim_step call (no pageable copies,
+  size_t h_events_cap = 0;           //   no synchronisation inside the call)
+  cudaEvent_t ev_upload = nullptr;   // recorded after the staging buffer's copy: it may be rewritten once this fired
+  bool failed = false;               // a launch failed part-way through a step: the device state is undefined
+  // device-resident checkpoint (swim_sim_save / swim_sim_load): one slot per handle
+  std::vector<std::pair<void *, size_t>> ckpt_arrays; // (copy, bytes) in the order of ckpt_sources()
+  uint32_t ckpt_round = 0;
+  uint64_t view_epoch = 0, ckpt_epoch = 0; // build_in_edges counts views; a checkpoint belongs to one
+  bool ckpt_valid = false;
+  std::vector<swim_event_t> ckpt_events;
   unsigned long long *d_scratch = nullptr;
   void *d_sargs = nullptr; // scalar-call argument block (swim_scalar.cu)
   std::vector<swim_event_t> events; // pending, sorted by round (stable)

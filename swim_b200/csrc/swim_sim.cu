@@ -107,6 +107,9 @@ static int dalloc(swim_sim *sim, T **p, size_t count, int fill) {
   return SWIM_OK;
 }
 
+template <int W>
+static void prepare_kernels(swim_sim *sim); // grid sizes + kernel preload, defined with the round driver
+
 extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   if (!out) return SWIM_EINVAL;
   *out = nullptr;
@@ -153,6 +156,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     sim->stream = sim->own_stream;
     CUDA_TRY(sim, cudaEventCreate(&sim->ev_start));
     CUDA_TRY(sim, cudaEventCreate(&sim->ev_stop));
+    CUDA_TRY(sim, cudaEventCreateWithFlags(&sim->ev_upload, cudaEventDisableTiming));
     if ((r = dalloc(sim, &d.alive, d.N, 1))) return r;       // every node up
     if ((r = dalloc(sim, &d.self_inc, n, 0))) return r;      // Util.hs:80
     if ((r = dalloc(sim, &d.seqno, n, 0))) return r;         // Util.hs:79
@@ -197,6 +201,12 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     return SWIM_OK;
   }();
   if (rc) { g_last_error = sim->last_error; swim_sim_destroy(sim); return rc; }
+  switch (d.cap / 32) {
+    case 1: prepare_kernels<1>(sim); break;
+    case 2: prepare_kernels<2>(sim); break;
+    case 4: prepare_kernels<4>(sim); break;
+    default: prepare_kernels<8>(sim); break;
+  }
   *out = sim;
   return SWIM_OK;
 }
@@ -210,6 +220,10 @@ extern "C" void swim_sim_destroy(swim_sim_t *sim) {
   if (sim->d_in_src) cudaFree(sim->d_in_src);
   if (sim->d_eflag) cudaFree(sim->d_eflag);
   if (sim->d_events) cudaFree(sim->d_events);
+  if (sim->dev.tl) cudaFree(sim->dev.tl);
+  if (sim->h_events) cudaFreeHost(sim->h_events);
+  if (sim->ev_upload) cudaEventDestroy(sim->ev_upload);
+  for (auto &c : sim->ckpt_arrays) cudaFree(c.first);
   if (sim->d_eslot) { cudaFree(sim->d_eslot); sim->d_eslot = nullptr; }
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   if (sim->h_bar_err) cudaFreeHost(sim->h_bar_err);
@@ -283,6 +297,7 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
     CUDA_TRY(sim, cudaMemcpy(d.obs_slot, obs_slot.data(), (size_t)d.n * cap * 4, cudaMemcpyHostToDevice));
   }
   sim->tdead_dirty = true;
+  ++sim->view_epoch;
   if (sim->d_in_src) { cudaFree(sim->d_in_src); sim->d_in_src = nullptr; }
   if (sim->d_eflag) { cudaFree(sim->d_eflag); sim->d_eflag = nullptr; }
   const size_t Ea = E ? (size_t)E : 1;
@@ -368,9 +383,13 @@ extern "C" int swim_sim_inject(swim_sim_t *sim, const swim_event_t *ev, size_t n
       if (m.incarnation < 0 || m.incarnation > 0xFFFFFFFFll) return SWIM_ERANGE;
     }
   }
+  // the queue stays sorted by round (stable: same-round events keep the order they were given in): only the new batch
+  // is sorted, then merged in
+  const auto by_round = [](const swim_event_t &a, const swim_event_t &b) { return a.round < b.round; };
+  const size_t old_n = sim->events.size();
   sim->events.insert(sim->events.end(), ev, ev + n);
-  std::stable_sort(sim->events.begin(), sim->events.end(),
-                   [](const swim_event_t &a, const swim_event_t &b) { return a.round < b.round; });
+  std::stable_sort(sim->events.begin() + old_n, sim->events.end(), by_round);
+  std::inplace_merge(sim->events.begin(), sim->events.begin() + old_n, sim->events.end(), by_round);
   return SWIM_OK;
 }
 
@@ -408,42 +427,77 @@ static cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, const Sim
   return cudaLaunchKernelEx(&cfg, kernel, d);
 }
 
+// Once per handle, at create: the one-wave grid sizes (occupancy queries), and every kernel of the bulk path is loaded
+// now — with lazy module loading the first launch of a kernel pays its load, and for event_kernel that first launch
+// would sit in the middle of a timed swim_sim_step call.
+template <int W>
+static void prepare_kernels(swim_sim *sim) {
+  const SimDev &d = sim->dev;
+  sim->grids[0] = wave_grid(sim, tick_scan_kernel<W>, ((size_t)d.n + 128 * kScanGroups) / (128 * kScanGroups) + 1);
+  sim->grids[1] = wave_grid(sim, tick_work_kernel<W>, (size_t)d.n);
+  sim->grids[2] = wave_grid(sim, recv_kernel<W>, (size_t)d.n);
+  sim->grids[3] = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
+  sim->grids[4] = wave_grid(sim, round_kernel<W>, (size_t)d.n);
+#ifndef SWIM_EMU
+  cudaFuncAttributes a;
+  cudaFuncGetAttributes(&a, event_kernel<W>);
+  cudaFuncGetAttributes(&a, derive_meta_kernel);
+  cudaFuncGetAttributes(&a, digest_kernel);
+  cudaFuncGetAttributes(&a, mismatch_kernel);
+  cudaFuncGetAttributes(&a, peer_barrier_kernel);
+  cudaGetLastError();
+#endif
+}
+
 template <int W>
 static int run_rounds(swim_sim *sim, uint32_t rounds) {
   SimDev &d = sim->dev;
-  if (!sim->grids[0]) { // occupancy queries once per handle, not once per call
-    sim->grids[0] = wave_grid(sim, tick_scan_kernel<W>, ((size_t)d.n + 128 * kScanGroups) / (128 * kScanGroups) + 1);
-    sim->grids[1] = wave_grid(sim, tick_work_kernel<W>, (size_t)d.n);
-    sim->grids[2] = wave_grid(sim, recv_kernel<W>, (size_t)d.n);
-    sim->grids[3] = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
-    sim->grids[4] = wave_grid(sim, round_kernel<W>, (size_t)d.n);
-  }
   const int grid = sim->grids[0], wgrid = sim->grids[1], rgrid = sim->grids[2];
   if (sim->tdead_dirty) {
     SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
     ++sim->launches;
     sim->tdead_dirty = false;
   }
-  // upload the events that fall inside this call
+  // The events that fall inside this call leave the queue now (a failure further down must not replay them) and go to
+  // the device through a pinned staging buffer: one asynchronous copy on the handle's stream, no synchronisation. Each
+  // round's events are grouped by node (stable), which is what event_kernel's run ownership needs; events of different
+  // nodes commute (a crash / rejoin touches alive[node] and the observers' crashed-member bits, an injected datagram its
+  // own node's store), so only the per-node order is part of the semantics (phase E).
   size_t n_ev = 0;
   while (n_ev < sim->events.size() && sim->events[n_ev].round <= sim->round + rounds) ++n_ev;
+  std::vector<uint32_t> ev_round; // round of staged event x
   if (n_ev) {
-    std::vector<DevEvent> dev(n_ev);
+    if (n_ev > sim->d_events_cap) {
+      CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+      if (sim->d_events) { cudaFree(sim->d_events); sim->d_events = nullptr; }
+      if (sim->h_events) { cudaFreeHost(sim->h_events); sim->h_events = nullptr; }
+      sim->d_events_cap = sim->h_events_cap = 0;
+      const size_t cap = n_ev * 2 + 1024;
+      CUDA_TRY(sim, cudaMalloc((void **)&sim->d_events, cap * sizeof(DevEvent)));
+      CUDA_TRY(sim, cudaHostAlloc((void **)&sim->h_events, cap * sizeof(DevEvent), cudaHostAllocDefault));
+      sim->d_events_cap = sim->h_events_cap = cap;
+    } else {
+      CUDA_TRY(sim, cudaEventSynchronize(sim->ev_upload)); // the previous call's copy has left the staging buffer (long ago)
+    }
+    std::vector<uint32_t> order(n_ev);
+    for (size_t x = 0; x < n_ev; ++x) order[x] = (uint32_t)x;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+      const swim_event_t &ea = sim->events[a], &eb = sim->events[b];
+      return ea.round != eb.round ? ea.round < eb.round : ea.node < eb.node;
+    });
+    DevEvent *dev = (DevEvent *)sim->h_events;
+    ev_round.resize(n_ev);
     for (size_t x = 0; x < n_ev; ++x) {
-      const swim_event_t &e = sim->events[x];
+      const swim_event_t &e = sim->events[order[x]];
+      ev_round[x] = e.round;
       dev[x].node = e.node;
       dev[x].kind = e.kind;
       dev[x].rec = make_uint4(e.msg.node, (uint32_t)e.msg.incarnation,
                               e.msg.kind == SWIM_MSG_DEAD ? e.msg.dead_from : 0u, e.msg.kind);
     }
-    if (n_ev > sim->d_events_cap) {
-      if (sim->d_events) { CUDA_TRY(sim, cudaStreamSynchronize(sim->stream)); cudaFree(sim->d_events); sim->d_events = nullptr; }
-      sim->d_events_cap = n_ev * 2;
-      CUDA_TRY(sim, cudaMalloc((void **)&sim->d_events, sim->d_events_cap * sizeof(DevEvent)));
-    }
-    // stream-ordered, blocking w.r.t. the (pageable) host vector
-    CUDA_TRY(sim, cudaMemcpyAsync(sim->d_events, dev.data(), n_ev * sizeof(DevEvent), cudaMemcpyHostToDevice, sim->stream));
-    CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+    sim->events.erase(sim->events.begin(), sim->events.begin() + n_ev);
+    CUDA_TRY(sim, cudaMemcpyAsync(sim->d_events, dev, n_ev * sizeof(DevEvent), cudaMemcpyHostToDevice, sim->stream));
+    CUDA_TRY(sim, cudaEventRecord(sim->ev_upload, sim->stream));
   }
   size_t ev_pos = 0;
   // Pipelining: inside one call, K2 of round r is deferred and runs fused with K1a of round r+1
@@ -470,10 +524,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   for (uint32_t r = 0; r < rounds; ++r) {
     d.round = ++sim->round;
     size_t ev_end = ev_pos;
-    while (ev_end < n_ev && sim->events[ev_end].round == d.round) ++ev_end;
+    while (ev_end < n_ev && ev_round[ev_end] == d.round) ++ev_end;
     if (ev_end > ev_pos) {
       const uint32_t cnt = (uint32_t)(ev_end - ev_pos);
-      const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count);
+      const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count * 4);
       int mk = prof_begin(sim, 0);
       SWIM_LAUNCH(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt);
       prof_end(sim, mk);
@@ -482,7 +536,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     }
     if (single_kernel) { // K1a + K1b + K2 in one launch (grid barriers inside), for every round up to the next event
       uint32_t nr = rounds - r;
-      if (ev_pos < n_ev) nr = std::min<uint32_t>(nr, sim->events[ev_pos].round - d.round);
+      if (ev_pos < n_ev) nr = std::min<uint32_t>(nr, ev_round[ev_pos] - d.round);
       if (multi_round_off) nr = 1;
       d.nrounds = nr;
       d.qbatch = sim->opt_quiet_batch;
@@ -503,7 +557,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     prof_end(sim, mk);
     d.pipe = 0;
     sim->launches += 2;
-    const bool next_has_events = ev_pos < n_ev && sim->events[ev_pos].round == d.round + 1;
+    const bool next_has_events = ev_pos < n_ev && ev_round[ev_pos] == d.round + 1;
     pending = pipelined && r + 1 < rounds && !next_has_events;
     if (!pending) {
       if (d.world > 1) {
@@ -524,7 +578,6 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     }
     if (sim->profile) sim->prof_ms[5] += 1;
   }
-  sim->events.erase(sim->events.begin(), sim->events.begin() + n_ev);
   CUDA_TRY(sim, cudaGetLastError());
   return SWIM_OK;
 }
@@ -538,6 +591,7 @@ extern "C" int swim_sim_step_async(swim_sim_t *sim, uint32_t rounds) {
     if (rc) return rc;
   }
   if (sim->dev.world > 1 && !sim->connected) { set_error(sim, "swim_sim_step: world > 1 needs swim_sim_ipc_connect or swim_sim_connect"); return SWIM_ESTATE; }
+  if (sim->failed) { set_error(sim, "swim_sim_step: an earlier step failed part-way; the handle's device state is undefined"); return SWIM_ESTATE; }
   swim::refresh_peer_tables(sim);
   CUDA_TRY(sim, cudaEventRecord(sim->ev_start, sim->stream));
   int rc;
@@ -547,7 +601,7 @@ extern "C" int swim_sim_step_async(swim_sim_t *sim, uint32_t rounds) {
     case 4: rc = run_rounds<4>(sim, rounds); break;
     default: rc = run_rounds<8>(sim, rounds); break;
   }
-  if (rc) return rc;
+  if (rc) { sim->failed = true; return rc; } // rounds and events were consumed: no retry on this handle
   CUDA_TRY(sim, cudaEventRecord(sim->ev_stop, sim->stream));
   sim->timed = true;
   return SWIM_OK;
@@ -586,6 +640,30 @@ extern "C" int swim_sim_last_step_ms(const swim_sim_t *sim, float *ms) {
   return e == cudaSuccess ? SWIM_OK : SWIM_ECUDA;
 }
 
+// Everything on the device that is stamped with a round number or holds one round's transient mail: after the round
+// counter moves backwards (swim_sim_set_round on a handle that has stepped, swim_sim_load) a stale stamp would equal a
+// round that is about to run again — recv_pass would take a receiver as "already claimed" and drop its mail.
+static int reset_round_state(swim_sim *sim) {
+  SimDev &d = sim->dev;
+  const size_t n = d.n ? d.n : 1;
+  CUDA_TRY(sim, cudaMemsetAsync(d.claim, 0, n * 4, sim->stream));
+  CUDA_TRY(sim, cudaMemsetAsync(d.claim2, 0, n * 4, sim->stream));
+  CUDA_TRY(sim, cudaMemsetAsync(d.wl_cnt, 0, 16, sim->stream));
+  CUDA_TRY(sim, cudaMemsetAsync(d.xtra, 0, 16, sim->stream));
+  CUDA_TRY(sim, cudaMemsetAsync(d.qm, 0, 16, sim->stream));
+  CUDA_TRY(sim, cudaMemsetAsync(d.gbar, 0, 4, sim->stream)); // arrival count; the generation word keeps counting
+  CUDA_TRY(sim, cudaMemsetAsync(d.xcnt, 0, SWIM_MAX_WORLD * 4, sim->stream));
+  if (sim->d_eflag) CUDA_TRY(sim, cudaMemsetAsync(sim->d_eflag, 0, 2 * (size_t)d.estride, sim->stream));
+  if (d.world > 1 && d.rcnt) CUDA_TRY(sim, cudaMemsetAsync(d.rcnt, 0, 2 * (size_t)d.world * 4, sim->stream));
+  // cross-GPU barrier words: "peer q has published round r" — every peer stands at sim->round now (the caller holds
+  // all ranks between steps while round counters move)
+  uint32_t bar[SWIM_MAX_WORLD];
+  for (uint32_t q = 0; q < SWIM_MAX_WORLD; ++q) bar[q] = sim->round;
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  CUDA_TRY(sim, cudaMemcpy(sim->d_bar, bar, sizeof bar, cudaMemcpyHostToDevice));
+  return SWIM_OK;
+}
+
 extern "C" int swim_sim_set_round(swim_sim_t *sim, uint32_t round) {
   if (!sim) return SWIM_EINVAL;
   if (!sim->events.empty() && sim->events.front().round <= round) {
@@ -595,7 +673,63 @@ extern "C" int swim_sim_set_round(swim_sim_t *sim, uint32_t round) {
   cudaSetDevice(sim->device);
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   sim->round = round;
+  sim->tdead_dirty = true; // the per-node records are rebuilt (mail stamps included) before the next round
+  return reset_round_state(sim);
+}
+
+// ------------------------------------------------------------------ device-resident checkpoint
+static void ckpt_sources(const swim_sim *sim, std::vector<std::pair<void *, size_t>> &v) {
+  const SimDev &d = sim->dev;
+  const size_t n = d.n, slots = n * d.cap;
+  v = {{d.alive, (size_t)d.N}, {d.self_inc, n * 4}, {d.seqno, n * 4}, {d.vst, slots}, {d.vinc, slots * 4},
+       {d.vlast, slots * 4}, {d.pb, n * d.B * sizeof(uint4)}, {d.pb_cnt, n}, {d.meta, slots / 32 * sizeof(uint4)},
+       {sim->d_scratch, (2 + SWIM_CTR__COUNT) * sizeof(unsigned long long)}};
+}
+
+extern "C" int swim_sim_save(swim_sim_t *sim) {
+  if (!sim) return SWIM_EINVAL;
+  if (!sim->view_set || sim->edges_dirty) { set_error(sim, "swim_sim_save: no view installed, or memberships changed since the last step"); return SWIM_ESTATE; }
+  cudaSetDevice(sim->device);
+  const SimDev &d = sim->dev;
+  if (sim->tdead_dirty) { // the saved per-node records are current
+    SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
+    ++sim->launches;
+    sim->tdead_dirty = false;
+  }
+  std::vector<std::pair<void *, size_t>> src;
+  ckpt_sources(sim, src);
+  if (sim->ckpt_arrays.empty()) {
+    for (auto &a : src) {
+      void *p = nullptr;
+      CUDA_TRY(sim, cudaMalloc(&p, a.second ? a.second : 1));
+      sim->ckpt_arrays.push_back({p, a.second});
+    }
+  }
+  for (size_t x = 0; x < src.size(); ++x)
+    CUDA_TRY(sim, cudaMemcpyAsync(sim->ckpt_arrays[x].first, src[x].first, src[x].second, cudaMemcpyDeviceToDevice, sim->stream));
+  sim->ckpt_round = sim->round;
+  sim->ckpt_events = sim->events;
+  sim->ckpt_epoch = sim->view_epoch;
+  sim->ckpt_valid = true;
   return SWIM_OK;
+}
+
+extern "C" int swim_sim_load(swim_sim_t *sim) {
+  if (!sim) return SWIM_EINVAL;
+  if (!sim->ckpt_valid || sim->edges_dirty || sim->ckpt_epoch != sim->view_epoch) {
+    set_error(sim, "swim_sim_load: no checkpoint of this view (swim_sim_save first; a new view or a membership change drops it)");
+    return SWIM_ESTATE;
+  }
+  cudaSetDevice(sim->device);
+  std::vector<std::pair<void *, size_t>> dst;
+  ckpt_sources(sim, dst);
+  for (size_t x = 0; x < dst.size(); ++x)
+    CUDA_TRY(sim, cudaMemcpyAsync(dst[x].first, sim->ckpt_arrays[x].first, dst[x].second, cudaMemcpyDeviceToDevice, sim->stream));
+  sim->round = sim->ckpt_round;
+  sim->events = sim->ckpt_events;
+  sim->tdead_dirty = false;
+  sim->failed = false;
+  return reset_round_state(sim);
 }
 
 extern "C" int swim_sim_round(const swim_sim_t *sim, uint32_t *round) {
@@ -652,6 +786,104 @@ extern "C" int swim_sim_profile_ms(swim_sim_t *sim, double *out, size_t n) {
   int rc = swim::prof_collect(sim);
   if (rc) return rc;
   for (size_t x = 0; x < n && x < SWIM_PROFILE_SLOTS; ++x) out[x] = sim->prof_ms[x];
+  return SWIM_OK;
+}
+
+// Phase timeline of round_kernel (profiling aid; see tl_mark in swim_device.cuh): room for `rounds` rounds starting at
+// the next round to run; 0 switches it off. Costs one %globaltimer read + one store by one thread per phase.
+extern "C" int swim_sim_set_timeline(swim_sim_t *sim, uint32_t rounds) {
+  if (!sim) return SWIM_EINVAL;
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  SimDev &d = sim->dev;
+  if (d.tl) { cudaFree(d.tl); d.tl = nullptr; }
+  d.tl_cap = 0;
+  if (!rounds) return SWIM_OK;
+  CUDA_TRY(sim, cudaMalloc((void **)&d.tl, (size_t)rounds * 8 * sizeof(unsigned long long)));
+  CUDA_TRY(sim, cudaMemset(d.tl, 0, (size_t)rounds * 8 * sizeof(unsigned long long)));
+  d.tl_cap = rounds;
+  d.tl_round0 = sim->round + 1;
+  return SWIM_OK;
+}
+
+extern "C" int swim_sim_get_timeline(swim_sim_t *sim, uint64_t *out, size_t rounds) {
+  if (!sim || !out) return SWIM_EINVAL;
+  const SimDev &d = sim->dev;
+  if (!d.tl || rounds > d.tl_cap) { set_error(sim, "swim_sim_get_timeline: not enabled for %zu rounds", rounds); return SWIM_ESTATE; }
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  CUDA_TRY(sim, cudaMemcpy(out, d.tl, rounds * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return SWIM_OK;
+}
+
+// ------------------------------------------------------------------ calibration of the latency floor
+// What a round of the fused kernel cannot go below on this machine: the cost of one grid barrier of the resident wave
+// (measured with the kernel's own barrier) and the latency of one dependent global load (pointer chase by one thread
+// over a footprint beyond L2 for HBM, and well inside it for L2). bench.py turns them into roofline.latency_floor.
+namespace {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) calib_barrier_kernel(SimDev d, uint32_t reps, unsigned long long *out) {
+  barrier_begin(d);
+  grid_barrier(d); // everybody is here
+  unsigned long long t0 = 0, t1 = 0;
+#ifndef SWIM_EMU
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
+  for (uint32_t r = 0; r < reps; ++r) grid_barrier(d);
+#ifndef SWIM_EMU
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+#endif
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = t1 - t0;
+}
+__global__ void calib_fill_kernel(uint32_t *next, uint32_t mask) { // full-period LCG over [0, mask]: a single cycle
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i <= mask; i += (size_t)gridDim.x * blockDim.x)
+    next[i] = ((uint32_t)i * 1664525u + 1013904223u) & mask;
+}
+__global__ void calib_chase_kernel(const uint32_t *next, uint32_t hops, unsigned long long *out) {
+  uint32_t x = 12345u & 0xFFFFu;
+  unsigned long long t0 = 0, t1 = 0;
+#ifndef SWIM_EMU
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
+  for (uint32_t h = 0; h < hops; ++h) x = __ldcg(next + x);
+#ifndef SWIM_EMU
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+#endif
+  out[0] = t1 - t0;
+  out[1] = x;
+}
+} // namespace
+
+extern "C" int swim_sim_calibrate(swim_sim_t *sim, double *out, size_t n) {
+  if (!sim || !out || n < 4) return SWIM_EINVAL;
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  const SimDev &d = sim->dev;
+  unsigned long long *d_out = nullptr, h[2];
+  uint32_t *next = nullptr;
+  const uint32_t big = (1u << 27) - 1, small = (1u << 18) - 1; // 512 MB (beyond L2) and 1 MB (inside it)
+  CUDA_TRY(sim, cudaMalloc((void **)&d_out, 16));
+  int blocks = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, calib_barrier_kernel, kThreads, 0) != cudaSuccess || blocks < 1) blocks = 1;
+  const int grid = std::min(sim->grids[4], sim->sm_count * blocks); // the fused kernel's wave
+  const uint32_t reps = 200;
+  SWIM_LAUNCH(calib_barrier_kernel, grid, kThreads, sim->stream, d, reps, d_out);
+  CUDA_TRY(sim, cudaMemcpyAsync(h, d_out, 8, cudaMemcpyDeviceToHost, sim->stream));
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  out[0] = (double)h[0] / reps;
+  out[3] = (double)grid * kWarpsPerBlock;
+  if (cudaMalloc((void **)&next, ((size_t)big + 1) * 4) != cudaSuccess) { cudaFree(d_out); set_error(sim, "swim_sim_calibrate: out of memory"); return SWIM_ENOMEM; }
+  for (int pass = 0; pass < 2; ++pass) {
+    const uint32_t mask = pass == 0 ? big : small, hops = 4000;
+    SWIM_LAUNCH(calib_fill_kernel, sim->sm_count * 8, 256, sim->stream, next, mask);
+    if (pass == 1) SWIM_LAUNCH(calib_chase_kernel, 1, 1, sim->stream, next, mask + 1, d_out); // walk the whole cycle once: L2 warm
+    SWIM_LAUNCH(calib_chase_kernel, 1, 1, sim->stream, next, hops, d_out);
+    CUDA_TRY(sim, cudaMemcpyAsync(h, d_out, 16, cudaMemcpyDeviceToHost, sim->stream));
+    CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+    out[1 + pass] = (double)h[0] / hops;
+  }
+  cudaFree(next);
+  cudaFree(d_out);
+  CUDA_TRY(sim, cudaGetLastError());
   return SWIM_OK;
 }
 

@@ -190,6 +190,22 @@ class Simulator:
         check(lib().swim_sim_profile_ms(self._h, out, 6), "swim_sim_profile_ms", self._h)
         return dict(zip(["events", "tick_scan", "exchange", "recv", "tick_work", "rounds"], list(out)))
 
+    def calibrate(self):
+        """Latency calibration of this GPU (swim_sim_calibrate), nanoseconds."""
+        out = (C.c_double * 4)()
+        check(lib().swim_sim_calibrate(self._h, out, 4), "swim_sim_calibrate", self._h)
+        return {"grid_barrier_ns": out[0], "hbm_load_ns": out[1], "l2_load_ns": out[2], "resident_warps": int(out[3])}
+
+    def set_timeline(self, rounds):
+        """Record the phase boundaries of the next `rounds` rounds of the fused kernel (0 = off)."""
+        check(lib().swim_sim_set_timeline(self._h, rounds), "swim_sim_set_timeline", self._h)
+
+    def timeline(self, rounds):
+        """[rounds, 8] uint64 nanosecond stamps (swim_sim_get_timeline); 0 = phase not run."""
+        out = np.zeros((rounds, 8), dtype=np.uint64)
+        check(lib().swim_sim_get_timeline(self._h, out.ctypes.data, rounds), "swim_sim_get_timeline", self._h)
+        return out
+
     def observe(self, digest=True, mismatches=True):
         """(counters, digest, mismatches) with one device synchronisation; a part that is switched off is not
         computed (its kernel is not launched) and comes back as None."""
@@ -226,6 +242,14 @@ class Simulator:
 
     def set_round(self, r):
         check(lib().swim_sim_set_round(self._h, r), "swim_sim_set_round", self._h)
+
+    def save(self):
+        """Device-resident checkpoint (swim_sim_save): state, counters, round and pending events, no host traffic."""
+        check(lib().swim_sim_save(self._h), "swim_sim_save", self._h)
+
+    def load(self):
+        """Back to the last save() (swim_sim_load)."""
+        check(lib().swim_sim_load(self._h), "swim_sim_load", self._h)
 
     def checkpoint(self):
         """Everything a single-shard run needs to be resumed bit for bit: the state arrays and the round (the counter of

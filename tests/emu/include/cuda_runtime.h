@@ -119,6 +119,7 @@ static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { uint64_t v[32]; uint32_t
 static inline void __syncthreads() { uint64_t v[32]; uint32_t m; swim_emu::exchange(swim_emu::OP_SYNCTHREADS, 0, v, &m); }
 
 // ------------------------------------------------------------------ scalar intrinsics, atomics, fences
+template <typename T> static inline T __ldcg(const T *p) { return *p; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
@@ -199,6 +200,8 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { delete s; return c
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline double swim_emu_now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new EmuEvent{0.0}; return cudaSuccess; }
+#define cudaEventDisableTiming 2u
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t_ms = swim_emu_now_ms(); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }

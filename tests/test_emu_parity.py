@@ -310,3 +310,65 @@ def test_batched_quiet_scans(qbatch, flags, cap, monkeypatch):
         sim.step(chunk)
         orc.step(chunk)
         assert_same_state(sim, orc, f"qbatch {qbatch} after {sim.round} rounds")
+
+
+def test_many_events_per_round_grouped_by_node():
+    """event_kernel gets a round's events grouped by node (stable) and gives each same-node run to one warp: several
+    events on one node in one round (crash, rejoin, crash again, injected datagrams) must keep their order, across
+    separate swim_sim_inject calls and interleaved with other nodes' events."""
+    rng = np.random.default_rng(21)
+    n = 200
+    cfg = default_config(n_nodes=n, seed=5)
+    nbr = generate_topology("random", n, 32, 24, seed=4)
+    sim, orc = make_pair(cfg, nbr)
+    from swim_b200.sim import make_events
+    parts = []
+    for r in (2, 3, 5):
+        nodes = rng.integers(0, 12, size=60).astype(np.uint32)  # few nodes: long same-node runs
+        kinds = rng.choice([A.EV_CRASH, A.EV_REJOIN, A.EV_INJECT], size=60).astype(np.uint8)
+        parts.append(make_events(np.full(60, r, np.uint32), nodes, kinds,
+                                 msg_kind=rng.choice([A.MSG_SUSPECT, A.MSG_ALIVE, A.MSG_DEAD], size=60).astype(np.uint8),
+                                 msg_node=rng.integers(0, n, size=60).astype(np.uint32), msg_inc=rng.integers(0, 3, size=60),
+                                 msg_from=rng.integers(0, n, size=60).astype(np.uint32)))
+    # two inject calls whose rounds interleave
+    a, b = concat_events([parts[0], parts[2]]), parts[1]
+    for x in (a, b):
+        sim.inject(x)
+        orc.inject(x)
+    for r in range(12):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"round {r + 1}")
+
+
+def test_save_load_replays_the_same_rounds():
+    """swim_sim_save / swim_sim_load: the device-resident checkpoint brings back state, counters, round and pending events;
+    replayed rounds give the same result, also after the handle ran far past the checkpoint (round-stamped scratch arrays
+    are cleared), and swim_sim_set_round on a handle that has stepped does the same for the host-side checkpoint."""
+    rng = np.random.default_rng(33)
+    n = 400
+    cfg = default_config(n_nodes=n, seed=91)
+    nbr = generate_topology("random", n, 32, 20, seed=6)
+    sim, orc = make_pair(cfg, nbr)
+    ev = random_events(rng, n, 60, n_crash=30, n_rejoin=8, n_inject=12)
+    sim.inject(ev)
+    orc.inject(ev)
+    sim.step(25)
+    orc.step(25)
+    assert_same_state(sim, orc, "round 25")
+    sim.save()
+    ck = sim.checkpoint()
+    sim.step(35)
+    orc.step(35)
+    assert_same_state(sim, orc, "round 60")
+    ref = (sim.digest(), sim.counters().tolist())
+    for rep in range(2):
+        sim.load()
+        assert sim.round == 25
+        sim.step(35)
+        assert (sim.digest(), sim.counters().tolist()) == ref, f"replay {rep}"
+    # the host-side checkpoint on the SAME handle: arrays + round (events after round 25 re-injected by the caller)
+    sim.restore(ck)
+    sim.inject(ev[ev["round"] > 25])
+    sim.step(35)
+    assert sim.digest() == ref[0]
