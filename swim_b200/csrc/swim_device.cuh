@@ -88,11 +88,15 @@ struct SimDev {
   uint32_t *obs_off;         // [N+1] observers of member m among this shard's rows ...
   uint32_t *obs_slot;        // [n*cap] ... as linear slot indices l*cap + s
   uint32_t *wl, *wl_cnt;     // work list of K1b [n]; counters indexed by round % 3
-  uint32_t *xtra;            // [3] (round % 3) work items K1b added itself (re-scanned receivers)
-  uint32_t *rl;              // [2][n*fanout] receiver candidates (round parity): slot*fanout + f
-  uint32_t *claim2;          // [n] round stamp: a receiver of round r-1 is re-scanned once in round r
-  uint32_t pipe;             // bit0: this round's K1a skipped last round's receivers; K1b re-scans them
-  uint32_t stamping;         // 1: senders stamp their receivers' meta records (pipelined rounds only)
+  uint2 *rl;                 // [2][n*fanout] recipient slots (round parity), slot = item*fanout + f:
+                             //   .x = local receiver (bit 31 set: sent, but not delivered — see `bloom`), .y = the sender
+  uint32_t *ncand;           // [3] (round % 3) slots of this round that were delivered to a local receiver
+  // Static membership filter of every node's view row (all N nodes, replicated on every rank): 256 W bits per node, two
+  // hash positions per member id. A sender tests its records against the recipient's filter: an envelope none of whose
+  // records is about the recipient or about a member the recipient may know cannot change the recipient's state
+  // (Core.hs:147-148 `we don't know this node. ignore`), so it is counted and dropped at the sender instead of being
+  // flagged, listed and walked by K2. False positives are delivered and ignored there; there are no false negatives.
+  const uint32_t *bloom;     // [N * 8 W]
   // Round-parity double buffering: everything a round's senders write for its receivers exists twice
   // (index = round & 1), so round r+1's senders never touch what round r's receivers still read and ONE
   // cross-GPU barrier per round (between K1b and K2) is enough.
@@ -104,7 +108,6 @@ struct SimDev {
   uint32_t estride_p[SWIM_MAX_WORLD];
   const uint4 *out_p[SWIM_MAX_WORLD];    // [2][per*B] sender snapshots
   const uint8_t *out_cnt_p[SWIM_MAX_WORLD]; // [2][per]
-  uint4 *meta_p[SWIM_MAX_WORLD];         // receivers' meta records (mail stamps are written by senders)
   uint32_t *bar_err;                     // set by a cross-GPU / grid wait that timed out
   uint32_t *gbar;                        // [2] grid barrier of round_kernel: arrival count, generation
   uint32_t *qm;                          // [3] busy masks of round_kernel's batched quiet scans (batch number % 3)
@@ -476,13 +479,13 @@ __device__ __forceinline__ void peer_publish_cta(const SimDev &d, uint32_t mail_
 
 constexpr int kScanGroups = 2; // Philox groups (of 4 nodes) per lane per iteration: 8 nodes, 8 loads in flight
 
-// Pipelining of consecutive rounds: the receive phase of round r-1 (latency bound) runs in the same
-// kernel as the scan of round r (throughput bound). Senders stamp their receivers' meta records with
-// stamp_of(round); the scan of the next round skips stamped nodes, and K1b re-scans exactly those
-// (after their mail has been applied) and clears the stamp.
-__device__ __forceinline__ uint32_t stamp_of(uint32_t round) { return round % 65535u + 1u; } // 16 bit, never 0
-__device__ __forceinline__ uint32_t ci(uint32_t round) { return round % 3u; }                 // counter slot
-__device__ __forceinline__ uint16_t *stamp_ptr(uint4 *meta) { return reinterpret_cast<uint16_t *>(meta) + 7; }
+__device__ __forceinline__ uint32_t ci(uint32_t round) { return round % 3u; } // slot of the per-round list counters
+
+// The two filter positions of member id x in a node's 256 W-bit membership filter (SimDev::bloom); the host builds the
+// filters with the same two lines (swim_sim.cu: build_in_edges).
+SWIM_HD uint32_t bloom_pos(uint32_t x, int which, uint32_t bits) {
+  return SWIM_UMULHI(x * (which ? 0x85EBCA77u : 0x9E3779B1u), bits);
+}
 
 // The Philox block holding the target draws of the four nodes 4g..4g+3, and the pick itself (random: kRandomMembers
 // store 1 [], Core.hs:239 over shuffle, Util.hs:36-42; round-robin: see rr_pick). `am` is consumed.
@@ -527,9 +530,9 @@ __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags,
 // calls, and eight r-th-set-bit picks (shuffle, Util.hs:36-42) tested against the crashed-member
 // bitmap. A warp covers 256 consecutive nodes = 4 KB contiguous. Nodes that need more — a Suspect
 // slot to count down, a failed probe, a non-empty piggyback buffer — are appended to the round's
-// work list for K1b. skip_stamp != 0: nodes carrying that mail stamp are left to K1b's re-scan.
+// work list for K1b.
 template <int W>
-__device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint32_t skip_stamp, uint32_t warp, uint32_t nwarps,
+__device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps,
                                           int lane, uint32_t &pings) {
   constexpr int U = kScanGroups;
   uint32_t *wl_cnt = d.wl_cnt + ci(round);
@@ -563,7 +566,6 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (!(valid >> (u * 4 + j) & 1u)) continue;
-        if (skip_stamp && (m[u][j].w >> 16) == skip_stamp) continue; // has mail from last round: K1b re-scans it
         uint32_t am[W], td[W], sus = m[u][j].y;
         am[0] = m[u][j].x; td[0] = m[u][j].z;
         if (W > 1) {
@@ -607,7 +609,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tick_scan_kernel(SimDev 
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t pings = 0;
-  scan_pass<W>(d, round, 0, warp, nwarps, lane, pings);
+  scan_pass<W>(d, round, warp, nwarps, lane, pings);
   pings = __reduce_add_sync(kFull, pings);
   if (lane == 0 && pings) atomicAdd(&d.ctr[SWIM_CTR_PINGS], (unsigned long long)pings);
 }
@@ -683,72 +685,20 @@ __device__ __forceinline__ uint32_t first_work_entry(const SimDev &d, uint32_t w
   return warp < d.n ? *(volatile const uint32_t *)(d.wl + warp) : 0u;
 }
 
-// K1b — warp-per-node over the work list (plus, when pipelined, last round's receivers): countdown
-// and expiry -> Dead, probe escalation (k proxies), local suspicion, piggyback send. Lane s owns view
-// slot s; the piggyback buffer is staged in shared memory. Everything K1a derived is recomputed
-// from the row with warp ballots.
+// K1b — warp-per-node over the work list: countdown and expiry -> Dead, probe escalation (k proxies), local suspicion,
+// piggyback send. Lane s owns view slot s; the piggyback buffer is staged in shared memory. Everything K1a derived is
+// recomputed from the row with warp ballots.
 template <int W>
 __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps, int lane,
                                           PbStage &pbs, Ctr &c, uint32_t first_ln) {
   const uint32_t n_work = d.wl_cnt[ci(round)];
   const uint32_t par = round & 1;
-  uint32_t *rl_out = d.rl + (size_t)par * d.n * d.fanout;
-  const uint32_t my_stamp = stamp_of(round);
+  uint2 *rl_out = d.rl + (size_t)par * d.n * d.fanout;
   bool did_remote = false; // this lane stored into a peer GPU's memory
-  // pipelined rounds: last round's receivers were skipped by K1a; their mail has been applied by now
-  uint32_t seg_end[SWIM_MAX_WORLD + 1];
-  uint32_t n_rescan = 0;
-  const uint32_t ppar = par ^ 1;
-  if (d.pipe & 1u) {
-    n_rescan = (d.wl_cnt[ci(round - 1)] + d.xtra[ci(round - 1)]) * d.fanout;
-    seg_end[0] = n_rescan;
-    if (d.world > 1)
-      for (uint32_t a = 0; a < d.world; ++a) {
-        if (a != d.rank) n_rescan += d.rcnt[ppar * d.world + a];
-        seg_end[1 + a] = n_rescan;
-      }
-  }
+  uint32_t listed = 0;     // recipient slots this warp delivered to local receivers
 
-  for (uint32_t idx = warp; idx < n_work + n_rescan; idx += nwarps) {
-    uint32_t ln, slot;
-    if (idx < n_work) {
-      ln = idx == warp ? first_ln : d.wl[idx];
-      slot = idx;
-    } else {
-      const uint32_t cidx = idx - n_work;
-      if (cidx < seg_end[0]) {
-        ln = d.rl[(size_t)ppar * d.n * d.fanout + cidx];
-        if (ln == 0xFFFFFFFFu) continue; // empty candidate slot
-      } else {
-        uint32_t a = 0;
-        while (cidx >= seg_end[1 + a]) ++a;
-        ln = d.rlr[((size_t)ppar * d.world + a) * d.rcap + (cidx - seg_end[a])];
-      }
-      uint32_t old = 0;
-      if (lane == 0) old = atomicExch(&d.claim2[ln], round);
-      if (__shfl_sync(kFull, old, 0) == round) continue; // this receiver is already being re-scanned
-      // the scan step K1a skipped for this node
-      uint32_t am[W], td[W], sus = 0, flags = 0;
-#pragma unroll
-      for (int w = 0; w < W; ++w) {
-        const uint4 mw = d.meta[(size_t)ln * W + w];
-        am[w] = mw.x; sus |= mw.y; td[w] = mw.z;
-        if (w == 0) flags = mw.w;
-      }
-      // retire last round's mail stamp — unless a sender of THIS round has already re-stamped the node
-      if (lane == 0) atomicCAS(reinterpret_cast<unsigned short *>(stamp_ptr(d.meta + (size_t)ln * W)), (unsigned short)stamp_of(round - 1), (unsigned short)0);
-      const uint32_t self = d.first + ln;
-      const uint4 x = target_block<W>(d, round, self >> 2);
-      uint4 y = make_uint4(0, 0, 0, 0);
-      if (d.loss_ppm) y = philox4x32_10(make_uint4(round, self >> 2, P_LOSS0, 0), d.key0, d.key1);
-      uint32_t pings = 0;
-      const bool need = node_needs_work<W>(d, flags, am, td, sus, word_of(x, self & 3), word_of(y, self & 3), round, pings);
-      if (lane == 0) c.v[SWIM_CTR_PINGS] += pings;
-      if (!need) continue;
-      uint32_t k = 0;
-      if (lane == 0) k = atomicAdd(&d.xtra[ci(round)], 1u);
-      slot = n_work + __shfl_sync(kFull, k, 0);
-    }
+  for (uint32_t idx = warp; idx < n_work; idx += nwarps) {
+    const uint32_t ln = idx == warp ? first_ln : d.wl[idx];
     const uint32_t self = d.first + ln;
     Row<W> row;
     row_load<W>(row, d, ln, lane);
@@ -829,7 +779,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
     }
     row_store<W>(row, d, ln, lane, round);
     // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
-    uint32_t cand = 0xFFFFFFFFu; // lane f < fanout: local receiver of recipient f (K2's candidate slot)
+    uint2 cand = make_uint2(0xFFFFFFFFu, ln); // lane f < fanout: recipient slot f
     if (L && pbs.cnt) {
       uint32_t nr = 1, rslot = tslot; // lane f carries recipient f
       for (uint32_t j = 0; j < np && nr < d.fanout; ++j)
@@ -842,20 +792,47 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           const uint32_t a = __shfl_sync(kFull, row.nb[w], rslot & 31), b = __shfl_sync(kFull, rix[w], rslot & 31);
           if ((uint32_t)w == (rslot >> 5)) { dst_c = a; ridx_c = b; }
         }
+      uint32_t n_up = 0;
       if ((uint32_t)lane < nr) {
         const size_t e = (size_t)ln * d.cap + rslot;
         const uint32_t dst = kCarry ? dst_c : d.nbr[e], ridx = kCarry ? ridx_c : d.ridx[e];
+        // A datagram to a crashed process is lost (the crashed-member bitmap says so without touching alive[]); one to a
+        // live process is received (counted here), but it is only DELIVERED — flagged and listed for K2 — if one of its
+        // records is about the recipient itself or passes the recipient's membership filter: anything else would run
+        // into `we don't know this node. ignore` (Core.hs:147-148) record by record and change nothing.
+        const bool r_up = (td[rslot >> 5] >> (rslot & 31) & 1u) == 0;
+        n_up = r_up ? 1u : 0u;
+        bool deliver = false;
+        if (r_up) {
+          constexpr uint32_t kBits = 256u * W;
+          const uint32_t *bf = d.bloom + (size_t)dst * (kBits / 32);
+          uint32_t w0[SWIM_MAX_PB / 4], w1[SWIM_MAX_PB / 4]; // the two filter words of up to 8 records at a time
+          for (uint32_t q0 = 0; q0 < pbs.cnt; q0 += SWIM_MAX_PB / 4) {
+#pragma unroll
+            for (uint32_t q = 0; q < SWIM_MAX_PB / 4; ++q) {
+              const uint32_t x = q0 + q < pbs.cnt ? pbs.s[q0 + q].x : dst;
+              w0[q] = bf[bloom_pos(x, 0, kBits) >> 5];
+              w1[q] = bf[bloom_pos(x, 1, kBits) >> 5];
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < SWIM_MAX_PB / 4; ++q) {
+              if (q0 + q >= pbs.cnt) continue;
+              const uint32_t x = pbs.s[q0 + q].x;
+              deliver |= x == dst || ((w0[q] >> (bloom_pos(x, 0, kBits) & 31) & 1u) && (w1[q] >> (bloom_pos(x, 1, kBits) & 31) & 1u));
+            }
+          }
+        }
         const uint32_t owner = d.world == 1 ? 0u : dst / d.per;
         const uint32_t dl = dst - owner * d.per;
-        if (owner == d.rank) {
+        if (owner == d.rank) cand.x = dl | (deliver ? 0u : 0x80000000u); // bit 31: sent, nothing for K2 to do
+        if (!deliver) {
+          // dropped at the sender
+        } else if (owner == d.rank) {
           d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
-          if (d.stamping) *stamp_ptr(d.meta + (size_t)dl * W) = (uint16_t)my_stamp; // "has mail from this round"
-          cand = dl;
         } else if (d.p2p) {
-          // fused exchange: flag, mail stamp and receiver-list entry go straight into the owner GPU's
-          // memory over NVLink (plain stores, nothing comes back); the receiver pulls our snapshot
+          // fused exchange: flag and receiver-list entry go straight into the owner GPU's memory over NVLink (plain
+          // stores, nothing comes back); the receiver pulls our snapshot
           d.eflag_p[owner][(size_t)par * d.estride_p[owner] + ridx] = 1;
-          if (d.stamping) *stamp_ptr(d.meta_p[owner] + (size_t)dl * W) = (uint16_t)my_stamp;
           const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
           d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
           did_remote = true;
@@ -869,10 +846,13 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           }
         }
       }
+      n_up = __reduce_add_sync(kFull, n_up);
+      listed += __popc(__ballot_sync(kFull, cand.x < 0x80000000u));
       if (lane == 0) {
         d.out_cnt[(size_t)par * d.per + ln] = (uint8_t)pbs.cnt;
         c.v[SWIM_CTR_MSGS] += nr;
         c.v[SWIM_CTR_RECS_SENT] += nr * pbs.cnt;
+        c.v[SWIM_CTR_MSGS_RECV] += n_up; // envelopes that reach a live process
       }
       // snapshot, then one transmission is spent on every record
       uint4 mine = make_uint4(0, 0, 0, 0);
@@ -897,8 +877,9 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
       __syncwarp();
     }
     pb_store(pbs, d, ln, lane);
-    if ((uint32_t)lane < d.fanout) rl_out[(size_t)slot * d.fanout + lane] = cand; // no atomics, no shared counter
+    if ((uint32_t)lane < d.fanout) rl_out[(size_t)idx * d.fanout + lane] = cand; // no atomics, no shared counter
   }
+  if (lane == 0 && listed) atomicAdd(&d.ncand[ci(round)], listed);
   if (did_remote) __threadfence_system(); // peer-memory stores are performed before the grid reports completion
 }
 
@@ -910,7 +891,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tick_work_kernel(SimDev 
   pdl_launch();
   pdl_wait();
   const uint32_t round = d.round;
-  if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
+  if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.ncand[ci(round + 1)] = 0; }
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_work_entry(d, warp));
@@ -967,115 +948,118 @@ static __global__ void peer_barrier_kernel(SimDev d) {
 }
 
 // =================================================================== K2: receive
-// warp-per-candidate over the receivers of `round`: claim, in-edge flags -> sender snapshots (local
-// or peer-GPU memory) -> row_apply per record, re-broadcast enqueue. Loads that do not depend on each
-// other are issued together: (row, buffer, in-list bounds) -> (edge flags, sender ids) -> (snapshots).
+// One receiver of `round`: claim, in-edge flags -> sender snapshots (local or peer-GPU memory) -> row_apply per record,
+// re-broadcast enqueue. Loads that do not depend on each other are issued together: (claim, row, buffer, in-list bounds,
+// the snapshot of the sender the slot names) -> (edge flags, sender ids) -> (other senders' snapshots).
 template <int W>
-__device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, bool clear_stamp, uint32_t warp, uint32_t nwarps,
+__device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32_t ln, bool early, uint32_t snd, int lane,
+                                         PbStage &pbs, Ctr &c) {
+  const uint32_t par = round & 1;
+  const size_t ebase = (size_t)par * d.estride;
+  // the claim and every load that depends only on `ln` are issued together (one memory round trip)
+  uint32_t old = 0;
+  if (lane == 0) old = atomicExch(&d.claim[ln], round);
+  const uint32_t self = d.first + ln;
+  const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
+  Row<W> row;
+  row_load<W>(row, d, ln, lane);
+  pb_load(pbs, d, ln, lane);
+  uint32_t self_inc = d.self_inc[ln];
+  const uint32_t self_inc0 = self_inc;
+  // A recipient slot names one sender of its receiver; that sender's snapshot is fetched together with the receiver's
+  // row, ahead of the in-edge flags that will ask for it — for the usual envelope (one sender per receiver per round) the
+  // pass is one dependent round trip shorter. The flags still decide what is applied and in which order.
+  uint4 early_rec = make_uint4(0, 0, 0, 0);
+  uint32_t early_cnt = 0;
+  if (early) {
+    if ((uint32_t)lane < d.B) early_rec = d.out_p[d.rank][((size_t)par * d.per + snd) * d.B + lane];
+    early_cnt = d.out_cnt_p[d.rank][(size_t)par * d.per + snd];
+  }
+  if (__shfl_sync(kFull, old, 0) == round) return; // another warp has this receiver
+  // (a listed receiver is a live process: senders deliver only to members whose crashed-member bit is clear)
+  for (uint32_t eb = e0; eb < e1; eb += 32) {
+    const uint32_t e = eb + lane;
+    uint32_t f = 0, src = 0;
+    if (e < e1) { f = d.eflag[ebase + e]; src = d.in_src[e]; }
+    if (f) d.eflag[ebase + e] = 0;
+    unsigned fm = __ballot_sync(kFull, f != 0);
+    while (fm) { // ascending sender id: the in-list is sorted
+      const int q = __ffs(fm) - 1;
+      fm &= fm - 1;
+      const uint32_t s_id = __shfl_sync(kFull, src, q), s_kind = __shfl_sync(kFull, f, q);
+      uint32_t cnt;
+      uint4 mine = make_uint4(0, 0, 0, 0);
+      if (s_kind == 1 && early && s_id == d.first + snd) { // the sender this slot came from: already here
+        mine = early_rec;
+        cnt = early_cnt;
+      } else if (s_kind == 1) { // pull the sender's snapshot (from a peer GPU's memory if it lives there)
+        const uint32_t s_rank = d.world == 1 ? 0u : s_id / d.per, sl = s_id - s_rank * d.per;
+        if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][((size_t)par * d.per + sl) * d.B + lane];
+        cnt = d.out_cnt_p[s_rank][(size_t)par * d.per + sl];
+      } else {           // staged NCCL path: the envelope arrived in the exchange buffer
+        const uint32_t xslot = d.eslot[eb + q];
+        const uint4 *env = d.xrecv + (size_t)xslot * (1 + d.B);
+        if ((uint32_t)lane < d.B) mine = env[1 + lane];
+        cnt = env[0].y;
+      }
+      for (uint32_t r = 0; r < cnt; ++r) { // records in buffer order (newest first)
+        uint4 rec;
+        rec.x = __shfl_sync(kFull, mine.x, r); rec.y = __shfl_sync(kFull, mine.y, r);
+        rec.z = __shfl_sync(kFull, mine.z, r); rec.w = __shfl_sync(kFull, mine.w, r);
+        uint4 rb;
+        if (row_apply<W>(row, d, self, self_inc, rec, rb, lane, c.v[SWIM_CTR_REFUTES]) == 1) {
+          pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // maybeBroadcast (Core.hs:119-121)
+          if (lane == 0) ++c.v[SWIM_CTR_RECS_APPLIED];
+        }
+      }
+    }
+  }
+  row_store<W>(row, d, ln, lane, round);
+  pb_store(pbs, d, ln, lane);
+  if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
+}
+
+// warp-per-receiver over the receivers of `round`: the recipient slots K1b wrote (fanout per work item; most are empty
+// or were dropped at the sender), then one list per source rank (cross-shard senders). A receiver can be listed more
+// than once: the claim stamp lets exactly one warp process it.
+template <int W>
+__device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps,
                                           int lane, PbStage &pbs, Ctr &c) {
   const uint32_t par = round & 1;
-  // receivers of this round: the candidate slots written by K1b (fanout per work item, some empty),
-  // then one list per source rank (cross-shard senders). A receiver can appear many times: the claim
-  // stamp lets exactly one warp process it.
-  uint32_t seg_end[SWIM_MAX_WORLD + 1];
-  const uint32_t n_listed = d.wl_cnt[ci(round)]; // candidate slots [0, n_listed * fanout) belong to the senders wl[0..)
-  uint32_t n_recv = (n_listed + d.xtra[ci(round)]) * d.fanout;
-  seg_end[0] = n_recv;
-  if (d.world > 1)
+  const uint32_t n_slots = d.wl_cnt[ci(round)] * d.fanout;
+  if (d.ncand[ci(round)] != 0) { // some slot was delivered locally
+    const uint2 *rl_in = d.rl + (size_t)par * d.n * d.fanout;
+    constexpr uint32_t kBatch = 4; // slots fetched per round trip: a warp's slots are nwarps apart
+    for (uint32_t base = warp; base < n_slots; base += nwarps * kBatch) {
+      uint2 e[kBatch];
+#pragma unroll
+      for (uint32_t t = 0; t < kBatch; ++t) {
+        const uint32_t item = base + t * nwarps;
+        e[t] = item < n_slots ? rl_in[item] : make_uint2(0xFFFFFFFFu, 0u);
+      }
+#pragma unroll
+      for (uint32_t t = 0; t < kBatch; ++t)
+        if (e[t].x < 0x80000000u) recv_one<W>(d, round, e[t].x, true, e[t].y, lane, pbs, c);
+    }
+  }
+  if (d.world > 1) {
+    uint32_t seg_end[SWIM_MAX_WORLD + 1];
+    uint32_t n_recv = 0;
+    seg_end[0] = 0;
     for (uint32_t a = 0; a < d.world; ++a) {
       if (a != d.rank) n_recv += d.rcnt[par * d.world + a];
       seg_end[1 + a] = n_recv;
     }
-  const size_t ebase = (size_t)par * d.estride;
-  const uint32_t *rl_in = d.rl + (size_t)par * d.n * d.fanout;
-  // as in K1b: the warp's first candidate is fetched together with the counts
-  const uint32_t first_cand = warp < d.n * d.fanout ? rl_in[warp] : 0xFFFFFFFFu;
-  // A candidate slot also names one sender of its receiver: slot / fanout is that sender's position in the work list.
-  // Its snapshot is fetched together with the receiver's row, ahead of the in-edge flags that will ask for it — for the
-  // usual envelope (one sender per receiver per round) the pass is one dependent round trip shorter. The flags still
-  // decide what is applied and in which order; the early copy only replaces the load of that one sender.
-  const uint32_t first_snd = warp / d.fanout < d.n ? d.wl[warp / d.fanout] : 0u;
-
-  for (uint32_t item = warp; item < n_recv; item += nwarps) {
-    uint32_t ln, snd = 0;
-    bool early = false;
-    if (item < seg_end[0]) {
-      ln = item == warp ? first_cand : rl_in[item];
-      const uint32_t si = item / d.fanout;
-      if (si < n_listed) { snd = item == warp ? first_snd : d.wl[si]; early = true; }
-      if (ln == 0xFFFFFFFFu) continue; // empty candidate slot
-    } else {
+    for (uint32_t item = warp; item < n_recv; item += nwarps) {
       uint32_t a = 0;
       while (item >= seg_end[1 + a]) ++a;
-      ln = d.rlr[((size_t)par * d.world + a) * d.rcap + (item - seg_end[a])];
+      const uint32_t ln = d.rlr[((size_t)par * d.world + a) * d.rcap + (item - seg_end[a])];
+      recv_one<W>(d, round, ln, false, 0u, lane, pbs, c);
     }
-    // the claim and every load that depends only on `ln` are issued together (one memory round trip)
-    uint32_t old = 0;
-    if (lane == 0) old = atomicExch(&d.claim[ln], round);
-    const uint32_t self = d.first + ln;
-    const bool up = d.alive[self] != 0; // datagrams to a crashed process are lost
-    const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
-    Row<W> row;
-    row_load<W>(row, d, ln, lane);
-    pb_load(pbs, d, ln, lane);
-    uint32_t self_inc = d.self_inc[ln];
-    const uint32_t self_inc0 = self_inc;
-    uint4 early_rec = make_uint4(0, 0, 0, 0);
-    uint32_t early_cnt = 0;
-    if (early) {
-      if ((uint32_t)lane < d.B) early_rec = d.out_p[d.rank][((size_t)par * d.per + snd) * d.B + lane];
-      early_cnt = d.out_cnt_p[d.rank][(size_t)par * d.per + snd];
-    }
-    if (__shfl_sync(kFull, old, 0) == round) continue; // another warp has this receiver
-    for (uint32_t eb = e0; eb < e1; eb += 32) {
-      const uint32_t e = eb + lane;
-      uint32_t f = 0, src = 0;
-      if (e < e1) { f = d.eflag[ebase + e]; src = d.in_src[e]; }
-      if (f) d.eflag[ebase + e] = 0;
-      unsigned fm = __ballot_sync(kFull, f != 0);
-      if (!up) continue;
-      while (fm) { // ascending sender id: the in-list is sorted
-        const int q = __ffs(fm) - 1;
-        fm &= fm - 1;
-        const uint32_t s_id = __shfl_sync(kFull, src, q), s_kind = __shfl_sync(kFull, f, q);
-        uint32_t cnt;
-        uint4 mine = make_uint4(0, 0, 0, 0);
-        if (s_kind == 1 && early && s_id == d.first + snd) { // the sender this candidate slot came from: already here
-          mine = early_rec;
-          cnt = early_cnt;
-        } else if (s_kind == 1) { // pull the sender's snapshot (from a peer GPU's memory if it lives there)
-          const uint32_t s_rank = d.world == 1 ? 0u : s_id / d.per, sl = s_id - s_rank * d.per;
-          if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][((size_t)par * d.per + sl) * d.B + lane];
-          cnt = d.out_cnt_p[s_rank][(size_t)par * d.per + sl];
-        } else {           // staged NCCL path: the envelope arrived in the exchange buffer
-          const uint32_t xslot = d.eslot[eb + q];
-          const uint4 *env = d.xrecv + (size_t)xslot * (1 + d.B);
-          if ((uint32_t)lane < d.B) mine = env[1 + lane];
-          cnt = env[0].y;
-        }
-        if (lane == 0) ++c.v[SWIM_CTR_MSGS_RECV];
-        for (uint32_t r = 0; r < cnt; ++r) { // records in buffer order (newest first)
-          uint4 rec;
-          rec.x = __shfl_sync(kFull, mine.x, r); rec.y = __shfl_sync(kFull, mine.y, r);
-          rec.z = __shfl_sync(kFull, mine.z, r); rec.w = __shfl_sync(kFull, mine.w, r);
-          uint4 rb;
-          if (row_apply<W>(row, d, self, self_inc, rec, rb, lane, c.v[SWIM_CTR_REFUTES]) == 1) {
-            pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // maybeBroadcast (Core.hs:119-121)
-            if (lane == 0) ++c.v[SWIM_CTR_RECS_APPLIED];
-          }
-        }
-      }
-    }
-    if (up) {
-      row_store<W>(row, d, ln, lane, round);
-      pb_store(pbs, d, ln, lane);
-      if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
-    }
-    if (clear_stamp && lane == 0) *stamp_ptr(d.meta + (size_t)ln * W) = 0;
   }
 }
 
-// stand-alone K2 (last round of a call, rounds next to events, profiling, staged NCCL exchange)
+// stand-alone K2 (profiling, staged NCCL exchange, sharded runs)
 template <int W>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) recv_kernel(SimDev d) {
   SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
@@ -1086,35 +1070,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) recv_kernel(SimDev d) {
   const uint32_t round = d.round;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c); // sharded runs: the host launched peer_barrier_kernel before this
-  c.flush(d.ctr, lane);
-}
-
-// pipelined K2(r-1) + K1a(r): odd warps receive first and scan second, even warps the other way
-// round, so at any moment half the warps wait on dependent loads while the other half issue the scan.
-template <int W>
-__global__ void __launch_bounds__(kThreads, kMinBlocks) recv_scan_kernel(SimDev d) {
-  SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
-  pdl_launch();
-  pdl_wait();
-  const uint32_t round = d.round; // the round being scanned; mail of round - 1 is applied
-  Ctr c; c.clear();
-  PbStage pbs; pbs.s = s_pb[wib];
-  const bool sync_peers = d.world > 1 && d.p2p;
-  if (sync_peers) peer_publish(d, round - 1);
-  uint32_t pings = 0;
-  if (warp & 1u) {
-    if (sync_peers) peer_wait(d, round - 1, lane);
-    recv_pass<W>(d, round - 1, false, warp, nwarps, lane, pbs, c);
-    scan_pass<W>(d, round, stamp_of(round - 1), warp, nwarps, lane, pings);
-  } else {
-    scan_pass<W>(d, round, stamp_of(round - 1), warp, nwarps, lane, pings);
-    if (sync_peers) peer_wait(d, round - 1, lane);
-    recv_pass<W>(d, round - 1, false, warp, nwarps, lane, pbs, c);
-  }
-  c.v[SWIM_CTR_PINGS] += pings;
+  recv_pass<W>(d, round, warp, nwarps, lane, pbs, c); // sharded runs: the host launched peer_barrier_kernel before this
   c.flush(d.ctr, lane);
 }
 
@@ -1224,7 +1180,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     tl_mark(d, round, 0);
     // slot (round + 1) % 3 of the list counters was last used two rounds ago: clear it now, well before the
     // next round's scan (which starts after this round's first barrier) appends to it
-    if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.xtra[ci(round + 1)] = 0; }
+    if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.ncand[ci(round + 1)] = 0; }
     if (batching && prev_quiet && d.nrounds - it >= 2) {
       const uint32_t Q = d.qbatch < d.nrounds - it ? d.qbatch : d.nrounds - it;
       if (warp == 0 && lane == 0) d.qm[(nb + 1) % 3] = 0;
@@ -1245,7 +1201,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
       // fb == 0: this very round has work — the ordinary scan below lists it
     }
     uint32_t pings = 0;
-    scan_pass<W>(d, round, 0, warp, nwarps, lane, pings);                // K1a
+    scan_pass<W>(d, round, warp, nwarps, lane, pings);                   // K1a
     c.v[SWIM_CTR_PINGS] += pings;
     tl_mark(d, round, 1);
     grid_barrier(d);                                                      // the work list is complete
@@ -1259,7 +1215,10 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     if (d.world > 1 && d.p2p) grid_peer_barrier(d, round);                // ... on every rank (one thread per GPU polls)
     else grid_barrier(d);                                                 // every flag and snapshot is written
     tl_mark(d, round, 4);
-    recv_pass<W>(d, round, true, warp, nwarps, lane, pbs, c);             // K2
+    // Nothing was delivered (every envelope of the round was dropped at its sender, or nobody sent): K2 has no work and
+    // the barrier just passed already separates K1b's writes from the next scan.
+    if (d.world == 1 && *(volatile uint32_t *)&d.ncand[ci(round)] == 0) continue;
+    recv_pass<W>(d, round, warp, nwarps, lane, pbs, c);                   // K2
     tl_mark(d, round, 5);
     if (it + 1 < d.nrounds) grid_barrier(d);                              // views and buffers settled before the next scan
     tl_mark(d, round, 6);

@@ -160,7 +160,7 @@ extern "C" int swim_sim_connect(swim_sim_t *sim, const uint8_t *id) {
 namespace {
 struct IpcBlob {
   uint32_t magic, rank, n, estride;
-  cudaIpcMemHandle_t h[7]; // eflag, out, out_cnt, rlr, rcnt, bar, meta
+  cudaIpcMemHandle_t h[6]; // eflag, out, out_cnt, rlr, rcnt, bar
 };
 static_assert(sizeof(IpcBlob) <= SWIM_IPC_BLOB_BYTES, "blob too small");
 constexpr uint32_t kBlobMagic = 0x53574D49u; // "SWMI"
@@ -174,8 +174,8 @@ extern "C" int swim_sim_ipc_export(swim_sim_t *sim, uint8_t *blob) {
   IpcBlob b;
   memset(&b, 0, sizeof b);
   b.magic = kBlobMagic; b.rank = d.rank; b.n = d.n; b.estride = d.estride;
-  void *ptrs[7] = {d.eflag, d.out, d.out_cnt, d.rlr, d.rcnt, sim->d_bar, d.meta};
-  for (int x = 0; x < 7; ++x) CUDA_TRY(sim, cudaIpcGetMemHandle(&b.h[x], ptrs[x]));
+  void *ptrs[6] = {d.eflag, d.out, d.out_cnt, d.rlr, d.rcnt, sim->d_bar};
+  for (int x = 0; x < 6; ++x) CUDA_TRY(sim, cudaIpcGetMemHandle(&b.h[x], ptrs[x]));
   memset(blob, 0, SWIM_IPC_BLOB_BYTES);
   memcpy(blob, &b, sizeof b);
   return SWIM_OK;
@@ -192,15 +192,14 @@ extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
     memcpy(&b, blobs + (size_t)r * SWIM_IPC_BLOB_BYTES, sizeof b);
     if (b.magic != kBlobMagic || b.rank != r) { set_error(sim, "swim_sim_ipc_connect: blob %u is not rank %u's export", r, r); return SWIM_EINVAL; }
     if (r == d.rank) continue;
-    void *p[7];
-    for (int x = 0; x < 7; ++x) {
+    void *p[6];
+    for (int x = 0; x < 6; ++x) {
       CUDA_TRY(sim, cudaIpcOpenMemHandle(&p[x], b.h[x], cudaIpcMemLazyEnablePeerAccess));
       sim->ipc_opened.push_back(p[x]);
     }
     d.eflag_p[r] = (uint8_t *)p[0]; d.estride_p[r] = b.estride;
     d.out_p[r] = (const uint4 *)p[1]; d.out_cnt_p[r] = (const uint8_t *)p[2];
     d.rlr_p[r] = (uint32_t *)p[3]; d.rcnt_p[r] = (uint32_t *)p[4]; d.bar_p[r] = (uint32_t *)p[5];
-    d.meta_p[r] = (uint4 *)p[6];
   }
   d.p2p = 1;
   sim->connected = true;
@@ -213,7 +212,7 @@ void refresh_peer_tables(swim_sim *sim) { // entry [rank] always aliases this ra
   SimDev &d = sim->dev;
   const uint32_t r = d.rank;
   d.eflag_p[r] = d.eflag; d.estride_p[r] = d.estride; d.out_p[r] = d.out; d.out_cnt_p[r] = d.out_cnt;
-  d.rlr_p[r] = d.rlr; d.rcnt_p[r] = d.rcnt; d.bar_p[r] = sim->d_bar; d.meta_p[r] = d.meta;
+  d.rlr_p[r] = d.rlr; d.rcnt_p[r] = d.rcnt; d.bar_p[r] = sim->d_bar;
 }
 
 int dist_alloc_edges(swim_sim *sim) { // eslot follows the in-edge count

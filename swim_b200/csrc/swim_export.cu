@@ -58,15 +58,18 @@ extern "C" int swim_sim_export_round(swim_sim_t *sim, uint8_t *buf, size_t cap, 
   cudaSetDevice(sim->device);
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   const uint32_t round = sim->round, par = round & 1, slot3 = round % 3;
-  uint32_t n_work = 0, n_xtra = 0;
+  uint32_t n_work = 0;
   CUDA_TRY(sim, cudaMemcpy(&n_work, d.wl_cnt + slot3, 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(sim, cudaMemcpy(&n_xtra, d.xtra + slot3, 4, cudaMemcpyDeviceToHost));
-  if (n_xtra) { set_error(sim, "swim_sim_export_round: not available after pipelined rounds (SWIM_PIPELINE)"); return SWIM_ESTATE; }
   if (n_work == 0) return SWIM_OK;
   const uint32_t F = d.fanout, B = d.B;
   std::vector<uint32_t> wl(n_work), rl((size_t)n_work * F);
   CUDA_TRY(sim, cudaMemcpy(wl.data(), d.wl, (size_t)n_work * 4, cudaMemcpyDeviceToHost));
-  CUDA_TRY(sim, cudaMemcpy(rl.data(), d.rl + (size_t)par * d.n * F, rl.size() * 4, cudaMemcpyDeviceToHost));
+  {
+    // recipient slots {receiver | bit 31 = dropped at the sender (it still went on the wire), sender}
+    std::vector<uint2> slots((size_t)n_work * F);
+    CUDA_TRY(sim, cudaMemcpy(slots.data(), d.rl + (size_t)par * d.n * F, slots.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+    for (size_t x = 0; x < slots.size(); ++x) rl[x] = slots[x].x == 0xFFFFFFFFu ? 0xFFFFFFFFu : (slots[x].x & 0x7FFFFFFFu);
+  }
   // sender snapshots: gather only the listed senders
   std::vector<uint8_t> cnt(n_work);
   std::vector<swim_record_t> recs((size_t)n_work * B);

@@ -27,6 +27,7 @@ struct swim_sim {
   std::vector<void *> allocs;
   uint32_t *d_in_src = nullptr;
   uint8_t *d_eflag = nullptr;
+  uint32_t *d_bloom = nullptr; // membership filters of all N rows (rebuilt with the in-edge index)
   uint32_t *d_eslot = nullptr; // exchange-buffer slot per in-edge (world > 1)
   void *d_events = nullptr;
   size_t d_events_cap = 0;
@@ -48,7 +49,7 @@ struct swim_sim {
   uint64_t launches = 0;
   bool profile = false;
   // launch-path switches, read from the environment once per handle (swim_sim_create), not once per call
-  bool opt_pipeline = false, opt_split = false, opt_round_kernel = false, opt_one_round = false;
+  bool opt_split = false, opt_round_kernel = false, opt_one_round = false;
   uint32_t opt_quiet_batch = 4;
   std::vector<cudaEvent_t> prof_events; // pool, reused
   std::vector<std::pair<int, int>> prof_marks; // (phase, index of start event); stop = start + 1

@@ -125,7 +125,6 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   swim_sim *sim = new (std::nothrow) swim_sim();
   if (!sim) return SWIM_ENOMEM;
   sim->cfg = *cfg;
-  sim->opt_pipeline = getenv("SWIM_PIPELINE") != nullptr;
   sim->opt_split = getenv("SWIM_SPLIT") != nullptr;
   sim->opt_round_kernel = getenv("SWIM_ROUND_KERNEL") != nullptr;
   sim->opt_one_round = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
@@ -183,9 +182,8 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.obs_slot, slots, 0))) return r;
     if ((r = dalloc(sim, &d.wl, n, 0))) return r;
     if ((r = dalloc(sim, &d.wl_cnt, 4, 0))) return r;
-    if ((r = dalloc(sim, &d.xtra, 4, 0))) return r;
-    if ((r = dalloc(sim, &d.claim2, n, 0))) return r;
-    if ((r = dalloc(sim, &d.rl, 2 * n * d.fanout, 0xFF))) return r; // [parity] candidate slots, empty = 0xFFFFFFFF
+    if ((r = dalloc(sim, &d.ncand, 4, 0))) return r;
+    if ((r = dalloc(sim, &d.rl, 2 * n * d.fanout, 0xFF))) return r; // [parity] recipient slots, empty = 0xFFFFFFFF
     // {digest, mismatch count} scratch and the counters share one block: swim_sim_observe reads both back in one copy
     if ((r = dalloc(sim, &sim->d_scratch, 2 + SWIM_CTR__COUNT, 0))) return r;
     d.ctr = sim->d_scratch + 2;
@@ -219,6 +217,7 @@ extern "C" void swim_sim_destroy(swim_sim_t *sim) {
   for (void *p : sim->allocs) cudaFree(p);
   if (sim->d_in_src) cudaFree(sim->d_in_src);
   if (sim->d_eflag) cudaFree(sim->d_eflag);
+  if (sim->d_bloom) cudaFree(sim->d_bloom);
   if (sim->d_events) cudaFree(sim->d_events);
   if (sim->dev.tl) cudaFree(sim->dev.tl);
   if (sim->h_events) cudaFreeHost(sim->h_events);
@@ -295,6 +294,28 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
       if (rows[x] != SWIM_NO_MEMBER) obs_slot[cur[rows[x]]++] = (uint32_t)x;
     CUDA_TRY(sim, cudaMemcpy(d.obs_off, obs_off.data(), obs_off.size() * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(sim, cudaMemcpy(d.obs_slot, obs_slot.data(), (size_t)d.n * cap * 4, cudaMemcpyHostToDevice));
+  }
+  // membership filters of ALL rows (a sender tests its records against the recipient's filter, wherever the recipient
+  // lives): 8 * cap bits per node, two positions per member id (bloom_pos, shared with the device code)
+  {
+    const uint32_t bits = 8 * cap, words = bits / 32;
+    std::vector<uint32_t> bloom((size_t)N * words, 0u);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)N; ++i) {
+      uint32_t *bf = bloom.data() + (size_t)i * words;
+      for (uint32_t s = 0; s < cap; ++s) {
+        const uint32_t m = nbr[(size_t)i * cap + s];
+        if (m == SWIM_NO_MEMBER) continue;
+        for (int which = 0; which < 2; ++which) {
+          const uint32_t pos = bloom_pos(m, which, bits);
+          bf[pos >> 5] |= 1u << (pos & 31);
+        }
+      }
+    }
+    if (sim->d_bloom) { cudaFree(sim->d_bloom); sim->d_bloom = nullptr; }
+    CUDA_TRY(sim, cudaMalloc((void **)&sim->d_bloom, bloom.size() * 4));
+    CUDA_TRY(sim, cudaMemcpy(sim->d_bloom, bloom.data(), bloom.size() * 4, cudaMemcpyHostToDevice));
+    d.bloom = sim->d_bloom;
   }
   sim->tdead_dirty = true;
   ++sim->view_epoch;
@@ -436,7 +457,6 @@ static void prepare_kernels(swim_sim *sim) {
   sim->grids[0] = wave_grid(sim, tick_scan_kernel<W>, ((size_t)d.n + 128 * kScanGroups) / (128 * kScanGroups) + 1);
   sim->grids[1] = wave_grid(sim, tick_work_kernel<W>, (size_t)d.n);
   sim->grids[2] = wave_grid(sim, recv_kernel<W>, (size_t)d.n);
-  sim->grids[3] = wave_grid(sim, recv_scan_kernel<W>, (size_t)d.n);
   sim->grids[4] = wave_grid(sim, round_kernel<W>, (size_t)d.n);
 #ifndef SWIM_EMU
   cudaFuncAttributes a;
@@ -500,15 +520,6 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     CUDA_TRY(sim, cudaEventRecord(sim->ev_upload, sim->stream));
   }
   size_t ev_pos = 0;
-  // Pipelining: inside one call, K2 of round r is deferred and runs fused with K1a of round r+1
-  // (recv_scan_kernel) unless something must observe the finished round in between: the end of the
-  // call, an event at round r+1, per-kernel profiling, or the staged (host-synchronised) NCCL exchange.
-  // Opt-in (SWIM_PIPELINE=1): bit-exact, but on B200 at C3 it measured no faster than the plain sequence
-  // (every warp's own dependent-load chain is the critical path either way). Single shard only: the scan of round
-  // r+1 skips nodes by the mail stamps of round r, and a peer GPU's stamps may still be in flight when it starts
-  // (the emulated two-rank run of tests/test_emu_parity.py diverges from the oracle with it).
-  const bool pipelined = !sim->profile && d.world == 1 && sim->opt_pipeline;
-  const int fgrid = sim->grids[3];
   // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
   // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
   // Sharded runs use the split sequence + peer_barrier_kernel (the path measured on hardware in round 1: 41-52 us per
@@ -516,11 +527,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   // grid_peer_barrier (the last CTA to arrive talks to the peers, ONE thread per GPU — an earlier form in which every
   // warp polled the peers' flags measured 136 ms/round) and consecutive event-free rounds share one launch. Bit-exact in
   // the emulated multi-rank runs (tests/test_emu_parity.py); not yet timed on NVLink hardware, hence opt-in.
-  const bool single_kernel = !sim->profile && !pipelined && !sim->opt_split &&
+  const bool single_kernel = !sim->profile && !sim->opt_split &&
                              (d.world == 1 || (d.p2p && sim->opt_round_kernel));
   const int kgrid = sim->grids[4];
   const bool multi_round_off = sim->opt_one_round;
-  bool pending = false; // K2 of the previous round has not run yet
   for (uint32_t r = 0; r < rounds; ++r) {
     d.round = ++sim->round;
     size_t ev_end = ev_pos;
@@ -547,35 +557,27 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       continue;
     }
     int mk = prof_begin(sim, 1);
-    d.pipe = pending ? 1u : 0u;
-    d.stamping = pipelined ? 1u : 0u;
-    if (pending) CUDA_TRY(sim, launch_pdl(recv_scan_kernel<W>, fgrid, sim->stream, d)); // K2(r-1) + K1a(r)
-    else CUDA_TRY(sim, launch_pdl(tick_scan_kernel<W>, grid, sim->stream, d));
+    CUDA_TRY(sim, launch_pdl(tick_scan_kernel<W>, grid, sim->stream, d));
     prof_end(sim, mk);
     mk = prof_begin(sim, 4);
     CUDA_TRY(sim, launch_pdl(tick_work_kernel<W>, wgrid, sim->stream, d));
     prof_end(sim, mk);
-    d.pipe = 0;
     sim->launches += 2;
-    const bool next_has_events = ev_pos < n_ev && ev_round[ev_pos] == d.round + 1;
-    pending = pipelined && r + 1 < rounds && !next_has_events;
-    if (!pending) {
-      if (d.world > 1) {
-        mk = prof_begin(sim, 2);
-        if (d.p2p) { // fused exchange: the data already sits in the peers' memory; synchronise the GPUs
-          CUDA_TRY(sim, launch_pdl(peer_barrier_kernel, 1, sim->stream, d)); // keeps the PDL chain K1b -> barrier -> K2
-          ++sim->launches;
-        } else {     // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
-          int rc = swim::dist_exchange(sim);
-          if (rc) return rc;
-        }
-        prof_end(sim, mk);
+    if (d.world > 1) {
+      mk = prof_begin(sim, 2);
+      if (d.p2p) { // fused exchange: the data already sits in the peers' memory; synchronise the GPUs
+        CUDA_TRY(sim, launch_pdl(peer_barrier_kernel, 1, sim->stream, d)); // keeps the PDL chain K1b -> barrier -> K2
+        ++sim->launches;
+      } else {     // staged exchange: envelopes moved by NCCL, flags raised by deliver_kernel
+        int rc = swim::dist_exchange(sim);
+        if (rc) return rc;
       }
-      mk = prof_begin(sim, 3);
-      CUDA_TRY(sim, launch_pdl(recv_kernel<W>, rgrid, sim->stream, d));
       prof_end(sim, mk);
-      ++sim->launches;
     }
+    mk = prof_begin(sim, 3);
+    CUDA_TRY(sim, launch_pdl(recv_kernel<W>, rgrid, sim->stream, d));
+    prof_end(sim, mk);
+    ++sim->launches;
     if (sim->profile) sim->prof_ms[5] += 1;
   }
   CUDA_TRY(sim, cudaGetLastError());
@@ -647,9 +649,8 @@ static int reset_round_state(swim_sim *sim) {
   SimDev &d = sim->dev;
   const size_t n = d.n ? d.n : 1;
   CUDA_TRY(sim, cudaMemsetAsync(d.claim, 0, n * 4, sim->stream));
-  CUDA_TRY(sim, cudaMemsetAsync(d.claim2, 0, n * 4, sim->stream));
   CUDA_TRY(sim, cudaMemsetAsync(d.wl_cnt, 0, 16, sim->stream));
-  CUDA_TRY(sim, cudaMemsetAsync(d.xtra, 0, 16, sim->stream));
+  CUDA_TRY(sim, cudaMemsetAsync(d.ncand, 0, 16, sim->stream));
   CUDA_TRY(sim, cudaMemsetAsync(d.qm, 0, 16, sim->stream));
   CUDA_TRY(sim, cudaMemsetAsync(d.gbar, 0, 4, sim->stream)); // arrival count; the generation word keeps counting
   CUDA_TRY(sim, cudaMemsetAsync(d.xcnt, 0, SWIM_MAX_WORLD * 4, sim->stream));

@@ -128,6 +128,34 @@ def test_c3_properties():
     assert c[A.CTR_SUSPECT_LOCAL] > 0 and c[A.CTR_DEAD_TIMEOUT] > 0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("qbatch", [None, "0", "8"])
+def test_c3_full_size_against_the_oracle(qbatch, monkeypatch):
+    """BASELINE config C3 at full size (N = 1,048,576, the bench workload: 1,048 crashes at round 10), 40 rounds through
+    the burst: digest, every counter and the convergence count equal the oracle's at chunk boundaries, on the default
+    launch path (one fused kernel per event-free stretch, batched quiet scans) and with batching off / at 8 rounds."""
+    if qbatch is not None:
+        monkeypatch.setenv("SWIM_QUIET_BATCH", qbatch)
+    n = 1 << 20
+    cfg = default_config(n_nodes=n, seed=0x5EED0001 + 3)
+    nbr = generate_topology("random", n, 32, 32, seed=3)
+    rng = np.random.default_rng(3)
+    crashed = np.sort(rng.choice(n, size=n // 1000, replace=False)).astype(np.uint32)
+    sim, orc = make_pair(cfg, nbr)
+    ev = crash_events(10, crashed)
+    sim.inject(ev)
+    orc.inject(ev)
+    for chunk in (5, 4, 1, 2, 8, 20):
+        sim.step(chunk)
+        orc.step(chunk)
+        assert sim.digest() == orc.digest(), f"digest differs at round {sim.round}"
+        assert sim.counters().tolist() == orc.counters().tolist(), f"counters differ at round {sim.round}"
+        assert sim.mismatches() == orc.mismatches()
+    for arr in (A.ARR_VST, A.ARR_VINC, A.ARR_PB_CNT, A.ARR_SELF_INC):
+        assert np.array_equal(sim.get_array(arr), orc.get_array(arr)), A.ARRAY_NAMES[arr]
+    sim.close()
+
+
 def test_set_array_alive_rebuilds_crash_bitmaps():
     """Bulk edits of alive[] (swim_sim_set_array) must reach the per-row crashed-member bitmaps."""
     n = 400
