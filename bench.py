@@ -97,13 +97,14 @@ def summarize_timeline(tl, warmup):
         n_busy += 1
         scan.append(t[2] - t[0]); own["scan"].append(t[1] - t[0])
         work.append(t[4] - t[2]); own["work"].append(t[3] - t[2])
-        end = t[6] if t[6] else t[5]
-        recv.append(end - t[4]); own["recv"].append(t[5] - t[4])
+        end = t[6] if t[6] else (t[5] if t[5] else t[4])  # K2 is skipped when nothing was delivered
+        if t[5]:
+            recv.append(end - t[4]); own["recv"].append(t[5] - t[4])
         busy_total.append(end - t[0])
         r += 1
     f = lambda v: float(np.mean(v)) / 1e3 if len(v) else None
     return {"busy_rounds": n_busy, "quiet_rounds": n_quiet, "busy_us": f(busy_total), "quiet_us": f(quiet_total),
-            "scan_us": f(scan), "work_us": f(work), "recv_us": f(recv),
+            "scan_us": f(scan), "work_us": f(work), "recv_us": f(recv), "recv_rounds": len(recv),
             "cta0_scan_us": f(own["scan"]), "cta0_work_us": f(own["work"]), "cta0_recv_us": f(own["recv"]),
             "busy_us_max": float(np.max(busy_total)) / 1e3 if busy_total else None,
             "what": "in-kernel %globaltimer stamps of CTA 0 at round_kernel's phase boundaries over the timed rounds; a phase "
@@ -367,6 +368,38 @@ def run_cuda(args):
     sim.step(args.steps)
     prof = sim.profile_ms()
     sim.set_profile(False)
+
+    # ------------------------------------------------ parity leg: the rounds just timed, against the oracle on the same N
+    # (the checker, outside every timed region): global digest (shard digests add up), counters and convergence count
+    # after W + K rounds (at most 40: through the crash burst) from the same checkpoint
+    parity = None
+    if not args.no_parity:
+        rounds_chk = min(args.warmup + args.steps, 40)
+        barrier()
+        sim.load()
+        barrier()
+        sim.step(rounds_chk)
+        dg = sdist.global_digest(sim.digest())
+        gc = sdist.global_sum(sim.counters())
+        gm = int(sdist.global_sum([sim.mismatches()])[0])
+        if rank == 0:
+            from oracle.oracle import Oracle, set_num_threads
+            set_num_threads(int(os.environ.get("SWIM_CPU_THREADS", usable_cpus())))
+            orc = Oracle(default_config(**cfg_kw))
+            orc.set_view(nbr)
+            orc.inject(events)
+            orc.step(rounds_chk)
+            bad = []
+            if dg != orc.digest():
+                bad.append("digest")
+            if [int(x) for x in gc] != [int(x) for x in orc.counters()]:
+                bad.append("counters")
+            if gm != orc.mismatches():
+                bad.append("mismatches")
+            parity = {"status": "ok" if not bad else "FAILED: " + ",".join(bad), "rounds": rounds_chk, "n_nodes": n,
+                      "digest": f"{dg:016x}", "what": "global state digest + all counters + convergence count of the CUDA run "
+                      f"(all {world} shard(s)) == restated C oracle on the same N, seed and event trace"}
+            del orc
     sim.close()
     ab_round, ab_tick, m_bar, b_bar = algorithmic_bytes(cfg_kw, n, args.steps, ctr_delta)
     peaks = {}
@@ -485,6 +518,7 @@ def run_cuda(args):
                 "gpu_launches_note": "round_kernel<1> runs K1a, K1b and K2 of every consecutive event-free round of a call "
                                      "in ONE launch (grid barriers between phases), so the timed region of K rounds is a "
                                      "handful of launches, not 3K",
+                "parity_check": parity["status"] if parity else None, "parity": parity,
                 "roofline": roofline, "cpu_baseline": cpu, "convergence": conv,
                 "counters_timed_region": dict(zip(A.CTR_NAMES, [int(x) for x in ctr_delta]))}
     else:
@@ -519,6 +553,7 @@ def main():
     ap.add_argument("--nodes-per-gpu", type=int, default=N_PER_GPU)
     ap.add_argument("--converge-limit", type=int, default=1200)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity leg against the oracle")
     ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps rounds each; the median is reported")
     ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed rounds before the first window (GPU clocks)")
     ap.add_argument("--exchange", default=None, choices=[None, "p2p", "nccl"],

@@ -90,13 +90,14 @@ struct SimDev {
   uint32_t *wl, *wl_cnt;     // work list of K1b [n]; counters indexed by round % 3
   uint2 *rl;                 // [2][n*fanout] recipient slots (round parity), slot = item*fanout + f:
                              //   .x = local receiver (bit 31 set: sent, but not delivered — see `bloom`), .y = the sender
-  uint32_t *ncand;           // [3] (round % 3) slots of this round that were delivered to a local receiver
-  // Static membership filter of every node's view row (all N nodes, replicated on every rank): 256 W bits per node, two
-  // hash positions per member id. A sender tests its records against the recipient's filter: an envelope none of whose
+  uint2 *cl;                 // [2][n*fanout] the delivered slots of a round, compact (what K2 walks): {receiver, sender}
+  uint32_t *ncand;           // [3] (round % 3) length of this round's compact list
+  // Static membership filter of every node's view row (all N nodes, replicated on every rank): 512 W bits per node, two
+  // hash positions per member id (2 % false positives on a full row). A sender tests its records against the recipient's filter: an envelope none of whose
   // records is about the recipient or about a member the recipient may know cannot change the recipient's state
   // (Core.hs:147-148 `we don't know this node. ignore`), so it is counted and dropped at the sender instead of being
   // flagged, listed and walked by K2. False positives are delivered and ignored there; there are no false negatives.
-  const uint32_t *bloom;     // [N * 8 W]
+  const uint32_t *bloom;     // [N * 16 W]
   // Round-parity double buffering: everything a round's senders write for its receivers exists twice
   // (index = round & 1), so round r+1's senders never touch what round r's receivers still read and ONE
   // cross-GPU barrier per round (between K1b and K2) is enough.
@@ -144,6 +145,26 @@ __device__ __forceinline__ void pdl_launch() {}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
+
+// System-scope release / acquire on one word: what the cross-GPU handshake of the fused exchange needs (a rank's round
+// word is stored with release semantics after its mail — plain stores into peer memory, ordered before it by the CTA
+// barrier and a fence.sys of the arriving threads —, and polled with acquire semantics by the owner). sm_70+ PTX.
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+#ifdef SWIM_EMU
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+#ifdef SWIM_EMU
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
 
 // Phase timeline of round_kernel: one thread of CTA 0 stores %globaltimer (ns) at each phase boundary. Slots per round:
 // 0 start, 1 scan done (CTA 0), 2 barrier 1 passed (every CTA's scan done), 3 work done (CTA 0), 4 barrier 2 passed,
@@ -481,7 +502,7 @@ constexpr int kScanGroups = 2; // Philox groups (of 4 nodes) per lane per iterat
 
 __device__ __forceinline__ uint32_t ci(uint32_t round) { return round % 3u; } // slot of the per-round list counters
 
-// The two filter positions of member id x in a node's 256 W-bit membership filter (SimDev::bloom); the host builds the
+// The two filter positions of member id x in a node's 512 W-bit membership filter (SimDev::bloom); the host builds the
 // filters with the same two lines (swim_sim.cu: build_in_edges).
 SWIM_HD uint32_t bloom_pos(uint32_t x, int which, uint32_t bits) {
   return SWIM_UMULHI(x * (which ? 0x85EBCA77u : 0x9E3779B1u), bits);
@@ -695,7 +716,6 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
   const uint32_t par = round & 1;
   uint2 *rl_out = d.rl + (size_t)par * d.n * d.fanout;
   bool did_remote = false; // this lane stored into a peer GPU's memory
-  uint32_t listed = 0;     // recipient slots this warp delivered to local receivers
 
   for (uint32_t idx = warp; idx < n_work; idx += nwarps) {
     const uint32_t ln = idx == warp ? first_ln : d.wl[idx];
@@ -804,7 +824,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
         n_up = r_up ? 1u : 0u;
         bool deliver = false;
         if (r_up) {
-          constexpr uint32_t kBits = 256u * W;
+          constexpr uint32_t kBits = 512u * W;
           const uint32_t *bf = d.bloom + (size_t)dst * (kBits / 32);
           uint32_t w0[SWIM_MAX_PB / 4], w1[SWIM_MAX_PB / 4]; // the two filter words of up to 8 records at a time
           for (uint32_t q0 = 0; q0 < pbs.cnt; q0 += SWIM_MAX_PB / 4) {
@@ -847,7 +867,13 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
         }
       }
       n_up = __reduce_add_sync(kFull, n_up);
-      listed += __popc(__ballot_sync(kFull, cand.x < 0x80000000u));
+      const unsigned dm = __ballot_sync(kFull, cand.x < 0x80000000u); // delivered to a local receiver
+      if (dm) { // compact list for K2: one counter bump per sender that delivered anything (few do)
+        uint32_t pos = 0;
+        if (lane == 0) pos = atomicAdd(&d.ncand[ci(round)], (uint32_t)__popc(dm));
+        pos = __shfl_sync(kFull, pos, 0);
+        if (dm >> lane & 1u) d.cl[(size_t)par * d.n * d.fanout + pos + __popc(dm & ((1u << lane) - 1))] = cand;
+      }
       if (lane == 0) {
         d.out_cnt[(size_t)par * d.per + ln] = (uint8_t)pbs.cnt;
         c.v[SWIM_CTR_MSGS] += nr;
@@ -879,7 +905,6 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
     pb_store(pbs, d, ln, lane);
     if ((uint32_t)lane < d.fanout) rl_out[(size_t)idx * d.fanout + lane] = cand; // no atomics, no shared counter
   }
-  if (lane == 0 && listed) atomicAdd(&d.ncand[ci(round)], listed);
   if (did_remote) __threadfence_system(); // peer-memory stores are performed before the grid reports completion
 }
 
@@ -914,26 +939,23 @@ __device__ __forceinline__ void peer_publish(const SimDev &d, uint32_t mail_roun
 __device__ __forceinline__ void peer_publish_cta(const SimDev &d, uint32_t mail_round) {
   const uint32_t q = threadIdx.x;
   if (q >= d.world) return;
-  __threadfence_system();
   if (q != d.rank) {
-    volatile uint32_t *cnt = d.rcnt_p[q] + (mail_round & 1) * d.world + d.rank;
-    *cnt = d.xcnt[q];
+    d.rcnt_p[q][(mail_round & 1) * d.world + d.rank] = d.xcnt[q];
     d.xcnt[q] = 0;
-    __threadfence_system();
   }
-  volatile uint32_t *theirs = d.bar_p[q] + d.rank;
-  *theirs = mail_round;
+  // release: this rank's mail of the round (K1b completed before this kernel started) and the count above are visible to
+  // whoever acquires the round word
+  st_release_sys(d.bar_p[q] + d.rank, mail_round);
 }
 
 __device__ __forceinline__ void peer_wait(const SimDev &d, uint32_t mail_round, int lane) {
   if ((uint32_t)lane < d.world) {
-    volatile uint32_t *mine = d.bar_p[d.rank] + lane;
+    const uint32_t *mine = d.bar_p[d.rank] + lane;
     const long long t0 = clock64();
-    while ((int32_t)(*mine - mail_round) < 0) {
+    while ((int32_t)(ld_acquire_sys(mine) - mail_round) < 0) {
       if (clock64() - t0 > kPeerWaitCycles) { *d.bar_err = 1; break; } // a peer stopped stepping
-      __nanosleep(200);
+      __nanosleep(100);
     }
-    __threadfence_system(); // acquire: the peers' stores that preceded their flag are visible now
   }
   __syncwarp();
 }
@@ -1019,28 +1041,18 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
   if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
 }
 
-// warp-per-receiver over the receivers of `round`: the recipient slots K1b wrote (fanout per work item; most are empty
-// or were dropped at the sender), then one list per source rank (cross-shard senders). A receiver can be listed more
+// warp-per-receiver over the receivers of `round`: the compact list of delivered slots K1b wrote, then one list per
+// source rank (cross-shard senders). A receiver can be listed more
 // than once: the claim stamp lets exactly one warp process it.
 template <int W>
 __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps,
                                           int lane, PbStage &pbs, Ctr &c) {
   const uint32_t par = round & 1;
-  const uint32_t n_slots = d.wl_cnt[ci(round)] * d.fanout;
-  if (d.ncand[ci(round)] != 0) { // some slot was delivered locally
-    const uint2 *rl_in = d.rl + (size_t)par * d.n * d.fanout;
-    constexpr uint32_t kBatch = 4; // slots fetched per round trip: a warp's slots are nwarps apart
-    for (uint32_t base = warp; base < n_slots; base += nwarps * kBatch) {
-      uint2 e[kBatch];
-#pragma unroll
-      for (uint32_t t = 0; t < kBatch; ++t) {
-        const uint32_t item = base + t * nwarps;
-        e[t] = item < n_slots ? rl_in[item] : make_uint2(0xFFFFFFFFu, 0u);
-      }
-#pragma unroll
-      for (uint32_t t = 0; t < kBatch; ++t)
-        if (e[t].x < 0x80000000u) recv_one<W>(d, round, e[t].x, true, e[t].y, lane, pbs, c);
-    }
+  const uint32_t n_cl = d.ncand[ci(round)];
+  const uint2 *cl_in = d.cl + (size_t)par * d.n * d.fanout;
+  for (uint32_t item = warp; item < n_cl; item += nwarps) {
+    const uint2 e = cl_in[item];
+    recv_one<W>(d, round, e.x, true, e.y, lane, pbs, c);
   }
   if (d.world > 1) {
     uint32_t seg_end[SWIM_MAX_WORLD + 1];
@@ -1122,27 +1134,22 @@ __device__ __forceinline__ void grid_peer_barrier(const SimDev &d, uint32_t mail
     const uint32_t g = (*barrier_generation())++;
     __threadfence_system(); // this CTA's stores into peer memory are performed before it reports arrival
     if (atomicAdd(d.gbar, 1u) == gridDim.x - 1) {
+      __threadfence(); // acquire side of the arrivals: every CTA's fenced stores happen-before what follows
       for (uint32_t q = 0; q < d.world; ++q) {
         if (q == d.rank) continue;
-        volatile uint32_t *cnt = d.rcnt_p[q] + (mail_round & 1) * d.world + d.rank;
-        *cnt = atomicExch(&d.xcnt[q], 0u);
+        d.rcnt_p[q][(mail_round & 1) * d.world + d.rank] = atomicExch(&d.xcnt[q], 0u);
       }
-      __threadfence_system();
-      for (uint32_t q = 0; q < d.world; ++q) {
-        volatile uint32_t *theirs = d.bar_p[q] + d.rank;
-        *theirs = mail_round;
-      }
+      for (uint32_t q = 0; q < d.world; ++q) st_release_sys(d.bar_p[q] + d.rank, mail_round); // counts + all mail first
       const long long t0 = clock64();
       for (uint32_t q = 0; q < d.world; ++q) {
-        volatile uint32_t *mine = d.bar_p[d.rank] + q;
-        while ((int32_t)(*mine - mail_round) < 0) {
+        const uint32_t *mine = d.bar_p[d.rank] + q;
+        while ((int32_t)(ld_acquire_sys(mine) - mail_round) < 0) {
           if (clock64() - t0 > kPeerWaitCycles) { *d.bar_err = 1; break; } // a peer stopped stepping
-          __nanosleep(100);
+          __nanosleep(40);
         }
       }
-      __threadfence_system(); // acquire: what the peers stored before their round word is visible from here on
       d.gbar[0] = 0;
-      __threadfence();
+      __threadfence(); // release (gpu scope is enough from here: the peers' data sits in this GPU's memory)
       atomicAdd(d.gbar + 1, 1u);
     } else {
       const long long t0 = clock64();

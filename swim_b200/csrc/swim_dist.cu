@@ -11,6 +11,7 @@
 // NCCL is bound lazily (dlopen) so that single-GPU users of the C ABI need only the CUDA driver,
 // and so that a Python process that already loaded torch's NCCL shares that copy.
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -161,6 +162,11 @@ namespace {
 struct IpcBlob {
   uint32_t magic, rank, n, estride;
   cudaIpcMemHandle_t h[6]; // eflag, out, out_cnt, rlr, rcnt, bar
+  // the exporting process and its raw device pointers: ranks that live in ONE process (several handles, on one device or
+  // on peer devices) cannot open each other's IPC handles — they use the pointers as they are
+  uint64_t pid;
+  int32_t device, _pad;
+  uint64_t raw[6];
 };
 static_assert(sizeof(IpcBlob) <= SWIM_IPC_BLOB_BYTES, "blob too small");
 constexpr uint32_t kBlobMagic = 0x53574D49u; // "SWMI"
@@ -175,7 +181,12 @@ extern "C" int swim_sim_ipc_export(swim_sim_t *sim, uint8_t *blob) {
   memset(&b, 0, sizeof b);
   b.magic = kBlobMagic; b.rank = d.rank; b.n = d.n; b.estride = d.estride;
   void *ptrs[6] = {d.eflag, d.out, d.out_cnt, d.rlr, d.rcnt, sim->d_bar};
-  for (int x = 0; x < 6; ++x) CUDA_TRY(sim, cudaIpcGetMemHandle(&b.h[x], ptrs[x]));
+  for (int x = 0; x < 6; ++x) {
+    CUDA_TRY(sim, cudaIpcGetMemHandle(&b.h[x], ptrs[x]));
+    b.raw[x] = (uint64_t)(uintptr_t)ptrs[x];
+  }
+  b.pid = (uint64_t)getpid();
+  b.device = sim->device;
   memset(blob, 0, SWIM_IPC_BLOB_BYTES);
   memcpy(blob, &b, sizeof b);
   return SWIM_OK;
@@ -193,9 +204,18 @@ extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
     if (b.magic != kBlobMagic || b.rank != r) { set_error(sim, "swim_sim_ipc_connect: blob %u is not rank %u's export", r, r); return SWIM_EINVAL; }
     if (r == d.rank) continue;
     void *p[6];
-    for (int x = 0; x < 6; ++x) {
-      CUDA_TRY(sim, cudaIpcOpenMemHandle(&p[x], b.h[x], cudaIpcMemLazyEnablePeerAccess));
-      sim->ipc_opened.push_back(p[x]);
+    if (b.pid == (uint64_t)getpid()) { // a rank of this very process: its pointers are valid here as they are
+      if (b.device != sim->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(sim, "swim_sim_ipc_connect: no peer access to device %d: %s", b.device, cudaGetErrorString(e)); return SWIM_ECUDA; }
+        cudaGetLastError();
+      }
+      for (int x = 0; x < 6; ++x) p[x] = (void *)(uintptr_t)b.raw[x];
+    } else {
+      for (int x = 0; x < 6; ++x) {
+        CUDA_TRY(sim, cudaIpcOpenMemHandle(&p[x], b.h[x], cudaIpcMemLazyEnablePeerAccess));
+        sim->ipc_opened.push_back(p[x]);
+      }
     }
     d.eflag_p[r] = (uint8_t *)p[0]; d.estride_p[r] = b.estride;
     d.out_p[r] = (const uint4 *)p[1]; d.out_cnt_p[r] = (const uint8_t *)p[2];

@@ -126,7 +126,9 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   if (!sim) return SWIM_ENOMEM;
   sim->cfg = *cfg;
   sim->opt_split = getenv("SWIM_SPLIT") != nullptr;
-  sim->opt_round_kernel = getenv("SWIM_ROUND_KERNEL") != nullptr;
+  // sharded runs with the fused exchange: one fused kernel per event-free stretch (grid_peer_barrier between K1b and K2)
+  // or the split launch sequence with peer_barrier_kernel; SWIM_ROUND_KERNEL=0|1 overrides the default
+  if (const char *rk = getenv("SWIM_ROUND_KERNEL")) sim->opt_round_kernel = atoi(rk) != 0;
   sim->opt_one_round = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
   // rounds decided per batched quiet scan of round_kernel (1..8; 0 or 1 turns batching off)
   if (const char *qb = getenv("SWIM_QUIET_BATCH")) sim->opt_quiet_batch = (uint32_t)std::min(8l, std::max(0l, strtol(qb, nullptr, 10)));
@@ -184,6 +186,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.wl_cnt, 4, 0))) return r;
     if ((r = dalloc(sim, &d.ncand, 4, 0))) return r;
     if ((r = dalloc(sim, &d.rl, 2 * n * d.fanout, 0xFF))) return r; // [parity] recipient slots, empty = 0xFFFFFFFF
+    if ((r = dalloc(sim, &d.cl, 2 * n * d.fanout, 0xFF))) return r; // [parity] delivered slots, compact
     // {digest, mismatch count} scratch and the counters share one block: swim_sim_observe reads both back in one copy
     if ((r = dalloc(sim, &sim->d_scratch, 2 + SWIM_CTR__COUNT, 0))) return r;
     d.ctr = sim->d_scratch + 2;
@@ -296,9 +299,9 @@ static int build_in_edges(swim_sim *sim, const uint32_t *nbr) {
     CUDA_TRY(sim, cudaMemcpy(d.obs_slot, obs_slot.data(), (size_t)d.n * cap * 4, cudaMemcpyHostToDevice));
   }
   // membership filters of ALL rows (a sender tests its records against the recipient's filter, wherever the recipient
-  // lives): 8 * cap bits per node, two positions per member id (bloom_pos, shared with the device code)
+  // lives): 16 * cap bits per node, two positions per member id (bloom_pos, shared with the device code)
   {
-    const uint32_t bits = 8 * cap, words = bits / 32;
+    const uint32_t bits = 16 * cap, words = bits / 32;
     std::vector<uint32_t> bloom((size_t)N * words, 0u);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)N; ++i) {
