@@ -349,9 +349,10 @@ def run_cuda(args):
 
     # ------------------------------------------------ phase timeline of the same rounds (fused kernel, in-kernel timer)
     timeline = None
-    if world == 1:
+    if True:  # (sharded runs: stamps exist only on the fused-kernel path, SWIM_ROUND_KERNEL; each rank reports its own CTA 0)
         barrier()
         sim.load()
+        barrier()
         sim.step(args.warmup)
         sim.set_timeline(args.steps)
         sim.step(args.steps)

@@ -41,21 +41,26 @@ data CConfig = CConfig
   , cfgSeed :: !Word64
   , cfgRank, cfgWorld :: !Word32
   , cfgDevice :: !Int32
-  , cfgBasePort :: !Word32 }
+  , cfgBasePort :: !Word32
+  , cfgChurnPpm, cfgRejoinMin, cfgRejoinMax, cfgProbesPerRound, cfgSuspicionMax :: !Word32 }
 
 instance Storable CConfig where
-  sizeOf _ = 64
+  sizeOf _ = 88
   alignment _ = 8
   peek p = CConfig <$> peekByteOff p 0 <*> peekByteOff p 4 <*> peekByteOff p 8 <*> peekByteOff p 12
                    <*> peekByteOff p 16 <*> peekByteOff p 20 <*> peekByteOff p 24 <*> peekByteOff p 28
                    <*> peekByteOff p 32 <*> peekByteOff p 36 <*> peekByteOff p 40 <*> peekByteOff p 48
-                   <*> peekByteOff p 52 <*> peekByteOff p 56 <*> peekByteOff p 60
+                   <*> peekByteOff p 52 <*> peekByteOff p 56 <*> peekByteOff p 60 <*> peekByteOff p 64
+                   <*> peekByteOff p 68 <*> peekByteOff p 72 <*> peekByteOff p 76 <*> peekByteOff p 80
   poke p CConfig{..} = do
+    fillBytes p 0 88
     pokeByteOff p 0 cfgAbiVersion; pokeByteOff p 4 cfgNNodes; pokeByteOff p 8 cfgViewCap
     pokeByteOff p 12 cfgKIndirect; pokeByteOff p 16 cfgFanout; pokeByteOff p 20 cfgPbCap
     pokeByteOff p 24 cfgSuspicionRounds; pokeByteOff p 28 cfgRetransmit; pokeByteOff p 32 cfgLossPpm
     pokeByteOff p 36 cfgFlags; pokeByteOff p 40 cfgSeed; pokeByteOff p 48 cfgRank; pokeByteOff p 52 cfgWorld
-    pokeByteOff p 56 cfgDevice; pokeByteOff p 60 cfgBasePort
+    pokeByteOff p 56 cfgDevice; pokeByteOff p 60 cfgBasePort; pokeByteOff p 64 cfgChurnPpm
+    pokeByteOff p 68 cfgRejoinMin; pokeByteOff p 72 cfgRejoinMax; pokeByteOff p 76 cfgProbesPerRound
+    pokeByteOff p 80 cfgSuspicionMax
 
 -- | swim_member_t (Member, Types.hs:62-68; name -> id, memberHostNew -> addr/port, lastChange -> round)
 data CMember = CMember

@@ -32,7 +32,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define SWIM_ABI_VERSION 1u
+#define SWIM_ABI_VERSION 2u
 
 /* Opaque handle: N simulated `Store`s (Types.hs:53-60) resident in HBM. */
 typedef struct swim_sim swim_sim_t;
@@ -69,6 +69,8 @@ enum {
 #define SWIM_MAX_K 7u              /* indirect fan-out k <= 7 (1+k draws = two Philox blocks) */
 #define SWIM_MAX_PB 32u            /* piggyback buffer records per node (one lane each) */
 #define SWIM_MAX_TIMER 63u         /* suspicion rounds fit the 6-bit countdown in vst */
+#define SWIM_MAX_TIMER_LIFEGUARD 15u /* with suspicion_max: 4-bit countdown + 2-bit confirmation count */
+#define SWIM_MAX_PROBES 4u         /* probes_per_round */
 #define SWIM_MAX_VIEW 256u         /* view_cap is 32*W, W in {1,2,4,8} */
 
 /* ---- Config (Types.hs:46-51, Util.hs:44-50) + the simulator's extra knobs -------------
@@ -92,6 +94,21 @@ typedef struct swim_config {
   uint32_t world;            /* number of shards == GPUs; 1 = single GPU */
   int32_t device;            /* CUDA device ordinal; -1 = current device */
   uint32_t base_port;        /* port reported in swim_member_t (reference fixture: 4000) */
+  /* Seeded churn, generated on the device (BASELINE config C5; no reference counterpart — the reference has no fault
+   * injection): at the start of every round, before the events of that round, each live process crashes with probability
+   * churn_ppm / 1e6 and comes back after a delay uniform in [rejoin_min, rejoin_max] rounds with incarnation + 1 and an
+   * Alive broadcast (exactly what SWIM_EV_CRASH / SWIM_EV_REJOIN do). 0 = off. Draws: Philox purpose 7. */
+  uint32_t churn_ppm;
+  uint32_t rejoin_min, rejoin_max; /* 1 <= rejoin_min <= rejoin_max */
+  /* Reference-literal probing: `kRandomMembers store numToGossip []` probes numToGossip members per period,
+   * one after the other (Core.hs:239-240). 1 = one probe target per node per round (SWIM; the default). */
+  uint32_t probes_per_round;
+  /* Lifeguard-style dynamic suspicion timeout: 0 = off (every suspicion lasts suspicion_rounds). Otherwise a
+   * suspicion starts with suspicion_max rounds (suspicion_rounds <= suspicion_max <= 15) and every further Suspect message
+   * received about the suspected member shortens it logarithmically, down to suspicion_rounds after 3 confirmations:
+   * timeout(c) = max - (max - min) * log(c + 1) / log(4). */
+  uint32_t suspicion_max;
+  uint32_t _reserved;
 } swim_config_t;
 
 #define SWIM_F_NONE 0u
@@ -176,12 +193,13 @@ enum {
   SWIM_ARR_SELF_INC = 1, /* u32[n]      storeIncarnation (Types.hs:54) */
   SWIM_ARR_SEQNO = 2,    /* u32[n]      storeSeqNo (Types.hs:53); scalar API only */
   SWIM_ARR_NBR = 3,      /* u32[n*cap]  member ids, ascending, SWIM_NO_MEMBER padded */
-  SWIM_ARR_VST = 4,      /* u8 [n*cap]  liveness | timer<<2 */
+  SWIM_ARR_VST = 4,      /* u8 [n*cap]  liveness | timer<<2  (with suspicion_max: liveness | timer<<2 | confirmations<<6) */
   SWIM_ARR_VINC = 5,     /* u32[n*cap]  memberIncarnation */
   SWIM_ARR_VLAST = 6,    /* u32[n*cap]  memberLastChange as a round number */
   SWIM_ARR_PB = 7,       /* swim_record_t[n*B], newest first; entries >= cnt are zero */
   SWIM_ARR_PB_CNT = 8,   /* u8 [n] */
-  SWIM_ARR__COUNT = 9
+  SWIM_ARR_BACK_AT = 9,  /* u32[N]      churn: round at which a crashed process rejoins, 0 = none (replicated on every rank) */
+  SWIM_ARR__COUNT = 10
 };
 
 /* ---- per-run counters (swim_sim_counters), cumulative since create ------------------- */

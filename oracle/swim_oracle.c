@@ -13,7 +13,7 @@
  * PARITY PINNING
  *   pinned   : the rules exercised by the reference's own test/Spec.hs (removeDeadNodes
  *              98-106, kRandomMembers 111-139, Ping->Ack 150-153, Ping-other 155-158,
- *              IndirectPing->Ping 166-174) — tests/test_oracle_spec.py replays them.
+ *              IndirectPing->Ping 166-174) — tests/test_oracle_kat.py replays them.
  *   derived  : suspectOrDeadNode' (Core.hs:142-187) known-answer vectors E1..E16 worked by
  *              hand from the source (the reference leaves those tests `pending`,
  *              Spec.hs:176-183).
@@ -80,7 +80,7 @@ EXPORT void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 /* counter layout: (a, id, purpose, block); key = seed lo, hi. The target draw and the
  * direct-leg loss draw of node i are word (i & 3) of the block with id = i >> 2 (four nodes share a
  * block); proxy draws and indirect-leg loss draws use per-node blocks. */
-enum { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6 };
+enum { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6, P_CHURN = 7 };
 
 /* bounded draw: floor(x * L / 2^32) — `randomR (0, L-1)` of Util.hs:40 on our stream */
 static uint32_t bounded(uint32_t x, uint32_t L) { return (uint32_t)(((uint64_t)x * L) >> 32); }
@@ -101,6 +101,7 @@ typedef struct oracle {
   uint32_t round;
   uint64_t scalar_calls;
   uint8_t *alive;     /* [N] global truth */
+  uint32_t *back_at;  /* [N] churn: round at which a crashed process rejoins (0 = none) */
   uint32_t *self_inc; /* [n] */
   uint32_t *seqno;    /* [n] */
   uint32_t *nbr;      /* [n*cap] */
@@ -142,6 +143,9 @@ EXPORT oracle_t *oracle_create(const swim_config_t *cfg) {
   if (cfg->retransmit < 1 || cfg->retransmit > 255 || cfg->loss_ppm > 1000000u) return NULL;
   if (cfg->flags & ~SWIM_F__ALL) return NULL;
   if ((cfg->flags & SWIM_F_ROUND_ROBIN) && (cfg->view_cap & (cfg->view_cap - 1))) return NULL; /* xor order */
+  if (cfg->churn_ppm > 1000000u || (cfg->churn_ppm && (cfg->rejoin_min < 1 || cfg->rejoin_max < cfg->rejoin_min))) return NULL;
+  if (cfg->probes_per_round < 1 || cfg->probes_per_round > SWIM_MAX_PROBES) return NULL;
+  if (cfg->suspicion_max && (cfg->suspicion_max < cfg->suspicion_rounds || cfg->suspicion_max > SWIM_MAX_TIMER_LIFEGUARD)) return NULL;
   oracle_t *o = (oracle_t *)calloc(1, sizeof *o);
   o->cfg = *cfg;
   o->N = cfg->n_nodes; o->cap = cfg->view_cap; o->k = cfg->k_indirect; o->fanout = cfg->fanout;
@@ -151,6 +155,7 @@ EXPORT oracle_t *oracle_create(const swim_config_t *cfg) {
   o->n = owner_first(o->N, cfg->world, cfg->rank + 1) - o->first;
   size_t n = o->n ? o->n : 1, slots = n * o->cap;
   o->alive = (uint8_t *)malloc(o->N); memset(o->alive, 1, o->N); /* every node up */
+  o->back_at = (uint32_t *)calloc(o->N, 4);
   o->self_inc = (uint32_t *)calloc(n, 4);                        /* Util.hs:80 */
   o->seqno = (uint32_t *)calloc(n, 4);                           /* Util.hs:79 */
   o->nbr = (uint32_t *)malloc(slots * 4); memset(o->nbr, 0xFF, slots * 4); /* Util.hs:78: empty */
@@ -168,7 +173,7 @@ EXPORT oracle_t *oracle_create(const swim_config_t *cfg) {
 
 EXPORT void oracle_destroy(oracle_t *o) {
   if (!o) return;
-  free(o->alive); free(o->self_inc); free(o->seqno); free(o->nbr); free(o->state); free(o->timer);
+  free(o->alive); free(o->back_at); free(o->self_inc); free(o->seqno); free(o->nbr); free(o->state); free(o->timer);
   free(o->vinc); free(o->vlast); free(o->pb); free(o->pb_cnt); free(o->out); free(o->out_cnt);
   free(o->send_to); free(o->ev); free(o->outbox); free(o->inbox); free(o);
 }
@@ -506,6 +511,41 @@ static void run_events(oracle_t *o) {
   o->n_ev = w;
 }
 
+/* ------------------------------------------------------------------ phase C: seeded churn (BASELINE config C5)
+ * At the start of round r, before the events of r: every live process crashes with probability churn_ppm / 1e6; a
+ * crashed process whose rejoin round has come restarts with incarnation + 1 and announces Alive (the effects of
+ * SWIM_EV_CRASH / SWIM_EV_REJOIN). Draws: words (i & 3) of the Philox blocks (r, i >> 2, P_CHURN, 0) — crash — and
+ * (r, i >> 2, P_CHURN, 1) — rejoin delay, uniform in [rejoin_min, rejoin_max]. Every shard runs it for all N nodes. */
+static void run_churn(oracle_t *o) {
+  const uint32_t ppm = o->cfg.churn_ppm;
+  if (!ppm) return;
+  const uint32_t span = o->cfg.rejoin_max - o->cfg.rejoin_min + 1;
+  for (uint32_t g = 0; 4 * g < o->N; ++g) {
+    uint32_t c0[4] = {o->round, g, P_CHURN, 0}, c1[4] = {o->round, g, P_CHURN, 1}, x[4], y[4];
+    philox4x32_10(c0, o->key, x);
+    int have_y = 0;
+    for (uint32_t j = 0; j < 4 && 4 * g + j < o->N; ++j) {
+      const uint32_t i = 4 * g + j;
+      if (o->alive[i]) {
+        if (bounded(x[j], 1000000u) < ppm) {
+          if (!have_y) { philox4x32_10(c1, o->key, y); have_y = 1; }
+          o->alive[i] = 0;
+          o->back_at[i] = o->round + o->cfg.rejoin_min + bounded(y[j], span);
+        }
+      } else if (o->back_at[i] == o->round) {
+        o->alive[i] = 1;
+        o->back_at[i] = 0;
+        if (i >= o->first && i < o->first + o->n) { /* restart: incarnation + 1, announce Alive */
+          const uint32_t l = i - o->first;
+          o->self_inc[l]++;
+          rec_t a = {i, o->self_inc[l], 0, SWIM_MSG_ALIVE, 0, 0};
+          pb_enqueue(o, l, a, o->ctr);
+        }
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------ round driver */
 static void push_env(env_t **arr, size_t *n, size_t *cap, const env_t *e) {
   if (*n == *cap) { *cap = *cap ? *cap * 2 : 1024; *arr = (env_t *)realloc(*arr, *cap * sizeof(env_t)); }
@@ -522,6 +562,7 @@ static uint32_t owner_of(const oracle_t *o, uint32_t node) {
 EXPORT int oracle_round_begin(oracle_t *o) {
   if (!o->view_set) return SWIM_ESTATE;
   o->round++;
+  run_churn(o);
   run_events(o);
   o->n_outbox = 0; o->n_inbox = 0;
   uint64_t tot[SWIM_CTR__COUNT] = {0};
@@ -657,6 +698,7 @@ EXPORT size_t oracle_array_bytes(const oracle_t *o, int arr) {
   size_t n = o->n, slots = n * o->cap;
   switch (arr) {
     case SWIM_ARR_ALIVE: return o->N;
+    case SWIM_ARR_BACK_AT: return (size_t)o->N * 4;
     case SWIM_ARR_SELF_INC: case SWIM_ARR_SEQNO: return n * 4;
     case SWIM_ARR_NBR: case SWIM_ARR_VINC: case SWIM_ARR_VLAST: return slots * 4;
     case SWIM_ARR_VST: return slots;
@@ -680,6 +722,7 @@ EXPORT int oracle_get_array(const oracle_t *o, int arr, void *buf, size_t bytes)
     case SWIM_ARR_VLAST: memcpy(buf, o->vlast, bytes); break;
     case SWIM_ARR_PB: memcpy(buf, o->pb, bytes); break;
     case SWIM_ARR_PB_CNT: memcpy(buf, o->pb_cnt, bytes); break;
+    case SWIM_ARR_BACK_AT: memcpy(buf, o->back_at, bytes); break;
   }
   return SWIM_OK;
 }
@@ -700,6 +743,7 @@ EXPORT int oracle_set_array(oracle_t *o, int arr, const void *buf, size_t bytes)
     case SWIM_ARR_VLAST: memcpy(o->vlast, buf, bytes); break;
     case SWIM_ARR_PB: memcpy(o->pb, buf, bytes); break;
     case SWIM_ARR_PB_CNT: memcpy(o->pb_cnt, buf, bytes); break;
+    case SWIM_ARR_BACK_AT: memcpy(o->back_at, buf, bytes); break;
   }
   return SWIM_OK;
 }

@@ -2,7 +2,7 @@
 tests/test_abi.py checks sizeof/offsets against a compiled probe."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # error codes
 OK, EINVAL, ENOMEM, ECUDA, ERANGE, EDECODE, ENODEV, ENCCL, ECAP, ESTATE = 0, -1, -2, -3, -4, -5, -6, -7, -8, -9
@@ -22,8 +22,9 @@ EV_CRASH, EV_REJOIN, EV_INJECT = 0, 1, 2
 F_NONE, F_STRICT_OVERRIDE, F_ROUND_ROBIN = 0, 1, 2  # SWIM_F_*: protocol variants
 TOPO_COMPLETE, TOPO_RANDOM, TOPO_RING = 0, 1, 2
 
-(ARR_ALIVE, ARR_SELF_INC, ARR_SEQNO, ARR_NBR, ARR_VST, ARR_VINC, ARR_VLAST, ARR_PB, ARR_PB_CNT) = range(9)
-ARR_COUNT = 9
+(ARR_ALIVE, ARR_SELF_INC, ARR_SEQNO, ARR_NBR, ARR_VST, ARR_VINC, ARR_VLAST, ARR_PB, ARR_PB_CNT, ARR_BACK_AT) = range(10)
+ARR_COUNT = 10
+REPLICATED_ARRAYS = (ARR_ALIVE, ARR_BACK_AT)  # [N] on every rank; the others are per shard
 (CTR_PINGS, CTR_DIRECT_FAIL, CTR_INDIRECT_PINGS, CTR_SUSPECT_LOCAL, CTR_DEAD_TIMEOUT, CTR_MSGS,
  CTR_RECS_SENT, CTR_RECS_APPLIED, CTR_REFUTES, CTR_PB_DROPPED, CTR_MSGS_RECV) = range(11)
 CTR_COUNT = 11
@@ -36,7 +37,9 @@ class Config(C.Structure):
                 ("k_indirect", C.c_uint32), ("fanout", C.c_uint32), ("pb_cap", C.c_uint32),
                 ("suspicion_rounds", C.c_uint32), ("retransmit", C.c_uint32), ("loss_ppm", C.c_uint32),
                 ("flags", C.c_uint32), ("seed", C.c_uint64), ("rank", C.c_uint32), ("world", C.c_uint32),
-                ("device", C.c_int32), ("base_port", C.c_uint32)]
+                ("device", C.c_int32), ("base_port", C.c_uint32), ("churn_ppm", C.c_uint32),
+                ("rejoin_min", C.c_uint32), ("rejoin_max", C.c_uint32), ("probes_per_round", C.c_uint32),
+                ("suspicion_max", C.c_uint32), ("_reserved", C.c_uint32)]
 
 
 class Member(C.Structure):
@@ -89,7 +92,8 @@ EVENT_DTYPE = _np.dtype({"names": ["round", "node", "kind", "msg_kind", "msg_nod
 ARRAY_DTYPES = {
     ARR_ALIVE: _np.dtype("u1"), ARR_SELF_INC: _np.dtype("<u4"), ARR_SEQNO: _np.dtype("<u4"),
     ARR_NBR: _np.dtype("<u4"), ARR_VST: _np.dtype("u1"), ARR_VINC: _np.dtype("<u4"),
-    ARR_VLAST: _np.dtype("<u4"), ARR_PB: RECORD_DTYPE, ARR_PB_CNT: _np.dtype("u1"),
+    ARR_VLAST: _np.dtype("<u4"), ARR_PB: RECORD_DTYPE, ARR_PB_CNT: _np.dtype("u1"), ARR_BACK_AT: _np.dtype("<u4"),
 }
 ARRAY_NAMES = {ARR_ALIVE: "alive", ARR_SELF_INC: "self_inc", ARR_SEQNO: "seqno", ARR_NBR: "nbr",
-               ARR_VST: "vst", ARR_VINC: "vinc", ARR_VLAST: "vlast", ARR_PB: "pb", ARR_PB_CNT: "pb_cnt"}
+               ARR_VST: "vst", ARR_VINC: "vinc", ARR_VLAST: "vlast", ARR_PB: "pb", ARR_PB_CNT: "pb_cnt",
+               ARR_BACK_AT: "back_at"}

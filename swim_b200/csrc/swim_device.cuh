@@ -42,6 +42,8 @@
 
 namespace swim {
 
+struct DevEvent;
+
 // CTA shape of the per-round kernels: 8 warps x 4 CTAs per SM by default. -DSWIM_WARPS_PER_BLOCK=16|32 (build.py: env
 // SWIM_WPB) keeps 32 resident warps per SM at 64 registers with fewer, larger CTAs: fewer arrivals on the grid barrier.
 #ifndef SWIM_WARPS_PER_BLOCK
@@ -58,7 +60,7 @@ constexpr long long kPeerWaitCycles = 120000000000ll; // ~60 s at 2 GHz, then th
 
 // Philox counter purposes. TARGET and LOSS0 blocks are shared by the four nodes
 // 4g..4g+3 (counter word 1 = node >> 2, draw = word node & 3): one Philox call serves four probes.
-enum : uint32_t { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6 };
+enum : uint32_t { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6, P_CHURN = 7 };
 
 struct SimDev {
   uint32_t N, first, n, cap;
@@ -69,6 +71,11 @@ struct SimDev {
   uint32_t nrounds;          // round_kernel: consecutive rounds in this launch (>= 1)
   uint32_t world, rank, per; // per = nodes per shard
   uint8_t *alive;            // [N]
+  uint32_t *back_at;         // [N] churn: round at which a crashed process rejoins (0 = none)
+  uint32_t churn_ppm, rejoin_min, rejoin_span; // seeded churn (phase C); rejoin delay = rejoin_min + U[0, span)
+  struct DevEvent *churn_ev; // [churn_cap] crash / rejoin events of the round, generated on the device
+  uint32_t *churn_cnt;       // [0] their number (the host clears it on the stream ahead of every round)
+  uint32_t churn_cap;
   uint32_t *self_inc;        // [n]
   uint32_t *seqno;           // [n]
   uint32_t *nbr;             // [n*cap]
@@ -1271,14 +1278,54 @@ struct DevEvent {
   uint4 rec; // SWIM_EV_INJECT
 };
 
+// Phase C — seeded churn (BASELINE config C5), one thread per Philox group of four nodes, every rank for all N nodes
+// (alive[] and back_at[] are replicated): a live process crashes with probability churn_ppm / 1e6 and is given its rejoin
+// round; a crashed process whose round has come rejoins. The kernel only decides and schedules: the effects (alive[],
+// crashed-member bitmaps of the observers, incarnation + 1 and the Alive broadcast of a rejoin) are event_kernel's, fed
+// with the list written here — the very code path of host-injected SWIM_EV_CRASH / SWIM_EV_REJOIN events.
+static __global__ void __launch_bounds__(256) churn_kernel(SimDev d) {
+  const uint32_t round = d.round;
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; 4 * g < d.N; g += gridDim.x * blockDim.x) {
+    const uint32_t base = 4 * g;
+    uint32_t up4 = 0; // alive bytes of the four nodes
+    if (base + 4 <= d.N) up4 = *reinterpret_cast<const uint32_t *>(d.alive + base);
+    else for (uint32_t j = 0; base + j < d.N; ++j) up4 |= (uint32_t)d.alive[base + j] << (8 * j);
+    const uint4 x = philox4x32_10(make_uint4(round, g, P_CHURN, 0), d.key0, d.key1);
+    uint4 y = make_uint4(0, 0, 0, 0);
+    bool have_y = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t i = base + j;
+      if (i >= d.N) break;
+      uint32_t kind = 0xFFFFFFFFu;
+      if (up4 >> (8 * j) & 0xFFu) {
+        if (bounded(word_of(x, j), 1000000u) < d.churn_ppm) {
+          if (!have_y) { y = philox4x32_10(make_uint4(round, g, P_CHURN, 1), d.key0, d.key1); have_y = true; }
+          d.back_at[i] = round + d.rejoin_min + bounded(word_of(y, j), d.rejoin_span);
+          kind = SWIM_EV_CRASH;
+        }
+      } else if (d.back_at[i] == round) {
+        d.back_at[i] = 0;
+        kind = SWIM_EV_REJOIN;
+      }
+      if (kind != 0xFFFFFFFFu) {
+        const uint32_t k = atomicAdd(d.churn_cnt, 1u);
+        if (k < d.churn_cap) { d.churn_ev[k].node = i; d.churn_ev[k].kind = kind; d.churn_ev[k].rec = make_uint4(0, 0, 0, 0); }
+        else *d.bar_err = 3; // list overflow: reported by swim_sim_sync, never silent
+      }
+    }
+  }
+}
+
 template <int W>
-__global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEvent *ev, uint32_t n_ev) {
+__global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEvent *ev, uint32_t n_ev, const uint32_t *n_ev_dev) {
   SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
   const uint32_t round = d.round; // events run outside captured graphs
+  if (n_ev_dev) n_ev = *n_ev_dev < d.churn_cap ? *n_ev_dev : d.churn_cap; // device-generated list (churn_kernel)
   // The host hands over one round's events grouped by node (stable: a node's events keep the order they were given in).
   // A run of same-node events belongs to the warp whose stride position is the run's first event, so a warp looks at
   // n_ev / nwarps list entries plus the runs it owns — not at the whole list.

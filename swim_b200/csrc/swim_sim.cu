@@ -76,6 +76,11 @@ extern "C" int swim_config_default(swim_config_t *cfg) {
   cfg->world = 1;
   cfg->device = -1;
   cfg->base_port = 4000;
+  cfg->churn_ppm = 0;
+  cfg->rejoin_min = 10; // BASELINE config C5: rejoin after U[10, 50] rounds
+  cfg->rejoin_max = 50;
+  cfg->probes_per_round = 1;
+  cfg->suspicion_max = 0;
   return SWIM_OK;
 }
 
@@ -88,6 +93,9 @@ static int validate(const swim_config_t *c) {
   if (c->suspicion_rounds < 1 || c->suspicion_rounds > SWIM_MAX_TIMER) return SWIM_EINVAL;
   if (c->retransmit < 1 || c->retransmit > 255 || c->loss_ppm > 1000000u) return SWIM_EINVAL;
   if (c->flags & ~SWIM_F__ALL) return SWIM_EINVAL;
+  if (c->churn_ppm > 1000000u || (c->churn_ppm && (c->rejoin_min < 1 || c->rejoin_max < c->rejoin_min))) return SWIM_EINVAL;
+  if (c->probes_per_round < 1 || c->probes_per_round > SWIM_MAX_PROBES) return SWIM_EINVAL;
+  if (c->suspicion_max && (c->suspicion_max < c->suspicion_rounds || c->suspicion_max > SWIM_MAX_TIMER_LIFEGUARD)) return SWIM_EINVAL;
   return SWIM_OK;
 }
 
@@ -145,6 +153,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   d.N = cfg->n_nodes; d.cap = cfg->view_cap; d.k = cfg->k_indirect; d.fanout = cfg->fanout;
   d.B = cfg->pb_cap; d.S = cfg->suspicion_rounds; d.T = cfg->retransmit; d.loss_ppm = cfg->loss_ppm;
   d.flags = cfg->flags;
+  d.churn_ppm = cfg->churn_ppm; d.rejoin_min = cfg->rejoin_min; d.rejoin_span = cfg->rejoin_max - cfg->rejoin_min + 1;
   d.key0 = (uint32_t)cfg->seed; d.key1 = (uint32_t)(cfg->seed >> 32);
   d.world = cfg->world; d.rank = cfg->rank;
   d.per = (uint32_t)(((uint64_t)d.N + d.world - 1) / d.world);
@@ -159,6 +168,12 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     CUDA_TRY(sim, cudaEventCreate(&sim->ev_stop));
     CUDA_TRY(sim, cudaEventCreateWithFlags(&sim->ev_upload, cudaEventDisableTiming));
     if ((r = dalloc(sim, &d.alive, d.N, 1))) return r;       // every node up
+    if ((r = dalloc(sim, &d.back_at, d.N, 0))) return r;     // churn: no rejoin scheduled
+    if (d.churn_ppm) { // device-generated crash / rejoin events of one round: expected 2 N p, room for 4x + slack
+      d.churn_cap = (uint32_t)std::min<uint64_t>((uint64_t)d.N * 2, (uint64_t)d.N * d.churn_ppm / 1000000ull * 8 + 4096);
+      if ((r = dalloc(sim, &d.churn_ev, d.churn_cap, 0))) return r;
+      if ((r = dalloc(sim, &d.churn_cnt, 4, 0))) return r;
+    }
     if ((r = dalloc(sim, &d.self_inc, n, 0))) return r;      // Util.hs:80
     if ((r = dalloc(sim, &d.seqno, n, 0))) return r;         // Util.hs:79
     if ((r = dalloc(sim, &d.nbr, slots, 0xFF))) return r;    // Util.hs:78 empty member map
@@ -464,6 +479,7 @@ static void prepare_kernels(swim_sim *sim) {
 #ifndef SWIM_EMU
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, event_kernel<W>);
+  cudaFuncGetAttributes(&a, churn_kernel);
   cudaFuncGetAttributes(&a, derive_meta_kernel);
   cudaFuncGetAttributes(&a, digest_kernel);
   cudaFuncGetAttributes(&a, mismatch_kernel);
@@ -538,11 +554,19 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     d.round = ++sim->round;
     size_t ev_end = ev_pos;
     while (ev_end < n_ev && ev_round[ev_end] == d.round) ++ev_end;
+    if (d.churn_ppm) { // phase C: seeded churn of this round, generated and applied on the device
+      int mk = prof_begin(sim, 0);
+      CUDA_TRY(sim, cudaMemsetAsync(d.churn_cnt, 0, 4, sim->stream));
+      SWIM_LAUNCH(churn_kernel, sim->sm_count * 8, 256, sim->stream, d);
+      SWIM_LAUNCH(event_kernel<W>, sim->sm_count * 4, kThreads, sim->stream, d, (const DevEvent *)d.churn_ev, 0u, (const uint32_t *)d.churn_cnt);
+      prof_end(sim, mk);
+      sim->launches += 2;
+    }
     if (ev_end > ev_pos) {
       const uint32_t cnt = (uint32_t)(ev_end - ev_pos);
       const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count * 4);
       int mk = prof_begin(sim, 0);
-      SWIM_LAUNCH(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt);
+      SWIM_LAUNCH(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt, (const uint32_t *)nullptr);
       prof_end(sim, mk);
       ++sim->launches;
       ev_pos = ev_end;
@@ -550,7 +574,7 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     if (single_kernel) { // K1a + K1b + K2 in one launch (grid barriers inside), for every round up to the next event
       uint32_t nr = rounds - r;
       if (ev_pos < n_ev) nr = std::min<uint32_t>(nr, ev_round[ev_pos] - d.round);
-      if (multi_round_off) nr = 1;
+      if (multi_round_off || d.churn_ppm) nr = 1; // churn: events every round
       d.nrounds = nr;
       d.qbatch = sim->opt_quiet_batch;
       CUDA_TRY(sim, launch_pdl(round_kernel<W>, kgrid, sim->stream, d));
@@ -618,7 +642,9 @@ extern "C" int swim_sim_sync(swim_sim_t *sim) {
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   const uint32_t err = *(volatile uint32_t *)sim->h_bar_err;
   if (err) {
-    set_error(sim, err == 1 ? "a cross-GPU wait timed out (a peer rank stopped stepping)" : "an in-kernel grid barrier timed out");
+    set_error(sim, err == 1 ? "a cross-GPU wait timed out (a peer rank stopped stepping)"
+                   : err == 3 ? "the device-side churn event list overflowed (churn_ppm too high for its capacity)"
+                              : "an in-kernel grid barrier timed out");
     return SWIM_ESTATE;
   }
   return SWIM_OK;
@@ -685,7 +711,7 @@ extern "C" int swim_sim_set_round(swim_sim_t *sim, uint32_t round) {
 static void ckpt_sources(const swim_sim *sim, std::vector<std::pair<void *, size_t>> &v) {
   const SimDev &d = sim->dev;
   const size_t n = d.n, slots = n * d.cap;
-  v = {{d.alive, (size_t)d.N}, {d.self_inc, n * 4}, {d.seqno, n * 4}, {d.vst, slots}, {d.vinc, slots * 4},
+  v = {{d.alive, (size_t)d.N}, {d.back_at, (size_t)d.N * 4}, {d.self_inc, n * 4}, {d.seqno, n * 4}, {d.vst, slots}, {d.vinc, slots * 4},
        {d.vlast, slots * 4}, {d.pb, n * d.B * sizeof(uint4)}, {d.pb_cnt, n}, {d.meta, slots / 32 * sizeof(uint4)},
        {sim->d_scratch, (2 + SWIM_CTR__COUNT) * sizeof(unsigned long long)}};
 }
@@ -911,6 +937,7 @@ static void *array_ptr(const swim_sim *sim, int arr, size_t *bytes) {
     case SWIM_ARR_VLAST: *bytes = slots * 4; return d.vlast;
     case SWIM_ARR_PB: *bytes = n * d.B * sizeof(swim_record_t); return d.pb;
     case SWIM_ARR_PB_CNT: *bytes = n; return d.pb_cnt;
+    case SWIM_ARR_BACK_AT: *bytes = (size_t)d.N * 4; return d.back_at;
   }
   *bytes = 0;
   return nullptr;

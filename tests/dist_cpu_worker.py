@@ -33,7 +33,7 @@ def main():
     if rank == 0:
         full = {}
         for name in arrays:
-            full[name] = gathered[0][name] if name == "alive" else np.concatenate([g[name] for g in gathered])
+            full[name] = gathered[0][name] if name in ("alive", "back_at") else np.concatenate([g[name] for g in gathered])
         np.savez(out_path, digest=np.uint64(digest), counters=counters, mismatches=mism, **full)
     dist.barrier()
     dist.destroy_process_group()

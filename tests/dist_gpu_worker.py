@@ -38,7 +38,7 @@ def main():
     if rank == 0:
         full = {}
         for name in arrays:
-            full[name] = gathered[0][name] if name == "alive" else np.concatenate([g[name] for g in gathered])
+            full[name] = gathered[0][name] if name in ("alive", "back_at") else np.concatenate([g[name] for g in gathered])
         np.savez(out_path, digests=np.array(digests, dtype=np.uint64), counters=counters, mismatches=mism, **full)
     dist.barrier()
     sim.close()

@@ -109,7 +109,7 @@ def one_sharded(seed):
         assert sum(x.mismatches() for x in sims) == ref.mismatches(), where
     assert np.sum([x.counters() for x in sims], axis=0).tolist() == ref.counters().tolist()
     for a in range(A.ARR_COUNT):
-        got = sims[0].get_array(a) if a == A.ARR_ALIVE else np.concatenate([x.get_array(a) for x in sims])
+        got = sims[0].get_array(a) if a in A.REPLICATED_ARRAYS else np.concatenate([x.get_array(a) for x in sims])
         assert np.array_equal(got, ref.get_array(a)), A.ARRAY_NAMES[a]
     for x in sims:
         x.close()

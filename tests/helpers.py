@@ -54,7 +54,7 @@ def random_events(rng, n_nodes, rounds, n_crash, n_rejoin=0, n_inject=0):
     return concat_events(evs)
 
 
-def run_sharded(world, n, chunks, loss, deg, flags=0, mode="p2p", devices=None):
+def run_sharded(world, n, chunks, loss, deg, flags=0, mode="p2p", devices=None, churn=None):
     """`world` handles in ONE process — on the emulator `world` emulated GPUs, on hardware all ranks on one device (or
     devices[r]): ranks of one process connect through raw device pointers (swim_sim_ipc_export / _connect), so the peers'
     arrays are addressed exactly as over NVLink. Each rank steps on its own host thread (its kernels wait for the others
@@ -66,6 +66,8 @@ def run_sharded(world, n, chunks, loss, deg, flags=0, mode="p2p", devices=None):
     total = sum(chunks)
     events = random_events(rng, n, total, n_crash=max(2, n // 12), n_rejoin=max(1, n // 40), n_inject=n // 10)
     kw = dict(n_nodes=n, k_indirect=3, fanout=4, pb_cap=6, suspicion_rounds=4, retransmit=5, loss_ppm=loss, seed=4242, flags=flags)
+    if churn:
+        kw.update(churn_ppm=churn[0], rejoin_min=churn[1], rejoin_max=churn[2])
     sims = [Simulator(default_config(rank=r, world=world, device=(devices[r] if devices else -1), **kw)) for r in range(world)]
     for s in sims:
         s.set_view(nbr)
@@ -105,7 +107,7 @@ def run_sharded(world, n, chunks, loss, deg, flags=0, mode="p2p", devices=None):
         assert sum(s.mismatches() for s in sims) == ref.mismatches()
     assert np.sum([s.counters() for s in sims], axis=0).tolist() == ref.counters().tolist()
     for a in range(A.ARR_COUNT):
-        got = sims[0].get_array(a) if a == A.ARR_ALIVE else np.concatenate([s.get_array(a) for s in sims])
+        got = sims[0].get_array(a) if a in A.REPLICATED_ARRAYS else np.concatenate([s.get_array(a) for s in sims])
         assert np.array_equal(got, ref.get_array(a)), A.ARRAY_NAMES[a]
     assert ref.counters()[A.CTR_MSGS_RECV] > 0
     for s in sims:

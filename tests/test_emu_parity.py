@@ -281,6 +281,41 @@ def test_sender_side_membership_filter(kind, deg, cap):
     assert c[A.CTR_MSGS] > 500 and c[A.CTR_MSGS_RECV] > 0
 
 
+@pytest.mark.parametrize("flags,ppm", [(0, 20000), (A.F_STRICT_OVERRIDE | A.F_ROUND_ROBIN, 60000)])
+def test_device_side_churn_equals_oracle(flags, ppm):
+    """BASELINE config C5's churn, generated on the device (churn_kernel -> event_kernel): per-round per-node crash draws
+    and rejoin delays from Philox purpose 7, mirrored by the oracle's phase C; mixed with host events on the same nodes."""
+    rng = np.random.default_rng(ppm)
+    n = 700
+    cfg = default_config(n_nodes=n, seed=77, churn_ppm=ppm, rejoin_min=2, rejoin_max=9, suspicion_rounds=3, flags=flags)
+    nbr = generate_topology("ring", n, 32, 16, seed=1)
+    sim, orc = make_pair(cfg, nbr)
+    ev = random_events(rng, n, 40, n_crash=30, n_rejoin=10, n_inject=30)
+    sim.inject(ev)
+    orc.inject(ev)
+    for chunk in (1, 1, 3, 10, 25):
+        sim.step(chunk)
+        orc.step(chunk)
+        assert_same_state(sim, orc, f"churn {ppm} after {sim.round} rounds")
+    back = sim.get_array(A.ARR_BACK_AT)
+    alive = sim.get_array(A.ARR_ALIVE)
+    assert (back > 0).sum() > 0 and (alive == 0).sum() > 0 and sim.counters()[A.CTR_REFUTES] >= 0
+    # save / load carry the rejoin schedule
+    sim.save()
+    d0 = sim.digest()
+    sim.step(15)
+    orc.step(15)
+    assert_same_state(sim, orc, "churn after save + 15")
+    sim.load()
+    assert sim.digest() == d0
+    sim.step(15)
+    assert sim.digest() == orc.digest()
+
+
+def test_device_side_churn_sharded():
+    run_sharded(3, n=500, chunks=[1, 2, 9, 20], loss=10000, deg=20, churn=(30000, 2, 7))
+
+
 def test_many_events_per_round_grouped_by_node():
     """event_kernel gets a round's events grouped by node (stable) and gives each same-node run to one warp: several
     events on one node in one round (crash, rejoin, crash again, injected datagrams) must keep their order, across

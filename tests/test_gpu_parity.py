@@ -156,6 +156,21 @@ def test_c3_full_size_against_the_oracle(qbatch, monkeypatch):
     sim.close()
 
 
+@pytest.mark.parametrize("kind,n", [("random", 4096), ("ring", 20000)])
+def test_device_side_churn(kind, n):
+    """BASELINE config C5 in miniature: 1 % of the processes crash per round and rejoin after U[3, 12] rounds (incarnation
+    + 1, Alive broadcast), generated on the device from Philox purpose 7; every array equals the oracle's phase C."""
+    cfg = default_config(n_nodes=n, seed=0x5EED0001 + 5, churn_ppm=10000, rejoin_min=3, rejoin_max=12, suspicion_rounds=3)
+    nbr = generate_topology(kind, n, 32, 32 if kind == "random" else 16, seed=5)
+    sim, orc = make_pair(cfg, nbr)
+    for chunk in (1, 2, 5, 12, 40):
+        sim.step(chunk)
+        orc.step(chunk)
+        assert_same_state(sim, orc, f"{kind} churn after {sim.round} rounds")
+    c = sim.counters()
+    assert c[A.CTR_DEAD_TIMEOUT] > 0 and c[A.CTR_RECS_APPLIED] > 0
+
+
 def test_set_array_alive_rebuilds_crash_bitmaps():
     """Bulk edits of alive[] (swim_sim_set_array) must reach the per-row crashed-member bitmaps."""
     n = 400
