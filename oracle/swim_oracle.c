@@ -107,6 +107,9 @@ typedef struct oracle {
   uint32_t *nbr;      /* [n*cap] */
   uint8_t *state;     /* [n*cap] */
   uint8_t *timer;     /* [n*cap] */
+  uint8_t *conf;      /* [n*cap] suspicion_max > 0: further Suspect messages seen about a suspected member (0..3) */
+  uint32_t s_arm;     /* rounds a new suspicion starts with */
+  uint32_t lg_delta[4]; /* lg_delta[c]: what the c-th confirmation takes off the countdown */
   uint32_t *vinc;     /* [n*cap] */
   uint32_t *vlast;    /* [n*cap] */
   rec_t *pb;          /* [n*B] */
@@ -161,6 +164,14 @@ EXPORT oracle_t *oracle_create(const swim_config_t *cfg) {
   o->nbr = (uint32_t *)malloc(slots * 4); memset(o->nbr, 0xFF, slots * 4); /* Util.hs:78: empty */
   o->state = (uint8_t *)malloc(slots); memset(o->state, SWIM_VACANT, slots);
   o->timer = (uint8_t *)calloc(slots, 1);
+  o->conf = (uint8_t *)calloc(slots, 1);
+  o->s_arm = cfg->suspicion_max ? cfg->suspicion_max : cfg->suspicion_rounds;
+  if (cfg->suspicion_max) { /* Lifeguard's timeout(c) = max - (max - min) log(c+1)/log(K+1), K = 3, in 1/256ths: 0, .5, log(3)/log(4), 1 */
+    static const uint32_t frac[4] = {0, 128, 203, 256};
+    uint32_t T[4];
+    for (int c = 0; c < 4; ++c) T[c] = cfg->suspicion_max - ((cfg->suspicion_max - cfg->suspicion_rounds) * frac[c] + 128) / 256;
+    for (int c = 1; c < 4; ++c) o->lg_delta[c] = T[c - 1] - T[c];
+  }
   o->vinc = (uint32_t *)calloc(slots, 4);
   o->vlast = (uint32_t *)calloc(slots, 4);
   o->pb = (rec_t *)calloc(n * o->B, sizeof(rec_t));
@@ -173,7 +184,7 @@ EXPORT oracle_t *oracle_create(const swim_config_t *cfg) {
 
 EXPORT void oracle_destroy(oracle_t *o) {
   if (!o) return;
-  free(o->alive); free(o->back_at); free(o->self_inc); free(o->seqno); free(o->nbr); free(o->state); free(o->timer);
+  free(o->alive); free(o->back_at); free(o->self_inc); free(o->seqno); free(o->nbr); free(o->state); free(o->timer); free(o->conf);
   free(o->vinc); free(o->vlast); free(o->pb); free(o->pb_cnt); free(o->out); free(o->out_cnt);
   free(o->send_to); free(o->ev); free(o->outbox); free(o->inbox); free(o);
 }
@@ -197,7 +208,7 @@ EXPORT int oracle_set_view(oracle_t *o, const uint32_t *nbr_global) {
       size_t x = (size_t)l * o->cap + s;
       o->nbr[x] = row[s];
       o->state[x] = row[s] == SWIM_NO_MEMBER ? SWIM_VACANT : SWIM_ALIVE;
-      o->timer[x] = 0; o->vinc[x] = 0; o->vlast[x] = 0;
+      o->timer[x] = 0; o->conf[x] = 0; o->vinc[x] = 0; o->vlast[x] = 0;
     }
   }
   o->view_set = 1;
@@ -229,13 +240,24 @@ static void pb_enqueue(oracle_t *o, uint32_t l, rec_t r, uint64_t *ctr) {
  * suspectOrDeadNode' (Core.hs:142-187) + aliveNode (Core.hs:197-218, [Q7]).
  * Returns 1 and fills *rb with the message to re-broadcast (`Just`), else 0 (`Nothing`).
  * allow_insert: scalar aliveNode adds unknown members (Core.hs:206-216); *err on full row. */
-static int apply_record(oracle_t *o, uint32_t l, rec_t r, int allow_insert, rec_t *rb, int *err, uint64_t *ctr) {
+/* net: the record came in a datagram (receive phase, injected event, scalar `process`), not from this node's own probe.
+ * [Lifeguard] with suspicion_max, a Suspect received about a member that is already Suspect (same or newer incarnation)
+ * is still `Nothing` (Core.hs:151,183) but counts as a confirmation: the countdown loses lg_delta[c], never below 1. */
+static void confirm_suspicion(oracle_t *o, size_t x) {
+  if (o->conf[x] >= 3) return;
+  const uint32_t c = ++o->conf[x], dlt = o->lg_delta[c];
+  o->timer[x] = (uint8_t)(o->timer[x] > dlt ? o->timer[x] - dlt : 1);
+}
+
+static int apply_record(oracle_t *o, uint32_t l, rec_t r, int allow_insert, int net, rec_t *rb, int *err, uint64_t *ctr) {
   uint32_t self = o->first + l;
   uint32_t *ids = o->nbr + (size_t)l * o->cap;
   uint8_t *st = o->state + (size_t)l * o->cap;
   uint8_t *tm = o->timer + (size_t)l * o->cap;
   uint32_t *inc = o->vinc + (size_t)l * o->cap;
   uint32_t *last = o->vlast + (size_t)l * o->cap;
+  uint8_t *cf = o->conf + (size_t)l * o->cap;
+  const int lg = o->cfg.suspicion_max != 0;
   const int strict = (o->cfg.flags & SWIM_F_STRICT_OVERRIDE) != 0;
   if (err) *err = 0;
   if (r.member == self) {
@@ -265,9 +287,9 @@ static int apply_record(oracle_t *o, uint32_t l, rec_t r, int allow_insert, rec_
     uint32_t pos = 0;
     while (pos < used && ids[pos] < r.member) ++pos; /* Map.insert keeps key order */
     for (uint32_t x = used; x > pos; --x) {
-      ids[x] = ids[x - 1]; st[x] = st[x - 1]; tm[x] = tm[x - 1]; inc[x] = inc[x - 1]; last[x] = last[x - 1];
+      ids[x] = ids[x - 1]; st[x] = st[x - 1]; tm[x] = tm[x - 1]; cf[x] = cf[x - 1]; inc[x] = inc[x - 1]; last[x] = last[x - 1];
     }
-    ids[pos] = r.member; st[pos] = SWIM_ALIVE; tm[pos] = 0; inc[pos] = r.incarnation; last[pos] = o->round;
+    ids[pos] = r.member; st[pos] = SWIM_ALIVE; tm[pos] = 0; cf[pos] = 0; inc[pos] = r.incarnation; last[pos] = o->round;
     *rb = r;
     return 1;
   }
@@ -279,19 +301,22 @@ static int apply_record(oracle_t *o, uint32_t l, rec_t r, int allow_insert, rec_
     switch (r.kind) {
       case SWIM_MSG_SUSPECT:
         if (st[s] == SWIM_DEAD) return 0;
-        if (st[s] == SWIM_ALIVE ? r.incarnation < inc[s] : r.incarnation <= inc[s]) return 0;
-        inc[s] = r.incarnation; st[s] = SWIM_SUSPECT; tm[s] = (uint8_t)o->S; last[s] = o->round;
+        if (st[s] == SWIM_ALIVE ? r.incarnation < inc[s] : r.incarnation <= inc[s]) {
+          if (lg && net && st[s] == SWIM_SUSPECT && r.incarnation == inc[s]) confirm_suspicion(o, (size_t)l * o->cap + s);
+          return 0;
+        }
+        inc[s] = r.incarnation; st[s] = SWIM_SUSPECT; tm[s] = (uint8_t)o->s_arm; cf[s] = 0; last[s] = o->round;
         *rb = r;
         return 1;
       case SWIM_MSG_DEAD:
         if (st[s] == SWIM_DEAD) return 0;
         if (r.incarnation > inc[s]) inc[s] = r.incarnation; /* keeps max(i, j) */
-        st[s] = SWIM_DEAD; tm[s] = 0; last[s] = o->round;
+        st[s] = SWIM_DEAD; tm[s] = 0; cf[s] = 0; last[s] = o->round;
         *rb = r;
         return 1;
       case SWIM_MSG_ALIVE:
         if (r.incarnation <= inc[s]) return 0;
-        inc[s] = r.incarnation; st[s] = SWIM_ALIVE; tm[s] = 0; last[s] = o->round;
+        inc[s] = r.incarnation; st[s] = SWIM_ALIVE; tm[s] = 0; cf[s] = 0; last[s] = o->round;
         *rb = r;
         return 1;
     }
@@ -300,21 +325,24 @@ static int apply_record(oracle_t *o, uint32_t l, rec_t r, int allow_insert, rec_
   switch (r.kind) {
     case SWIM_MSG_SUSPECT:
       /* Core.hs:151 + livenessCheck IsSuspect = memberAlive /= IsAliveC (Core.hs:183) */
-      if (r.incarnation < inc[s] || st[s] != SWIM_ALIVE) return 0;
-      inc[s] = r.incarnation; st[s] = SWIM_SUSPECT; tm[s] = (uint8_t)o->S; /* [Q8] arm timer */
+      if (r.incarnation < inc[s] || st[s] != SWIM_ALIVE) {
+        if (lg && net && st[s] == SWIM_SUSPECT && r.incarnation >= inc[s]) confirm_suspicion(o, (size_t)l * o->cap + s);
+        return 0;
+      }
+      inc[s] = r.incarnation; st[s] = SWIM_SUSPECT; tm[s] = (uint8_t)o->s_arm; cf[s] = 0; /* [Q8] arm timer */
       last[s] = o->round;                                                  /* Core.hs:176 */
       *rb = r;                                                             /* Core.hs:179 */
       return 1;
     case SWIM_MSG_DEAD:
       /* livenessCheck IsDead = memberAlive == IsDeadC (Core.hs:184) */
       if (r.incarnation < inc[s] || st[s] == SWIM_DEAD) return 0;
-      inc[s] = r.incarnation; st[s] = SWIM_DEAD; tm[s] = 0; last[s] = o->round;
+      inc[s] = r.incarnation; st[s] = SWIM_DEAD; tm[s] = 0; cf[s] = 0; last[s] = o->round;
       *rb = r; /* deadFrom preserved */
       return 1;
     case SWIM_MSG_ALIVE:
       /* [Q7] SWIM §4.2: Alive(i) overrides Suspect(j)/Alive(j)/(Dead j) iff i > j */
       if (r.incarnation <= inc[s]) return 0;
-      inc[s] = r.incarnation; st[s] = SWIM_ALIVE; tm[s] = 0; last[s] = o->round;
+      inc[s] = r.incarnation; st[s] = SWIM_ALIVE; tm[s] = 0; cf[s] = 0; last[s] = o->round;
       *rb = r;
       return 1;
   }
@@ -355,7 +383,7 @@ static uint32_t tick_timers(oracle_t *o, uint32_t l, uint64_t *ctr) {
   uint32_t *last = o->vlast + (size_t)l * o->cap;
   for (uint32_t s = 0; s < o->cap; ++s)
     if (st[s] == SWIM_SUSPECT && --tm[s] == 0) {
-      st[s] = SWIM_DEAD; last[s] = o->round;
+      st[s] = SWIM_DEAD; last[s] = o->round; o->conf[(size_t)l * o->cap + s] = 0;
       rec_t d = {ids[s], inc[s], self, SWIM_MSG_DEAD, 0, 0};
       pb_enqueue(o, l, d, ctr);
       ctr[SWIM_CTR_DEAD_TIMEOUT]++;
@@ -429,7 +457,7 @@ static void tick_node(oracle_t *o, uint32_t l, uint64_t *ctr) {
   if (!acked) {
     /* suspectNode store $ Suspect (memberIncarnation m) (memberName m) (Core.hs:253) */
     rec_t sus = {tn, tinc, 0, SWIM_MSG_SUSPECT, 0, 0}, rb;
-    if (apply_record(o, l, sus, 0, &rb, NULL, ctr)) {
+    if (apply_record(o, l, sus, 0, 0, &rb, NULL, ctr)) {
       pb_enqueue(o, l, rb, ctr); /* yield . Broadcast (Core.hs:254) */
       ctr[SWIM_CTR_SUSPECT_LOCAL]++;
     }
@@ -500,7 +528,7 @@ static void run_events(oracle_t *o) {
       case SWIM_EV_INJECT:
         if (local && o->alive[e->node]) { /* one datagram through `process` (Core.hs:110-117) */
           rec_t rb;
-          if (apply_record(o, l, rec_of_msg(&e->msg), 0, &rb, NULL, o->ctr)) {
+          if (apply_record(o, l, rec_of_msg(&e->msg), 0, 1, &rb, NULL, o->ctr)) {
             pb_enqueue(o, l, rb, o->ctr);
             o->ctr[SWIM_CTR_RECS_APPLIED]++;
           }
@@ -664,7 +692,7 @@ EXPORT int oracle_round_end(oracle_t *o) {
     o->ctr[SWIM_CTR_MSGS_RECV]++;
     for (uint32_t q = 0; q < e->cnt; ++q) {
       rec_t rb;
-      if (apply_record(o, l, e->recs[q], 0, &rb, NULL, o->ctr)) {
+      if (apply_record(o, l, e->recs[q], 0, 1, &rb, NULL, o->ctr)) {
         pb_enqueue(o, l, rb, o->ctr);
         o->ctr[SWIM_CTR_RECS_APPLIED]++;
       }
@@ -716,7 +744,7 @@ EXPORT int oracle_get_array(const oracle_t *o, int arr, void *buf, size_t bytes)
     case SWIM_ARR_SEQNO: memcpy(buf, o->seqno, bytes); break;
     case SWIM_ARR_NBR: memcpy(buf, o->nbr, bytes); break;
     case SWIM_ARR_VST:
-      for (size_t x = 0; x < bytes; ++x) ((uint8_t *)buf)[x] = (uint8_t)(o->state[x] | (o->timer[x] << 2));
+      for (size_t x = 0; x < bytes; ++x) ((uint8_t *)buf)[x] = (uint8_t)(o->state[x] | (o->timer[x] << 2) | (o->conf[x] << 6));
       break;
     case SWIM_ARR_VINC: memcpy(buf, o->vinc, bytes); break;
     case SWIM_ARR_VLAST: memcpy(buf, o->vlast, bytes); break;
@@ -736,7 +764,10 @@ EXPORT int oracle_set_array(oracle_t *o, int arr, const void *buf, size_t bytes)
     case SWIM_ARR_NBR: return SWIM_EINVAL;
     case SWIM_ARR_VST:
       for (size_t x = 0; x < bytes; ++x) {
-        o->state[x] = ((const uint8_t *)buf)[x] & 3; o->timer[x] = ((const uint8_t *)buf)[x] >> 2;
+        const uint8_t b = ((const uint8_t *)buf)[x];
+        o->state[x] = b & 3;
+        o->timer[x] = o->cfg.suspicion_max ? (b >> 2) & 15 : b >> 2;
+        o->conf[x] = o->cfg.suspicion_max ? b >> 6 : 0;
       }
       break;
     case SWIM_ARR_VINC: memcpy(o->vinc, buf, bytes); break;
@@ -765,7 +796,7 @@ EXPORT uint64_t oracle_digest(const oracle_t *o) {
     d += dg3(1, g, (uint64_t)o->self_inc[l] | ((uint64_t)o->seqno[l] << 32), (uint64_t)o->alive[g] | ((uint64_t)o->pb_cnt[l] << 8));
     for (uint32_t s = 0; s < o->cap; ++s) {
       size_t x = (size_t)l * o->cap + s;
-      uint64_t st = (uint64_t)(o->state[x] | (o->timer[x] << 2));
+      uint64_t st = (uint64_t)(o->state[x] | (o->timer[x] << 2) | (o->conf[x] << 6));
       d += dg3(2, g * o->cap + s, (uint64_t)o->nbr[x] | ((uint64_t)o->vinc[x] << 32), st | ((uint64_t)o->vlast[x] << 8));
     }
     for (uint32_t q = 0; q < o->pb_cnt[l]; ++q) {
@@ -825,7 +856,7 @@ EXPORT int oracle_set_members(oracle_t *o, uint32_t node, const swim_member_t *m
   qsort(tmp, n, sizeof *tmp, member_cmp); /* Map.fromList orders by key */
   for (size_t x = 0; x < n; ++x) {
     if (tmp[x].id == SWIM_NO_MEMBER || tmp[x].id == node || tmp[x].liveness > SWIM_DEAD ||
-        tmp[x].timer > SWIM_MAX_TIMER || (x && tmp[x].id == tmp[x - 1].id))
+        tmp[x].timer > (o->cfg.suspicion_max ? SWIM_MAX_TIMER_LIFEGUARD : SWIM_MAX_TIMER) || (x && tmp[x].id == tmp[x - 1].id))
       return SWIM_EINVAL;
   }
   uint32_t l = node - o->first;
@@ -834,10 +865,11 @@ EXPORT int oracle_set_members(oracle_t *o, uint32_t node, const swim_member_t *m
     if (s < n) {
       /* the countdown only exists while Suspect; a Suspect member given without one is armed with S */
       o->nbr[x] = tmp[s].id; o->state[x] = tmp[s].liveness;
-      o->timer[x] = tmp[s].liveness != SWIM_SUSPECT ? 0 : tmp[s].timer ? tmp[s].timer : (uint8_t)o->S;
+      o->timer[x] = tmp[s].liveness != SWIM_SUSPECT ? 0 : tmp[s].timer ? tmp[s].timer : (uint8_t)o->s_arm;
+      o->conf[x] = 0;
       o->vinc[x] = tmp[s].incarnation; o->vlast[x] = (uint32_t)tmp[s].last_change;
     } else {
-      o->nbr[x] = SWIM_NO_MEMBER; o->state[x] = SWIM_VACANT; o->timer[x] = 0; o->vinc[x] = 0; o->vlast[x] = 0;
+      o->nbr[x] = SWIM_NO_MEMBER; o->state[x] = SWIM_VACANT; o->timer[x] = 0; o->conf[x] = 0; o->vinc[x] = 0; o->vlast[x] = 0;
     }
   }
   o->view_set = 1;
@@ -880,13 +912,13 @@ EXPORT int oracle_remove_dead_nodes(oracle_t *o, uint32_t node) {
   for (uint32_t s = 0; s < o->cap; ++s) {
     size_t x = (size_t)l * o->cap + s, y = (size_t)l * o->cap + w;
     if (o->state[x] == SWIM_VACANT || o->state[x] == SWIM_DEAD) continue;
-    o->nbr[y] = o->nbr[x]; o->state[y] = o->state[x]; o->timer[y] = o->timer[x];
+    o->nbr[y] = o->nbr[x]; o->state[y] = o->state[x]; o->timer[y] = o->timer[x]; o->conf[y] = o->conf[x];
     o->vinc[y] = o->vinc[x]; o->vlast[y] = o->vlast[x];
     ++w;
   }
   for (; w < o->cap; ++w) {
     size_t y = (size_t)l * o->cap + w;
-    o->nbr[y] = SWIM_NO_MEMBER; o->state[y] = SWIM_VACANT; o->timer[y] = 0; o->vinc[y] = 0; o->vlast[y] = 0;
+    o->nbr[y] = SWIM_NO_MEMBER; o->state[y] = SWIM_VACANT; o->timer[y] = 0; o->conf[y] = 0; o->vinc[y] = 0; o->vlast[y] = 0;
   }
   return SWIM_OK;
 }
@@ -917,7 +949,7 @@ EXPORT int oracle_apply_message(oracle_t *o, uint32_t node, int want, const swim
   if (msg->kind != want) return SWIM_EINVAL; /* reference: `undefined` (Core.hs:191,195,218) */
   if (msg->incarnation < 0 || msg->incarnation > 0xFFFFFFFFll) return SWIM_ERANGE;
   rec_t rb; int err = 0;
-  int applied = apply_record(o, node - o->first, rec_of_msg(msg), 1, &rb, &err, o->ctr);
+  int applied = apply_record(o, node - o->first, rec_of_msg(msg), 1, 1, &rb, &err, o->ctr);
   if (err) return err;
   *has_out = applied;
   if (applied) {

@@ -66,6 +66,10 @@ struct SimDev {
   uint32_t N, first, n, cap;
   uint32_t k, fanout, B, S, T, loss_ppm;
   uint32_t flags;            // SWIM_F_* protocol variants
+  // suspicion countdown in the state byte: liveness | timer << 2 (6 bits); with cfg.suspicion_max (Lifeguard-style dynamic
+  // timeout) liveness | timer << 2 (4 bits) | confirmations << 6
+  uint32_t S_arm, tmask, lg; // rounds a new suspicion starts with; timer mask (63 / 15); dynamic timeout on
+  uint32_t lg_delta[4];      // lg_delta[c]: what the c-th confirmation takes off the countdown
   uint32_t key0, key1;
   uint32_t round;
   uint32_t nrounds;          // round_kernel: consecutive rounds in this launch (>= 1)
@@ -408,7 +412,7 @@ __device__ __forceinline__ void row_store(const Row<W> &r, const SimDev &d, uint
 //   would insert; bulk rounds ignore, the scalar call inserts).
 template <int W>
 __device__ __forceinline__ int row_apply(Row<W> &r, const SimDev &d, uint32_t self, uint32_t &self_inc,
-                                         uint4 rec, uint4 &rb, int lane, uint32_t &refutes) {
+                                         uint4 rec, uint4 &rb, int lane, uint32_t &refutes, bool net = true) {
   const uint32_t kind = rec_kind(rec);
   if (rec.x == self) {
     // own entry is virtual: (Alive, storeIncarnation)
@@ -437,10 +441,17 @@ __device__ __forceinline__ int row_apply(Row<W> &r, const SimDev &d, uint32_t se
   }
   const uint32_t live = st_s & 3u;
   uint32_t nst, ninc = rec.y;
+  // [Lifeguard] a Suspect received (net: in a datagram, not raised by this node's own probe) about a member that is
+  // already Suspect is `Nothing` for the reference (Core.hs:151,183) and stays so, but with cfg.suspicion_max it counts as
+  // a confirmation: the countdown loses lg_delta[c], never below 1 (timeout(c) = max - (max - min) log(c+1) / log 4).
+  bool confirm = false;
   if (d.flags & SWIM_F_STRICT_OVERRIDE) { // SWIM paper 4.2 instead of the reference's guards (include/swim.h)
     if (kind == SWIM_MSG_SUSPECT) {
-      if (live == SWIM_DEAD || (live == SWIM_ALIVE ? rec.y < inc_s : rec.y <= inc_s)) return 0;
-      nst = SWIM_SUSPECT | (d.S << 2);
+      if (live == SWIM_DEAD || (live == SWIM_ALIVE ? rec.y < inc_s : rec.y <= inc_s)) {
+        confirm = live == SWIM_SUSPECT && rec.y == inc_s;
+        if (!(confirm && d.lg && net)) return 0;
+      }
+      nst = SWIM_SUSPECT | (d.S_arm << 2);
     } else if (kind == SWIM_MSG_DEAD) {
       if (live == SWIM_DEAD) return 0;
       ninc = rec.y > inc_s ? rec.y : inc_s;
@@ -450,14 +461,28 @@ __device__ __forceinline__ int row_apply(Row<W> &r, const SimDev &d, uint32_t se
       nst = SWIM_ALIVE;
     }
   } else if (kind == SWIM_MSG_SUSPECT) {
-    if (rec.y < inc_s || live != SWIM_ALIVE) return 0; // Core.hs:151,183
-    nst = SWIM_SUSPECT | (d.S << 2);                   // [Q8] arm the countdown
+    if (rec.y < inc_s || live != SWIM_ALIVE) {           // Core.hs:151,183
+      confirm = live == SWIM_SUSPECT && rec.y >= inc_s;
+      if (!(confirm && d.lg && net)) return 0;
+    }
+    nst = SWIM_SUSPECT | (d.S_arm << 2);               // [Q8] arm the countdown
   } else if (kind == SWIM_MSG_DEAD) {
     if (rec.y < inc_s || live == SWIM_DEAD) return 0;  // Core.hs:151,184
     nst = SWIM_DEAD;
   } else {
     if (rec.y <= inc_s) return 0;                      // [Q7] Alive(i) applies iff i > j
     nst = SWIM_ALIVE;
+  }
+  if (confirm) { // only the state byte changes; nothing is re-broadcast
+    const uint32_t c = st_s >> 6;
+    if (c < 3u && lane == hl) {
+      const uint32_t t = (st_s >> 2) & 15u, dl = d.lg_delta[c + 1];
+      const uint32_t nt = t > dl ? t - dl : 1u;
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        if (w == hw) { r.st[w] = SWIM_SUSPECT | (nt << 2) | ((c + 1u) << 6); r.ticked |= 1u << w; }
+    }
+    return 0;
   }
   if (lane == hl) {
 #pragma unroll
@@ -749,7 +774,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       if ((row.st[w] & 3u) == SWIM_SUSPECT) { row.st[w] -= 4u; row.ticked |= 1u << w; } // timer >= 1 while Suspect
-      unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && (row.st[w] >> 2) == 0);
+      unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && ((row.st[w] >> 2) & d.tmask) == 0);
       if (em >> lane & 1u) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
       while (em) {
         const int s = __ffs(em) - 1;
@@ -797,7 +822,7 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
           uint4 rb;
           uint32_t no_self_inc = 0xFFFFFFFFu; // a probe never targets self
           if (row_apply<W>(row, d, self, no_self_inc, make_rec(tnode, tinc, 0, SWIM_MSG_SUSPECT), rb, lane,
-                           c.v[SWIM_CTR_REFUTES]) == 1) {
+                           c.v[SWIM_CTR_REFUTES], false) == 1) {
             pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // yield . Broadcast (Core.hs:254)
             if (lane == 0) ++c.v[SWIM_CTR_SUSPECT_LOCAL];
           }

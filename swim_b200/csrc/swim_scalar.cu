@@ -129,7 +129,7 @@ __global__ void scalar_kernel(SimDev d, ScalarArgs *a) {
 #pragma unroll
       for (int w = 0; w < W; ++w) {
         if ((row.st[w] & 3u) == SWIM_SUSPECT) { row.st[w] -= 4u; row.ticked |= 1u << w; }
-        unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && (row.st[w] >> 2) == 0);
+        unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && ((row.st[w] >> 2) & d.tmask) == 0);
         if (em >> lane & 1u) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
         while (em) {
           const int s = __ffs(em) - 1;
@@ -234,7 +234,7 @@ int fetch_row(swim_sim *sim, uint32_t node, std::vector<swim_member_t> &out) {
     swim_member_t m;
     memset(&m, 0, sizeof m);
     m.id = nb[s]; m.addr = nb[s]; m.port = (uint16_t)sim->cfg.base_port;
-    m.liveness = st[s] & 3u; m.timer = st[s] >> 2; m.incarnation = inc[s]; m.last_change = last[s];
+    m.liveness = st[s] & 3u; m.timer = (st[s] >> 2) & sim->dev.tmask; m.incarnation = inc[s]; m.last_change = last[s];
     out.push_back(m);
   }
   return SWIM_OK;
@@ -304,7 +304,7 @@ extern "C" int swim_set_members(swim_sim_t *sim, uint32_t node, const swim_membe
   std::vector<swim_member_t> v(ms, ms + n);
   std::sort(v.begin(), v.end(), [](const swim_member_t &a, const swim_member_t &b) { return a.id < b.id; }); // Map.fromList
   for (size_t x = 0; x < n; ++x)
-    if (v[x].id >= d.N || v[x].id == node || v[x].liveness > SWIM_DEAD || v[x].timer > SWIM_MAX_TIMER ||
+    if (v[x].id >= d.N || v[x].id == node || v[x].liveness > SWIM_DEAD || v[x].timer > d.tmask ||
         (x && v[x].id == v[x - 1].id)) {
       set_error(sim, "swim_set_members: member %zu (id %u) is invalid (range, self, liveness, duplicate)", x, v[x].id);
       return SWIM_EINVAL;
@@ -313,7 +313,7 @@ extern "C" int swim_set_members(swim_sim_t *sim, uint32_t node, const swim_membe
   std::vector<uint8_t> st(d.cap, SWIM_VACANT);
   for (size_t x = 0; x < n; ++x) {
     // the countdown only exists while Suspect; a Suspect member given without one is armed with S
-    const uint32_t timer = v[x].liveness != SWIM_SUSPECT ? 0u : v[x].timer ? v[x].timer : d.S;
+    const uint32_t timer = v[x].liveness != SWIM_SUSPECT ? 0u : v[x].timer ? v[x].timer : d.S_arm;
     nb[x] = v[x].id; st[x] = (uint8_t)(v[x].liveness | (timer << 2)); inc[x] = v[x].incarnation;
     last[x] = (uint32_t)v[x].last_change;
   }

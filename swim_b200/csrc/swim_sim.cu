@@ -153,6 +153,15 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   d.N = cfg->n_nodes; d.cap = cfg->view_cap; d.k = cfg->k_indirect; d.fanout = cfg->fanout;
   d.B = cfg->pb_cap; d.S = cfg->suspicion_rounds; d.T = cfg->retransmit; d.loss_ppm = cfg->loss_ppm;
   d.flags = cfg->flags;
+  d.lg = cfg->suspicion_max ? 1u : 0u;
+  d.S_arm = cfg->suspicion_max ? cfg->suspicion_max : cfg->suspicion_rounds;
+  d.tmask = d.lg ? SWIM_MAX_TIMER_LIFEGUARD : SWIM_MAX_TIMER;
+  if (d.lg) { // Lifeguard's timeout(c) = max - (max - min) log(c + 1) / log(K + 1), K = 3, in 1/256ths: 0, .5, log 3 / log 4, 1
+    static const uint32_t frac[4] = {0, 128, 203, 256};
+    uint32_t T[4];
+    for (int c = 0; c < 4; ++c) T[c] = cfg->suspicion_max - ((cfg->suspicion_max - cfg->suspicion_rounds) * frac[c] + 128) / 256;
+    for (int c = 1; c < 4; ++c) d.lg_delta[c] = T[c - 1] - T[c];
+  }
   d.churn_ppm = cfg->churn_ppm; d.rejoin_min = cfg->rejoin_min; d.rejoin_span = cfg->rejoin_max - cfg->rejoin_min + 1;
   d.key0 = (uint32_t)cfg->seed; d.key1 = (uint32_t)(cfg->seed >> 32);
   d.world = cfg->world; d.rank = cfg->rank;
@@ -972,6 +981,17 @@ extern "C" int swim_sim_set_array(swim_sim_t *sim, int arr, const void *buf, siz
   size_t want;
   void *p = array_ptr(sim, arr, &want);
   if (!p || want != bytes) { set_error(sim, "swim_sim_set_array(%d): expected %zu bytes, got %zu", arr, want, bytes); return SWIM_EINVAL; }
+  if (arr == SWIM_ARR_VST) { // the countdown exists exactly while Suspect: a Suspect entry with timer 0 would wrap on its next tick
+    const uint8_t *b = (const uint8_t *)buf;
+    const SimDev &d = sim->dev;
+    for (size_t x = 0; x < bytes; ++x) {
+      const uint32_t live = b[x] & 3u, timer = (b[x] >> 2) & d.tmask;
+      if (live == SWIM_SUSPECT ? (timer == 0 || timer > d.S_arm) : (b[x] >> 2) != 0) {
+        set_error(sim, "swim_sim_set_array(SWIM_ARR_VST): entry %zu = 0x%02x: a Suspect entry needs a countdown in 1..%u, any other entry none", x, b[x], d.S_arm);
+        return SWIM_EINVAL;
+      }
+    }
+  }
   cudaSetDevice(sim->device);
   CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
   CUDA_TRY(sim, cudaMemcpy(p, buf, bytes, cudaMemcpyHostToDevice));

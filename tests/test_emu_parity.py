@@ -376,3 +376,29 @@ def test_save_load_replays_the_same_rounds():
     sim.inject(ev[ev["round"] > 25])
     sim.step(35)
     assert sim.digest() == ref[0]
+
+
+@pytest.mark.parametrize("flags", [0, A.F_STRICT_OVERRIDE])
+def test_dynamic_suspicion_timeout(flags):
+    """cfg.suspicion_max (Lifeguard-style): a suspicion starts with suspicion_max rounds and every further Suspect received
+    about the suspected member shortens it (timeout(c) = max - (max - min) log(c+1)/log 4, at most 3 confirmations); the
+    state byte carries the confirmation count. Ring views so that suspicions about one member meet at its neighbours."""
+    rng = np.random.default_rng(8 + flags)
+    n = 400
+    cfg = default_config(n_nodes=n, seed=3, suspicion_rounds=3, suspicion_max=12, flags=flags, loss_ppm=30000)
+    nbr = generate_topology("ring", n, 32, 16, seed=1)
+    sim, orc = make_pair(cfg, nbr)
+    ev = random_events(rng, n, 50, n_crash=25, n_rejoin=5, n_inject=60)
+    sim.inject(ev)
+    orc.inject(ev)
+    seen_conf = 0
+    for r in range(50):
+        sim.step(1)
+        orc.step(1)
+        assert_same_state(sim, orc, f"flags {flags} round {r + 1}")
+        vst = sim.get_array(A.ARR_VST)
+        seen_conf = max(seen_conf, int((vst[(vst & 3) == A.SUSPECT] >> 6).max(initial=0)))
+    assert seen_conf >= 2  # confirmations did arrive
+    # detection is faster than with a fixed suspicion_max and never faster than suspicion_rounds allows
+    c = sim.counters()
+    assert c[A.CTR_DEAD_TIMEOUT] > 0
