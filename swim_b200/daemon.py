@@ -118,10 +118,16 @@ class Node:
             with self.lock:
                 out = core.process(self.store, sender, m)
             if isinstance(m, IndirectPing):
-                for g in out:  # the forwarded Ping carries OUR sequence number (Q4): remember whom to answer
+                for g in list(out):  # the forwarded Ping carries OUR sequence number (Q4): remember whom to answer
                     if isinstance(g, Direct) and isinstance(g.msg, Ping):
                         with self.lock:
                             self.relays[g.msg.seqNo] = (sender, m.seqNo, g.addr, time.monotonic())
+                        # Q4 also means that relaying bumped storeIncarnation (Core.hs:105-108, pinned by Spec.hs:166-174):
+                        # announce it. The state machine drops a Suspect/Dead about self whose incarnation is below
+                        # storeIncarnation (Core.hs:151), so a proxy whose peers still hold the old number would never
+                        # refute a false suspicion and would be declared Dead while alive.
+                        sa = self.store.storeSelf.memberHostNew
+                        out.append(Broadcast(Alive(g.msg.seqNo, self.store.storeSelf.memberName, sa.host, sa.port)))
             gossip.extend(out)
         self._flush(gossip)
 

@@ -49,6 +49,17 @@ def scenario_probe_escalation_and_relay():
         msgs, frm, raw = recv_msgs(b)
         assert len(msgs) == 1 and isinstance(msgs[0], Ping) and msgs[0].node == "b" and frm == c.addr
         proxy_seq = msgs[0].seqNo
+        # relaying bumped c's storeIncarnation (Q4: the forwarded Ping's seqNo IS the new incarnation, Spec.hs:166-174); c
+        # announces it, otherwise a later Suspect(old incarnation, c) would be dropped as stale by c itself (Core.hs:151)
+        # and never refuted. The announcement overrides such a suspicion at everybody who hears it (Alive i > Suspect j).
+        from swim_b200 import core as _core
+        from swim_b200.types import Alive, Suspect
+        with c.lock:
+            pend = _core.pending_broadcasts(c.store)
+            assert any(isinstance(m, Alive) and m.node == "c" and m.incarnation == proxy_seq for m in pend), pend
+            assert _core.suspectNode(c.store, Suspect(proxy_seq - 1, "c")) is None        # stale for c itself ...
+            refute = _core.suspectNode(c.store, Suspect(proxy_seq, "c"))                   # ... the announced one is refuted
+            assert isinstance(refute, Alive) and refute.incarnation == proxy_seq + 1
         b.handle_datagram(raw, c.addr)
         msgs, frm, raw = recv_msgs(c)
         assert msgs == [Ack(proxy_seq, ())] and frm == b.addr
