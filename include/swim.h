@@ -199,7 +199,10 @@ enum {
   SWIM_ARR_PB = 7,       /* swim_record_t[n*B], newest first; entries >= cnt are zero */
   SWIM_ARR_PB_CNT = 8,   /* u8 [n] */
   SWIM_ARR_BACK_AT = 9,  /* u32[N]      churn: round at which a crashed process rejoins, 0 = none (replicated on every rank) */
-  SWIM_ARR__COUNT = 10
+  SWIM_ARR_LAST_CRASH = 10,  /* u32[N]  round of the process's last crash (up -> down), 0 = never (replicated) */
+  SWIM_ARR_LAST_REJOIN = 11, /* u32[N]  round of its last rejoin (down -> up), 0 = never (replicated): what a convergence
+                                        study needs to tell a late detection from a false positive */
+  SWIM_ARR__COUNT = 12
 };
 
 /* ---- per-run counters (swim_sim_counters), cumulative since create ------------------- */
@@ -290,6 +293,12 @@ int swim_sim_set_round(swim_sim_t *sim, uint32_t round);
  * shard while ALL ranks are between steps (host-side barrier before and after). */
 int swim_sim_save(swim_sim_t *sim);
 int swim_sim_load(swim_sim_t *sim);
+
+/* Change the protocol scalars of a live handle between steps — suspicion_rounds, suspicion_max, retransmit, loss_ppm,
+ * flags, churn_ppm, rejoin_min / rejoin_max and seed are taken from `cfg`; every other field must equal the handle's
+ * (SWIM_EINVAL otherwise: sizes and the shard layout are fixed at create). With swim_sim_save / swim_sim_load this is a
+ * parameter sweep on ONE handle: the view, its in-edge index and the device arrays are built once. */
+int swim_sim_set_params(swim_sim_t *sim, const swim_config_t *cfg);
 
 /* Bulk copies of one state array (SWIM_ARR_*) between device and a host buffer of exactly
  * `bytes` bytes. set_array(SWIM_ARR_NBR) is rejected: use swim_sim_set_view. */

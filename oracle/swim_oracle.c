@@ -102,6 +102,7 @@ typedef struct oracle {
   uint64_t scalar_calls;
   uint8_t *alive;     /* [N] global truth */
   uint32_t *back_at;  /* [N] churn: round at which a crashed process rejoins (0 = none) */
+  uint32_t *last_crash, *last_rejoin; /* [N] round of the last up -> down / down -> up transition (0 = never) */
   uint32_t *self_inc; /* [n] */
   uint32_t *seqno;    /* [n] */
   uint32_t *nbr;      /* [n*cap] */
@@ -159,6 +160,8 @@ EXPORT oracle_t *oracle_create(const swim_config_t *cfg) {
   size_t n = o->n ? o->n : 1, slots = n * o->cap;
   o->alive = (uint8_t *)malloc(o->N); memset(o->alive, 1, o->N); /* every node up */
   o->back_at = (uint32_t *)calloc(o->N, 4);
+  o->last_crash = (uint32_t *)calloc(o->N, 4);
+  o->last_rejoin = (uint32_t *)calloc(o->N, 4);
   o->self_inc = (uint32_t *)calloc(n, 4);                        /* Util.hs:80 */
   o->seqno = (uint32_t *)calloc(n, 4);                           /* Util.hs:79 */
   o->nbr = (uint32_t *)malloc(slots * 4); memset(o->nbr, 0xFF, slots * 4); /* Util.hs:78: empty */
@@ -184,7 +187,7 @@ EXPORT oracle_t *oracle_create(const swim_config_t *cfg) {
 
 EXPORT void oracle_destroy(oracle_t *o) {
   if (!o) return;
-  free(o->alive); free(o->back_at); free(o->self_inc); free(o->seqno); free(o->nbr); free(o->state); free(o->timer); free(o->conf);
+  free(o->alive); free(o->back_at); free(o->last_crash); free(o->last_rejoin); free(o->self_inc); free(o->seqno); free(o->nbr); free(o->state); free(o->timer); free(o->conf);
   free(o->vinc); free(o->vlast); free(o->pb); free(o->pb_cnt); free(o->out); free(o->out_cnt);
   free(o->send_to); free(o->ev); free(o->outbox); free(o->inbox); free(o);
 }
@@ -514,10 +517,13 @@ static void run_events(oracle_t *o) {
     int local = e->node >= o->first && e->node < o->first + o->n;
     uint32_t l = e->node - o->first;
     switch (e->kind) {
-      case SWIM_EV_CRASH: o->alive[e->node] = 0; break;
+      case SWIM_EV_CRASH:
+        if (o->alive[e->node]) { o->alive[e->node] = 0; o->last_crash[e->node] = o->round; }
+        break;
       case SWIM_EV_REJOIN:
         if (!o->alive[e->node]) {
           o->alive[e->node] = 1;
+          o->last_rejoin[e->node] = o->round;
           if (local) { /* restart: incarnation+1 and announce Alive (BASELINE config C5) */
             o->self_inc[l]++;
             rec_t a = {e->node, o->self_inc[l], 0, SWIM_MSG_ALIVE, 0, 0};
@@ -558,10 +564,12 @@ static void run_churn(oracle_t *o) {
         if (bounded(x[j], 1000000u) < ppm) {
           if (!have_y) { philox4x32_10(c1, o->key, y); have_y = 1; }
           o->alive[i] = 0;
+          o->last_crash[i] = o->round;
           o->back_at[i] = o->round + o->cfg.rejoin_min + bounded(y[j], span);
         }
       } else if (o->back_at[i] == o->round) {
         o->alive[i] = 1;
+        o->last_rejoin[i] = o->round;
         o->back_at[i] = 0;
         if (i >= o->first && i < o->first + o->n) { /* restart: incarnation + 1, announce Alive */
           const uint32_t l = i - o->first;
@@ -726,7 +734,7 @@ EXPORT size_t oracle_array_bytes(const oracle_t *o, int arr) {
   size_t n = o->n, slots = n * o->cap;
   switch (arr) {
     case SWIM_ARR_ALIVE: return o->N;
-    case SWIM_ARR_BACK_AT: return (size_t)o->N * 4;
+    case SWIM_ARR_BACK_AT: case SWIM_ARR_LAST_CRASH: case SWIM_ARR_LAST_REJOIN: return (size_t)o->N * 4;
     case SWIM_ARR_SELF_INC: case SWIM_ARR_SEQNO: return n * 4;
     case SWIM_ARR_NBR: case SWIM_ARR_VINC: case SWIM_ARR_VLAST: return slots * 4;
     case SWIM_ARR_VST: return slots;
@@ -751,6 +759,8 @@ EXPORT int oracle_get_array(const oracle_t *o, int arr, void *buf, size_t bytes)
     case SWIM_ARR_PB: memcpy(buf, o->pb, bytes); break;
     case SWIM_ARR_PB_CNT: memcpy(buf, o->pb_cnt, bytes); break;
     case SWIM_ARR_BACK_AT: memcpy(buf, o->back_at, bytes); break;
+    case SWIM_ARR_LAST_CRASH: memcpy(buf, o->last_crash, bytes); break;
+    case SWIM_ARR_LAST_REJOIN: memcpy(buf, o->last_rejoin, bytes); break;
   }
   return SWIM_OK;
 }
@@ -775,6 +785,8 @@ EXPORT int oracle_set_array(oracle_t *o, int arr, const void *buf, size_t bytes)
     case SWIM_ARR_PB: memcpy(o->pb, buf, bytes); break;
     case SWIM_ARR_PB_CNT: memcpy(o->pb_cnt, buf, bytes); break;
     case SWIM_ARR_BACK_AT: memcpy(o->back_at, buf, bytes); break;
+    case SWIM_ARR_LAST_CRASH: memcpy(o->last_crash, buf, bytes); break;
+    case SWIM_ARR_LAST_REJOIN: memcpy(o->last_rejoin, buf, bytes); break;
   }
   return SWIM_OK;
 }

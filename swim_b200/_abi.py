@@ -22,9 +22,10 @@ EV_CRASH, EV_REJOIN, EV_INJECT = 0, 1, 2
 F_NONE, F_STRICT_OVERRIDE, F_ROUND_ROBIN = 0, 1, 2  # SWIM_F_*: protocol variants
 TOPO_COMPLETE, TOPO_RANDOM, TOPO_RING = 0, 1, 2
 
-(ARR_ALIVE, ARR_SELF_INC, ARR_SEQNO, ARR_NBR, ARR_VST, ARR_VINC, ARR_VLAST, ARR_PB, ARR_PB_CNT, ARR_BACK_AT) = range(10)
-ARR_COUNT = 10
-REPLICATED_ARRAYS = (ARR_ALIVE, ARR_BACK_AT)  # [N] on every rank; the others are per shard
+(ARR_ALIVE, ARR_SELF_INC, ARR_SEQNO, ARR_NBR, ARR_VST, ARR_VINC, ARR_VLAST, ARR_PB, ARR_PB_CNT, ARR_BACK_AT,
+ ARR_LAST_CRASH, ARR_LAST_REJOIN) = range(12)
+ARR_COUNT = 12
+REPLICATED_ARRAYS = (ARR_ALIVE, ARR_BACK_AT, ARR_LAST_CRASH, ARR_LAST_REJOIN)  # [N] on every rank; the others are per shard
 (CTR_PINGS, CTR_DIRECT_FAIL, CTR_INDIRECT_PINGS, CTR_SUSPECT_LOCAL, CTR_DEAD_TIMEOUT, CTR_MSGS,
  CTR_RECS_SENT, CTR_RECS_APPLIED, CTR_REFUTES, CTR_PB_DROPPED, CTR_MSGS_RECV) = range(11)
 CTR_COUNT = 11
@@ -93,7 +94,8 @@ ARRAY_DTYPES = {
     ARR_ALIVE: _np.dtype("u1"), ARR_SELF_INC: _np.dtype("<u4"), ARR_SEQNO: _np.dtype("<u4"),
     ARR_NBR: _np.dtype("<u4"), ARR_VST: _np.dtype("u1"), ARR_VINC: _np.dtype("<u4"),
     ARR_VLAST: _np.dtype("<u4"), ARR_PB: RECORD_DTYPE, ARR_PB_CNT: _np.dtype("u1"), ARR_BACK_AT: _np.dtype("<u4"),
+    ARR_LAST_CRASH: _np.dtype("<u4"), ARR_LAST_REJOIN: _np.dtype("<u4"),
 }
 ARRAY_NAMES = {ARR_ALIVE: "alive", ARR_SELF_INC: "self_inc", ARR_SEQNO: "seqno", ARR_NBR: "nbr",
                ARR_VST: "vst", ARR_VINC: "vinc", ARR_VLAST: "vlast", ARR_PB: "pb", ARR_PB_CNT: "pb_cnt",
-               ARR_BACK_AT: "back_at"}
+               ARR_BACK_AT: "back_at", ARR_LAST_CRASH: "last_crash", ARR_LAST_REJOIN: "last_rejoin"}

@@ -47,6 +47,7 @@ def lib():
     sig("swim_topology_generate", i, i, u32, u32, u32, u64, vp)
     sig("swim_sim_set_round", i, vp, u32)
     sig("swim_sim_save", i, vp)
+    sig("swim_sim_set_params", i, vp, P(A.Config))
     sig("swim_sim_calibrate", i, vp, vp, sz)
     sig("swim_sim_set_timeline", i, vp, u32)
     sig("swim_sim_get_timeline", i, vp, vp, sz)

@@ -76,6 +76,7 @@ struct SimDev {
   uint32_t world, rank, per; // per = nodes per shard
   uint8_t *alive;            // [N]
   uint32_t *back_at;         // [N] churn: round at which a crashed process rejoins (0 = none)
+  uint32_t *last_crash, *last_rejoin; // [N] round of the last up -> down / down -> up transition (0 = never)
   uint32_t churn_ppm, rejoin_min, rejoin_span; // seeded churn (phase C); rejoin delay = rejoin_min + U[0, span)
   struct DevEvent *churn_ev; // [churn_cap] crash / rejoin events of the round, generated on the device
   uint32_t *churn_cnt;       // [0] their number (the host clears it on the stream ahead of every round)
@@ -1362,8 +1363,11 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
     const bool local = node >= d.first && node < d.first + d.n;
     const uint32_t ln = node - d.first;
     if (kind == SWIM_EV_CRASH) {
+      const bool was_up = d.alive[node] != 0;
+      __syncwarp();
       if (lane == 0) {
         d.alive[node] = 0;
+        if (was_up) d.last_crash[node] = round;
         if (local) reinterpret_cast<uint8_t *>(d.meta + (size_t)ln * (d.cap >> 5))[12] = 0; // flags byte 0: up
       }
       mark_observers(d, node, true, lane);
@@ -1373,6 +1377,7 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
       if (!was_up) {
         if (lane == 0) {
           d.alive[node] = 1;
+          d.last_rejoin[node] = round;
           if (local) reinterpret_cast<uint8_t *>(d.meta + (size_t)ln * (d.cap >> 5))[12] = 1;
         }
         mark_observers(d, node, false, lane);

@@ -118,6 +118,34 @@ static int dalloc(swim_sim *sim, T **p, size_t count, int fill) {
 template <int W>
 static void prepare_kernels(swim_sim *sim); // grid sizes + kernel preload, defined with the round driver
 
+// suspicion countdown parameters: fixed timeout, or Lifeguard's timeout(c) = max - (max - min) log(c + 1) / log(K + 1) with
+// K = 3 confirmations, the logarithms in 1/256ths (0, .5, log 3 / log 4, 1) so that host, device and oracle agree exactly
+static void set_suspicion_params(SimDev &d, const swim_config_t *cfg) {
+  d.lg = cfg->suspicion_max ? 1u : 0u;
+  d.S_arm = cfg->suspicion_max ? cfg->suspicion_max : cfg->suspicion_rounds;
+  d.tmask = d.lg ? SWIM_MAX_TIMER_LIFEGUARD : SWIM_MAX_TIMER;
+  for (int c = 0; c < 4; ++c) d.lg_delta[c] = 0;
+  if (d.lg) {
+    static const uint32_t frac[4] = {0, 128, 203, 256};
+    uint32_t T[4];
+    for (int c = 0; c < 4; ++c) T[c] = cfg->suspicion_max - ((cfg->suspicion_max - cfg->suspicion_rounds) * frac[c] + 128) / 256;
+    for (int c = 1; c < 4; ++c) d.lg_delta[c] = T[c - 1] - T[c];
+  }
+}
+
+// device-generated crash / rejoin events of one round (churn_kernel): expected 2 N p of them, room for 4x + slack
+static int alloc_churn_list(swim_sim *sim) {
+  SimDev &d = sim->dev;
+  if (!d.churn_ppm) return SWIM_OK;
+  const uint32_t want = (uint32_t)std::min<uint64_t>((uint64_t)d.N * 2, (uint64_t)d.N * d.churn_ppm / 1000000ull * 8 + 4096);
+  if (d.churn_ev && want <= d.churn_cap) return SWIM_OK;
+  int r;
+  if ((r = dalloc(sim, &d.churn_ev, want, 0))) return r; // (an outgrown list stays in `allocs` until destroy)
+  d.churn_cap = want;
+  if (!d.churn_cnt && (r = dalloc(sim, &d.churn_cnt, 4, 0))) return r;
+  return SWIM_OK;
+}
+
 extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   if (!out) return SWIM_EINVAL;
   *out = nullptr;
@@ -153,15 +181,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   d.N = cfg->n_nodes; d.cap = cfg->view_cap; d.k = cfg->k_indirect; d.fanout = cfg->fanout;
   d.B = cfg->pb_cap; d.S = cfg->suspicion_rounds; d.T = cfg->retransmit; d.loss_ppm = cfg->loss_ppm;
   d.flags = cfg->flags;
-  d.lg = cfg->suspicion_max ? 1u : 0u;
-  d.S_arm = cfg->suspicion_max ? cfg->suspicion_max : cfg->suspicion_rounds;
-  d.tmask = d.lg ? SWIM_MAX_TIMER_LIFEGUARD : SWIM_MAX_TIMER;
-  if (d.lg) { // Lifeguard's timeout(c) = max - (max - min) log(c + 1) / log(K + 1), K = 3, in 1/256ths: 0, .5, log 3 / log 4, 1
-    static const uint32_t frac[4] = {0, 128, 203, 256};
-    uint32_t T[4];
-    for (int c = 0; c < 4; ++c) T[c] = cfg->suspicion_max - ((cfg->suspicion_max - cfg->suspicion_rounds) * frac[c] + 128) / 256;
-    for (int c = 1; c < 4; ++c) d.lg_delta[c] = T[c - 1] - T[c];
-  }
+  set_suspicion_params(d, cfg);
   d.churn_ppm = cfg->churn_ppm; d.rejoin_min = cfg->rejoin_min; d.rejoin_span = cfg->rejoin_max - cfg->rejoin_min + 1;
   d.key0 = (uint32_t)cfg->seed; d.key1 = (uint32_t)(cfg->seed >> 32);
   d.world = cfg->world; d.rank = cfg->rank;
@@ -178,11 +198,9 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     CUDA_TRY(sim, cudaEventCreateWithFlags(&sim->ev_upload, cudaEventDisableTiming));
     if ((r = dalloc(sim, &d.alive, d.N, 1))) return r;       // every node up
     if ((r = dalloc(sim, &d.back_at, d.N, 0))) return r;     // churn: no rejoin scheduled
-    if (d.churn_ppm) { // device-generated crash / rejoin events of one round: expected 2 N p, room for 4x + slack
-      d.churn_cap = (uint32_t)std::min<uint64_t>((uint64_t)d.N * 2, (uint64_t)d.N * d.churn_ppm / 1000000ull * 8 + 4096);
-      if ((r = dalloc(sim, &d.churn_ev, d.churn_cap, 0))) return r;
-      if ((r = dalloc(sim, &d.churn_cnt, 4, 0))) return r;
-    }
+    if ((r = dalloc(sim, &d.last_crash, d.N, 0))) return r;
+    if ((r = dalloc(sim, &d.last_rejoin, d.N, 0))) return r;
+    if ((r = alloc_churn_list(sim))) return r;
     if ((r = dalloc(sim, &d.self_inc, n, 0))) return r;      // Util.hs:80
     if ((r = dalloc(sim, &d.seqno, n, 0))) return r;         // Util.hs:79
     if ((r = dalloc(sim, &d.nbr, slots, 0xFF))) return r;    // Util.hs:78 empty member map
@@ -716,11 +734,33 @@ extern "C" int swim_sim_set_round(swim_sim_t *sim, uint32_t round) {
   return reset_round_state(sim);
 }
 
+extern "C" int swim_sim_set_params(swim_sim_t *sim, const swim_config_t *cfg) {
+  if (!sim || !cfg) return SWIM_EINVAL;
+  int rc = validate(cfg);
+  if (rc) { set_error(sim, "swim_sim_set_params: invalid config"); return rc; }
+  swim_config_t a = *cfg, b = sim->cfg; // everything but the protocol scalars must match the handle
+  a.suspicion_rounds = b.suspicion_rounds; a.suspicion_max = b.suspicion_max; a.retransmit = b.retransmit;
+  a.loss_ppm = b.loss_ppm; a.flags = b.flags; a.churn_ppm = b.churn_ppm; a.rejoin_min = b.rejoin_min;
+  a.rejoin_max = b.rejoin_max; a.seed = b.seed; a._reserved = b._reserved;
+  if (memcmp(&a, &b, sizeof a) != 0) { set_error(sim, "swim_sim_set_params: only suspicion_rounds, suspicion_max, retransmit, loss_ppm, flags, churn_ppm, rejoin_min/max and seed may change"); return SWIM_EINVAL; }
+  if ((cfg->flags & SWIM_F_ROUND_ROBIN) && (cfg->view_cap & (cfg->view_cap - 1))) return SWIM_EINVAL;
+  cudaSetDevice(sim->device);
+  CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+  sim->cfg = *cfg;
+  SimDev &d = sim->dev;
+  d.S = cfg->suspicion_rounds; d.T = cfg->retransmit; d.loss_ppm = cfg->loss_ppm; d.flags = cfg->flags;
+  d.key0 = (uint32_t)cfg->seed; d.key1 = (uint32_t)(cfg->seed >> 32);
+  set_suspicion_params(d, cfg);
+  d.churn_ppm = cfg->churn_ppm; d.rejoin_min = cfg->rejoin_min; d.rejoin_span = cfg->rejoin_max - cfg->rejoin_min + 1;
+  return alloc_churn_list(sim);
+}
+
 // ------------------------------------------------------------------ device-resident checkpoint
 static void ckpt_sources(const swim_sim *sim, std::vector<std::pair<void *, size_t>> &v) {
   const SimDev &d = sim->dev;
   const size_t n = d.n, slots = n * d.cap;
-  v = {{d.alive, (size_t)d.N}, {d.back_at, (size_t)d.N * 4}, {d.self_inc, n * 4}, {d.seqno, n * 4}, {d.vst, slots}, {d.vinc, slots * 4},
+  v = {{d.alive, (size_t)d.N}, {d.back_at, (size_t)d.N * 4}, {d.last_crash, (size_t)d.N * 4}, {d.last_rejoin, (size_t)d.N * 4},
+       {d.self_inc, n * 4}, {d.seqno, n * 4}, {d.vst, slots}, {d.vinc, slots * 4},
        {d.vlast, slots * 4}, {d.pb, n * d.B * sizeof(uint4)}, {d.pb_cnt, n}, {d.meta, slots / 32 * sizeof(uint4)},
        {sim->d_scratch, (2 + SWIM_CTR__COUNT) * sizeof(unsigned long long)}};
 }
@@ -947,6 +987,8 @@ static void *array_ptr(const swim_sim *sim, int arr, size_t *bytes) {
     case SWIM_ARR_PB: *bytes = n * d.B * sizeof(swim_record_t); return d.pb;
     case SWIM_ARR_PB_CNT: *bytes = n; return d.pb_cnt;
     case SWIM_ARR_BACK_AT: *bytes = (size_t)d.N * 4; return d.back_at;
+    case SWIM_ARR_LAST_CRASH: *bytes = (size_t)d.N * 4; return d.last_crash;
+    case SWIM_ARR_LAST_REJOIN: *bytes = (size_t)d.N * 4; return d.last_rejoin;
   }
   *bytes = 0;
   return nullptr;

@@ -251,6 +251,15 @@ class Simulator:
         """Back to the last save() (swim_sim_load)."""
         check(lib().swim_sim_load(self._h), "swim_sim_load", self._h)
 
+    def set_params(self, **kw):
+        """Change protocol scalars of the live handle between steps (swim_sim_set_params): suspicion_rounds, suspicion_max,
+        retransmit, loss_ppm, flags, churn_ppm, rejoin_min, rejoin_max, seed."""
+        cfg = A.Config.from_buffer_copy(self.cfg)
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        check(lib().swim_sim_set_params(self._h, C.byref(cfg)), "swim_sim_set_params", self._h)
+        self.cfg = cfg
+
     def checkpoint(self):
         """Everything a single-shard run needs to be resumed bit for bit: the state arrays and the round (the counter of
         every Philox draw). Pending events and the config are the caller's (they are inputs, not state)."""

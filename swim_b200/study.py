@@ -33,7 +33,8 @@ def event_history(events, n_nodes, upto_round):
 
 def view_report(sim, events, round_now, max_latency=256):
     """Classify every view entry of this rank's live observers (see the module docstring). Returns a dict of counts
-    plus `latency_hist` (index = rounds from crash to the Dead mark, clipped to max_latency)."""
+    plus `latency_hist` (index = rounds from crash to the Dead mark, clipped to max_latency). events = None: the crash /
+    rejoin rounds come from the handle's SWIM_ARR_LAST_CRASH / SWIM_ARR_LAST_REJOIN arrays (seeded device-side churn)."""
     cap = sim.cfg.view_cap
     alive = sim.get_array(A.ARR_ALIVE).astype(bool)                  # [N] truth, replicated on every rank
     n_total = alive.shape[0]
@@ -42,7 +43,11 @@ def view_report(sim, events, round_now, max_latency=256):
     vlast = sim.get_array(A.ARR_VLAST).reshape(-1, cap).astype(np.int64)
     first = getattr(sim, "first", 0)
     n_local = nbr.shape[0]
-    last_crash, last_rejoin = event_history(events, n_total, round_now)
+    if events is None:  # the library keeps the transition rounds itself (device-side churn has no host trace)
+        last_crash = sim.get_array(A.ARR_LAST_CRASH).astype(np.int64)
+        last_rejoin = sim.get_array(A.ARR_LAST_REJOIN).astype(np.int64)
+    else:
+        last_crash, last_rejoin = event_history(events, n_total, round_now)
     observer_up = alive[first:first + n_local][:, None]
     occupied = (st != A.VACANT) & observer_up
     member = np.where(occupied, nbr, 0).astype(np.int64)

@@ -88,3 +88,21 @@ def test_round_robin_bounds_the_detection_latency():
         res = run_sweep_point(o, ev, 2 * cap + S + 6, sample_every=10)
         assert res["mismatch_series"][-1][1] == 0
         assert res["report"]["latency"]["max"] <= 2 * cap - 1 + S + 1
+
+
+def test_report_with_seeded_churn_needs_no_event_trace():
+    """cfg.churn_ppm: crashes and rejoins are drawn inside the simulator; the report takes the transition rounds from
+    SWIM_ARR_LAST_CRASH / SWIM_ARR_LAST_REJOIN."""
+    n = 384
+    nbr = generate_topology("ring", n, 32, 16, seed=8)
+    o = Oracle(default_config(n_nodes=n, suspicion_rounds=3, seed=5, churn_ppm=5000, rejoin_min=5, rejoin_max=20))
+    o.set_view(nbr)
+    for upto in (30, 80, 150):
+        o.step(upto - o.round)
+        rep = view_report(o, None, upto)
+        assert rep["mismatches"] == o.mismatches()
+        assert rep["down_entries"] == rep["detected"] + rep["stale_dead"] + rep["undetected"]
+    lc, lr = o.get_array(A.ARR_LAST_CRASH), o.get_array(A.ARR_LAST_REJOIN)
+    assert (lc > 0).sum() > 20 and (lr > 0).sum() > 5 and rep["detected"] > 0
+    res = run_sweep_point(o, None, 20, sample_every=10)
+    assert res["report"]["latency"]["n"] > 0
