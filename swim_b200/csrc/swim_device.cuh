@@ -168,6 +168,25 @@ __device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #endif
 }
+// relaxed system-scope loads (never served from a stale L1 line): peer-GPU memory that changes from round to round
+__device__ __forceinline__ uint4 ld_sys_u4(const uint4 *p) {
+#ifdef SWIM_EMU
+  return *p;
+#else
+  uint4 v;
+  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+#endif
+}
+__device__ __forceinline__ uint32_t ld_sys_u8(const uint8_t *p) {
+#ifdef SWIM_EMU
+  return *p;
+#else
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
 #ifdef SWIM_EMU
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
@@ -743,8 +762,8 @@ __device__ __forceinline__ uint32_t first_work_entry(const SimDev &d, uint32_t w
 // piggyback send. Lane s owns view slot s; the piggyback buffer is staged in shared memory. Everything K1a derived is
 // recomputed from the row with warp ballots.
 template <int W>
-__device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps, int lane,
-                                          PbStage &pbs, Ctr &c, uint32_t first_ln) {
+__device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps, int lane,
+                                          PbStage &pbs, Ctr &c, uint32_t first_ln, bool fence_remote = true) {
   const uint32_t n_work = d.wl_cnt[ci(round)];
   const uint32_t par = round & 1;
   uint2 *rl_out = d.rl + (size_t)par * d.n * d.fanout;
@@ -938,7 +957,8 @@ __device__ __forceinline__ void work_pass(const SimDev &d, uint32_t round, uint3
     pb_store(pbs, d, ln, lane);
     if ((uint32_t)lane < d.fanout) rl_out[(size_t)idx * d.fanout + lane] = cand; // no atomics, no shared counter
   }
-  if (did_remote) __threadfence_system(); // peer-memory stores are performed before the grid reports completion
+  if (did_remote && fence_remote) __threadfence_system(); // peer-memory stores are performed before the grid reports completion
+  return did_remote;
 }
 
 template <int W>
@@ -1027,8 +1047,8 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
   uint4 early_rec = make_uint4(0, 0, 0, 0);
   uint32_t early_cnt = 0;
   if (early) {
-    if ((uint32_t)lane < d.B) early_rec = d.out_p[d.rank][((size_t)par * d.per + snd) * d.B + lane];
-    early_cnt = d.out_cnt_p[d.rank][(size_t)par * d.per + snd];
+    if ((uint32_t)lane < d.B) early_rec = d.out[((size_t)par * d.per + snd) * d.B + lane];
+    early_cnt = d.out_cnt[(size_t)par * d.per + snd];
   }
   if (__shfl_sync(kFull, old, 0) == round) return; // another warp has this receiver
   // (a listed receiver is a live process: senders deliver only to members whose crashed-member bit is clear)
@@ -1049,8 +1069,13 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
         cnt = early_cnt;
       } else if (s_kind == 1) { // pull the sender's snapshot (from a peer GPU's memory if it lives there)
         const uint32_t s_rank = d.world == 1 ? 0u : s_id / d.per, sl = s_id - s_rank * d.per;
-        if ((uint32_t)lane < d.B) mine = d.out_p[s_rank][((size_t)par * d.per + sl) * d.B + lane];
-        cnt = d.out_cnt_p[s_rank][(size_t)par * d.per + sl];
+        if (s_rank == d.rank) {
+          if ((uint32_t)lane < d.B) mine = d.out[((size_t)par * d.per + sl) * d.B + lane];
+          cnt = d.out_cnt[(size_t)par * d.per + sl];
+        } else {
+          if ((uint32_t)lane < d.B) mine = ld_sys_u4(d.out_p[s_rank] + ((size_t)par * d.per + sl) * d.B + lane);
+          cnt = ld_sys_u8(d.out_cnt_p[s_rank] + (size_t)par * d.per + sl);
+        }
       } else {           // staged NCCL path: the envelope arrived in the exchange buffer
         const uint32_t xslot = d.eslot[eb + q];
         const uint4 *env = d.xrecv + (size_t)xslot * (1 + d.B);
@@ -1155,43 +1180,67 @@ __device__ __forceinline__ void grid_barrier(const SimDev &d) {
   __syncthreads();
 }
 
-// The same barrier for sharded runs with the fused exchange, placed between K1b and K2: it also synchronises the
-// GPUs, and only ONE thread per GPU talks to the peers. The last CTA to arrive — by then every CTA of this rank has
-// finished K1b and fenced its peer-memory stores — publishes the per-peer receiver counts and this rank's round word
-// into every peer's memory, waits until every peer's word for this round has landed here, and only then releases the
-// local grid. Everybody else spins on the local generation word, exactly as in grid_barrier.
-__device__ __forceinline__ void grid_peer_barrier(const SimDev &d, uint32_t mail_round) {
+// The cross-GPU handshake of round `mail_round`, run by ALL threads of one CTA (the last one to arrive at a grid barrier —
+// by then every CTA of this rank has finished its K1b of the round, and those that stored into peer memory have fenced
+// at system scope): thread q publishes to peer q the number of receivers this rank listed there and then, with release
+// semantics, this rank's round word; it then waits (acquire) for peer q's word. One thread per peer, all peers in
+// parallel; the wait is bounded (a missing peer sets *bar_err instead of hanging the GPU).
+__device__ __forceinline__ void peer_handshake_cta(const SimDev &d, uint32_t mail_round) {
+  const uint32_t q = threadIdx.x;
+  if (q < d.world && q != d.rank) {
+    d.rcnt_p[q][(mail_round & 1) * d.world + d.rank] = atomicExch(&d.xcnt[q], 0u);
+    st_release_sys(d.bar_p[q] + d.rank, mail_round);
+    const uint32_t *mine = d.bar_p[d.rank] + q;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(mine) - mail_round) < 0)
+      if (clock64() - t0 > kPeerWaitCycles) { *d.bar_err = 1; break; } // a peer stopped stepping
+  }
+}
+
+// CTA-wide OR of a per-thread predicate (every thread of the CTA must call it)
+__device__ __forceinline__ bool cta_or(bool pred) {
+  SWIM_SHARED_1D(uint32_t, s_or, 1);
+  if (threadIdx.x == 0) s_or[0] = 0;
+  __syncthreads();
+  if (pred) s_or[0] = 1; // same value from every writer
+  __syncthreads();
+  return s_or[0] != 0;
+}
+
+// grid_barrier with a job for the last CTA to arrive: `handshake` = 0 none, else the round whose cross-GPU handshake that
+// CTA performs before it releases the grid (everybody else spins on the local generation word as in grid_barrier).
+// fence_sys: this CTA stored into peer memory since the last barrier (its arrival must order those stores system-wide).
+// want(): evaluated by the last CTA only, after every arrival is visible — whether the handshake is due at this barrier
+// (round_kernel folds it into the scan barrier of a round that listed no work).
+template <typename Want>
+__device__ __forceinline__ void grid_barrier_leader(const SimDev &d, bool fence_sys, uint32_t mail_round, Want want) {
+  SWIM_SHARED_1D(uint32_t, s_last, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
+    if (fence_sys) __threadfence_system(); else __threadfence();
+    const bool last = atomicAdd(d.gbar, 1u) == gridDim.x - 1;
+    if (last) __threadfence(); // acquire side of the arrivals
+    s_last[0] = last ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last[0]) {
+    if (want()) peer_handshake_cta(d, mail_round);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      (*barrier_generation())++;
+      d.gbar[0] = 0;
+      __threadfence();
+      atomicAdd(d.gbar + 1, 1u);
+    }
+  } else if (threadIdx.x == 0) {
     volatile uint32_t *gen = d.gbar + 1;
     const uint32_t g = (*barrier_generation())++;
-    __threadfence_system(); // this CTA's stores into peer memory are performed before it reports arrival
-    if (atomicAdd(d.gbar, 1u) == gridDim.x - 1) {
-      __threadfence(); // acquire side of the arrivals: every CTA's fenced stores happen-before what follows
-      for (uint32_t q = 0; q < d.world; ++q) {
-        if (q == d.rank) continue;
-        d.rcnt_p[q][(mail_round & 1) * d.world + d.rank] = atomicExch(&d.xcnt[q], 0u);
-      }
-      for (uint32_t q = 0; q < d.world; ++q) st_release_sys(d.bar_p[q] + d.rank, mail_round); // counts + all mail first
-      const long long t0 = clock64();
-      for (uint32_t q = 0; q < d.world; ++q) {
-        const uint32_t *mine = d.bar_p[d.rank] + q;
-        while ((int32_t)(ld_acquire_sys(mine) - mail_round) < 0) {
-          if (clock64() - t0 > kPeerWaitCycles) { *d.bar_err = 1; break; } // a peer stopped stepping
-          __nanosleep(40);
-        }
-      }
-      d.gbar[0] = 0;
-      __threadfence(); // release (gpu scope is enough from here: the peers' data sits in this GPU's memory)
-      atomicAdd(d.gbar + 1, 1u);
-    } else {
-      const long long t0 = clock64();
-      while (*gen == g) {
-        if (clock64() - t0 > kPeerWaitCycles + 6000000000ll) { *d.bar_err = 2; break; }
-        __nanosleep(20);
-      }
+    const long long t0 = clock64();
+    while (*gen == g) {
+      if (clock64() - t0 > kPeerWaitCycles + 6000000000ll) { *d.bar_err = 2; break; }
+      __nanosleep(20);
     }
-    __threadfence_system();
+    __threadfence();
   }
   __syncthreads();
 }
@@ -1244,20 +1293,32 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     scan_pass<W>(d, round, warp, nwarps, lane, pings);                   // K1a
     c.v[SWIM_CTR_PINGS] += pings;
     tl_mark(d, round, 1);
-    grid_barrier(d);                                                      // the work list is complete
+    const bool sharded = d.world > 1 && d.p2p;
+    const uint32_t *wl_cnt_r = d.wl_cnt + ci(round);
+    // the work list is complete. Sharded: a rank that listed nothing has no K1b to run, so its cross-GPU handshake of the
+    // round happens right here, inside this barrier (one barrier for a quiet round)
+    if (sharded) grid_barrier_leader(d, false, round, [&] { return *(volatile const uint32_t *)wl_cnt_r == 0; });
+    else grid_barrier(d);
     tl_mark(d, round, 2);
     const uint32_t n_work = d.wl_cnt[ci(round)];
     const uint32_t first_ln = first_work_entry(d, warp);                  // in flight together with the count
     prev_quiet = n_work == 0;
     if (n_work == 0 && d.world == 1) continue;                            // quiescent round: nothing was written
-    if (n_work) work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_ln); // K1b
-    tl_mark(d, round, 3);
-    if (d.world > 1 && d.p2p) grid_peer_barrier(d, round);                // ... on every rank (one thread per GPU polls)
-    else grid_barrier(d);                                                 // every flag and snapshot is written
+    if (n_work) {
+      const bool remote = work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_ln, false); // K1b
+      tl_mark(d, round, 3);
+      // every flag and snapshot is written; sharded: ... on every rank (the last CTA talks to the peers)
+      if (sharded) grid_barrier_leader(d, cta_or(remote), round, [] { return true; });
+      else grid_barrier(d);
+    }
     tl_mark(d, round, 4);
-    // Nothing was delivered (every envelope of the round was dropped at its sender, or nobody sent): K2 has no work and
-    // the barrier just passed already separates K1b's writes from the next scan.
-    if (d.world == 1 && *(volatile uint32_t *)&d.ncand[ci(round)] == 0) continue;
+    // Nothing was delivered (every envelope of the round was dropped at its sender, or nobody sent) and no peer listed a
+    // receiver here: K2 has no work and the barrier just passed already separates K1b's writes from the next scan.
+    uint32_t mail = *(volatile uint32_t *)&d.ncand[ci(round)];
+    if (sharded)
+      for (uint32_t a = 0; a < d.world; ++a)
+        if (a != d.rank) mail |= *(volatile uint32_t *)&d.rcnt[(round & 1) * d.world + a];
+    if (mail == 0) continue;
     recv_pass<W>(d, round, warp, nwarps, lane, pbs, c);                   // K2
     tl_mark(d, round, 5);
     if (it + 1 < d.nrounds) grid_barrier(d);                              // views and buffers settled before the next scan

@@ -49,7 +49,7 @@ struct swim_sim {
   uint64_t launches = 0;
   bool profile = false;
   // launch-path switches, read from the environment once per handle (swim_sim_create), not once per call
-  bool opt_split = false, opt_round_kernel = false, opt_one_round = false;
+  bool opt_split = false, opt_round_kernel = true, opt_one_round = false;
   uint32_t opt_quiet_batch = 4;
   std::vector<cudaEvent_t> prof_events; // pool, reused
   std::vector<std::pair<int, int>> prof_marks; // (phase, index of start event); stop = start + 1

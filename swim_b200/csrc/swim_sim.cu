@@ -162,7 +162,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   if (!sim) return SWIM_ENOMEM;
   sim->cfg = *cfg;
   sim->opt_split = getenv("SWIM_SPLIT") != nullptr;
-  // sharded runs with the fused exchange: one fused kernel per event-free stretch (grid_peer_barrier between K1b and K2)
+  // sharded runs with the fused exchange: one fused kernel per event-free stretch (the last CTA of a grid barrier does the cross-GPU handshake)
   // or the split launch sequence with peer_barrier_kernel; SWIM_ROUND_KERNEL=0|1 overrides the default
   if (const char *rk = getenv("SWIM_ROUND_KERNEL")) sim->opt_round_kernel = atoi(rk) != 0;
   sim->opt_one_round = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
@@ -568,11 +568,9 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   size_t ev_pos = 0;
   // Default: one kernel per round. The split sequence (K1a, K1b, [exchange], K2 as separate launches) serves
   // per-kernel profiling, the staged NCCL exchange and SWIM_SPLIT=1.
-  // Sharded runs use the split sequence + peer_barrier_kernel (the path measured on hardware in round 1: 41-52 us per
-  // round at 2-8 GPUs). SWIM_ROUND_KERNEL=1 selects round_kernel for them too: its K1b/K2 barrier is then
-  // grid_peer_barrier (the last CTA to arrive talks to the peers, ONE thread per GPU — an earlier form in which every
-  // warp polled the peers' flags measured 136 ms/round) and consecutive event-free rounds share one launch. Bit-exact in
-  // the emulated multi-rank runs (tests/test_emu_parity.py); not yet timed on NVLink hardware, hence opt-in.
+  // Sharded runs with the fused exchange: round_kernel too (grid_barrier_leader: the last CTA to arrive at the barrier after
+  // K1b — or at the scan barrier of a round without work — does the cross-GPU handshake, one thread per peer);
+  // SWIM_ROUND_KERNEL=0 selects the split sequence + peer_barrier_kernel instead.
   const bool single_kernel = !sim->profile && !sim->opt_split &&
                              (d.world == 1 || (d.p2p && sim->opt_round_kernel));
   const int kgrid = sim->grids[4];

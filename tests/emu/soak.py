@@ -30,6 +30,10 @@ def one(seed):
     cfg = default_config(n_nodes=n, view_cap=cap, k_indirect=k, fanout=int(rng.integers(1, k + 2)), pb_cap=int(rng.integers(1, 33)),
                          suspicion_rounds=int(rng.integers(1, 14)), retransmit=int(rng.integers(1, 14)),
                          loss_ppm=int(rng.choice([0, 0, 20000, 200000, 600000])), seed=int(rng.integers(0, 2 ** 63)), flags=flags)
+    if rng.random() < 0.4:   # seeded device-side churn
+        cfg.churn_ppm, cfg.rejoin_min, cfg.rejoin_max = int(rng.choice([3000, 30000, 150000])), 1 + int(rng.integers(0, 4)), 5 + int(rng.integers(0, 12))
+    if rng.random() < 0.4 and cfg.suspicion_rounds <= 15:   # Lifeguard-style dynamic suspicion timeout
+        cfg.suspicion_max = int(rng.integers(cfg.suspicion_rounds, 16))
     kind = str(rng.choice(["random", "ring"])) if deg < n - 1 else "complete"
     nbr = generate_topology(kind, n, cap, deg, seed=int(rng.integers(1, 1000)))
     sim, orc = make_pair(cfg, nbr)
@@ -62,10 +66,11 @@ def one_sharded(seed):
     kw = dict(n_nodes=n, k_indirect=k, fanout=int(rng.integers(1, k + 2)), pb_cap=int(rng.integers(1, 17)),
               suspicion_rounds=int(rng.integers(1, 9)), retransmit=int(rng.integers(1, 9)),
               loss_ppm=int(rng.choice([0, 20000, 200000])), seed=int(rng.integers(0, 2 ** 63)), flags=int(rng.integers(0, 4)))
-    if rng.random() < 0.5:
-        os.environ["SWIM_ROUND_KERNEL"] = "1"
-    else:
-        os.environ.pop("SWIM_ROUND_KERNEL", None)
+    os.environ["SWIM_ROUND_KERNEL"] = "1" if rng.random() < 0.6 else "0"
+    if rng.random() < 0.4:
+        kw.update(churn_ppm=int(rng.choice([3000, 30000])), rejoin_min=2, rejoin_max=9)
+    if rng.random() < 0.4:
+        kw.update(suspicion_max=int(rng.integers(kw["suspicion_rounds"], 16)))
     nbr = generate_topology("random" if deg < n - 1 else "complete", n, 32, deg, seed=int(rng.integers(1, 1000)))
     rounds = int(rng.integers(10, 50))
     ev = random_events(rng, n, rounds, n_crash=max(1, n // 8), n_rejoin=max(1, n // 30), n_inject=n // 5)

@@ -165,10 +165,9 @@ from helpers import run_sharded  # noqa: E402
 @pytest.mark.parametrize("path", ["split", "round_kernel"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_fused_exchange_equals_oracle(world, path, monkeypatch):
-    """split: K1a / K1b / peer_barrier_kernel / K2 as separate launches (the default for shards); round_kernel
-    (SWIM_ROUND_KERNEL=1): one launch per event-free stretch, grid_peer_barrier between K1b and K2."""
-    if path == "round_kernel":
-        monkeypatch.setenv("SWIM_ROUND_KERNEL", "1")
+    """round_kernel (the default for shards): one launch per event-free stretch, the last CTA of a grid barrier does the
+    cross-GPU handshake; split (SWIM_ROUND_KERNEL=0): K1a / K1b / peer_barrier_kernel / K2 as separate launches."""
+    monkeypatch.setenv("SWIM_ROUND_KERNEL", "1" if path == "round_kernel" else "0")
     run_sharded(world, n=403, chunks=[1] * 6 + [12], loss=20000, deg=24)
 
 
