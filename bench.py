@@ -497,6 +497,74 @@ def run_cuda(args):
         conv = {"rounds_to_convergence": r0, "checked_every": "8 rounds, every round once fewer than 64 view entries are wrong", "limit": args.converge_limit, "mismatches_at_end": mm0,
                 "crash_round": CRASH_ROUND, "rounds_to_convergence_round_robin": r1, "mismatches_at_end_round_robin": mm1}
 
+    # ------------------------------------------------ second workload: the state machine under load (ring-lattice views)
+    # C3's uniformly random views almost never let a receiver know the member a record is about (32 of 2^20), so its
+    # dissemination path idles. With ring-lattice views (each node knows its 32 nearest ids) records reach nodes that know
+    # the member: every delivered record runs through suspectOrDeadNode' (Core.hs:142-187) and many change state. Same N,
+    # k, fanout, B, S, T, crash set and window; reported beside the headline workload, not instead of it.
+    ring = None
+    if world == 1 and not args.no_ring:
+        from swim_b200.sim import generate_topology
+        nbr_ring = generate_topology("ring", n, 32, 32, seed=3)
+        sim = Simulator(default_config(rank=rank, world=world, device=local, **cfg_kw))
+        sim.set_view(nbr_ring)
+        sim.inject(events)
+        sim.set_stream(stream.cuda_stream)
+        sim.save()
+        wins = []
+        cdelta = None
+        for w in range(args.windows):
+            sim.load()
+            sim.step(args.warmup)
+            c0 = sim.counters()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            ev0.record(stream)
+            sim.step_async(args.steps)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            wins.append(ev0.elapsed_time(ev1))
+            sim.sync()
+            cdelta = sim.counters() - c0
+        sim.load()
+        sim.step(args.warmup)
+        sim.set_timeline(args.steps)
+        sim.step(args.steps)
+        tl_ring = summarize_timeline(sim.timeline(args.steps).astype(np.int64), args.warmup)
+        sim.set_timeline(0)
+        # rounds to convergence, checked every round
+        sim.load()
+        sim.step(CRASH_ROUND)
+        r_conv = None
+        for r in range(CRASH_ROUND + 1, min(args.converge_limit, 400) + 1):
+            sim.step(1)
+            if sim.mismatches() == 0:
+                r_conv = r
+                break
+        # parity of this workload too (the oracle, outside every timed region)
+        ring_parity = None
+        if not args.no_parity:
+            from oracle.oracle import Oracle
+            rounds_chk = min(args.warmup + args.steps, 40)
+            sim.load()
+            sim.step(rounds_chk)
+            orc = Oracle(default_config(**cfg_kw))
+            orc.set_view(nbr_ring)
+            orc.inject(events)
+            orc.step(rounds_chk)
+            ring_parity = "ok" if (sim.digest() == orc.digest() and sim.counters().tolist() == orc.counters().tolist()) else "FAILED"
+            del orc
+        sim.close()
+        ms_r = float(np.median(wins))
+        cd = dict(zip(A.CTR_NAMES, [int(x) for x in cdelta]))
+        ring = {"workload": f"ring-lattice views: node i knows i-16..i+16, N={n}, otherwise C3 (k=3, fanout=4, B=8, S=5, T=8, "
+                            f"{CRASH_PPM / 1e4:.1f}% crash at round {CRASH_ROUND})",
+                "value": n * args.steps / (ms_r * 1e-3), "unit": "node-rounds/s", "ms_per_step": ms_r / args.steps,
+                "windows_ms": [round(x, 5) for x in wins], "rounds_to_convergence": r_conv,
+                "recs_applied_over_recs_sent": cd["recs_applied"] / max(1, cd["recs_sent"]),
+                "msgs_delivered_to_k2_note": "ring views: nearly every envelope passes the recipient's membership filter",
+                "counters_timed_region": cd, "timeline": tl_ring, "parity_check": ring_parity}
+
     # ------------------------------------------------ CPU baseline (rank 0, N=1 only): bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -520,7 +588,7 @@ def run_cuda(args):
                                      "in ONE launch (grid barriers between phases), so the timed region of K rounds is a "
                                      "handful of launches, not 3K",
                 "parity_check": parity["status"] if parity else None, "parity": parity,
-                "roofline": roofline, "cpu_baseline": cpu, "convergence": conv,
+                "roofline": roofline, "cpu_baseline": cpu, "convergence": conv, "state_machine_workload": ring,
                 "counters_timed_region": dict(zip(A.CTR_NAMES, [int(x) for x in ctr_delta]))}
     else:
         line = None
@@ -555,6 +623,7 @@ def main():
     ap.add_argument("--converge-limit", type=int, default=1200)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run parity leg against the oracle")
+    ap.add_argument("--no-ring", action="store_true", help="skip the second (ring-lattice) workload")
     ap.add_argument("--windows", type=int, default=5, help="timed windows of --steps rounds each; the median is reported")
     ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed rounds before the first window (GPU clocks)")
     ap.add_argument("--exchange", default=None, choices=[None, "p2p", "nccl"],

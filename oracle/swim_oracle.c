@@ -80,7 +80,7 @@ EXPORT void oracle_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 /* counter layout: (a, id, purpose, block); key = seed lo, hi. The target draw and the
  * direct-leg loss draw of node i are word (i & 3) of the block with id = i >> 2 (four nodes share a
  * block); proxy draws and indirect-leg loss draws use per-node blocks. */
-enum { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6, P_CHURN = 7 };
+enum { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6, P_CHURN = 7, P_TARGETS = 8, P_LOSSD = 9 };
 
 /* bounded draw: floor(x * L / 2^32) — `randomR (0, L-1)` of Util.hs:40 on our stream */
 static uint32_t bounded(uint32_t x, uint32_t L) { return (uint32_t)(((uint64_t)x * L) >> 32); }
@@ -409,70 +409,95 @@ static void tick_node(oracle_t *o, uint32_t l, uint64_t *ctr) {
 
   tick_timers(o, l, ctr); /* T1 */
 
-  /* T2 kRandomMembers store 1 [] (Core.hs:239, [Q11]) and kRandomMembers store k [] (Core.hs:249) */
+  /* T2 kRandomMembers store P [] (Core.hs:239; P = probes_per_round, [Q11]: 1 by default, the reference's literal
+   * numToGossip otherwise) and, per failed probe, kRandomMembers store k [] (Core.hs:249) */
+  const uint32_t P = o->cfg.probes_per_round, K = o->k;
   uint32_t cand[SWIM_MAX_VIEW], L = 0;
   for (uint32_t s = 0; s < o->cap; ++s)
     if (st[s] == SWIM_ALIVE) cand[L++] = s; /* filter isAlive over Map.elems */
   if (L == 0) return;
-  uint32_t draws[1 + SWIM_MAX_K], grp[4];
+  uint32_t grp[4], tdraw[SWIM_MAX_PROBES], pdraw[SWIM_MAX_PROBES * SWIM_MAX_K + 1];
   draws_for(o, o->round, self >> 2, P_TARGET, 4, grp);
-  draws[0] = grp[self & 3];
-  draws_for(o, o->round, self, P_PROXY, o->k, draws + 1);
-  uint32_t t, prox[SWIM_MAX_K], tmp[SWIM_MAX_VIEW];
+  tdraw[0] = grp[self & 3];                                      /* probe 0: the group stream (four nodes per block) */
+  if (P > 1) draws_for(o, o->round, self, P_TARGETS, P - 1, tdraw + 1); /* probes 1..: a per-node stream */
+  draws_for(o, o->round, self, P_PROXY, P * K, pdraw);           /* probe j's proxies: draws j*k .. j*k + k-1 */
+  uint32_t targets[SWIM_MAX_PROBES], nt = P < L ? P : L, tmp[SWIM_MAX_VIEW];
   if (o->cfg.flags & SWIM_F_ROUND_ROBIN) {
     /* `-- FIXME: move from random to robust scheme` (Core.hs:232), SWIM paper §4.3. Rounds are grouped in epochs of
      * `cap` rounds; within epoch e node i walks its view in the order  slot(p) = p xor b,  p = (round + r) mod cap,
      * (b, r) drawn once per (epoch, node); the target is the first Alive slot at or after p in that order (cyclic).
-     * Every slot position comes up exactly once per epoch, so an Alive member waits < 2 cap rounds for a probe. */
+     * Every slot position comes up exactly once per epoch, so an Alive member waits < 2 cap rounds for a probe.
+     * Further probes of the period take the next Alive slots of the same walk. */
     draws_for(o, o->round / o->cap, self >> 2, P_RR, 4, grp);
     const uint32_t word = grp[self & 3], b = word & (o->cap - 1), r = (word >> 16) & (o->cap - 1);
     const uint32_t p = (o->round + r) & (o->cap - 1);
-    t = SWIM_NO_MEMBER;
-    for (uint32_t x = 0; x < o->cap && t == SWIM_NO_MEMBER; ++x) {
+    uint32_t got = 0;
+    for (uint32_t x = 0; x < o->cap && got < nt; ++x) {
       const uint32_t slot = ((p + x) & (o->cap - 1)) ^ b;
-      if (st[slot] == SWIM_ALIVE) t = slot;
+      if (st[slot] == SWIM_ALIVE) targets[got++] = slot;
     }
   } else {
     memcpy(tmp, cand, L * 4);
-    shuffle_take(tmp, L, 1, draws, &t);
+    shuffle_take(tmp, L, nt, tdraw, targets); /* ONE shuffle, take P (Core.hs:239) */
   }
   memcpy(tmp, cand, L * 4); /* a fresh shuffle: target and self are not excluded (Core.hs:249) */
-  uint32_t np = shuffle_take(tmp, L, o->k, draws + 1, prox);
+  uint32_t prox0[SWIM_MAX_K];
+  const uint32_t np0 = shuffle_take(tmp, L, K, pdraw, prox0); /* probe 0's proxies double as the piggyback recipients (T4) */
 
-  /* T3 probe: Ping (Core.hs:246), unlessAck -> IndirectPings (250), unlessAck -> suspect (253) */
-  uint32_t lossw[1 + SWIM_MAX_K];
+  /* T3 the probes, one after the other (mapM_ probeNode', Core.hs:240): Ping (Core.hs:246), unlessAck -> IndirectPings
+   * (250), unlessAck -> suspect (253). A suspicion raised by an earlier probe of the period is in the store when a later
+   * probe draws its proxies; the incarnations were captured when the targets were chosen (Core.hs:239, 243). */
+  uint32_t lossd[SWIM_MAX_PROBES], lossi[SWIM_MAX_PROBES * SWIM_MAX_K + 1];
   if (o->loss_ppm) {
     draws_for(o, o->round, self >> 2, P_LOSS0, 4, grp);
-    lossw[0] = grp[self & 3];
-    draws_for(o, o->round, self, P_LOSS, o->k, lossw + 1);
+    lossd[0] = grp[self & 3];
+    if (P > 1) draws_for(o, o->round, self, P_LOSSD, P - 1, lossd + 1);
+    draws_for(o, o->round, self, P_LOSS, P * K, lossi);
   }
-#define LOST(leg) (o->loss_ppm && bounded(lossw[leg], 1000000u) < o->loss_ppm)
-  uint32_t tn = ids[t], tinc = inc[t]; /* `m` is captured when the probe starts (Core.hs:243) */
-  ctr[SWIM_CTR_PINGS]++;
-  int acked = o->alive[tn] && !LOST(0);
-  if (!acked) {
-    ctr[SWIM_CTR_DIRECT_FAIL]++;
-    ctr[SWIM_CTR_INDIRECT_PINGS] += np;
-    for (uint32_t j = 0; j < np; ++j)
-      if (o->alive[ids[prox[j]]] && o->alive[tn] && !LOST(1 + j)) acked = 1;
-  }
-#undef LOST
-  if (!acked) {
-    /* suspectNode store $ Suspect (memberIncarnation m) (memberName m) (Core.hs:253) */
-    rec_t sus = {tn, tinc, 0, SWIM_MSG_SUSPECT, 0, 0}, rb;
-    if (apply_record(o, l, sus, 0, 0, &rb, NULL, ctr)) {
-      pb_enqueue(o, l, rb, ctr); /* yield . Broadcast (Core.hs:254) */
-      ctr[SWIM_CTR_SUSPECT_LOCAL]++;
+#define LOST(w) (o->loss_ppm && bounded((w), 1000000u) < o->loss_ppm)
+  uint32_t tn0 = ids[targets[0]], tincs[SWIM_MAX_PROBES];
+  for (uint32_t j = 0; j < nt; ++j) tincs[j] = inc[targets[j]];
+  for (uint32_t j = 0; j < nt; ++j) {
+    const uint32_t t = targets[j], tn = ids[t];
+    ctr[SWIM_CTR_PINGS]++;
+    int acked = o->alive[tn] && !LOST(lossd[j]);
+    if (!acked) {
+      uint32_t prox[SWIM_MAX_K], np;
+      if (j == 0) { np = np0; memcpy(prox, prox0, sizeof prox); }
+      else { /* kRandomMembers on the store as it is now */
+        uint32_t Lc = 0;
+        for (uint32_t s = 0; s < o->cap; ++s)
+          if (st[s] == SWIM_ALIVE) tmp[Lc++] = s;
+        np = shuffle_take(tmp, Lc, K, pdraw + j * K, prox);
+      }
+      ctr[SWIM_CTR_DIRECT_FAIL]++;
+      ctr[SWIM_CTR_INDIRECT_PINGS] += np;
+      for (uint32_t x = 0; x < np; ++x)
+        if (o->alive[ids[prox[x]]] && o->alive[tn] && !LOST(lossi[j * K + x])) acked = 1;
+    }
+    if (!acked) {
+      /* suspectNode store $ Suspect (memberIncarnation m) (memberName m) (Core.hs:253) */
+      rec_t sus = {tn, tincs[j], 0, SWIM_MSG_SUSPECT, 0, 0}, rb;
+      if (apply_record(o, l, sus, 0, 0, &rb, NULL, ctr)) {
+        pb_enqueue(o, l, rb, ctr); /* yield . Broadcast (Core.hs:254) */
+        ctr[SWIM_CTR_SUSPECT_LOCAL]++;
+      }
     }
   }
+#undef LOST
 
   /* T4 [Q5] piggyback: the buffer rides on the messages to the target and the proxies */
   uint32_t cnt = o->pb_cnt[l];
   if (cnt == 0) return;
+  /* recipients: the probe targets in order, then probe 0's proxies that are not targets, the first `fanout` of them */
   uint32_t nr = 0;
-  to[nr++] = tn;
-  for (uint32_t j = 0; j < np && nr < o->fanout; ++j)
-    if (prox[j] != t) to[nr++] = ids[prox[j]];
+  (void)tn0;
+  for (uint32_t j = 0; j < nt && nr < o->fanout; ++j) to[nr++] = ids[targets[j]];
+  for (uint32_t x = 0; x < np0 && nr < o->fanout; ++x) {
+    int is_target = 0;
+    for (uint32_t j = 0; j < nt; ++j) is_target |= prox0[x] == targets[j];
+    if (!is_target) to[nr++] = ids[prox0[x]];
+  }
   rec_t *q = o->pb + (size_t)l * o->B, *snap = o->out + (size_t)l * o->B;
   memcpy(snap, q, cnt * sizeof(rec_t));
   o->out_cnt[l] = (uint8_t)cnt;

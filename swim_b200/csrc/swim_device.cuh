@@ -60,11 +60,12 @@ constexpr long long kPeerWaitCycles = 120000000000ll; // ~60 s at 2 GHz, then th
 
 // Philox counter purposes. TARGET and LOSS0 blocks are shared by the four nodes
 // 4g..4g+3 (counter word 1 = node >> 2, draw = word node & 3): one Philox call serves four probes.
-enum : uint32_t { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6, P_CHURN = 7 };
+enum : uint32_t { P_TARGET = 0, P_LOSS0 = 1, P_SCALAR = 2, P_TOPO = 3, P_PROXY = 4, P_LOSS = 5, P_RR = 6, P_CHURN = 7, P_TARGETS = 8, P_LOSSD = 9 };
 
 struct SimDev {
   uint32_t N, first, n, cap;
   uint32_t k, fanout, B, S, T, loss_ppm;
+  uint32_t P;                // probes per node per round (cfg.probes_per_round; 1 = SWIM)
   uint32_t flags;            // SWIM_F_* protocol variants
   // suspicion countdown in the state byte: liveness | timer << 2 (6 bits); with cfg.suspicion_max (Lifeguard-style dynamic
   // timeout) liveness | timer << 2 (4 bits) | confirmations << 6
@@ -269,6 +270,13 @@ SWIM_HD uint32_t pick_remove(uint32_t (&m)[W], uint32_t r) {
     r -= c;
   }
   return 0; // unreachable when r < total
+}
+
+template <int W>
+SWIM_HD void clear_slot(uint32_t (&m)[W], uint32_t slot) {
+#pragma unroll
+  for (int w = 0; w < W; ++w)
+    if ((uint32_t)w == (slot >> 5)) m[w] &= ~(1u << (slot & 31));
 }
 
 // ---- SWIM_F_ROUND_ROBIN (`-- FIXME: move from random to robust scheme`, Core.hs:232; SWIM paper 4.3) ----------------
@@ -547,6 +555,13 @@ __device__ __forceinline__ bool leg_lost(const SimDev &d, uint32_t round, uint32
   else { y = philox4x32_10(make_uint4(round, self, P_LOSS, (leg - 1) >> 2), d.key0, d.key1); w = (leg - 1) & 3; }
   return bounded(word_of(y, w), 1000000u) < d.loss_ppm;
 }
+// the direct leg of probe j >= 1 of a period (cfg.probes_per_round > 1): a per-node stream
+__device__ __forceinline__ bool direct_leg_lost(const SimDev &d, uint32_t round, uint32_t self, uint32_t j) {
+  if (j == 0) return leg_lost(d, round, self, 0);
+  if (!d.loss_ppm) return false;
+  const uint4 y = philox4x32_10(make_uint4(round, self, P_LOSSD, (j - 1) >> 2), d.key0, d.key1);
+  return bounded(word_of(y, (j - 1) & 3), 1000000u) < d.loss_ppm;
+}
 
 __device__ __forceinline__ void peer_publish_cta(const SimDev &d, uint32_t mail_round); // defined with the cross-GPU sync
 
@@ -577,21 +592,32 @@ __device__ __forceinline__ uint32_t pick_target(const SimDev &d, uint32_t (&am)[
 // whether the node needs K1b. Shared by the scan and by K1b's re-scan of last round's receivers.
 template <int W>
 __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags, uint32_t (&am)[W], const uint32_t (&td)[W],
-                                                uint32_t sus, uint32_t tdraw, uint32_t ldraw, uint32_t round, uint32_t &pings) {
+                                                uint32_t sus, uint32_t tdraw, uint32_t ldraw, uint32_t round, uint32_t &pings,
+                                                uint32_t self) {
   if ((flags & 0xFFu) == 0) return false;              // a crashed process does nothing
   bool need = (flags & 0xFF00u) != 0 || sus != 0;       // piggyback to send, or a countdown to run [Q8]
   uint32_t L = 0, risk = d.loss_ppm;
 #pragma unroll
   for (int w = 0; w < W; ++w) { L += __popc(am[w]); risk |= am[w] & td[w]; }
   if (L) {
-    ++pings;                                                         // Ping (Core.hs:246)
-    // No crashed process among the Alive slots and no message loss: whichever slot the draw selects, the Ack comes
-    // back, so the pick (and, in the scan, the Philox block behind `tdraw`) is not needed — the common case.
+    const uint32_t nt = d.P < L ? d.P : L;
+    pings += nt;                                                     // Ping (Core.hs:246), one per probe of the period
+    // No crashed process among the Alive slots and no message loss: whichever slot a draw selects, the Ack comes
+    // back, so the picks (and, in the scan, the Philox block behind `tdraw`) are not needed — the common case.
     if (risk) {
-      const uint32_t tslot = pick_target<W>(d, am, tdraw, L, round); // kRandomMembers store 1 [] (Core.hs:239)
-      bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;       // Ack iff the target process is up
-      if (acked && d.loss_ppm) acked = !(bounded(ldraw, 1000000u) < d.loss_ppm);
-      need |= !acked;
+      uint4 tb = make_uint4(0, 0, 0, 0);
+      for (uint32_t j = 0; j < nt; ++j) { // kRandomMembers store P [] (Core.hs:239): ONE shuffle, take P
+        uint32_t draw = tdraw; // round-robin order: one walk (one word) for all probes of the period
+        if (j && !(d.flags & SWIM_F_ROUND_ROBIN)) {
+          if (((j - 1) & 3) == 0) tb = philox4x32_10(make_uint4(round, self, P_TARGETS, (j - 1) >> 2), d.key0, d.key1);
+          draw = word_of(tb, (j - 1) & 3);
+        }
+        const uint32_t tslot = pick_target<W>(d, am, draw, L - j, round);
+        clear_slot<W>(am, tslot);                                      // (round-robin order: the walk goes on behind it)
+        bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;       // Ack iff the target process is up
+        if (acked && d.loss_ppm) acked = j ? !direct_leg_lost(d, round, self, j) : !(bounded(ldraw, 1000000u) < d.loss_ppm);
+        need |= !acked;
+      }
     }
   }
   return need;
@@ -649,7 +675,7 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
             am[w] = mw.x; sus |= mw.y; td[w] = mw.z;
           }
         }
-        const bool need = node_needs_work<W>(d, m[u][j].w, am, td, sus, word_of(x, j), word_of(y, j), round, pings);
+        const bool need = node_needs_work<W>(d, m[u][j].w, am, td, sus, word_of(x, j), word_of(y, j), round, pings, 4 * g + j);
         work |= (uint32_t)need << (u * 4 + j);
       }
     }
@@ -733,7 +759,7 @@ __device__ __forceinline__ uint32_t quiet_scan(const SimDev &d, uint32_t round, 
 #pragma unroll
         for (int w = 0; w < W; ++w) risk |= am[w] & td[w];
         if (!risk) { // the draw is never looked at: one decision for the whole batch
-          if (node_needs_work<W>(d, m[u][j].w, am, td, sus, 0, 0, round, pings)) busy = allq;
+          if (node_needs_work<W>(d, m[u][j].w, am, td, sus, 0, 0, round, pings, 4 * g + j)) busy = allq;
           continue;
         }
         uint32_t p = 0;
@@ -743,7 +769,7 @@ __device__ __forceinline__ uint32_t quiet_scan(const SimDev &d, uint32_t round, 
           for (int w = 0; w < W; ++w) amq[w] = am[w];
           const uint4 x = target_block<W>(d, round + q, g);
           p = 0;
-          if (node_needs_work<W>(d, m[u][j].w, amq, td, sus, word_of(x, j), 0, round + q, p)) busy |= 1u << q;
+          if (node_needs_work<W>(d, m[u][j].w, amq, td, sus, word_of(x, j), 0, round + q, p, 4 * g + j)) busy |= 1u << q;
         }
         pings += p;
       }
@@ -804,15 +830,31 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
         if (lane == 0) ++c.v[SWIM_CTR_DEAD_TIMEOUT];
       }
     }
-    uint32_t tslot = 0, np = 0, prox[SWIM_MAX_K];
+    // T2: the period's probe targets — kRandomMembers store P [] (Core.hs:239): ONE shuffle of the alive list, take P
+    // (P = cfg.probes_per_round; 1 = SWIM's single probe [Q11]); draw 0 is the node's TARGET word of the group block,
+    // draws 1.. come from a per-node stream. Probe 0's proxies — kRandomMembers store k [] (Core.hs:249), a fresh shuffle
+    // over the same alive list, neither self nor the target excluded — double as piggyback recipients (T4), so they are
+    // drawn whether or not the probe escalates.
+    uint32_t tslots[SWIM_MAX_PROBES], nt = 0, np = 0, prox[SWIM_MAX_K];
+#pragma unroll
+    for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) tslots[j] = 0;
     if (L) {
-      // target: the node's TARGET draw; proxies: kRandomMembers store k [] (Core.hs:249), a fresh shuffle
-      // over the same alive list (neither self nor the target excluded), draws of the PROXY stream
+      nt = d.P < L ? d.P : L;
       uint4 blk = target_block<W>(d, round, self >> 2);
       uint32_t tmp[W];
 #pragma unroll
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
-      tslot = pick_target<W>(d, tmp, word_of(blk, self & 3), L, round);
+      uint32_t draw = word_of(blk, self & 3);
+#pragma unroll
+      for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
+        if (j >= nt) break;
+        if (j && !(d.flags & SWIM_F_ROUND_ROBIN)) { // (round-robin order: one walk, one word, for all probes of the period)
+          if (((j - 1) & 3) == 0) blk = philox4x32_10(make_uint4(round, self, P_TARGETS, (j - 1) >> 2), d.key0, d.key1);
+          draw = word_of(blk, (j - 1) & 3);
+        }
+        tslots[j] = pick_target<W>(d, tmp, draw, L - j, round);
+        clear_slot<W>(tmp, tslots[j]);
+      }
 #pragma unroll
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
       np = d.k < L ? d.k : L;
@@ -820,31 +862,61 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
         if ((j & 3) == 0) blk = philox4x32_10(make_uint4(round, self, P_PROXY, j >> 2), d.key0, d.key1);
         prox[j] = pick_remove<W>(tmp, bounded(word_of(blk, j & 3), L - j));
       }
-      // T3: Ping (Core.hs:246); unlessAck -> IndirectPings (247-250); unlessAck -> suspectNode (251-254)
-      const bool t_up = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;
-      const bool acked = t_up && !leg_lost(d, round, self, 0);
-      if (!acked) {
-        if (lane == 0) { ++c.v[SWIM_CTR_DIRECT_FAIL]; c.v[SWIM_CTR_INDIRECT_PINGS] += np; }
-        bool ok = false;
-        if ((uint32_t)lane < np && t_up) {
-          const uint32_t ps = prox[lane];
-          ok = (td[ps >> 5] >> (ps & 31) & 1u) == 0 && !leg_lost(d, round, self, 1 + lane);
+      // T3: the probes one after the other (mapM_ probeNode', Core.hs:240) — Ping (Core.hs:246); unlessAck ->
+      // IndirectPings (247-250); unlessAck -> suspectNode (251-254). The incarnations are those of the moment the targets
+      // were chosen; a later probe's proxies are drawn from the store as the earlier probes left it.
+      uint32_t tincs = 0, tnodes = 0; // lane j: incarnation / id of target j as loaded (captured before any suspicion)
+#pragma unroll
+      for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
+        if (j >= nt) break;
+        uint32_t a = 0, b = 0;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          const uint32_t x = __shfl_sync(kFull, row.inc[w], tslots[j] & 31), y = __shfl_sync(kFull, row.nb[w], tslots[j] & 31);
+          if ((uint32_t)w == (tslots[j] >> 5)) { a = x; b = y; }
         }
+        if ((uint32_t)lane == j) { tincs = a; tnodes = b; }
+      }
+      uint32_t cur[W], Lc = L; // the alive list as the probes so far left it
+#pragma unroll
+      for (int w = 0; w < W; ++w) cur[w] = am[w];
+#pragma unroll
+      for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
+        if (j >= nt) break;
+        const uint32_t tslot = tslots[j];
+        const bool t_up = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;
+        const bool acked = t_up && !direct_leg_lost(d, round, self, j);
+        if (acked) continue;
+        uint32_t npj = np;
+        uint32_t ps = (uint32_t)lane < np ? prox[lane] : 0u; // lane x: proxy x of this probe
+        if (j) { // kRandomMembers store k [] on the store as it is now: draws j k .. j k + k - 1 of the PROXY stream
+          uint32_t t2[W];
+#pragma unroll
+          for (int w = 0; w < W; ++w) t2[w] = cur[w];
+          npj = d.k < Lc ? d.k : Lc;
+          ps = 0;
+          for (uint32_t x = 0; x < npj; ++x) {
+            const uint32_t q = j * d.k + x;
+            if (x == 0 || (q & 3) == 0) blk = philox4x32_10(make_uint4(round, self, P_PROXY, q >> 2), d.key0, d.key1);
+            const uint32_t pick = pick_remove<W>(t2, bounded(word_of(blk, q & 3), Lc - x));
+            if ((uint32_t)lane == x) ps = pick;
+          }
+        }
+        if (lane == 0) { ++c.v[SWIM_CTR_DIRECT_FAIL]; c.v[SWIM_CTR_INDIRECT_PINGS] += npj; }
+        bool ok = false;
+        if ((uint32_t)lane < npj && t_up)
+          ok = (td[ps >> 5] >> (ps & 31) & 1u) == 0 && !leg_lost(d, round, self, 1 + j * d.k + lane);
         if (!__any_sync(kFull, ok)) {
           // Suspect (memberIncarnation m) (memberName m) with m captured at probe start
-          const int tw = tslot >> 5, tl = tslot & 31;
-          uint32_t tinc = 0, tnode = 0;
-#pragma unroll
-          for (int w = 0; w < W; ++w) {
-            const uint32_t a = __shfl_sync(kFull, row.inc[w], tl), b = __shfl_sync(kFull, row.nb[w], tl);
-            if (w == tw) { tinc = a; tnode = b; }
-          }
+          const uint32_t tinc = __shfl_sync(kFull, tincs, j), tnode = __shfl_sync(kFull, tnodes, j);
           uint4 rb;
           uint32_t no_self_inc = 0xFFFFFFFFu; // a probe never targets self
           if (row_apply<W>(row, d, self, no_self_inc, make_rec(tnode, tinc, 0, SWIM_MSG_SUSPECT), rb, lane,
                            c.v[SWIM_CTR_REFUTES], false) == 1) {
             pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // yield . Broadcast (Core.hs:254)
             if (lane == 0) ++c.v[SWIM_CTR_SUSPECT_LOCAL];
+            clear_slot<W>(cur, tslot);
+            --Lc;
           }
         }
       }
@@ -853,9 +925,18 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
     // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
     uint2 cand = make_uint2(0xFFFFFFFFu, ln); // lane f < fanout: recipient slot f
     if (L && pbs.cnt) {
-      uint32_t nr = 1, rslot = tslot; // lane f carries recipient f
-      for (uint32_t j = 0; j < np && nr < d.fanout; ++j)
-        if (prox[j] != tslot) { if ((uint32_t)lane == nr) rslot = prox[j]; ++nr; }
+      // recipients: the probe targets in order, then probe 0's proxies that are no targets, the first `fanout` of them;
+      // lane f carries recipient f
+      uint32_t nr = 0, rslot = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j)
+        if (j < nt && nr < d.fanout) { if ((uint32_t)lane == nr) rslot = tslots[j]; ++nr; }
+      for (uint32_t j = 0; j < np && nr < d.fanout; ++j) {
+        bool is_target = false;
+#pragma unroll
+        for (uint32_t t = 0; t < SWIM_MAX_PROBES; ++t) is_target |= t < nt && prox[j] == tslots[t];
+        if (!is_target) { if ((uint32_t)lane == nr) rslot = prox[j]; ++nr; }
+      }
       uint32_t xs = 0xFFFFFFFFu; // exchange-bucket slot when lane f's recipient lives on another shard
       uint32_t dst_c = 0, ridx_c = 0; // recipient id and in-edge index of lane f's slot, from the lanes that hold them
       if (kCarry)

@@ -179,6 +179,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   SimDev &d = sim->dev;
   memset(&d, 0, sizeof d);
   d.N = cfg->n_nodes; d.cap = cfg->view_cap; d.k = cfg->k_indirect; d.fanout = cfg->fanout;
+  d.P = cfg->probes_per_round;
   d.B = cfg->pb_cap; d.S = cfg->suspicion_rounds; d.T = cfg->retransmit; d.loss_ppm = cfg->loss_ppm;
   d.flags = cfg->flags;
   set_suspicion_params(d, cfg);

@@ -32,6 +32,8 @@ def one(seed):
                          loss_ppm=int(rng.choice([0, 0, 20000, 200000, 600000])), seed=int(rng.integers(0, 2 ** 63)), flags=flags)
     if rng.random() < 0.4:   # seeded device-side churn
         cfg.churn_ppm, cfg.rejoin_min, cfg.rejoin_max = int(rng.choice([3000, 30000, 150000])), 1 + int(rng.integers(0, 4)), 5 + int(rng.integers(0, 12))
+    if rng.random() < 0.35:
+        cfg.probes_per_round = int(rng.integers(2, 5))
     if rng.random() < 0.4 and cfg.suspicion_rounds <= 15:   # Lifeguard-style dynamic suspicion timeout
         cfg.suspicion_max = int(rng.integers(cfg.suspicion_rounds, 16))
     kind = str(rng.choice(["random", "ring"])) if deg < n - 1 else "complete"
@@ -71,6 +73,8 @@ def one_sharded(seed):
         kw.update(churn_ppm=int(rng.choice([3000, 30000])), rejoin_min=2, rejoin_max=9)
     if rng.random() < 0.4:
         kw.update(suspicion_max=int(rng.integers(kw["suspicion_rounds"], 16)))
+    if rng.random() < 0.3:
+        kw.update(probes_per_round=int(rng.integers(2, 5)))
     nbr = generate_topology("random" if deg < n - 1 else "complete", n, 32, deg, seed=int(rng.integers(1, 1000)))
     rounds = int(rng.integers(10, 50))
     ev = random_events(rng, n, rounds, n_crash=max(1, n // 8), n_rejoin=max(1, n // 30), n_inject=n // 5)

@@ -401,3 +401,24 @@ def test_dynamic_suspicion_timeout(flags):
     # detection is faster than with a fixed suspicion_max and never faster than suspicion_rounds allows
     c = sim.counters()
     assert c[A.CTR_DEAD_TIMEOUT] > 0
+
+
+@pytest.mark.parametrize("probes,flags,loss", [(2, 0, 0), (4, 0, 40000), (3, A.F_ROUND_ROBIN, 0), (4, A.F_STRICT_OVERRIDE | A.F_ROUND_ROBIN, 30000)])
+def test_probes_per_round(probes, flags, loss):
+    """cfg.probes_per_round = P: the reference's literal `kRandomMembers store numToGossip []` then `mapM_ probeNode'`
+    (Core.hs:239-240) — P targets from ONE shuffle, probed one after the other within the period, each with its
+    own proxy draw on the store as the earlier probes left it."""
+    rng = np.random.default_rng(probes * 10 + flags)
+    n = 300
+    cfg = default_config(n_nodes=n, seed=5 + probes, probes_per_round=probes, suspicion_rounds=3, loss_ppm=loss, flags=flags)
+    nbr = generate_topology("random", n, 32, 12, seed=2)
+    sim, orc = make_pair(cfg, nbr)
+    ev = random_events(rng, n, 40, n_crash=40, n_rejoin=8, n_inject=20)
+    sim.inject(ev)
+    orc.inject(ev)
+    for chunk in [1] * 8 + [4, 9, 19]:
+        sim.step(chunk)
+        orc.step(chunk)
+        assert_same_state(sim, orc, f"P {probes} flags {flags} after {sim.round} rounds")
+    c = sim.counters()
+    assert c[A.CTR_PINGS] > (probes - 0.5) * 0.8 * n * 40 * 0.5 and c[A.CTR_SUSPECT_LOCAL] > 0
