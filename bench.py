@@ -97,10 +97,7 @@ def summarize_timeline(tl, warmup):
         n_busy += 1
         scan.append(t[2] - t[0]); own["scan"].append(t[1] - t[0])
         work.append(t[4] - t[2]); own["work"].append(t[3] - t[2])
-        end = t[6] if t[6] else (t[5] if t[5] else t[4])  # K2 is skipped when nothing was delivered
-        if t[5]:
-            recv.append(end - t[4]); own["recv"].append(t[5] - t[4])
-        busy_total.append(end - t[0])
+        busy_total.append(t[4] - t[0])  # (the receive pass of a round runs inside the next round's scan phase)
         r += 1
     f = lambda v: float(np.mean(v)) / 1e3 if len(v) else None
     return {"busy_rounds": n_busy, "quiet_rounds": n_quiet, "busy_us": f(busy_total), "quiet_us": f(quiet_total),
@@ -108,7 +105,8 @@ def summarize_timeline(tl, warmup):
             "cta0_scan_us": f(own["scan"]), "cta0_work_us": f(own["work"]), "cta0_recv_us": f(own["recv"]),
             "busy_us_max": float(np.max(busy_total)) / 1e3 if busy_total else None,
             "what": "in-kernel %globaltimer stamps of CTA 0 at round_kernel's phase boundaries over the timed rounds; a phase "
-                    "runs from one grid barrier to the next (scan | work = K1b | recv = K2), cta0_* is CTA 0's own part of it"}
+                    "runs from one grid barrier to the next: scan (+ the receive pass of the round before, on otherwise idle "
+                    "warps) | work = K1b; cta0_* is CTA 0's own part of it"}
 
 
 def make_roofline(cfg_kw, n_local, ms_per_round, ab_round, m_bar, b_bar, peak, measured_peak, prof, rounds_p, timeline,
@@ -132,18 +130,19 @@ def make_roofline(cfg_kw, n_local, ms_per_round, ab_round, m_bar, b_bar, peak, m
         calib = json.load(open(cp))
     floor = None
     if calib and timeline and timeline.get("busy_rounds"):
-        # a busy round: 3 grid barriers + the dependent-load chains (K1b: list entry -> row; K2: candidate -> row -> flags ->
-        # [snapshot]), each warp walking its items one after the other
+        # a busy round: 2 grid barriers + the dependent-load chains, each warp walking its items one after the other
         nwarps = calib.get("resident_warps", 4736)
         items_w = max(1.0, msgs / max(1.0, cfg_kw["fanout"] * 0.97) / nwarps)
         items_r = max(1.0, msgs / nwarps)
         hop = calib["hbm_load_ns"] / 1e3
-        floor_busy = 3 * calib["grid_barrier_ns"] / 1e3 + hop * (2 * items_w + 3 * items_r)
+        floor_busy = 2 * calib["grid_barrier_ns"] / 1e3 + hop * (1 + 2 * items_w)
         floor = {"busy_round_us": floor_busy, "measured_busy_round_us": timeline["busy_us"],
                  "frac_of_floor": floor_busy / timeline["busy_us"] if timeline["busy_us"] else None,
                  "grid_barrier_us": calib["grid_barrier_ns"] / 1e3, "hbm_dependent_load_us": hop,
                  "l2_dependent_load_us": calib.get("l2_load_ns", 0) / 1e3,
-                 "model": "3 barriers + hop x (2 x K1b items per warp + 3 x K2 items per warp), mean items of the timed rounds"}
+                 "model": "2 grid barriers + dependent-load hops (1 for the scan's records, 2 per K1b item: list entry -> row "
+                          "-> recipients' filters) x K1b items per warp, mean items of the timed rounds; the receive pass "
+                          "overlaps the scan"}
     return {"bound": "hbm", "kernel": "round_kernel<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if measured_peak else "6650 GB/s (of fallback)",

@@ -367,7 +367,7 @@ int swim_sim_connect(swim_sim_t *sim, const uint8_t id[SWIM_NCCL_ID_BYTES]);
  * swim_sim_set_view: every rank exports a blob (CUDA IPC handles of its mail arrays), the host
  * side all-gathers the blobs in rank order, every rank connects. Without this call (only
  * swim_sim_connect) the staged NCCL all-to-all is used. */
-#define SWIM_IPC_BLOB_BYTES 512
+#define SWIM_IPC_BLOB_BYTES 1024
 int swim_sim_ipc_export(swim_sim_t *sim, uint8_t blob[SWIM_IPC_BLOB_BYTES]);
 int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs /* world x SWIM_IPC_BLOB_BYTES */);
 

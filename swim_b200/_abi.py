@@ -16,7 +16,7 @@ MAX_K, MAX_PB, MAX_TIMER, MAX_VIEW = 7, 32, 63, 256
 ACK_PAYLOAD_MAX = 16
 NAME_MAX = 255
 NCCL_ID_BYTES = 128
-IPC_BLOB_BYTES = 512
+IPC_BLOB_BYTES = 1024
 
 EV_CRASH, EV_REJOIN, EV_INJECT = 0, 1, 2
 F_NONE, F_STRICT_OVERRIDE, F_ROUND_ROBIN = 0, 1, 2  # SWIM_F_*: protocol variants

@@ -103,6 +103,13 @@ struct SimDev {
   uint32_t *wl, *wl_cnt;     // work list of K1b [n]; counters indexed by round % 3
   uint2 *rl;                 // [2][n*fanout] recipient slots (round parity), slot = item*fanout + f:
                              //   .x = local receiver (bit 31 set: sent, but not delivered — see `bloom`), .y = the sender
+  // Mail bitmap (fused kernel only, `fused` != 0): bit l of parity (r & 1) = local node l was delivered mail in round r.
+  // The scan of round r + 1 leaves such nodes alone — their views are being updated by the warps that apply the mail in
+  // the same phase, and those warps take the node's tick decision themselves afterwards.
+  uint32_t *mailbits;        // [2][mbw]
+  uint32_t *mailbits_p[SWIM_MAX_WORLD];
+  uint32_t mbw;              // words per parity = ceil(per / 32), the same on every rank
+  uint32_t fused;            // this launch is round_kernel (senders mark their receivers in the mail bitmap)
   uint2 *cl;                 // [2][n*fanout] the delivered slots of a round, compact (what K2 walks): {receiver, sender}
   uint32_t *ncand;           // [3] (round % 3) length of this round's compact list
   // Static membership filter of every node's view row (all N nodes, replicated on every rank): 512 W bits per node, two
@@ -632,7 +639,7 @@ __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags,
 // work list for K1b.
 template <int W>
 __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps,
-                                          int lane, uint32_t &pings) {
+                                          int lane, uint32_t &pings, const uint32_t *skipbits = nullptr) {
   constexpr int U = kScanGroups;
   uint32_t *wl_cnt = d.wl_cnt + ci(round);
   const uint32_t g0 = d.first >> 2, g1 = (d.first + d.n + 3) >> 2; // Philox groups touching this shard
@@ -648,6 +655,16 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
         valid |= (uint32_t)ok << (u * 4 + j);
         m[u][j] = ok ? d.meta[(size_t)(node - d.first) * W] : make_uint4(0, 0, 0, 0);
       }
+    if (skipbits) { // nodes with mail from last round belong to the warps that apply it (recv_one takes their tick decision)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (valid >> (u * 4 + j) & 1u) {
+            const uint32_t l = 4 * (gb + u * 32 + lane) + j - d.first;
+            if (skipbits[l >> 5] >> (l & 31) & 1u) valid &= ~(1u << (u * 4 + j));
+          }
+    }
     uint32_t work = 0; // bit u*4+j: that node needs K1b
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -982,12 +999,14 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
           // dropped at the sender
         } else if (owner == d.rank) {
           d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
+          if (d.fused) atomicOr(&d.mailbits[(size_t)par * d.mbw + (dl >> 5)], 1u << (dl & 31));
         } else if (d.p2p) {
           // fused exchange: flag and receiver-list entry go straight into the owner GPU's memory over NVLink (plain
           // stores, nothing comes back); the receiver pulls our snapshot
           d.eflag_p[owner][(size_t)par * d.estride_p[owner] + ridx] = 1;
           const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
           d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
+          if (d.fused) atomicOr(&d.mailbits_p[owner][(size_t)par * d.mbw + (dl >> 5)], 1u << (dl & 31));
           did_remote = true;
         } else {
           const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
@@ -1107,9 +1126,12 @@ static __global__ void peer_barrier_kernel(SimDev d) {
 // One receiver of `round`: claim, in-edge flags -> sender snapshots (local or peer-GPU memory) -> row_apply per record,
 // re-broadcast enqueue. Loads that do not depend on each other are issued together: (claim, row, buffer, in-list bounds,
 // the snapshot of the sender the slot names) -> (edge flags, sender ids) -> (other senders' snapshots).
+// tick_round != 0 (fused kernel: the mail of `round` is applied during the scan phase of tick_round = round + 1, and the
+// scan leaves the node alone): after the mail, the node's tick decision of tick_round — what K1a would have computed —
+// is taken here from the fresh row, and the node is appended to that round's work list if it needs K1b.
 template <int W>
 __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32_t ln, bool early, uint32_t snd, int lane,
-                                         PbStage &pbs, Ctr &c) {
+                                         PbStage &pbs, Ctr &c, uint32_t tick_round = 0) {
   const uint32_t par = round & 1;
   const size_t ebase = (size_t)par * d.estride;
   // the claim and every load that depends only on `ln` are issued together (one memory round trip)
@@ -1178,6 +1200,25 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
   row_store<W>(row, d, ln, lane, round);
   pb_store(pbs, d, ln, lane);
   if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
+  if (tick_round) {
+    uint32_t am[W], td[W], sus = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      am[w] = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE);
+      sus |= __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT);
+      td[w] = d.meta[(size_t)ln * W + w].z; // crashed-member bits: events only, not touched by mail
+    }
+    const uint4 x = target_block<W>(d, tick_round, self >> 2);
+    uint4 y = make_uint4(0, 0, 0, 0);
+    if (d.loss_ppm) y = philox4x32_10(make_uint4(tick_round, self >> 2, P_LOSS0, 0), d.key0, d.key1);
+    uint32_t pings = 0;
+    const bool need = node_needs_work<W>(d, 1u | (pbs.cnt << 8), am, td, sus, word_of(x, self & 3), word_of(y, self & 3),
+                                         tick_round, pings, self); // (a receiver is a live process)
+    if (lane == 0) {
+      c.v[SWIM_CTR_PINGS] += pings;
+      if (need) d.wl[atomicAdd(&d.wl_cnt[ci(tick_round)], 1u)] = ln;
+    }
+  }
 }
 
 // warp-per-receiver over the receivers of `round`: the compact list of delivered slots K1b wrote, then one list per
@@ -1185,13 +1226,16 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
 // than once: the claim stamp lets exactly one warp process it.
 template <int W>
 __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps,
-                                          int lane, PbStage &pbs, Ctr &c) {
+                                          int lane, PbStage &pbs, Ctr &c, uint32_t tick_round = 0) {
   const uint32_t par = round & 1;
+  // items go to the warps from the top down: in the fused kernel this pass shares a phase with the scan, whose node ranges
+  // fill the warps from the bottom up (at C3 the last 640 of 4736 warps have no nodes to scan)
+  const uint32_t w0 = nwarps - 1 - warp;
   const uint32_t n_cl = d.ncand[ci(round)];
   const uint2 *cl_in = d.cl + (size_t)par * d.n * d.fanout;
-  for (uint32_t item = warp; item < n_cl; item += nwarps) {
+  for (uint32_t item = w0; item < n_cl; item += nwarps) {
     const uint2 e = cl_in[item];
-    recv_one<W>(d, round, e.x, true, e.y, lane, pbs, c);
+    recv_one<W>(d, round, e.x, true, e.y, lane, pbs, c, tick_round);
   }
   if (d.world > 1) {
     uint32_t seg_end[SWIM_MAX_WORLD + 1];
@@ -1201,11 +1245,11 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, uint3
       if (a != d.rank) n_recv += d.rcnt[par * d.world + a];
       seg_end[1 + a] = n_recv;
     }
-    for (uint32_t item = warp; item < n_recv; item += nwarps) {
+    for (uint32_t item = w0; item < n_recv; item += nwarps) {
       uint32_t a = 0;
       while (item >= seg_end[1 + a]) ++a;
       const uint32_t ln = d.rlr[((size_t)par * d.world + a) * d.rcap + (item - seg_end[a])];
-      recv_one<W>(d, round, ln, false, 0u, lane, pbs, c);
+      recv_one<W>(d, round, ln, false, 0u, lane, pbs, c, tick_round);
     }
   }
 }
@@ -1336,13 +1380,21 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
   barrier_begin(d);
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  // d.nrounds consecutive event-free rounds in this launch (the host splits calls at rounds that carry events)
-  // Batched quiet scans (single shard, no loss): after a round that listed no work, the next up to d.qbatch rounds are
-  // decided by ONE pass over the meta records and ONE barrier (quiet_scan). Its busy mask is OR-ed into qm[batch % 3];
-  // a slot is cleared two batches (>= two barriers) before it is used again, slot 0 here, ahead of the first round's
-  // barrier. While rounds are quiet all three list counters stay zero, so the ordinary path resumes at any round.
+  // d.nrounds consecutive event-free rounds in this launch (the host splits calls at rounds that carry events). Per round:
+  //   phase S  receive(round - 1) by the warps from the top down  ||  scan(round) by the warps from the bottom up
+  //   barrier  (sharded: + cross-GPU handshake, when the round has no work to do)
+  //   phase W  K1b(round): tick work and piggyback send            (skipped when the scan listed nothing)
+  //   barrier  (sharded: + cross-GPU handshake)
+  // The receive phase of a round has no barrier of its own: the few envelopes that survive the senders' membership
+  // filter are applied while the next round's scan runs; the scan leaves their receivers alone (mail bitmap) and the
+  // receiving warp takes their tick decision itself (recv_one). The last round's mail is applied before the launch ends.
+  // Batched quiet scans (single shard, no loss): after a round that listed no work and got no mail, the next up to
+  // d.qbatch rounds are decided by ONE pass over the meta records and ONE barrier (quiet_scan). Its busy mask is OR-ed
+  // into qm[batch % 3]; a slot is cleared two batches (>= two barriers) before it is used again, slot 0 here, ahead of the
+  // first round's barrier. While rounds are quiet all three list counters stay zero, so the ordinary path resumes at any round.
   const bool batching = d.qbatch > 1 && d.world == 1 && d.loss_ppm == 0;
-  bool prev_quiet = false;
+  const bool sharded = d.world > 1 && d.p2p;
+  bool prev_quiet = false, mail = false; // mail: round - 1 delivered envelopes to nodes of this rank
   uint32_t nb = 0;
   if (batching && warp == 0 && lane == 0) d.qm[0] = 0;
   for (uint32_t it = 0; it < d.nrounds; ++it) {
@@ -1370,11 +1422,16 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
       if (fb) { it += fb - 1; continue; }
       // fb == 0: this very round has work — the ordinary scan below lists it
     }
+    // ---- phase S
+    const uint32_t *skip = nullptr;
+    if (mail) {
+      recv_pass<W>(d, round - 1, warp, nwarps, lane, pbs, c, round);     // K2 of the round before + those nodes' tick decision
+      skip = d.mailbits + (size_t)((round - 1) & 1) * d.mbw;
+    }
     uint32_t pings = 0;
-    scan_pass<W>(d, round, warp, nwarps, lane, pings);                   // K1a
+    scan_pass<W>(d, round, warp, nwarps, lane, pings, skip);              // K1a
     c.v[SWIM_CTR_PINGS] += pings;
     tl_mark(d, round, 1);
-    const bool sharded = d.world > 1 && d.p2p;
     const uint32_t *wl_cnt_r = d.wl_cnt + ci(round);
     // the work list is complete. Sharded: a rank that listed nothing has no K1b to run, so its cross-GPU handshake of the
     // round happens right here, inside this barrier (one barrier for a quiet round)
@@ -1383,27 +1440,36 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     tl_mark(d, round, 2);
     const uint32_t n_work = d.wl_cnt[ci(round)];
     const uint32_t first_ln = first_work_entry(d, warp);                  // in flight together with the count
-    prev_quiet = n_work == 0;
-    if (n_work == 0 && d.world == 1) continue;                            // quiescent round: nothing was written
+    if (mail) { // last round's mail bitmap has been read by every scanner: clear it for the senders of round + 1
+      uint32_t *mb = d.mailbits + (size_t)((round - 1) & 1) * d.mbw;
+      for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) mb[x] = 0;
+    }
+    prev_quiet = n_work == 0 && !mail;
+    // ---- phase W
     if (n_work) {
       const bool remote = work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_ln, false); // K1b
       tl_mark(d, round, 3);
       // every flag and snapshot is written; sharded: ... on every rank (the last CTA talks to the peers)
       if (sharded) grid_barrier_leader(d, cta_or(remote), round, [] { return true; });
       else grid_barrier(d);
+      tl_mark(d, round, 4);
     }
-    tl_mark(d, round, 4);
-    // Nothing was delivered (every envelope of the round was dropped at its sender, or nobody sent) and no peer listed a
-    // receiver here: K2 has no work and the barrier just passed already separates K1b's writes from the next scan.
-    uint32_t mail = *(volatile uint32_t *)&d.ncand[ci(round)];
+    // (no barrier is owed to the bitmap clear: that parity is written again by the senders of round + 1 and read again by
+    // the scan of round + 2 — both behind the next round's scan barrier)
+    // Was anything delivered here in this round? (every envelope dropped at its sender, or nobody sent: no)
+    uint32_t got = n_work ? *(volatile uint32_t *)&d.ncand[ci(round)] : 0u;
     if (sharded)
       for (uint32_t a = 0; a < d.world; ++a)
-        if (a != d.rank) mail |= *(volatile uint32_t *)&d.rcnt[(round & 1) * d.world + a];
-    if (mail == 0) continue;
-    recv_pass<W>(d, round, warp, nwarps, lane, pbs, c);                   // K2
-    tl_mark(d, round, 5);
-    if (it + 1 < d.nrounds) grid_barrier(d);                              // views and buffers settled before the next scan
-    tl_mark(d, round, 6);
+        if (a != d.rank) got |= *(volatile uint32_t *)&d.rcnt[(round & 1) * d.world + a];
+    mail = got != 0;
+    if (mail) prev_quiet = false;
+  }
+  if (mail) { // the last round's mail, before the launch ends (no tick decision: the next launch scans everybody)
+    recv_pass<W>(d, d.round + d.nrounds - 1, warp, nwarps, lane, pbs, c, 0);
+    tl_mark(d, d.round + d.nrounds - 1, 5);
+    // its bitmap is not needed by anybody: clear it. (The receive pass does not read it, so no barrier in between.)
+    uint32_t *mb = d.mailbits + (size_t)((d.round + d.nrounds - 1) & 1) * d.mbw;
+    for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) mb[x] = 0;
   }
   c.flush(d.ctr, lane);
 }

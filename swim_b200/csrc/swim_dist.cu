@@ -161,12 +161,12 @@ extern "C" int swim_sim_connect(swim_sim_t *sim, const uint8_t *id) {
 namespace {
 struct IpcBlob {
   uint32_t magic, rank, n, estride;
-  cudaIpcMemHandle_t h[6]; // eflag, out, out_cnt, rlr, rcnt, bar
+  cudaIpcMemHandle_t h[7]; // eflag, out, out_cnt, rlr, rcnt, bar, mailbits
   // the exporting process and its raw device pointers: ranks that live in ONE process (several handles, on one device or
   // on peer devices) cannot open each other's IPC handles — they use the pointers as they are
   uint64_t pid;
   int32_t device, _pad;
-  uint64_t raw[6];
+  uint64_t raw[7];
 };
 static_assert(sizeof(IpcBlob) <= SWIM_IPC_BLOB_BYTES, "blob too small");
 constexpr uint32_t kBlobMagic = 0x53574D49u; // "SWMI"
@@ -180,8 +180,8 @@ extern "C" int swim_sim_ipc_export(swim_sim_t *sim, uint8_t *blob) {
   IpcBlob b;
   memset(&b, 0, sizeof b);
   b.magic = kBlobMagic; b.rank = d.rank; b.n = d.n; b.estride = d.estride;
-  void *ptrs[6] = {d.eflag, d.out, d.out_cnt, d.rlr, d.rcnt, sim->d_bar};
-  for (int x = 0; x < 6; ++x) {
+  void *ptrs[7] = {d.eflag, d.out, d.out_cnt, d.rlr, d.rcnt, sim->d_bar, d.mailbits};
+  for (int x = 0; x < 7; ++x) {
     CUDA_TRY(sim, cudaIpcGetMemHandle(&b.h[x], ptrs[x]));
     b.raw[x] = (uint64_t)(uintptr_t)ptrs[x];
   }
@@ -203,16 +203,16 @@ extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
     memcpy(&b, blobs + (size_t)r * SWIM_IPC_BLOB_BYTES, sizeof b);
     if (b.magic != kBlobMagic || b.rank != r) { set_error(sim, "swim_sim_ipc_connect: blob %u is not rank %u's export", r, r); return SWIM_EINVAL; }
     if (r == d.rank) continue;
-    void *p[6];
+    void *p[7];
     if (b.pid == (uint64_t)getpid()) { // a rank of this very process: its pointers are valid here as they are
       if (b.device != sim->device) {
         cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error(sim, "swim_sim_ipc_connect: no peer access to device %d: %s", b.device, cudaGetErrorString(e)); return SWIM_ECUDA; }
         cudaGetLastError();
       }
-      for (int x = 0; x < 6; ++x) p[x] = (void *)(uintptr_t)b.raw[x];
+      for (int x = 0; x < 7; ++x) p[x] = (void *)(uintptr_t)b.raw[x];
     } else {
-      for (int x = 0; x < 6; ++x) {
+      for (int x = 0; x < 7; ++x) {
         CUDA_TRY(sim, cudaIpcOpenMemHandle(&p[x], b.h[x], cudaIpcMemLazyEnablePeerAccess));
         sim->ipc_opened.push_back(p[x]);
       }
@@ -220,6 +220,7 @@ extern "C" int swim_sim_ipc_connect(swim_sim_t *sim, const uint8_t *blobs) {
     d.eflag_p[r] = (uint8_t *)p[0]; d.estride_p[r] = b.estride;
     d.out_p[r] = (const uint4 *)p[1]; d.out_cnt_p[r] = (const uint8_t *)p[2];
     d.rlr_p[r] = (uint32_t *)p[3]; d.rcnt_p[r] = (uint32_t *)p[4]; d.bar_p[r] = (uint32_t *)p[5];
+    d.mailbits_p[r] = (uint32_t *)p[6];
   }
   d.p2p = 1;
   sim->connected = true;
@@ -232,7 +233,7 @@ void refresh_peer_tables(swim_sim *sim) { // entry [rank] always aliases this ra
   SimDev &d = sim->dev;
   const uint32_t r = d.rank;
   d.eflag_p[r] = d.eflag; d.estride_p[r] = d.estride; d.out_p[r] = d.out; d.out_cnt_p[r] = d.out_cnt;
-  d.rlr_p[r] = d.rlr; d.rcnt_p[r] = d.rcnt; d.bar_p[r] = sim->d_bar;
+  d.rlr_p[r] = d.rlr; d.rcnt_p[r] = d.rcnt; d.bar_p[r] = sim->d_bar; d.mailbits_p[r] = d.mailbits;
 }
 
 int dist_alloc_edges(swim_sim *sim) { // eslot follows the in-edge count
