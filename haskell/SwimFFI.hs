@@ -16,7 +16,7 @@ module SwimFFI
   , suspectNode, deadNode, aliveNode, handleMessage, broadcast
   , msgPing, msgIndirectPing, msgAck, msgSuspect, msgAlive, msgDead
     -- raw imports of the bulk / codec / replay entry points (marshalled by the caller)
-  , c_simSetRound, c_simInject, c_simGetArray, c_simSetArray, c_simCounters, c_simObserve, c_simExportRound
+  , c_simSetRound, c_simSave, c_simLoad, c_simSetParams, c_simInject, c_simGetArray, c_simSetArray, c_simCounters, c_simObserve, c_simExportRound
   , c_simInjectDatagram, c_getBroadcasts, c_takeBroadcasts, c_tickTimers, c_envEncode, c_envDecode, simCounters
   ) where
 
@@ -110,6 +110,9 @@ foreign import ccall unsafe "swim_last_error"        c_lastError     :: Sim -> I
 foreign import ccall safe   "swim_sim_set_view"      c_simSetView    :: Sim -> Ptr Word32 -> IO CInt
 foreign import ccall safe   "swim_sim_step"          c_simStep       :: Sim -> Word32 -> IO CInt
 foreign import ccall safe   "swim_sim_set_round"     c_simSetRound   :: Sim -> Word32 -> IO CInt
+foreign import ccall safe   "swim_sim_save"          c_simSave       :: Sim -> IO CInt
+foreign import ccall safe   "swim_sim_load"          c_simLoad       :: Sim -> IO CInt
+foreign import ccall safe   "swim_sim_set_params"    c_simSetParams  :: Sim -> Ptr CConfig -> IO CInt
 foreign import ccall safe   "swim_sim_digest"        c_simDigest     :: Sim -> Ptr Word64 -> IO CInt
 foreign import ccall safe   "swim_sim_mismatches"    c_simMismatches :: Sim -> Ptr Word64 -> IO CInt
 foreign import ccall safe   "swim_get_members"       c_getMembers    :: Sim -> Word32 -> Ptr CMember -> CSize -> Ptr CSize -> IO CInt

@@ -597,6 +597,32 @@ __device__ __forceinline__ uint32_t pick_target(const SimDev &d, uint32_t (&am)[
 
 // One node's tick decision from its meta words (what K1a does per node): counts the Ping and tells
 // whether the node needs K1b. Shared by the scan and by K1b's re-scan of last round's receivers.
+// The period's direct probes of one node (kRandomMembers store P [] — ONE shuffle, take P, Core.hs:239 — each target
+// pinged once): true if some target's Ack will not come back (the target process is down, or the leg is lost), i.e. the
+// node must go through K1b. `am` is consumed; L = popc(am) > 0.
+template <int W>
+__device__ __forceinline__ bool probe_fails(const SimDev &d, uint32_t (&am)[W], const uint32_t (&td)[W], uint32_t L,
+                                            uint32_t tdraw, uint32_t ldraw, uint32_t round, uint32_t self) {
+  const uint32_t nt = d.P < L ? d.P : L;
+  bool fails = false;
+  uint4 tb = make_uint4(0, 0, 0, 0);
+  for (uint32_t j = 0; j < nt; ++j) {
+    uint32_t draw = tdraw; // round-robin order: one walk (one word) for all probes of the period
+    if (j && !(d.flags & SWIM_F_ROUND_ROBIN)) {
+      if (((j - 1) & 3) == 0) tb = philox4x32_10(make_uint4(round, self, P_TARGETS, (j - 1) >> 2), d.key0, d.key1);
+      draw = word_of(tb, (j - 1) & 3);
+    }
+    const uint32_t tslot = pick_target<W>(d, am, draw, L - j, round);
+    clear_slot<W>(am, tslot);                                      // (round-robin order: the walk goes on behind it)
+    bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;       // Ack iff the target process is up
+    if (acked && d.loss_ppm) acked = j ? !direct_leg_lost(d, round, self, j) : !(bounded(ldraw, 1000000u) < d.loss_ppm);
+    fails |= !acked;
+  }
+  return fails;
+}
+
+// One node's tick decision from its meta words (what K1a does per node): counts the Pings and tells
+// whether the node needs K1b. Shared by the scan (wide rows), the batched quiet scan and the receive pass.
 template <int W>
 __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags, uint32_t (&am)[W], const uint32_t (&td)[W],
                                                 uint32_t sus, uint32_t tdraw, uint32_t ldraw, uint32_t round, uint32_t &pings,
@@ -607,25 +633,10 @@ __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags,
 #pragma unroll
   for (int w = 0; w < W; ++w) { L += __popc(am[w]); risk |= am[w] & td[w]; }
   if (L) {
-    const uint32_t nt = d.P < L ? d.P : L;
-    pings += nt;                                                     // Ping (Core.hs:246), one per probe of the period
+    pings += d.P < L ? d.P : L;                                      // Ping (Core.hs:246), one per probe of the period
     // No crashed process among the Alive slots and no message loss: whichever slot a draw selects, the Ack comes
     // back, so the picks (and, in the scan, the Philox block behind `tdraw`) are not needed — the common case.
-    if (risk) {
-      uint4 tb = make_uint4(0, 0, 0, 0);
-      for (uint32_t j = 0; j < nt; ++j) { // kRandomMembers store P [] (Core.hs:239): ONE shuffle, take P
-        uint32_t draw = tdraw; // round-robin order: one walk (one word) for all probes of the period
-        if (j && !(d.flags & SWIM_F_ROUND_ROBIN)) {
-          if (((j - 1) & 3) == 0) tb = philox4x32_10(make_uint4(round, self, P_TARGETS, (j - 1) >> 2), d.key0, d.key1);
-          draw = word_of(tb, (j - 1) & 3);
-        }
-        const uint32_t tslot = pick_target<W>(d, am, draw, L - j, round);
-        clear_slot<W>(am, tslot);                                      // (round-robin order: the walk goes on behind it)
-        bool acked = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;       // Ack iff the target process is up
-        if (acked && d.loss_ppm) acked = j ? !direct_leg_lost(d, round, self, j) : !(bounded(ldraw, 1000000u) < d.loss_ppm);
-        need |= !acked;
-      }
-    }
+    if (risk) need |= probe_fails<W>(d, am, td, L, tdraw, ldraw, round, self);
   }
   return need;
 }
@@ -666,17 +677,46 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
           }
     }
     uint32_t work = 0; // bit u*4+j: that node needs K1b
+    if constexpr (W == 1) {
+      // Pass 1, every node: what the record alone decides (buffer to send, countdown to run, the Ping count). Only a node
+      // with a crashed process in an Alive slot (or any node, under message loss) depends on its draws: those are set
+      // aside per lane ...
+      uint32_t risky = 0;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int q = u * 4 + j;
+          const uint4 mr = m[u][j];
+          if (!(valid >> q & 1u) || (mr.w & 0xFFu) == 0) continue; // out of range, left to the receive pass, or crashed
+          const uint32_t L = __popc(mr.x);
+          if ((mr.w & 0xFF00u) != 0 || mr.y != 0) work |= 1u << q;
+          if (L) {
+            pings += d.P < L ? d.P : L;
+            if ((mr.x & mr.z) | d.loss_ppm) risky |= 1u << q;
+          }
+        }
+      // ... and pass 2 takes them one per lane and trip (Philox block, r-th-set-bit picks): a lane pays for its own risky
+      // nodes only, not — by divergence — for every risky node of the warp.
+      while (risky) {
+        const int q = __ffs(risky) - 1;
+        risky &= risky - 1;
+        uint32_t am1[1] = {0}, td1[1] = {0};
+#pragma unroll
+        for (int qq = 0; qq < 4 * U; ++qq)
+          if (q == qq) { am1[0] = m[qq >> 2][qq & 3].x; td1[0] = m[qq >> 2][qq & 3].z; }
+        const uint32_t g = gb + (q >> 2) * 32 + lane, self = 4 * g + (q & 3);
+        const uint4 x = target_block<W>(d, round, g);
+        uint32_t ldraw = 0;
+        if (d.loss_ppm) ldraw = word_of(philox4x32_10(make_uint4(round, g, P_LOSS0, 0), d.key0, d.key1), q & 3);
+        if (probe_fails<W>(d, am1, td1, (uint32_t)__popc(am1[0]), word_of(x, q & 3), ldraw, round, self)) work |= 1u << q;
+      }
+    } else {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const uint32_t g = gb + u * 32 + lane;
       if ((valid >> (u * 4) & 0xFu) == 0) continue;
-      // the four target draws are only looked at by nodes whose probe can fail (node_needs_work: `risk`)
-      bool draws = W > 1 || d.loss_ppm != 0;
-      if (W == 1)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) draws |= (m[u][j].x & m[u][j].z) != 0; // an Alive slot whose process is down
-      uint4 x = make_uint4(0, 0, 0, 0);
-      if (draws) x = target_block<W>(d, round, g);
+      uint4 x = target_block<W>(d, round, g);
       uint4 y = make_uint4(0, 0, 0, 0);
       if (d.loss_ppm) y = philox4x32_10(make_uint4(round, g, P_LOSS0, 0), d.key0, d.key1);
 #pragma unroll
@@ -684,17 +724,16 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
         if (!(valid >> (u * 4 + j) & 1u)) continue;
         uint32_t am[W], td[W], sus = m[u][j].y;
         am[0] = m[u][j].x; td[0] = m[u][j].z;
-        if (W > 1) {
-          const uint32_t l = 4 * g + j - d.first;
+        const uint32_t l = 4 * g + j - d.first;
 #pragma unroll
-          for (int w = 1; w < W; ++w) {
-            const uint4 mw = d.meta[(size_t)l * W + w];
-            am[w] = mw.x; sus |= mw.y; td[w] = mw.z;
-          }
+        for (int w = 1; w < W; ++w) {
+          const uint4 mw = d.meta[(size_t)l * W + w];
+          am[w] = mw.x; sus |= mw.y; td[w] = mw.z;
         }
         const bool need = node_needs_work<W>(d, m[u][j].w, am, td, sus, word_of(x, j), word_of(y, j), round, pings, 4 * g + j);
         work |= (uint32_t)need << (u * 4 + j);
       }
+    }
     }
     // warp-aggregated append of up to 4*U x 32 nodes
     if (__any_sync(kFull, work != 0)) {
@@ -976,20 +1015,14 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
         if (r_up) {
           constexpr uint32_t kBits = 512u * W;
           const uint32_t *bf = d.bloom + (size_t)dst * (kBits / 32);
-          uint32_t w0[SWIM_MAX_PB / 4], w1[SWIM_MAX_PB / 4]; // the two filter words of up to 8 records at a time
-          for (uint32_t q0 = 0; q0 < pbs.cnt; q0 += SWIM_MAX_PB / 4) {
-#pragma unroll
-            for (uint32_t q = 0; q < SWIM_MAX_PB / 4; ++q) {
-              const uint32_t x = q0 + q < pbs.cnt ? pbs.s[q0 + q].x : dst;
-              w0[q] = bf[bloom_pos(x, 0, kBits) >> 5];
-              w1[q] = bf[bloom_pos(x, 1, kBits) >> 5];
-            }
-#pragma unroll
-            for (uint32_t q = 0; q < SWIM_MAX_PB / 4; ++q) {
-              if (q0 + q >= pbs.cnt) continue;
-              const uint32_t x = pbs.s[q0 + q].x;
-              deliver |= x == dst || ((w0[q] >> (bloom_pos(x, 0, kBits) & 31) & 1u) && (w1[q] >> (bloom_pos(x, 1, kBits) & 31) & 1u));
-            }
+          // two records per trip: their four filter words are in flight together (most envelopes carry one record)
+          for (uint32_t q0 = 0; q0 < pbs.cnt && !deliver; q0 += 2) {
+            const uint32_t xa = pbs.s[q0].x, xb = q0 + 1 < pbs.cnt ? pbs.s[q0 + 1].x : xa;
+            const uint32_t pa0 = bloom_pos(xa, 0, kBits), pa1 = bloom_pos(xa, 1, kBits);
+            const uint32_t pb0 = bloom_pos(xb, 0, kBits), pb1 = bloom_pos(xb, 1, kBits);
+            const uint32_t wa0 = bf[pa0 >> 5], wa1 = bf[pa1 >> 5], wb0 = bf[pb0 >> 5], wb1 = bf[pb1 >> 5];
+            deliver = xa == dst || xb == dst || ((wa0 >> (pa0 & 31) & 1u) && (wa1 >> (pa1 & 31) & 1u)) ||
+                      ((wb0 >> (pb0 & 31) & 1u) && (wb1 >> (pb1 & 31) & 1u));
           }
         }
         const uint32_t owner = d.world == 1 ? 0u : dst / d.per;
