@@ -422,3 +422,32 @@ def test_probes_per_round(probes, flags, loss):
         assert_same_state(sim, orc, f"P {probes} flags {flags} after {sim.round} rounds")
     c = sim.counters()
     assert c[A.CTR_PINGS] > (probes - 0.5) * 0.8 * n * 40 * 0.5 and c[A.CTR_SUSPECT_LOCAL] > 0
+
+
+def test_parameter_sweep_on_one_handle():
+    """The C5 study's flow: ONE handle, swim_sim_save at round 0, then per sweep point swim_sim_load +
+    swim_sim_set_params (suspicion timeout, Lifeguard start value, churn rate) — each point equals a fresh oracle run with
+    that configuration; fields that size the handle are refused."""
+    from oracle.oracle import Oracle
+    from swim_b200._lib import SwimError
+    from swim_b200.study import run_sweep_point
+    n = 500
+    base = dict(n_nodes=n, seed=404, churn_ppm=8000, rejoin_min=3, rejoin_max=11)
+    nbr = generate_topology("ring", n, 32, 16, seed=2)
+    from swim_b200.sim import Simulator
+    sim = Simulator(default_config(suspicion_rounds=2, **base))
+    sim.set_view(nbr)
+    sim.save()
+    for S, smax, ppm in ((2, 0, 8000), (5, 0, 8000), (3, 11, 8000), (4, 0, 30000)):
+        sim.load()
+        sim.set_params(suspicion_rounds=S, suspicion_max=smax, churn_ppm=ppm)
+        orc = Oracle(default_config(suspicion_rounds=S, suspicion_max=smax, **{**base, "churn_ppm": ppm}))
+        orc.set_view(nbr)
+        res = run_sweep_point(sim, None, 40, sample_every=20)
+        orc.step(40)
+        assert_same_state(sim, orc, f"S {S} max {smax} ppm {ppm}")
+        assert res["mismatch_series"][-1][1] == orc.mismatches()
+    with pytest.raises(SwimError):
+        sim.set_params(pb_cap=4)
+    with pytest.raises(SwimError):
+        sim.set_params(suspicion_rounds=7, suspicion_max=3)
