@@ -103,10 +103,13 @@ struct SimDev {
   uint32_t *wl, *wl_cnt;     // work list of K1b [n]; counters indexed by round % 3
   uint2 *rl;                 // [2][n*fanout] recipient slots (round parity), slot = item*fanout + f:
                              //   .x = local receiver (bit 31 set: sent, but not delivered — see `bloom`), .y = the sender
-  // Mail bitmap (fused kernel only, `fused` != 0): bit l of parity (r & 1) = local node l was delivered mail in round r.
+  // Mail bitmap (fused kernel only, `fused` != 0): bit l of slot (r % 3) = local node l was delivered mail in round r.
   // The scan of round r + 1 leaves such nodes alone — their views are being updated by the warps that apply the mail in
-  // the same phase, and those warps take the node's tick decision themselves afterwards.
-  uint32_t *mailbits;        // [2][mbw]
+  // the same phase, and those warps take the node's tick decision themselves afterwards. THREE slots, not two: slot r % 3
+  // is cleared after the scan barrier of round r + 1, and that barrier may already contain the cross-GPU handshake of
+  // round r + 1 (a rank without work), after which a peer is free to mark receivers of round r + 2 — in slot (r + 2) % 3,
+  // never in the one being cleared. (With two slots a 2-GPU parity test lost marks exactly this way.)
+  uint32_t *mailbits;        // [3][mbw]
   uint32_t *mailbits_p[SWIM_MAX_WORLD];
   uint32_t mbw;              // words per parity = ceil(per / 32), the same on every rank
   uint32_t fused;            // this launch is round_kernel (senders mark their receivers in the mail bitmap)
@@ -1074,14 +1077,14 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
           // dropped at the sender
         } else if (owner == d.rank) {
           d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
-          if (d.fused) atomicOr(&d.mailbits[(size_t)par * d.mbw + (dl >> 5)], 1u << (dl & 31));
+          if (d.fused) atomicOr(&d.mailbits[(size_t)(round % 3u) * d.mbw + (dl >> 5)], 1u << (dl & 31));
         } else if (d.p2p) {
           // fused exchange: flag and receiver-list entry go straight into the owner GPU's memory over NVLink (plain
           // stores, nothing comes back); the receiver pulls our snapshot
           d.eflag_p[owner][(size_t)par * d.estride_p[owner] + ridx] = 1;
           const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
           d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
-          if (d.fused) atomicOr(&d.mailbits_p[owner][(size_t)par * d.mbw + (dl >> 5)], 1u << (dl & 31));
+          if (d.fused) atomicOr(&d.mailbits_p[owner][(size_t)(round % 3u) * d.mbw + (dl >> 5)], 1u << (dl & 31));
           did_remote = true;
         } else {
           const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
@@ -1501,7 +1504,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     const uint32_t *skip = nullptr;
     if (mail) {
       recv_pass<W>(d, round - 1, warp, nwarps, lane, pbs, c, round);     // K2 of the round before + those nodes' tick decision
-      skip = d.mailbits + (size_t)((round - 1) & 1) * d.mbw;
+      skip = d.mailbits + (size_t)((round - 1) % 3u) * d.mbw;
     }
     uint32_t pings = 0;
     scan_pass<W>(d, round, warp, nwarps, lane, pings, skip);              // K1a
@@ -1515,8 +1518,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     tl_mark(d, round, 2);
     const uint32_t n_work = d.wl_cnt[ci(round)];
     const uint32_t first_ln = first_work_entry(d, warp);                  // in flight together with the count
-    if (mail) { // last round's mail bitmap has been read by every scanner: clear it for the senders of round + 1
-      uint32_t *mb = d.mailbits + (size_t)((round - 1) & 1) * d.mbw;
+    if (mail) { // last round's mail bitmap has been read by every scanner: clear it (its next writers: senders of round + 2)
+      uint32_t *mb = d.mailbits + (size_t)((round - 1) % 3u) * d.mbw;
       for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) mb[x] = 0;
     }
     prev_quiet = n_work == 0 && !mail;
@@ -1529,8 +1532,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
       else grid_barrier(d);
       tl_mark(d, round, 4);
     }
-    // (no barrier is owed to the bitmap clear: that parity is written again by the senders of round + 1 and read again by
-    // the scan of round + 2 — both behind the next round's scan barrier)
+    // (no barrier is owed to the bitmap clear: that slot is written again by the senders of round + 2 and read again by
+    // the scan of round + 3 — both behind the next round's barriers, on this rank and, through the handshake, on its peers)
     // Was anything delivered here in this round? (every envelope dropped at its sender, or nobody sent: no)
     uint32_t got = n_work ? *(volatile uint32_t *)&d.ncand[ci(round)] : 0u;
     if (sharded)
@@ -1543,7 +1546,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     recv_pass<W>(d, d.round + d.nrounds - 1, warp, nwarps, lane, pbs, c, 0);
     tl_mark(d, d.round + d.nrounds - 1, 5);
     // its bitmap is not needed by anybody: clear it. (The receive pass does not read it, so no barrier in between.)
-    uint32_t *mb = d.mailbits + (size_t)((d.round + d.nrounds - 1) & 1) * d.mbw;
+    uint32_t *mb = d.mailbits + (size_t)((d.round + d.nrounds - 1) % 3u) * d.mbw;
     for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) mb[x] = 0;
   }
   c.flush(d.ctr, lane);
