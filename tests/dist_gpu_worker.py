@@ -36,9 +36,10 @@ def main():
     gathered = [None] * world
     dist.all_gather_object(gathered, arrays)
     if rank == 0:
+        REPLICATED = {A.ARRAY_NAMES[a] for a in A.REPLICATED_ARRAYS}  # [N] on every rank
         full = {}
         for name in arrays:
-            full[name] = gathered[0][name] if name in ("alive", "back_at") else np.concatenate([g[name] for g in gathered])
+            full[name] = gathered[0][name] if name in REPLICATED else np.concatenate([g[name] for g in gathered])
         np.savez(out_path, digests=np.array(digests, dtype=np.uint64), counters=counters, mismatches=mism, **full)
     dist.barrier()
     sim.close()
