@@ -429,12 +429,13 @@ def run_cuda(args):
             if arr is not None:
                 sim.inject(arr)  # host buffer -> library (pinned staging) -> device, uploaded by the step below
                 h2d += arr.nbytes
-            sim.step_async(1)
-            # the round's result as a convergence study reads it: counters + convergence count, one read-back and ONE
-            # synchronisation (the state digest is a parity tool: 370 MB of reads per call, not part of the metric)
-            c, dg, mm = sim.observe(digest=False)
-            d2h += c.nbytes + 8
-            return c, dg, mm
+            # one round, and its result as a convergence study reads it — the cumulative counters and the convergence
+            # count — in ONE C-ABI call (swim_sim_step_observe): the device writes them into mapped pinned host memory
+            # behind the round and the call polls a sequence number there (the state digest is a parity tool: 370 MB of
+            # reads per call, not part of the metric)
+            c, mm = sim.step_observe(1)
+            d2h += c.nbytes + 24
+            return c, None, mm
 
         e2e_windows = []
         for w in range(args.windows):
@@ -460,8 +461,9 @@ def run_cuda(args):
         e2e = {"value": n * args.steps / dt, "unit": "node-rounds/s", "h2d_bytes_per_step": h2d / args.steps,
                "d2h_bytes_per_step": d2h / args.steps,
                "windows_ms": [round(x * 1e3, 4) for x in e2e_windows],
-               "what": "per round: swim_sim_inject(host events) + swim_sim_step_async(1) + swim_sim_observe (counters, "
-                       "convergence count; one synchronisation) — host wall clock, max over ranks, median of the windows"}
+               "what": "per round: swim_sim_inject(host events, when the round has any) + swim_sim_step_observe(1): one round, then "
+                       "the counters and the convergence count written by the device into mapped pinned host memory — host "
+                       "wall clock, max over ranks, median of the windows"}
         sim.close()
     clk = clocks.stop() if clocks else None
 

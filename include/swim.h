@@ -318,6 +318,12 @@ int swim_sim_counters(swim_sim_t *sim, uint64_t *out, size_t n);
  * per-round read-back of a convergence-study loop. */
 int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_counters, uint64_t *digest, uint64_t *mismatches);
 
+/* swim_sim_step + the read-back of a study loop in one call: run `rounds` rounds, then deliver the cumulative counters
+ * and the convergence count. A kernel chained behind the rounds writes them into pinned host memory mapped into the
+ * device and the call polls a sequence number there: no memset, no copy-engine operation and no stream synchronisation
+ * on the path (what swim_sim_step_async + swim_sim_observe cost per round at one round per call). */
+int swim_sim_step_observe(swim_sim_t *sim, uint32_t rounds, uint64_t *counters, size_t n_counters, uint64_t *mismatches);
+
 /* Convergence detector: number of (live observer, member) view entries on this rank that
  * disagree with the truth (crashed member not Dead, or live member not Alive). */
 int swim_sim_mismatches(swim_sim_t *sim, uint64_t *count);

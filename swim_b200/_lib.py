@@ -65,6 +65,7 @@ def lib():
     sig("swim_sim_counters", i, vp, vp, sz)
     sig("swim_sim_mismatches", i, vp, P(u64))
     sig("swim_sim_observe", i, vp, vp, sz, P(u64), P(u64))
+    sig("swim_sim_step_observe", i, vp, u32, vp, sz, P(u64))
     sig("swim_sim_last_step_ms", i, vp, P(C.c_float))
     sig("swim_sim_launch_count", i, vp, P(u64))
     sig("swim_sim_set_profile", i, vp, i)

@@ -1740,7 +1740,7 @@ static __global__ void __launch_bounds__(kThreads) digest_kernel(SimDev d, unsig
 // a view entry of a live observer is wrong when the member is down and the entry is not Dead, or the member is up and
 // the entry is not Alive. Only entries that are neither Alive nor Suspect of members that are up need the state byte
 // (Dead is wrong, vacant is not counted) — none on a full row in steady state.
-static __global__ void __launch_bounds__(kThreads) mismatch_kernel(SimDev d, unsigned long long *out) {
+__device__ __forceinline__ uint32_t count_mismatches(const SimDev &d) {
   const uint32_t W = d.cap >> 5;
   uint32_t bad = 0;
   for (size_t l = (size_t)blockIdx.x * blockDim.x + threadIdx.x; l < d.n; l += (size_t)gridDim.x * blockDim.x) {
@@ -1757,8 +1757,43 @@ static __global__ void __launch_bounds__(kThreads) mismatch_kernel(SimDev d, uns
       }
     }
   }
-  bad = __reduce_add_sync(kFull, bad);
+  return bad;
+}
+
+static __global__ void __launch_bounds__(kThreads) mismatch_kernel(SimDev d, unsigned long long *out) {
+  const uint32_t bad = __reduce_add_sync(kFull, count_mismatches(d));
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(out, (unsigned long long)bad);
+}
+
+// swim_sim_step_observe: the read-back of a convergence-study loop without a copy engine operation and without a stream
+// synchronisation. Chained behind the round kernel (programmatic stream serialization), it counts the view entries
+// that disagree with the truth; the last CTA to finish writes the cumulative counters, that count and finally a sequence
+// number into pinned host memory mapped into the device (PCIe writes), and re-arms the accumulators. The host polls the
+// sequence number.
+static __global__ void __launch_bounds__(kThreads) observe_kernel(SimDev d, unsigned long long *acc, uint32_t *done,
+                                                                  volatile unsigned long long *host_out, unsigned long long seq) {
+  SWIM_SHARED_1D(uint32_t, s_last, 1);
+  pdl_launch();
+  pdl_wait();
+  const uint32_t bad = __reduce_add_sync(kFull, count_mismatches(d));
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(acc, (unsigned long long)bad);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last[0] = atomicAdd(done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __threadfence();
+  }
+  __syncthreads();
+  if (!s_last[0]) return;
+  if (threadIdx.x < SWIM_CTR__COUNT) host_out[threadIdx.x] = *(volatile unsigned long long *)&d.ctr[threadIdx.x];
+  if (threadIdx.x == 0) {
+    host_out[SWIM_CTR__COUNT] = atomicExch(acc, 0ull); // ... and the accumulator is zero again for the next call
+    host_out[SWIM_CTR__COUNT + 1] = *(volatile uint32_t *)d.bar_err;
+    *done = 0;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) host_out[SWIM_CTR__COUNT + 2] = seq;
 }
 
 } // namespace swim

@@ -58,6 +58,10 @@ struct swim_sim {
   uint32_t *d_bar = nullptr;     // [world] cross-GPU barrier words of this rank
   uint32_t *h_bar_err = nullptr;            // pinned + device-mapped watchdog word of the in-kernel waits
   unsigned long long *h_observe = nullptr;  // pinned staging of swim_sim_observe
+  // swim_sim_step_observe: results written by the device into mapped pinned memory [counters, mismatches, watchdog, seq]
+  unsigned long long *h_obs = nullptr, *d_obs = nullptr, *d_obs_acc = nullptr;
+  uint32_t *d_obs_done = nullptr;
+  unsigned long long obs_seq = 0;
   std::vector<void *> ipc_opened; // peer mappings to close
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };

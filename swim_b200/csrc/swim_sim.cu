@@ -242,6 +242,11 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     *sim->h_bar_err = 0;
     CUDA_TRY(sim, cudaHostGetDevicePointer((void **)&d.bar_err, sim->h_bar_err, 0));
     CUDA_TRY(sim, cudaHostAlloc((void **)&sim->h_observe, (SWIM_CTR__COUNT + 2) * sizeof(unsigned long long), cudaHostAllocDefault));
+    CUDA_TRY(sim, cudaHostAlloc((void **)&sim->h_obs, (SWIM_CTR__COUNT + 4) * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(sim->h_obs, 0, (SWIM_CTR__COUNT + 4) * sizeof(unsigned long long));
+    CUDA_TRY(sim, cudaHostGetDevicePointer((void **)&sim->d_obs, sim->h_obs, 0));
+    if ((r = dalloc(sim, &sim->d_obs_acc, 2, 0))) return r;
+    if ((r = dalloc(sim, &sim->d_obs_done, 2, 0))) return r;
     if ((r = dalloc(sim, &d.gbar, 4, 0))) return r;
     if ((r = dalloc(sim, &d.qm, 4, 0))) return r;
     return SWIM_OK;
@@ -275,6 +280,7 @@ extern "C" void swim_sim_destroy(swim_sim_t *sim) {
   for (cudaEvent_t e : sim->prof_events) cudaEventDestroy(e);
   if (sim->h_bar_err) cudaFreeHost(sim->h_bar_err);
   if (sim->h_observe) cudaFreeHost(sim->h_observe);
+  if (sim->h_obs) cudaFreeHost(sim->h_obs);
   if (sim->ev_start) cudaEventDestroy(sim->ev_start);
   if (sim->ev_stop) cudaEventDestroy(sim->ev_stop);
   if (sim->own_stream) cudaStreamDestroy(sim->own_stream);
@@ -513,6 +519,7 @@ static void prepare_kernels(swim_sim *sim) {
   cudaFuncGetAttributes(&a, derive_meta_kernel);
   cudaFuncGetAttributes(&a, digest_kernel);
   cudaFuncGetAttributes(&a, mismatch_kernel);
+  cudaFuncGetAttributes(&a, observe_kernel);
   cudaFuncGetAttributes(&a, peer_barrier_kernel);
   cudaGetLastError();
 #endif
@@ -1103,6 +1110,51 @@ extern "C" int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_co
   if (digest) *digest = h[0];
   if (mismatches) *mismatches = h[1];
   for (size_t i = 0; counters && i < n_counters && i < SWIM_CTR__COUNT; ++i) counters[i] = h[2 + i];
+  return SWIM_OK;
+}
+
+// Step and read back in ONE call: `rounds` rounds, then observe_kernel chained behind them writes the cumulative counters
+// and the convergence count straight into mapped pinned host memory; the host polls a sequence number there instead of
+// synchronising the stream. No memset, no copy-engine operation, no stream synchronisation on the path.
+extern "C" int swim_sim_step_observe(swim_sim_t *sim, uint32_t rounds, uint64_t *counters, size_t n_counters, uint64_t *mismatches) {
+  if (!sim) return SWIM_EINVAL;
+  int rc = swim_sim_step_async(sim, rounds);
+  if (rc) return rc;
+  const SimDev &d = sim->dev;
+  if (sim->tdead_dirty) { // (cannot be: the step above rebuilt the per-node records)
+    SWIM_LAUNCH(derive_meta_kernel, grid_for(sim, d.n), kThreads, sim->stream, d);
+    ++sim->launches;
+    sim->tdead_dirty = false;
+  }
+  const unsigned long long seq = ++sim->obs_seq;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>(((size_t)d.n + kThreads * 8 - 1) / (kThreads * 8), (size_t)sim->sm_count * 2));
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = sim->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(sim, cudaLaunchKernelEx(&cfg, observe_kernel, d, sim->d_obs_acc, sim->d_obs_done,
+                                     (volatile unsigned long long *)sim->d_obs, seq));
+  }
+  ++sim->launches;
+  volatile unsigned long long *h = sim->h_obs;
+  for (unsigned long long spins = 0; h[SWIM_CTR__COUNT + 2] != seq; ++spins) {
+#if defined(__x86_64__) && !defined(SWIM_EMU)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0xFFFFFull) == 0xFFFFFull && cudaStreamQuery(sim->stream) != cudaErrorNotReady) { // finished or failed
+      CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+      if (h[SWIM_CTR__COUNT + 2] != seq) { set_error(sim, "swim_sim_step_observe: the device did not report"); return SWIM_ECUDA; }
+    }
+  }
+  if (h[SWIM_CTR__COUNT + 1]) return swim_sim_sync(sim); // a watchdog fired: the usual report
+  if (mismatches) *mismatches = h[SWIM_CTR__COUNT];
+  for (size_t i = 0; counters && i < n_counters && i < SWIM_CTR__COUNT; ++i) counters[i] = h[i];
   return SWIM_OK;
 }
 

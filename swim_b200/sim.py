@@ -215,6 +215,13 @@ class Simulator:
                                      C.byref(mm) if mismatches else None), "swim_sim_observe", self._h)
         return out, dg.value if digest else None, mm.value if mismatches else None
 
+    def step_observe(self, rounds=1):
+        """`rounds` rounds, then (counters, mismatches) — one call, no stream synchronisation (swim_sim_step_observe)."""
+        out = np.zeros(A.CTR_COUNT, dtype=np.uint64)
+        mm = C.c_uint64()
+        check(lib().swim_sim_step_observe(self._h, rounds, out.ctypes.data, A.CTR_COUNT, C.byref(mm)), "swim_sim_step_observe", self._h)
+        return out, mm.value
+
     def export_round(self):
         """The last round's piggyback envelopes as real datagrams in the reference's wire format:
         [(src, dst, bytes)] — node i is called "n<i>" on the wire (swim_sim_export_round)."""

@@ -451,3 +451,20 @@ def test_parameter_sweep_on_one_handle():
         sim.set_params(pb_cap=4)
     with pytest.raises(SwimError):
         sim.set_params(suspicion_rounds=7, suspicion_max=3)
+
+
+def test_step_observe_equals_step_plus_observe():
+    """swim_sim_step_observe: one call = rounds + counters + convergence count, delivered through mapped host memory."""
+    rng = np.random.default_rng(12)
+    n = 300
+    cfg = default_config(n_nodes=n, seed=8)
+    nbr = generate_topology("ring", n, 32, 16, seed=3)
+    sim, orc = make_pair(cfg, nbr)
+    ev = random_events(rng, n, 30, n_crash=20, n_rejoin=5, n_inject=10)
+    sim.inject(ev)
+    orc.inject(ev)
+    for chunk in (1, 1, 1, 5, 1, 12, 1):
+        c, mm = sim.step_observe(chunk)
+        orc.step(chunk)
+        assert c.tolist() == orc.counters().tolist() and mm == orc.mismatches(), sim.round
+    assert_same_state(sim, orc, "after step_observe calls")

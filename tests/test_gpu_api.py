@@ -86,3 +86,31 @@ def test_profile_hooks_and_caller_stream():
     sim.set_stream(0)
     sim.step(1)
     assert sim.round == 51
+
+
+def test_step_observe_and_device_checkpoint():
+    """swim_sim_step_observe (rounds + counters + convergence count through mapped host memory, no stream synchronisation)
+    and swim_sim_save / swim_sim_load / swim_sim_set_params on hardware, against the oracle."""
+    from helpers import random_events
+    from oracle.oracle import Oracle
+    rng = np.random.default_rng(12)
+    n = 5000
+    base = dict(n_nodes=n, seed=8, churn_ppm=3000, rejoin_min=3, rejoin_max=9)
+    nbr = generate_topology("ring", n, 32, 16, seed=3)
+    sim = Simulator(default_config(suspicion_rounds=3, **base))
+    sim.set_view(nbr)
+    ev = random_events(rng, n, 40, n_crash=50, n_rejoin=10, n_inject=40)
+    sim.inject(ev)
+    sim.save()
+    for S, smax in ((3, 0), (5, 12)):
+        sim.load()
+        sim.set_params(suspicion_rounds=S, suspicion_max=smax)
+        orc = Oracle(default_config(suspicion_rounds=S, suspicion_max=smax, **base))
+        orc.set_view(nbr)
+        orc.inject(ev)
+        for chunk in (1, 1, 1, 7, 1, 25):
+            c, mm = sim.step_observe(chunk)
+            orc.step(chunk)
+            assert c.tolist() == orc.counters().tolist() and mm == orc.mismatches(), (S, sim.round)
+        assert sim.digest() == orc.digest()
+    sim.close()
