@@ -89,6 +89,7 @@ def test_profile_hooks_and_caller_stream():
 
 
 def test_step_observe_and_device_checkpoint():
+    from swim_b200.sim import Simulator
     """swim_sim_step_observe (rounds + counters + convergence count through mapped host memory, no stream synchronisation)
     and swim_sim_save / swim_sim_load / swim_sim_set_params on hardware, against the oracle."""
     from helpers import random_events
