@@ -896,12 +896,16 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
   uint2 *rl_out = d.rl + (size_t)par * d.n * d.fanout;
   bool did_remote = false; // this lane stored into a peer GPU's memory
 
+  uint32_t next_ln = first_ln;
   for (uint32_t idx = warp; idx < n_work; idx += nwarps) {
-    const uint32_t ln = idx == warp ? first_ln : d.wl[idx];
+    const uint32_t ln = next_ln;
     const uint32_t self = d.first + ln;
     Row<W> row;
     row_load<W>(row, d, ln, lane);
     pb_load(pbs, d, ln, lane);
+    // the next item's list entry is fetched now, and — once it is known, further down — its rows are pulled towards L2:
+    // a warp walks its items one after the other, so each dependent round trip it can start early is one it does not wait for
+    if (idx + nwarps < n_work) next_ln = *(volatile const uint32_t *)(d.wl + idx + nwarps);
     // the row's edge indices travel with the row (narrow rows): the send step below needs the recipients' in-edge
     // indices, and loading them there would be one more dependent memory round trip per item
     constexpr bool kCarry = W <= 2;
@@ -1023,6 +1027,14 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
       }
     }
     row_store<W>(row, d, ln, lane, round);
+#ifndef SWIM_EMU
+    if (idx + nwarps < n_work && lane < 5) { // next item's rows -> L2 (one 128-byte line each at cap 32)
+      const size_t nb = (size_t)next_ln * d.cap;
+      const void *pf = lane == 0 ? (const void *)(d.nbr + nb) : lane == 1 ? (const void *)(d.vinc + nb) : lane == 2 ? (const void *)(d.vst + nb)
+                     : lane == 3 ? (const void *)(d.pb + (size_t)next_ln * d.B) : (const void *)(d.ridx + nb);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+    }
+#endif
     // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
     uint2 cand = make_uint2(0xFFFFFFFFu, ln); // lane f < fanout: recipient slot f
     if (L && pbs.cnt) {

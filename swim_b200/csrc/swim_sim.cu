@@ -3,6 +3,7 @@
 // conduits and a ticker thread per OS process, one handle owns N stores in HBM and
 // swim_sim_step runs the protocol period for all of them.
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -1143,13 +1144,22 @@ extern "C" int swim_sim_step_observe(swim_sim_t *sim, uint32_t rounds, uint64_t 
   }
   ++sim->launches;
   volatile unsigned long long *h = sim->h_obs;
+  const auto t0 = std::chrono::steady_clock::now();
   for (unsigned long long spins = 0; h[SWIM_CTR__COUNT + 2] != seq; ++spins) {
 #if defined(__x86_64__) && !defined(SWIM_EMU)
     __builtin_ia32_pause();
 #endif
-    if ((spins & 0xFFFFFull) == 0xFFFFFull && cudaStreamQuery(sim->stream) != cudaErrorNotReady) { // finished or failed
-      CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
-      if (h[SWIM_CTR__COUNT + 2] != seq) { set_error(sim, "swim_sim_step_observe: the device did not report"); return SWIM_ECUDA; }
+    if ((spins & 0x3FFFFull) != 0x3FFFFull) continue;
+    // every few hundred microseconds: has the stream finished (or failed) without the report landing? has it taken too long?
+    const cudaError_t q = cudaStreamQuery(sim->stream);
+    const bool late = std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120);
+    if (q != cudaErrorNotReady || late) {
+      if (!late) CUDA_TRY(sim, cudaStreamSynchronize(sim->stream));
+      if (h[SWIM_CTR__COUNT + 2] != seq) {
+        set_error(sim, late ? "swim_sim_step_observe: no report from the device after 120 s" : "swim_sim_step_observe: the stream finished without a report");
+        sim->failed = true;
+        return SWIM_ECUDA;
+      }
     }
   }
   if (h[SWIM_CTR__COUNT + 1]) return swim_sim_sync(sim); // a watchdog fired: the usual report

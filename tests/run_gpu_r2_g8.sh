@@ -4,8 +4,8 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
-timeout 400 python -m pytest tests/test_gpu_dist.py -m gpu -q -p no:cacheprovider -k "small and p2p and 8" 2>&1 | tail -3
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29728 \
+# (world-8 parity: bench.py's parity_check leg below compares all 8 shards with the oracle at 8 x C3)
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29728 \
     bench.py --gpus 8 --no-cpu --steps 20 --warmup 5 --converge-limit 400 > gpurun_out/r2g8_bench20.json 2> gpurun_out/r2g8_bench20.err
 tail -2 gpurun_out/r2g8_bench20.err | cut -c1-300
 python - <<'PY'
@@ -17,7 +17,7 @@ except Exception as e:
     print('bench FAILED', e)
 PY
 ROUNDS=${1:-1000}
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29729 \
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29729 \
     studies/c5_suspicion_sweep.py --nodes-per-gpu 2097152 --rounds $ROUNDS --suspicion 2 3 5 8 13 --sample-every 50 \
     > gpurun_out/r2g8_c5.jsonl 2> gpurun_out/r2g8_c5.err
 tail -3 gpurun_out/r2g8_c5.err | cut -c1-300
