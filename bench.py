@@ -43,7 +43,13 @@ def usable_cpus():
     return n
 
 
-os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
+# host-side OpenMP code (the library's in-edge index build, the oracle): torchrun exports OMP_NUM_THREADS=1 to its workers,
+# which would make every rank build its index serially; give each local rank its share of the host cores instead
+_local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+if _local_world > 1:
+    os.environ["OMP_NUM_THREADS"] = str(max(1, usable_cpus() // _local_world))
+else:
+    os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
 
 N_PER_GPU = 1 << 20
 CRASH_ROUND = 10
@@ -79,6 +85,7 @@ def summarize_timeline(tl, warmup):
     """tl: [rounds, 8] ns stamps of round_kernel's phase boundaries (CTA 0; swim_sim_get_timeline). Per-phase means over
     the rounds that ran the phase; a round committed by a batched quiet scan shares its batch's stamps."""
     scan, work, recv, busy_total, quiet_total, bar3 = [], [], [], [], [], []
+    last_scan, last_work, rel1, rel2 = [], [], [], []  # slowest CTA's phase time; release latency of the two barriers
     own = {"scan": [], "work": [], "recv": []}  # CTA 0's own share of a phase (the rest is waiting at the barrier)
     n_busy = n_quiet = 0
     r = 0
@@ -98,15 +105,21 @@ def summarize_timeline(tl, warmup):
         scan.append(t[2] - t[0]); own["scan"].append(t[1] - t[0])
         work.append(t[4] - t[2]); own["work"].append(t[3] - t[2])
         busy_total.append(t[4] - t[0])  # (the receive pass of a round runs inside the next round's scan phase)
+        if t[5] and t[6]:
+            last_scan.append(t[5] - t[0]); rel1.append(t[2] - t[5])
+            last_work.append(t[6] - t[2]); rel2.append(t[4] - t[6])
         r += 1
     f = lambda v: float(np.mean(v)) / 1e3 if len(v) else None
     return {"busy_rounds": n_busy, "quiet_rounds": n_quiet, "busy_us": f(busy_total), "quiet_us": f(quiet_total),
             "scan_us": f(scan), "work_us": f(work), "recv_us": f(recv), "recv_rounds": len(recv),
             "cta0_scan_us": f(own["scan"]), "cta0_work_us": f(own["work"]), "cta0_recv_us": f(own["recv"]),
             "busy_us_max": float(np.max(busy_total)) / 1e3 if busy_total else None,
+            "slowest_cta_scan_us": f(last_scan), "slowest_cta_work_us": f(last_work),
+            "barrier1_release_us": f(rel1), "barrier2_release_us": f(rel2),
             "what": "in-kernel %globaltimer stamps of CTA 0 at round_kernel's phase boundaries over the timed rounds; a phase "
                     "runs from one grid barrier to the next: scan (+ the receive pass of the round before, on otherwise idle "
-                    "warps) | work = K1b; cta0_* is CTA 0's own part of it"}
+                    "warps) | work = K1b; cta0_* is CTA 0's own part of it, slowest_cta_* the arrival of the LAST CTA at the phase's "
+                    "barrier, barrierN_release_us what the barrier itself adds after that"}
 
 
 def make_roofline(cfg_kw, n_local, ms_per_round, ab_round, m_bar, b_bar, peak, measured_peak, prof, rounds_p, timeline,
@@ -291,13 +304,24 @@ def run_cuda(args):
         return sim
 
     def barrier():
+        # Drain this rank's streams BEFORE the NCCL barrier: a sharded round kernel is one resident wave that waits on the
+        # device for its peers; an NCCL kernel slipping onto the GPU between two of its launches could take a CTA slot and
+        # wait for a peer whose own NCCL kernel is queued behind a round kernel that waits for us.
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+
+    t_bench0 = time.perf_counter()
+
+    def log(msg):  # progress on stderr (stdout carries exactly one JSON line)
+        if rank == 0:
+            print(f"[bench +{time.perf_counter() - t_bench0:7.2f}s] {msg}", file=sys.stderr, flush=True)
 
     # ------------------------------------------------ device-resident timing (value)
     # One handle, one device-resident checkpoint (swim_sim_save at round 0, events pending): every timing window starts
     # from the same state and runs the same rounds, so the windows differ only by the machine.
+    log(f"workload built: {n} nodes, world {world}")
     sim = fresh()
     # a non-default torch stream: its handle is what the library launches on, so the torch events
     # below bracket the kernels (handle 0 would mean "the handle's private stream" to the C ABI)
@@ -344,6 +368,7 @@ def run_cuda(args):
                 ctr_delta = c1 - c0
             launches = int(l1 - l0)
     ms = float(np.median(windows))
+    log(f"timed windows done: {windows}")
     value = n * args.steps / (ms * 1e-3)
 
     # ------------------------------------------------ phase timeline of the same rounds (fused kernel, in-kernel timer)
@@ -359,6 +384,7 @@ def run_cuda(args):
         sim.set_timeline(0)
         timeline = summarize_timeline(tl, args.warmup)
 
+    log("timeline done")
     # ------------------------------------------------ per-kernel timing of the same rounds (split launches)
     barrier()
     sim.load()
@@ -369,6 +395,7 @@ def run_cuda(args):
     prof = sim.profile_ms()
     sim.set_profile(False)
 
+    log("split-kernel profile done")
     # ------------------------------------------------ parity leg: the rounds just timed, against the oracle on the same N
     # (the checker, outside every timed region): global digest (shard digests add up), counters and convergence count
     # after W + K rounds (at most 40: through the crash burst) from the same checkpoint
@@ -401,6 +428,7 @@ def run_cuda(args):
                       f"(all {world} shard(s)) == restated C oracle on the same N, seed and event trace"}
             del orc
     sim.close()
+    log(f"parity leg done: {parity['status'] if parity else None}")
     ab_round, ab_tick, m_bar, b_bar = algorithmic_bytes(cfg_kw, n, args.steps, ctr_delta)
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -485,6 +513,7 @@ def run_cuda(args):
                        "wall clock, max over ranks, median of the windows"}
         sim.close()
     clk = clocks.stop() if clocks else None
+    log("e2e done")
 
     # ------------------------------------------------ convergence metric (second half of BASELINE's metric)
     conv = None
@@ -517,6 +546,7 @@ def run_cuda(args):
         conv = {"rounds_to_convergence": r0, "checked_every": "8 rounds, every round once fewer than 64 view entries are wrong", "limit": args.converge_limit, "mismatches_at_end": mm0,
                 "crash_round": CRASH_ROUND, "rounds_to_convergence_round_robin": r1, "mismatches_at_end_round_robin": mm1}
 
+    log(f"convergence done: {conv}")
     # ------------------------------------------------ second workload: the state machine under load (ring-lattice views)
     # C3's uniformly random views almost never let a receiver know the member a record is about (32 of 2^20), so its
     # dissemination path idles. With ring-lattice views (each node knows its 32 nearest ids) records reach nodes that know
@@ -585,6 +615,7 @@ def run_cuda(args):
                 "msgs_delivered_to_k2_note": "ring views: nearly every envelope passes the recipient's membership filter",
                 "counters_timed_region": cd, "timeline": tl_ring, "parity_check": ring_parity}
 
+    log("ring workload done" if ring else "ring workload skipped")
     # ------------------------------------------------ CPU baseline (rank 0, N=1 only): bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

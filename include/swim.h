@@ -346,8 +346,9 @@ int swim_sim_profile_ms(swim_sim_t *sim, double *out, size_t n);
 
 /* Phase timeline of the fused per-round kernel (profiling aid): after swim_sim_set_timeline(sim, R) the next R rounds
  * record the device's nanosecond timer at their phase boundaries, 8 words per round — [0] round start, [1] scan done
- * (CTA 0), [2] first grid barrier passed, [3] tick work done (CTA 0), [4] second barrier passed, [5] receive done (CTA 0),
- * [6] third barrier passed, [7] rounds committed by a batched quiet scan; words of phases a round skipped stay 0.
+ * (CTA 0), [2] first grid barrier passed, [3] tick work done (CTA 0), [4] second barrier passed, [5] / [6] arrival of the
+ * LAST CTA at the first / second barrier (so [5]-[0] is what the slowest CTA's scan phase took and [2]-[5] the release
+ * latency of the barrier), [7] rounds committed by a batched quiet scan; words of phases a round skipped stay 0.
  * R = 0 switches it off. Single-kernel launch path only. */
 int swim_sim_set_timeline(swim_sim_t *sim, uint32_t rounds);
 int swim_sim_get_timeline(swim_sim_t *sim, uint64_t *out /* [rounds][8] */, size_t rounds);

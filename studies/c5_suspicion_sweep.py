@@ -55,10 +55,11 @@ def main():
     red = (lambda xs: [int(v) for v in sd.global_sum(xs)]) if world > 1 else None
 
     def barrier():
+        torch.cuda.synchronize()  # never an NCCL kernel next to a sharded round kernel in flight
         if world > 1:
             import torch.distributed as dist
             dist.barrier()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
 
     cfg = default_config(n_nodes=n, suspicion_rounds=args.suspicion[0], loss_ppm=args.loss_ppm, seed=args.seed, rank=rank,
                          world=world, device=local, flags=args.flags, churn_ppm=args.crash_ppm, rejoin_min=10, rejoin_max=50)
@@ -88,6 +89,8 @@ def main():
                     "entries": rep, "counters": res["counters"],
                     "false_positive_rate": (rep["false_dead"] + res["counters"]["refutes"]) / max(1, res["counters"]["pings"]),
                     "mismatch_series": res["mismatch_series"], "wall_s": wall,
+                    "device_us_per_round_rank0": res["device_us_per_round"],
+                    "node_rounds_per_s_device_rank0": n * args.rounds / max(1e-9, res["device_ms"] * 1e-3),
                     "node_rounds_per_s_wall": n * args.rounds / wall,
                     "setup_s": {"topology": t_topo, "create_set_view_connect_save": t_setup}}
             print(json.dumps(line), flush=True)

@@ -208,13 +208,35 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
 #endif
 }
 
+// Bounded waits: a wait that runs out of time sets *bar_err and gives up; every later wait of the launch then gives up
+// quickly (it looks at the word every 4096 polls), so a lost peer or a grid that is not co-resident costs ONE time-out and
+// swim_sim_sync reports it — not one time-out per barrier of every remaining round.
+__device__ __forceinline__ bool wait_expired(const SimDev &d, long long t0, long long limit, uint32_t &polls, uint32_t code) {
+  if ((++polls & 255u) != 0) return false;
+  if (clock64() - t0 > limit) { *d.bar_err = code; return true; }
+  return (polls & 4095u) == 0 && *(volatile uint32_t *)d.bar_err != 0; // (the word lives in mapped host memory: look rarely)
+}
+
 // Phase timeline of round_kernel: one thread of CTA 0 stores %globaltimer (ns) at each phase boundary. Slots per round:
 // 0 start, 1 scan done (CTA 0), 2 barrier 1 passed (every CTA's scan done), 3 work done (CTA 0), 4 barrier 2 passed,
-// 5 receive done (CTA 0), 6 barrier 3 passed, 7 = number of rounds a batched quiet scan committed at this round.
+// 5 / 6 the LAST CTA's arrival at the first / second barrier (tl_mark_last), 7 = number of rounds a batched quiet scan
+// committed at this round.
 __device__ __forceinline__ void tl_mark(const SimDev &d, uint32_t round, int slot, unsigned long long val = ~0ull) {
 #ifndef SWIM_EMU
   if (d.tl && blockIdx.x == 0 && threadIdx.x == 0 && round - d.tl_round0 < d.tl_cap) {
     if (val == ~0ull) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(val));
+    d.tl[(size_t)(round - d.tl_round0) * 8 + slot] = val;
+  }
+#endif
+}
+
+// the same stamp from thread 0 of ANY CTA: slots 5 / 6 = when the LAST CTA arrived at the round's first / second grid
+// barrier (what a phase really took; the difference to slot 2 / 4 is the release latency of the barrier itself)
+__device__ __forceinline__ void tl_mark_last(const SimDev &d, uint32_t round, int slot) {
+#ifndef SWIM_EMU
+  if (d.tl && slot >= 0 && round - d.tl_round0 < d.tl_cap) {
+    unsigned long long val;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(val));
     d.tl[(size_t)(round - d.tl_round0) * 8 + slot] = val;
   }
 #endif
@@ -611,6 +633,22 @@ __device__ __forceinline__ uint4 target_block(const SimDev &d, uint32_t round, u
   const bool rr = (d.flags & SWIM_F_ROUND_ROBIN) != 0; // one Philox call either way: only the counter words differ
   return philox4x32_10(make_uint4(rr ? round / (32u * W) : round, g, rr ? P_RR : P_TARGET, 0), d.key0, d.key1);
 }
+// K1b's draws of one node and round, computed by the warp in ONE Philox pass: lane 0 holds the group's TARGET block (or the
+// round-robin block), lanes 1..7 the node's PROXY blocks 0..6 (draw j k + x <= 27), lanes 8.. its TARGETS block 0 (draws
+// 0..2 of probes 1..3). tab_draw(tab, b, w) = word w of the block held by lane b (b, w warp-uniform).
+template <int W>
+__device__ __forceinline__ uint4 item_draws(const SimDev &d, uint32_t round, uint32_t self, int lane) {
+  const bool rr = (d.flags & SWIM_F_ROUND_ROBIN) != 0;
+  uint4 c;
+  if (lane == 0) c = make_uint4(rr ? round / (32u * W) : round, self >> 2, rr ? P_RR : P_TARGET, 0);
+  else if (lane < 8) c = make_uint4(round, self, P_PROXY, (uint32_t)lane - 1u);
+  else c = make_uint4(round, self, P_TARGETS, 0);
+  return philox4x32_10(c, d.key0, d.key1);
+}
+__device__ __forceinline__ uint32_t tab_draw(uint4 tab, uint32_t b, uint32_t w) {
+  return __shfl_sync(kFull, word_of(tab, (int)w), (int)b);
+}
+
 template <int W>
 __device__ __forceinline__ uint32_t pick_target(const SimDev &d, uint32_t (&am)[W], uint32_t word, uint32_t L, uint32_t round) {
   if (d.flags & SWIM_F_ROUND_ROBIN) return rr_pick<W>(am, word, round);
@@ -677,7 +715,8 @@ __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags,
 // work list for K1b.
 template <int W>
 __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps,
-                                          int lane, uint32_t &pings, const uint32_t *skipbits = nullptr) {
+                                          int lane, uint32_t &pings, const uint32_t *skipbits = nullptr,
+                                          uint4 *stage = nullptr) {
   constexpr int U = kScanGroups;
   uint32_t *wl_cnt = d.wl_cnt + ci(round);
   const uint32_t g0 = d.first >> 2, g1 = (d.first + d.n + 3) >> 2; // Philox groups touching this shard
@@ -702,7 +741,14 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
           m[u][j] = ok ? d.meta[(size_t)(node - d.first) * W] : make_uint4(0, 0, 0, 0);
         }
     }
-    if (skipbits) { // nodes with mail from last round belong to the warps that apply it (recv_one takes their tick decision)
+    if (skipbits && valid == (1u << (4 * U)) - 1u && (d.first & 3u) == 0) {
+      // (the lane's four nodes of a group are consecutive and 4-aligned in the shard: one bitmap word holds their bits)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const uint32_t l0 = 4 * (gb + u * 32 + lane) - d.first;
+        valid &= ~((skipbits[l0 >> 5] >> (l0 & 31) & 0xFu) << (u * 4));
+      }
+    } else if (skipbits) { // nodes with mail from last round belong to the warps that apply it (recv_one takes their tick decision)
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -713,27 +759,63 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
           }
     }
     uint32_t work = 0; // bit u*4+j: that node needs K1b
+    unsigned fb = 0;     // lanes whose STAGED node (see below) needs K1b ...
+    uint32_t fself = 0;  // ... and that node's id
     if constexpr (W == 1) {
       // Pass 1, every node: what the record alone decides (buffer to send, countdown to run, the Ping count). Only a node
-      // with a crashed process in an Alive slot (or any node, under message loss) depends on its draws: those are set
-      // aside per lane ...
-      uint32_t risky = 0;
+      // with a crashed process in an Alive slot (or any node, under message loss) depends on its draws — and only if the
+      // record has not already sent it to K1b. Those nodes are COMPACTED over the warp through `stage` (32 entries of the
+      // warp's shared memory: {alive bitmap, crashed-member bitmap, id}): pass 2 then spends one Philox block and one set
+      // of picks per lane on up to 32 of them at once, whichever lanes they came from (a burst round of C3 has ~8 per
+      // warp: one trip instead of the two or three a per-lane loop needs). Without a stage buffer, under message loss
+      // (every node is risky) and for the overflow, the per-lane loop below does the same work.
+      uint32_t risky = 0, nstaged = 0;
+      const bool can_stage = stage != nullptr && d.loss_ppm == 0;
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int q = u * 4 + j;
           const uint4 mr = m[u][j];
-          if (!(valid >> q & 1u) || (mr.w & 0xFFu) == 0) continue; // out of range, left to the receive pass, or crashed
-          const uint32_t L = __popc(mr.x);
-          if ((mr.w & 0xFF00u) != 0 || mr.y != 0) work |= 1u << q;
-          if (L) {
-            pings += d.P < L ? d.P : L;
-            if ((mr.x & mr.z) | d.loss_ppm) risky |= 1u << q;
+          bool rq = false;
+          if ((valid >> q & 1u) && (mr.w & 0xFFu) != 0) { // in range, not left to the receive pass, process up
+            const uint32_t L = __popc(mr.x);
+            const bool wk = (mr.w & 0xFF00u) != 0 || mr.y != 0;
+            if (wk) work |= 1u << q;
+            if (L) {
+              pings += d.P < L ? d.P : L;
+              rq = !wk && ((mr.x & mr.z) | d.loss_ppm) != 0;
+            }
+          }
+          if (can_stage) {
+            const unsigned rb = __ballot_sync(kFull, rq);
+            if (rb) {
+              const uint32_t pos = nstaged + __popc(rb & ((1u << lane) - 1u));
+              if (rq) {
+                if (pos < 32u) stage[pos] = make_uint4(mr.x, mr.z, 4 * (gb + u * 32 + lane) + j, 0u);
+                else risky |= 1u << q; // (more than 32 in one warp's 256 nodes: the per-lane loop takes the rest)
+              }
+              nstaged += __popc(rb);
+            }
+          } else if (rq) {
+            risky |= 1u << q;
           }
         }
-      // ... and pass 2 takes them one per lane and trip (Philox block, r-th-set-bit picks): a lane pays for its own risky
-      // nodes only, not — by divergence — for every risky node of the warp.
+      if (nstaged) {
+        __syncwarp();
+        bool fails = false;
+        if ((uint32_t)lane < (nstaged < 32u ? nstaged : 32u)) {
+          const uint4 e = stage[lane];
+          uint32_t am1[1] = {e.x}, td1[1] = {e.y};
+          const uint4 x = target_block<W>(d, round, e.z >> 2);
+          fails = probe_fails<W>(d, am1, td1, (uint32_t)__popc(e.x), word_of(x, e.z & 3), 0u, round, e.z);
+          fself = e.z;
+        }
+        fb = __ballot_sync(kFull, fails);
+        __syncwarp(); // the buffer is free again (next trip of this loop, or the passes that follow the scan)
+      }
+      // ... and pass 2 takes the others one per lane and trip (Philox block, r-th-set-bit picks): a lane pays for its own
+      // risky nodes only, not — by divergence — for every risky node of the warp.
       while (risky) {
         const int q = __ffs(risky) - 1;
         risky &= risky - 1;
@@ -772,9 +854,9 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
     }
     }
     // warp-aggregated append of up to 4*U x 32 nodes
-    if (__any_sync(kFull, work != 0)) {
+    if (__any_sync(kFull, work != 0) || fb) {
       unsigned b[4 * U];
-      uint32_t total = 0;
+      uint32_t total = __popc(fb);
 #pragma unroll
       for (int q = 0; q < 4 * U; ++q) { b[q] = __ballot_sync(kFull, work >> q & 1u); total += __popc(b[q]); }
       uint32_t pos = 0;
@@ -788,19 +870,21 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
         }
         pos += __popc(b[q]);
       }
+      if (fb >> lane & 1u) d.wl[pos + __popc(fb & ((1u << lane) - 1))] = fself - d.first; // the staged nodes whose probe fails
     }
   }
 }
 
 template <int W>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) tick_scan_kernel(SimDev d) {
+  SWIM_SHARED_2D(uint4, s_stage, kWarpsPerBlock, 32);
   pdl_launch();
   pdl_wait();
   const uint32_t round = d.round;
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
   uint32_t pings = 0;
-  scan_pass<W>(d, round, warp, nwarps, lane, pings);
+  scan_pass<W>(d, round, warp, nwarps, lane, pings, nullptr, s_stage[threadIdx.x >> 5]);
   pings = __reduce_add_sync(kFull, pings);
   if (lane == 0 && pings) atomicAdd(&d.ctr[SWIM_CTR_PINGS], (unsigned long long)pings);
 }
@@ -940,23 +1024,25 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
     // draws 1.. come from a per-node stream. Probe 0's proxies — kRandomMembers store k [] (Core.hs:249), a fresh shuffle
     // over the same alive list, neither self nor the target excluded — double as piggyback recipients (T4), so they are
     // drawn whether or not the probe escalates.
-    uint32_t tslots[SWIM_MAX_PROBES], nt = 0, np = 0, prox[SWIM_MAX_K];
+    uint32_t tslots[SWIM_MAX_PROBES], nt = 0, np = 0;
+    uint32_t prox_l = 0; // lane x < np: proxy x of probe 0 (a view slot)
 #pragma unroll
     for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) tslots[j] = 0;
     if (L) {
       nt = d.P < L ? d.P : L;
-      uint4 blk = target_block<W>(d, round, self >> 2);
+      // Every Philox block this item can ask for, in ONE pass of the warp: lane 0 computes the group's TARGET (or
+      // round-robin) block, lanes 1..7 the node's PROXY blocks 0..6 (draws j k + x <= 27), lane 8 its TARGETS block — a
+      // draw is then a shuffle from the lane that holds its block, instead of one warp-wide Philox call per block.
+      const uint4 tab = item_draws<W>(d, round, self, lane);
       uint32_t tmp[W];
 #pragma unroll
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
-      uint32_t draw = word_of(blk, self & 3);
+      uint32_t draw = tab_draw(tab, 0, self & 3);
 #pragma unroll
       for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
         if (j >= nt) break;
-        if (j && !(d.flags & SWIM_F_ROUND_ROBIN)) { // (round-robin order: one walk, one word, for all probes of the period)
-          if (((j - 1) & 3) == 0) blk = philox4x32_10(make_uint4(round, self, P_TARGETS, (j - 1) >> 2), d.key0, d.key1);
-          draw = word_of(blk, (j - 1) & 3);
-        }
+        if (j && !(d.flags & SWIM_F_ROUND_ROBIN)) // (round-robin order: one walk, one word, for all probes of the period)
+          draw = tab_draw(tab, 8, j - 1);          // TARGETS draw j - 1 (j - 1 <= 2: block 0)
         tslots[j] = pick_target_warp<W>(d, tmp, draw, L - j, round, lane);
         clear_slot<W>(tmp, tslots[j]);
       }
@@ -964,8 +1050,8 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
       for (int w = 0; w < W; ++w) tmp[w] = am[w];
       np = d.k < L ? d.k : L;
       for (uint32_t j = 0; j < np; ++j) {
-        if ((j & 3) == 0) blk = philox4x32_10(make_uint4(round, self, P_PROXY, j >> 2), d.key0, d.key1);
-        prox[j] = pick_remove_warp<W>(tmp, bounded(word_of(blk, j & 3), L - j), lane);
+        const uint32_t pick = pick_remove_warp<W>(tmp, bounded(tab_draw(tab, 1 + (j >> 2), j & 3), L - j), lane);
+        if ((uint32_t)lane == j) prox_l = pick;
       }
       // T3: the probes one after the other (mapM_ probeNode', Core.hs:240) — Ping (Core.hs:246); unlessAck ->
       // IndirectPings (247-250); unlessAck -> suspectNode (251-254). The incarnations are those of the moment the targets
@@ -993,7 +1079,7 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
         const bool acked = t_up && !direct_leg_lost(d, round, self, j);
         if (acked) continue;
         uint32_t npj = np;
-        uint32_t ps = (uint32_t)lane < np ? prox[lane] : 0u; // lane x: proxy x of this probe
+        uint32_t ps = (uint32_t)lane < np ? prox_l : 0u; // lane x: proxy x of this probe
         if (j) { // kRandomMembers store k [] on the store as it is now: draws j k .. j k + k - 1 of the PROXY stream
           uint32_t t2[W];
 #pragma unroll
@@ -1002,8 +1088,7 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
           ps = 0;
           for (uint32_t x = 0; x < npj; ++x) {
             const uint32_t q = j * d.k + x;
-            if (x == 0 || (q & 3) == 0) blk = philox4x32_10(make_uint4(round, self, P_PROXY, q >> 2), d.key0, d.key1);
-            const uint32_t pick = pick_remove_warp<W>(t2, bounded(word_of(blk, q & 3), Lc - x), lane);
+            const uint32_t pick = pick_remove_warp<W>(t2, bounded(tab_draw(tab, 1 + (q >> 2), q & 3), Lc - x), lane);
             if ((uint32_t)lane == x) ps = pick;
           }
         }
@@ -1040,15 +1125,20 @@ __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint3
     if (L && pbs.cnt) {
       // recipients: the probe targets in order, then probe 0's proxies that are no targets, the first `fanout` of them;
       // lane f carries recipient f
-      uint32_t nr = 0, rslot = 0;
+      uint32_t nr = nt < d.fanout ? nt : d.fanout, rslot = 0;
 #pragma unroll
       for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j)
-        if (j < nt && nr < d.fanout) { if ((uint32_t)lane == nr) rslot = tslots[j]; ++nr; }
-      for (uint32_t j = 0; j < np && nr < d.fanout; ++j) {
-        bool is_target = false;
+        if ((uint32_t)lane == j && j < nr) rslot = tslots[j];
+      bool is_target = false; // lane x: proxy x is one of the targets
 #pragma unroll
-        for (uint32_t t = 0; t < SWIM_MAX_PROBES; ++t) is_target |= t < nt && prox[j] == tslots[t];
-        if (!is_target) { if ((uint32_t)lane == nr) rslot = prox[j]; ++nr; }
+      for (uint32_t t = 0; t < SWIM_MAX_PROBES; ++t) is_target |= t < nt && prox_l == tslots[t];
+      unsigned pm = __ballot_sync(kFull, (uint32_t)lane < np && !is_target);
+      while (pm && nr < d.fanout) { // the remaining proxies in draw order
+        const int x = __ffs(pm) - 1;
+        pm &= pm - 1;
+        const uint32_t p = __shfl_sync(kFull, prox_l, x);
+        if ((uint32_t)lane == nr) rslot = p;
+        ++nr;
       }
       uint32_t xs = 0xFFFFFFFFu; // exchange-bucket slot when lane f's recipient lives on another shard
       uint32_t dst_c = 0, ridx_c = 0; // recipient id and in-edge index of lane f's slot, from the lanes that hold them
@@ -1195,8 +1285,9 @@ __device__ __forceinline__ void peer_wait(const SimDev &d, uint32_t mail_round, 
   if ((uint32_t)lane < d.world) {
     const uint32_t *mine = d.bar_p[d.rank] + lane;
     const long long t0 = clock64();
+    uint32_t polls = 0;
     while ((int32_t)(ld_acquire_sys(mine) - mail_round) < 0) {
-      if (clock64() - t0 > kPeerWaitCycles) { *d.bar_err = 1; break; } // a peer stopped stepping
+      if (wait_expired(d, t0, kPeerWaitCycles, polls, 1)) break; // a peer stopped stepping
       __nanosleep(100);
     }
   }
@@ -1373,20 +1464,22 @@ __device__ __forceinline__ uint32_t *barrier_generation() {
 __device__ __forceinline__ void barrier_begin(const SimDev &d) {
   if (threadIdx.x == 0) *barrier_generation() = *(volatile uint32_t *)(d.gbar + 1);
 }
-__device__ __forceinline__ void grid_barrier(const SimDev &d) {
+__device__ __forceinline__ void grid_barrier(const SimDev &d, uint32_t tl_round = 0, int tl_slot = -1) {
   __syncthreads();
   if (threadIdx.x == 0) {
     volatile uint32_t *gen = d.gbar + 1;
     const uint32_t g = (*barrier_generation())++;
     __threadfence();
     if (atomicAdd(d.gbar, 1u) == gridDim.x - 1) {
+      tl_mark_last(d, tl_round, tl_slot);
       d.gbar[0] = 0;
       __threadfence();
       atomicAdd(d.gbar + 1, 1u);
     } else {
       const long long t0 = clock64();
+      uint32_t polls = 0;
       while (*gen == g) {
-        if (clock64() - t0 > 6000000000ll) { *d.bar_err = 2; break; }
+        if (wait_expired(d, t0, 6000000000ll, polls, 2)) break;
         __nanosleep(20);
       }
     }
@@ -1407,8 +1500,9 @@ __device__ __forceinline__ void peer_handshake_cta(const SimDev &d, uint32_t mai
     st_release_sys(d.bar_p[q] + d.rank, mail_round);
     const uint32_t *mine = d.bar_p[d.rank] + q;
     const long long t0 = clock64();
+    uint32_t polls = 0;
     while ((int32_t)(ld_acquire_sys(mine) - mail_round) < 0)
-      if (clock64() - t0 > kPeerWaitCycles) { *d.bar_err = 1; break; } // a peer stopped stepping
+      if (wait_expired(d, t0, kPeerWaitCycles, polls, 1)) break; // a peer stopped stepping
   }
 }
 
@@ -1428,13 +1522,13 @@ __device__ __forceinline__ bool cta_or(bool pred) {
 // want(): evaluated by the last CTA only, after every arrival is visible — whether the handshake is due at this barrier
 // (round_kernel folds it into the scan barrier of a round that listed no work).
 template <typename Want>
-__device__ __forceinline__ void grid_barrier_leader(const SimDev &d, bool fence_sys, uint32_t mail_round, Want want) {
+__device__ __forceinline__ void grid_barrier_leader(const SimDev &d, bool fence_sys, uint32_t mail_round, Want want, int tl_slot = -1) {
   SWIM_SHARED_1D(uint32_t, s_last, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     if (fence_sys) __threadfence_system(); else __threadfence();
     const bool last = atomicAdd(d.gbar, 1u) == gridDim.x - 1;
-    if (last) __threadfence(); // acquire side of the arrivals
+    if (last) { __threadfence(); tl_mark_last(d, mail_round, tl_slot); } // acquire side of the arrivals
     s_last[0] = last ? 1u : 0u;
   }
   __syncthreads();
@@ -1451,8 +1545,9 @@ __device__ __forceinline__ void grid_barrier_leader(const SimDev &d, bool fence_
     volatile uint32_t *gen = d.gbar + 1;
     const uint32_t g = (*barrier_generation())++;
     const long long t0 = clock64();
+    uint32_t polls = 0;
     while (*gen == g) {
-      if (clock64() - t0 > kPeerWaitCycles + 6000000000ll) { *d.bar_err = 2; break; }
+      if (wait_expired(d, t0, kPeerWaitCycles + 6000000000ll, polls, 2)) break;
       __nanosleep(20);
     }
     __threadfence();
@@ -1501,7 +1596,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
       busy = __reduce_or_sync(kFull, busy);
       if (lane == 0 && busy) atomicOr(&d.qm[nb % 3], busy);
       tl_mark(d, round, 1);
-      grid_barrier(d);
+      grid_barrier(d, round, 5);
       const uint32_t mask = *(volatile uint32_t *)&d.qm[nb % 3];
       ++nb;
       const uint32_t fb = mask ? (uint32_t)__ffs(mask) - 1u : Q; // rounds round .. round+fb-1 are quiet: committed
@@ -1519,14 +1614,14 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
       skip = d.mailbits + (size_t)((round - 1) % 3u) * d.mbw;
     }
     uint32_t pings = 0;
-    scan_pass<W>(d, round, warp, nwarps, lane, pings, skip);              // K1a
+    scan_pass<W>(d, round, warp, nwarps, lane, pings, skip, pbs.s);       // K1a (the warp's staging area is free here)
     c.v[SWIM_CTR_PINGS] += pings;
     tl_mark(d, round, 1);
     const uint32_t *wl_cnt_r = d.wl_cnt + ci(round);
     // the work list is complete. Sharded: a rank that listed nothing has no K1b to run, so its cross-GPU handshake of the
     // round happens right here, inside this barrier (one barrier for a quiet round)
-    if (sharded) grid_barrier_leader(d, false, round, [&] { return *(volatile const uint32_t *)wl_cnt_r == 0; });
-    else grid_barrier(d);
+    if (sharded) grid_barrier_leader(d, false, round, [&] { return *(volatile const uint32_t *)wl_cnt_r == 0; }, 5);
+    else grid_barrier(d, round, 5);
     tl_mark(d, round, 2);
     const uint32_t n_work = d.wl_cnt[ci(round)];
     const uint32_t first_ln = first_work_entry(d, warp);                  // in flight together with the count
@@ -1540,8 +1635,8 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
       const bool remote = work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_ln, false); // K1b
       tl_mark(d, round, 3);
       // every flag and snapshot is written; sharded: ... on every rank (the last CTA talks to the peers)
-      if (sharded) grid_barrier_leader(d, cta_or(remote), round, [] { return true; });
-      else grid_barrier(d);
+      if (sharded) grid_barrier_leader(d, cta_or(remote), round, [] { return true; }, 6);
+      else grid_barrier(d, round, 6);
       tl_mark(d, round, 4);
     }
     // (no barrier is owed to the bitmap clear: that slot is written again by the senders of round + 2 and read again by
@@ -1556,7 +1651,6 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
   }
   if (mail) { // the last round's mail, before the launch ends (no tick decision: the next launch scans everybody)
     recv_pass<W>(d, d.round + d.nrounds - 1, warp, nwarps, lane, pbs, c, 0);
-    tl_mark(d, d.round + d.nrounds - 1, 5);
     // its bitmap is not needed by anybody: clear it. (The receive pass does not read it, so no barrier in between.)
     uint32_t *mb = d.mailbits + (size_t)((d.round + d.nrounds - 1) % 3u) * d.mbw;
     for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) mb[x] = 0;
@@ -1608,7 +1702,11 @@ struct DevEvent {
 // crashed-member bitmaps of the observers, incarnation + 1 and the Alive broadcast of a rejoin) are event_kernel's, fed
 // with the list written here — the very code path of host-injected SWIM_EV_CRASH / SWIM_EV_REJOIN events.
 static __global__ void __launch_bounds__(256) churn_kernel(SimDev d) {
+  pdl_launch();
+  pdl_wait();
   const uint32_t round = d.round;
+  uint32_t *const cnt = d.churn_cnt + (round & 1u); // this round's list counter; the other slot is cleared for round + 1
+  if (blockIdx.x == 0 && threadIdx.x == 0) d.churn_cnt[(round + 1u) & 1u] = 0;
   for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; 4 * g < d.N; g += gridDim.x * blockDim.x) {
     const uint32_t base = 4 * g;
     uint32_t up4 = 0; // alive bytes of the four nodes
@@ -1633,7 +1731,7 @@ static __global__ void __launch_bounds__(256) churn_kernel(SimDev d) {
         kind = SWIM_EV_REJOIN;
       }
       if (kind != 0xFFFFFFFFu) {
-        const uint32_t k = atomicAdd(d.churn_cnt, 1u);
+        const uint32_t k = atomicAdd(cnt, 1u);
         if (k < d.churn_cap) { d.churn_ev[k].node = i; d.churn_ev[k].kind = kind; d.churn_ev[k].rec = make_uint4(0, 0, 0, 0); }
         else *d.bar_err = 3; // list overflow: reported by swim_sim_sync, never silent
       }
@@ -1646,9 +1744,11 @@ __global__ void __launch_bounds__(kThreads) event_kernel(SimDev d, const DevEven
   SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  pdl_launch();
+  pdl_wait();
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  const uint32_t round = d.round; // events run outside captured graphs
+  const uint32_t round = d.round;
   if (n_ev_dev) n_ev = *n_ev_dev < d.churn_cap ? *n_ev_dev : d.churn_cap; // device-generated list (churn_kernel)
   // The host hands over one round's events grouped by node (stable: a node's events keep the order they were given in).
   // A run of same-node events belongs to the warp whose stride position is the run's first event, so a warp looks at

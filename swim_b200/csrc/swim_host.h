@@ -62,6 +62,7 @@ struct swim_sim {
   unsigned long long *h_obs = nullptr, *d_obs = nullptr, *d_obs_acc = nullptr;
   uint32_t *d_obs_done = nullptr;
   unsigned long long obs_seq = 0;
+  uint32_t churn_last_round = 0xFFFFFFF0u; // last round churn_kernel ran for (its list counter has round-parity slots)
   std::vector<void *> ipc_opened; // peer mappings to close
   void *dist = nullptr; // multi-GPU exchange state (swim_dist.cu)
 };

@@ -522,11 +522,11 @@ static int wave_grid(const swim_sim *sim, K kernel, size_t warps_needed) {
 }
 
 // launch with programmatic stream serialization (see pdl_wait / pdl_launch in swim_device.cuh)
-template <typename K>
-static cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, const SimDev &d) {
+template <typename K, typename... Args>
+static cudaError_t launch_pdl_ex(K kernel, int grid, int block, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3((unsigned)block);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -534,7 +534,11 @@ static cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, const Sim
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kernel, d);
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+template <typename K>
+static cudaError_t launch_pdl(K kernel, int grid, cudaStream_t stream, const SimDev &d) {
+  return launch_pdl_ex(kernel, grid, kThreads, stream, d);
 }
 
 // Once per handle, at create: the one-wave grid sizes (occupancy queries), and every kernel of the bulk path is loaded
@@ -626,9 +630,14 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
     while (ev_end < n_ev && ev_round[ev_end] == d.round) ++ev_end;
     if (d.churn_ppm) { // phase C: seeded churn of this round, generated and applied on the device
       int mk = prof_begin(sim, 0);
-      CUDA_TRY(sim, cudaMemsetAsync(d.churn_cnt, 0, 4, sim->stream));
-      SWIM_LAUNCH(churn_kernel, sim->sm_count * 8, 256, sim->stream, d);
-      SWIM_LAUNCH(event_kernel<W>, sim->sm_count * 4, kThreads, sim->stream, d, (const DevEvent *)d.churn_ev, 0u, (const uint32_t *)d.churn_cnt);
+      // the list counter has two slots (round parity): churn_kernel of round r fills slot r & 1 and clears the other one
+      // for round r + 1, so the chain churn -> events -> round kernel needs no memset between its launches and stays
+      // programmatically serialised; only a jump of the round counter (load, set_round, first use) clears both here
+      if (sim->churn_last_round + 1 != d.round) CUDA_TRY(sim, cudaMemsetAsync(d.churn_cnt, 0, 16, sim->stream));
+      sim->churn_last_round = d.round;
+      CUDA_TRY(sim, launch_pdl_ex(churn_kernel, sim->sm_count * 8, 256, sim->stream, d));
+      CUDA_TRY(sim, launch_pdl_ex(event_kernel<W>, sim->sm_count * 4, kThreads, sim->stream, d, (const DevEvent *)d.churn_ev, 0u,
+                                  (const uint32_t *)(d.churn_cnt + (d.round & 1u))));
       prof_end(sim, mk);
       sim->launches += 2;
     }
@@ -636,7 +645,8 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       const uint32_t cnt = (uint32_t)(ev_end - ev_pos);
       const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count * 4);
       int mk = prof_begin(sim, 0);
-      SWIM_LAUNCH(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt, (const uint32_t *)nullptr);
+      CUDA_TRY(sim, launch_pdl_ex(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt,
+                                  (const uint32_t *)nullptr));
       prof_end(sim, mk);
       ++sim->launches;
       ev_pos = ev_end;

@@ -100,9 +100,12 @@ def run_sweep_point(sim, events, rounds, sample_every=10, reduce_sum=None):
     red = reduce_sum or (lambda xs: xs)
     series = []
     done = 0
+    device_ms = 0.0
     while done < rounds:
         step = min(sample_every, rounds - done)
         sim.step(step)
+        if hasattr(sim, "last_step_ms"):
+            device_ms += float(sim.last_step_ms())  # CUDA events around the call's kernels, this rank
         done += step
         series.append((done, int(red([sim.mismatches()])[0])))
     counters = [int(x) for x in red([int(v) for v in sim.counters()])]
@@ -112,4 +115,5 @@ def run_sweep_point(sim, events, rounds, sample_every=10, reduce_sum=None):
     vals = red([rep[k] for k in keys])
     rep = dict(zip(keys, (int(v) for v in vals)))
     rep["latency"] = latency_stats(hist)
-    return {"mismatch_series": series, "counters": dict(zip(A.CTR_NAMES, counters)), "report": rep}
+    return {"mismatch_series": series, "counters": dict(zip(A.CTR_NAMES, counters)), "report": rep,
+            "device_ms": device_ms, "device_us_per_round": device_ms * 1e3 / max(1, rounds)}
