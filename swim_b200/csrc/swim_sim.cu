@@ -624,6 +624,13 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
                              (d.world == 1 || (d.p2p && sim->opt_round_kernel));
   const int kgrid = sim->grids[4];
   const bool multi_round_off = sim->opt_one_round;
+  // Event and churn kernels join the programmatic-serialization chain of the round kernels on a single shard only. A kernel
+  // launched that way may become resident (and then sit in griddepcontrol.wait, holding its CTA slots) as soon as its
+  // predecessor has started, so an unbroken chain lets a whole queue of future kernels pile up on the device. A shard's
+  // round kernel waits ON THE DEVICE for its peers; when several ranks share one GPU (tests/test_gpu_shards_one_device.py)
+  // the piled-up future kernels of one rank can take the slots another rank's current kernel still needs — a plain launch
+  // here bounds the pile, as it did before.
+  const bool chain_events = d.world == 1;
   for (uint32_t r = 0; r < rounds; ++r) {
     d.round = ++sim->round;
     size_t ev_end = ev_pos;
@@ -635,9 +642,14 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       // programmatically serialised; only a jump of the round counter (load, set_round, first use) clears both here
       if (sim->churn_last_round + 1 != d.round) CUDA_TRY(sim, cudaMemsetAsync(d.churn_cnt, 0, 16, sim->stream));
       sim->churn_last_round = d.round;
-      CUDA_TRY(sim, launch_pdl_ex(churn_kernel, sim->sm_count * 8, 256, sim->stream, d));
-      CUDA_TRY(sim, launch_pdl_ex(event_kernel<W>, sim->sm_count * 4, kThreads, sim->stream, d, (const DevEvent *)d.churn_ev, 0u,
-                                  (const uint32_t *)(d.churn_cnt + (d.round & 1u))));
+      const uint32_t *cnt_r = d.churn_cnt + (d.round & 1u);
+      if (chain_events) {
+        CUDA_TRY(sim, launch_pdl_ex(churn_kernel, sim->sm_count * 8, 256, sim->stream, d));
+        CUDA_TRY(sim, launch_pdl_ex(event_kernel<W>, sim->sm_count * 4, kThreads, sim->stream, d, (const DevEvent *)d.churn_ev, 0u, cnt_r));
+      } else {
+        SWIM_LAUNCH(churn_kernel, sim->sm_count * 8, 256, sim->stream, d);
+        SWIM_LAUNCH(event_kernel<W>, sim->sm_count * 4, kThreads, sim->stream, d, (const DevEvent *)d.churn_ev, 0u, cnt_r);
+      }
       prof_end(sim, mk);
       sim->launches += 2;
     }
@@ -645,8 +657,11 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       const uint32_t cnt = (uint32_t)(ev_end - ev_pos);
       const int eg = (int)std::min<size_t>((cnt + kWarpsPerBlock - 1) / kWarpsPerBlock, (size_t)sim->sm_count * 4);
       int mk = prof_begin(sim, 0);
-      CUDA_TRY(sim, launch_pdl_ex(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt,
-                                  (const uint32_t *)nullptr));
+      if (chain_events)
+        CUDA_TRY(sim, launch_pdl_ex(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt,
+                                    (const uint32_t *)nullptr));
+      else
+        SWIM_LAUNCH(event_kernel<W>, eg, kThreads, sim->stream, d, (const DevEvent *)sim->d_events + ev_pos, cnt, (const uint32_t *)nullptr);
       prof_end(sim, mk);
       ++sim->launches;
       ev_pos = ev_end;
