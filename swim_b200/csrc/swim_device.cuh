@@ -100,7 +100,13 @@ struct SimDev {
                              //        flags: byte0 = process up, byte1 = piggyback count (word 0 only)}
   uint32_t *obs_off;         // [N+1] observers of member m among this shard's rows ...
   uint32_t *obs_slot;        // [n*cap] ... as linear slot indices l*cap + s
-  uint32_t *wl, *wl_cnt;     // work list of K1b [n]; counters indexed by round % 3
+  uint32_t *wl, *wl_cnt;     // work lists of K1b [2][n] (round parity); counters indexed by round % 3
+  // one-barrier round kernel (round_kernel_x, `xmode`): a round's work list is still being extended (by the nodes whose mail
+  // made them need K1b after all) while its items are walked, so the barrier that completes the list freezes its length in
+  // wl_n[round % 3]; workbits: bit l of slot r % 3 = local node l is on the work list of round r
+  uint32_t *wl_n;            // [3]
+  uint32_t *workbits;        // [3][mbw]
+  uint32_t xmode;
   uint2 *rl;                 // [2][n*fanout] recipient slots (round parity), slot = item*fanout + f:
                              //   .x = local receiver (bit 31 set: sent, but not delivered — see `bloom`), .y = the sender
   // Mail bitmap (fused kernel only, `fused` != 0): bit l of slot (r % 3) = local node l was delivered mail in round r.
@@ -619,6 +625,7 @@ __device__ __forceinline__ void peer_publish_cta(const SimDev &d, uint32_t mail_
 constexpr int kScanGroups = 2; // Philox groups (of 4 nodes) per lane per iteration: 8 nodes, 8 loads in flight
 
 __device__ __forceinline__ uint32_t ci(uint32_t round) { return round % 3u; } // slot of the per-round list counters
+__device__ __forceinline__ uint32_t *wl_of(const SimDev &d, uint32_t round) { return d.wl + (size_t)(round & 1u) * d.n; } // that round's work list
 
 // The two filter positions of member id x in a node's 512 W-bit membership filter (SimDev::bloom); the host builds the
 // filters with the same two lines (swim_sim.cu: build_in_edges).
@@ -716,9 +723,12 @@ __device__ __forceinline__ bool node_needs_work(const SimDev &d, uint32_t flags,
 template <int W>
 __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps,
                                           int lane, uint32_t &pings, const uint32_t *skipbits = nullptr,
-                                          uint4 *stage = nullptr) {
+                                          uint4 *stage = nullptr, const uint32_t *skipbits2 = nullptr, uint32_t *listbits = nullptr) {
+  // skipbits / skipbits2: bitmaps of local nodes this scan leaves alone (somebody else takes their tick decision);
+  // listbits: bitmap in which every node appended to the work list is marked (round_kernel_x)
   constexpr int U = kScanGroups;
   uint32_t *wl_cnt = d.wl_cnt + ci(round);
+  uint32_t *const wl = wl_of(d, round);
   const uint32_t g0 = d.first >> 2, g1 = (d.first + d.n + 3) >> 2; // Philox groups touching this shard
   for (uint32_t gb = g0 + warp * (32 * U); gb < g1; gb += nwarps * (32 * U)) {
     uint4 m[U][4];
@@ -741,21 +751,27 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
           m[u][j] = ok ? d.meta[(size_t)(node - d.first) * W] : make_uint4(0, 0, 0, 0);
         }
     }
-    if (skipbits && valid == (1u << (4 * U)) - 1u && (d.first & 3u) == 0) {
+    if ((skipbits || skipbits2) && valid == (1u << (4 * U)) - 1u && (d.first & 3u) == 0) {
       // (the lane's four nodes of a group are consecutive and 4-aligned in the shard: one bitmap word holds their bits)
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const uint32_t l0 = 4 * (gb + u * 32 + lane) - d.first;
-        valid &= ~((skipbits[l0 >> 5] >> (l0 & 31) & 0xFu) << (u * 4));
+        uint32_t sk = 0;
+        if (skipbits) sk = skipbits[l0 >> 5];
+        if (skipbits2) sk |= skipbits2[l0 >> 5];
+        valid &= ~((sk >> (l0 & 31) & 0xFu) << (u * 4));
       }
-    } else if (skipbits) { // nodes with mail from last round belong to the warps that apply it (recv_one takes their tick decision)
+    } else if (skipbits || skipbits2) { // nodes with mail from last round belong to the warps that apply it (recv_one takes their tick decision)
 #pragma unroll
       for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (valid >> (u * 4 + j) & 1u) {
             const uint32_t l = 4 * (gb + u * 32 + lane) + j - d.first;
-            if (skipbits[l >> 5] >> (l & 31) & 1u) valid &= ~(1u << (u * 4 + j));
+            uint32_t sk = 0;
+            if (skipbits) sk = skipbits[l >> 5];
+            if (skipbits2) sk |= skipbits2[l >> 5];
+            if (sk >> (l & 31) & 1u) valid &= ~(1u << (u * 4 + j));
           }
     }
     uint32_t work = 0; // bit u*4+j: that node needs K1b
@@ -866,11 +882,16 @@ __device__ __forceinline__ void scan_pass(const SimDev &d, uint32_t round, uint3
       for (int q = 0; q < 4 * U; ++q) {
         if (work >> q & 1u) {
           const uint32_t l = 4 * (gb + (q >> 2) * 32 + lane) + (q & 3) - d.first;
-          d.wl[pos + __popc(b[q] & ((1u << lane) - 1))] = l;
+          wl[pos + __popc(b[q] & ((1u << lane) - 1))] = l;
+          if (listbits) atomicOr(&listbits[l >> 5], 1u << (l & 31));
         }
         pos += __popc(b[q]);
       }
-      if (fb >> lane & 1u) d.wl[pos + __popc(fb & ((1u << lane) - 1))] = fself - d.first; // the staged nodes whose probe fails
+      if (fb >> lane & 1u) { // the staged nodes whose probe fails
+        const uint32_t l = fself - d.first;
+        wl[pos + __popc(fb & ((1u << lane) - 1))] = l;
+        if (listbits) atomicOr(&listbits[l >> 5], 1u << (l & 31));
+      }
     }
   }
 }
@@ -965,277 +986,288 @@ __device__ __forceinline__ uint32_t quiet_scan(const SimDev &d, uint32_t round, 
 
 // This warp's first list entry, to be fetched together with the list count (one memory round trip instead of two); the
 // entry is only looked at when warp < n_work. Volatile: the load stays where it is written, ahead of the branch on the count.
-__device__ __forceinline__ uint32_t first_work_entry(const SimDev &d, uint32_t warp) {
-  return warp < d.n ? *(volatile const uint32_t *)(d.wl + warp) : 0u;
+__device__ __forceinline__ uint32_t first_work_entry(const SimDev &d, uint32_t round, uint32_t warp) {
+  return warp < d.n ? *(volatile const uint32_t *)(wl_of(d, round) + warp) : 0u;
 }
 
-// K1b — warp-per-node over the work list: countdown and expiry -> Dead, probe escalation (k proxies), local suspicion,
-// piggyback send. Lane s owns view slot s; the piggyback buffer is staged in shared memory. Everything K1a derived is
-// recomputed from the row with warp ballots.
+// K1b, one node — countdown and expiry -> Dead, probe escalation (k proxies), local suspicion, piggyback send — on a row
+// and a piggyback buffer that are already loaded (registers / the warp's shared-memory stage): work_pass walks the work
+// list with it; round_kernel_x also runs it right behind a node's mail. Lane s owns view slot s. Everything K1a derived is
+// recomputed from the row with warp ballots. Stores the row and the buffer; idx = the node's position on the round's work
+// list (its recipient slots, for the datagram export).
+template <int W>
+__device__ __forceinline__ void work_body(const SimDev &d, uint32_t round, uint32_t ln, uint32_t idx, Row<W> &row, const uint32_t (&rix)[W],
+                                          const uint32_t (&td)[W], PbStage &pbs, Ctr &c, int lane, bool &did_remote,
+                                          uint32_t next_ln, bool have_next) {
+  constexpr bool kCarry = W <= 2;
+  const uint32_t self = d.first + ln;
+  const uint32_t par = round & 1;
+  uint2 *rl_out = d.rl + (size_t)par * d.n * d.fanout;
+  uint32_t am[W], L = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    am[w] = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE);
+    L += __popc(am[w]);
+  }
+  // T1 [Q8]: countdown on every Suspect slot; expired -> Dead, broadcast Dead(inc, member,
+  // from = self) in slot order
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    if ((row.st[w] & 3u) == SWIM_SUSPECT) { row.st[w] -= 4u; row.ticked |= 1u << w; } // timer >= 1 while Suspect
+    unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && ((row.st[w] >> 2) & d.tmask) == 0);
+    if (em >> lane & 1u) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
+    while (em) {
+      const int s = __ffs(em) - 1;
+      em &= em - 1;
+      const uint32_t m = __shfl_sync(kFull, row.nb[w], s), i = __shfl_sync(kFull, row.inc[w], s);
+      pb_enqueue(pbs, d, make_rec(m, i, self, SWIM_MSG_DEAD), lane, c.v[SWIM_CTR_PB_DROPPED]);
+      if (lane == 0) ++c.v[SWIM_CTR_DEAD_TIMEOUT];
+    }
+  }
+  // T2: the period's probe targets — kRandomMembers store P [] (Core.hs:239): ONE shuffle of the alive list, take P
+  // (P = cfg.probes_per_round; 1 = SWIM's single probe [Q11]); draw 0 is the node's TARGET word of the group block,
+  // draws 1.. come from a per-node stream. Probe 0's proxies — kRandomMembers store k [] (Core.hs:249), a fresh shuffle
+  // over the same alive list, neither self nor the target excluded — double as piggyback recipients (T4), so they are
+  // drawn whether or not the probe escalates.
+  uint32_t tslots[SWIM_MAX_PROBES], nt = 0, np = 0;
+  uint32_t prox_l = 0; // lane x < np: proxy x of probe 0 (a view slot)
+#pragma unroll
+  for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) tslots[j] = 0;
+  if (L) {
+    nt = d.P < L ? d.P : L;
+    // Every Philox block this item can ask for, in ONE pass of the warp: lane 0 computes the group's TARGET (or
+    // round-robin) block, lanes 1..7 the node's PROXY blocks 0..6 (draws j k + x <= 27), lane 8 its TARGETS block — a
+    // draw is then a shuffle from the lane that holds its block, instead of one warp-wide Philox call per block.
+    const uint4 tab = item_draws<W>(d, round, self, lane);
+    uint32_t tmp[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) tmp[w] = am[w];
+    uint32_t draw = tab_draw(tab, 0, self & 3);
+#pragma unroll
+    for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
+      if (j >= nt) break;
+      if (j && !(d.flags & SWIM_F_ROUND_ROBIN)) // (round-robin order: one walk, one word, for all probes of the period)
+        draw = tab_draw(tab, 8, j - 1);          // TARGETS draw j - 1 (j - 1 <= 2: block 0)
+      tslots[j] = pick_target_warp<W>(d, tmp, draw, L - j, round, lane);
+      clear_slot<W>(tmp, tslots[j]);
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w) tmp[w] = am[w];
+    np = d.k < L ? d.k : L;
+    for (uint32_t j = 0; j < np; ++j) {
+      const uint32_t pick = pick_remove_warp<W>(tmp, bounded(tab_draw(tab, 1 + (j >> 2), j & 3), L - j), lane);
+      if ((uint32_t)lane == j) prox_l = pick;
+    }
+    // T3: the probes one after the other (mapM_ probeNode', Core.hs:240) — Ping (Core.hs:246); unlessAck ->
+    // IndirectPings (247-250); unlessAck -> suspectNode (251-254). The incarnations are those of the moment the targets
+    // were chosen; a later probe's proxies are drawn from the store as the earlier probes left it.
+    uint32_t tincs = 0, tnodes = 0; // lane j: incarnation / id of target j as loaded (captured before any suspicion)
+#pragma unroll
+    for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
+      if (j >= nt) break;
+      uint32_t a = 0, b = 0;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t x = __shfl_sync(kFull, row.inc[w], tslots[j] & 31), y = __shfl_sync(kFull, row.nb[w], tslots[j] & 31);
+        if ((uint32_t)w == (tslots[j] >> 5)) { a = x; b = y; }
+      }
+      if ((uint32_t)lane == j) { tincs = a; tnodes = b; }
+    }
+    uint32_t cur[W], Lc = L; // the alive list as the probes so far left it
+#pragma unroll
+    for (int w = 0; w < W; ++w) cur[w] = am[w];
+#pragma unroll
+    for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
+      if (j >= nt) break;
+      const uint32_t tslot = tslots[j];
+      const bool t_up = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;
+      const bool acked = t_up && !direct_leg_lost(d, round, self, j);
+      if (acked) continue;
+      uint32_t npj = np;
+      uint32_t ps = (uint32_t)lane < np ? prox_l : 0u; // lane x: proxy x of this probe
+      if (j) { // kRandomMembers store k [] on the store as it is now: draws j k .. j k + k - 1 of the PROXY stream
+        uint32_t t2[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) t2[w] = cur[w];
+        npj = d.k < Lc ? d.k : Lc;
+        ps = 0;
+        for (uint32_t x = 0; x < npj; ++x) {
+          const uint32_t q = j * d.k + x;
+          const uint32_t pick = pick_remove_warp<W>(t2, bounded(tab_draw(tab, 1 + (q >> 2), q & 3), Lc - x), lane);
+          if ((uint32_t)lane == x) ps = pick;
+        }
+      }
+      if (lane == 0) { ++c.v[SWIM_CTR_DIRECT_FAIL]; c.v[SWIM_CTR_INDIRECT_PINGS] += npj; }
+      bool ok = false;
+      if ((uint32_t)lane < npj && t_up)
+        ok = (td[ps >> 5] >> (ps & 31) & 1u) == 0 && !leg_lost(d, round, self, 1 + j * d.k + lane);
+      if (!__any_sync(kFull, ok)) {
+        // Suspect (memberIncarnation m) (memberName m) with m captured at probe start
+        const uint32_t tinc = __shfl_sync(kFull, tincs, j), tnode = __shfl_sync(kFull, tnodes, j);
+        uint4 rb;
+        uint32_t no_self_inc = 0xFFFFFFFFu; // a probe never targets self
+        if (row_apply<W>(row, d, self, no_self_inc, make_rec(tnode, tinc, 0, SWIM_MSG_SUSPECT), rb, lane,
+                         c.v[SWIM_CTR_REFUTES], false) == 1) {
+          pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // yield . Broadcast (Core.hs:254)
+          if (lane == 0) ++c.v[SWIM_CTR_SUSPECT_LOCAL];
+          clear_slot<W>(cur, tslot);
+          --Lc;
+        }
+      }
+    }
+  }
+  row_store<W>(row, d, ln, lane, round);
+#ifndef SWIM_EMU
+  if (have_next && lane < 5) { // next item's rows -> L2 (one 128-byte line each at cap 32)
+    const size_t nb = (size_t)next_ln * d.cap;
+    const void *pf = lane == 0 ? (const void *)(d.nbr + nb) : lane == 1 ? (const void *)(d.vinc + nb) : lane == 2 ? (const void *)(d.vst + nb)
+                   : lane == 3 ? (const void *)(d.pb + (size_t)next_ln * d.B) : (const void *)(d.ridx + nb);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+  }
+#endif
+  // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
+  uint2 cand = make_uint2(0xFFFFFFFFu, ln); // lane f < fanout: recipient slot f
+  if (L && pbs.cnt) {
+    // recipients: the probe targets in order, then probe 0's proxies that are no targets, the first `fanout` of them;
+    // lane f carries recipient f
+    uint32_t nr = nt < d.fanout ? nt : d.fanout, rslot = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j)
+      if ((uint32_t)lane == j && j < nr) rslot = tslots[j];
+    bool is_target = false; // lane x: proxy x is one of the targets
+#pragma unroll
+    for (uint32_t t = 0; t < SWIM_MAX_PROBES; ++t) is_target |= t < nt && prox_l == tslots[t];
+    unsigned pm = __ballot_sync(kFull, (uint32_t)lane < np && !is_target);
+    while (pm && nr < d.fanout) { // the remaining proxies in draw order
+      const int x = __ffs(pm) - 1;
+      pm &= pm - 1;
+      const uint32_t p = __shfl_sync(kFull, prox_l, x);
+      if ((uint32_t)lane == nr) rslot = p;
+      ++nr;
+    }
+    uint32_t xs = 0xFFFFFFFFu; // exchange-bucket slot when lane f's recipient lives on another shard
+    uint32_t dst_c = 0, ridx_c = 0; // recipient id and in-edge index of lane f's slot, from the lanes that hold them
+    if (kCarry)
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const uint32_t a = __shfl_sync(kFull, row.nb[w], rslot & 31), b = __shfl_sync(kFull, rix[w], rslot & 31);
+        if ((uint32_t)w == (rslot >> 5)) { dst_c = a; ridx_c = b; }
+      }
+    uint32_t n_up = 0;
+    if ((uint32_t)lane < nr) {
+      const size_t e = (size_t)ln * d.cap + rslot;
+      const uint32_t dst = kCarry ? dst_c : d.nbr[e], ridx = kCarry ? ridx_c : d.ridx[e];
+      // A datagram to a crashed process is lost (the crashed-member bitmap says so without touching alive[]); one to a
+      // live process is received (counted here), but it is only DELIVERED — flagged and listed for K2 — if one of its
+      // records is about the recipient itself or passes the recipient's membership filter: anything else would run
+      // into `we don't know this node. ignore` (Core.hs:147-148) record by record and change nothing.
+      const bool r_up = (td[rslot >> 5] >> (rslot & 31) & 1u) == 0;
+      n_up = r_up ? 1u : 0u;
+      bool deliver = false;
+      if (r_up) {
+        constexpr uint32_t kBits = 512u * W;
+        const uint32_t *bf = d.bloom + (size_t)dst * (kBits / 32);
+        // two records per trip: their four filter words are in flight together (most envelopes carry one record)
+        for (uint32_t q0 = 0; q0 < pbs.cnt && !deliver; q0 += 2) {
+          const uint32_t xa = pbs.s[q0].x, xb = q0 + 1 < pbs.cnt ? pbs.s[q0 + 1].x : xa;
+          const uint32_t pa0 = bloom_pos(xa, 0, kBits), pa1 = bloom_pos(xa, 1, kBits);
+          const uint32_t pb0 = bloom_pos(xb, 0, kBits), pb1 = bloom_pos(xb, 1, kBits);
+          const uint32_t wa0 = bf[pa0 >> 5], wa1 = bf[pa1 >> 5], wb0 = bf[pb0 >> 5], wb1 = bf[pb1 >> 5];
+          deliver = xa == dst || xb == dst || ((wa0 >> (pa0 & 31) & 1u) && (wa1 >> (pa1 & 31) & 1u)) ||
+                    ((wb0 >> (pb0 & 31) & 1u) && (wb1 >> (pb1 & 31) & 1u));
+        }
+      }
+      const uint32_t owner = d.world == 1 ? 0u : dst / d.per;
+      const uint32_t dl = dst - owner * d.per;
+      if (owner == d.rank) cand.x = dl | (deliver ? 0u : 0x80000000u); // bit 31: sent, nothing for K2 to do
+      if (!deliver) {
+        // dropped at the sender
+      } else if (owner == d.rank) {
+        d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
+        if (d.fused) atomicOr(&d.mailbits[(size_t)(round % 3u) * d.mbw + (dl >> 5)], 1u << (dl & 31));
+      } else if (d.p2p) {
+        // fused exchange: flag and receiver-list entry go straight into the owner GPU's memory over NVLink (plain
+        // stores, nothing comes back); the receiver pulls our snapshot
+        d.eflag_p[owner][(size_t)par * d.estride_p[owner] + ridx] = 1;
+        const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
+        d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
+        if (d.fused) atomicOr(&d.mailbits_p[owner][(size_t)(round % 3u) * d.mbw + (dl >> 5)], 1u << (dl & 31));
+        did_remote = true;
+      } else {
+        const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
+        if (k < d.xcap) {
+          xs = owner * d.xcap + k;
+          d.xsend[(size_t)xs * (1 + d.B)] = make_uint4(ridx, pbs.cnt, self, dl);
+        } else {
+          d.xsend_cnt[d.world] = 1; // overflow: reported by the host as SWIM_ECAP, never silent
+        }
+      }
+    }
+    n_up = __reduce_add_sync(kFull, n_up);
+    const unsigned dm = __ballot_sync(kFull, cand.x < 0x80000000u); // delivered to a local receiver
+    if (dm) { // compact list for K2: one counter bump per sender that delivered anything (few do)
+      uint32_t pos = 0;
+      if (lane == 0) pos = atomicAdd(&d.ncand[ci(round)], (uint32_t)__popc(dm));
+      pos = __shfl_sync(kFull, pos, 0);
+      if (dm >> lane & 1u) d.cl[(size_t)par * d.n * d.fanout + pos + __popc(dm & ((1u << lane) - 1))] = cand;
+    }
+    if (lane == 0) {
+      d.out_cnt[(size_t)par * d.per + ln] = (uint8_t)pbs.cnt;
+      c.v[SWIM_CTR_MSGS] += nr;
+      c.v[SWIM_CTR_RECS_SENT] += nr * pbs.cnt;
+      c.v[SWIM_CTR_MSGS_RECV] += n_up; // envelopes that reach a live process
+    }
+    // snapshot, then one transmission is spent on every record
+    uint4 mine = make_uint4(0, 0, 0, 0);
+    const bool have = (uint32_t)lane < pbs.cnt;
+    if (have) { mine = pbs.s[lane]; d.out[((size_t)par * d.per + ln) * d.B + lane] = mine; }
+    unsigned xm = __ballot_sync(kFull, xs != 0xFFFFFFFFu);
+    while (xm) { // cross-shard envelopes carry the records themselves (staged NCCL path)
+      const int f = __ffs(xm) - 1;
+      xm &= xm - 1;
+      const uint32_t xslot = __shfl_sync(kFull, xs, f);
+      if (have) d.xsend[(size_t)xslot * (1 + d.B) + 1 + lane] = mine;
+    }
+    const bool keep = have && rec_ttl(mine) > 1;
+    const unsigned km = __ballot_sync(kFull, keep);
+    __syncwarp();
+    if (keep) {
+      mine.w -= 1u << 8;
+      pbs.s[__popc(km & ((1u << lane) - 1))] = mine;
+    }
+    pbs.cnt = __popc(km);
+    pbs.dirty = true;
+    __syncwarp();
+  }
+  pb_store(pbs, d, ln, lane);
+  if ((uint32_t)lane < d.fanout) rl_out[(size_t)idx * d.fanout + lane] = cand; // no atomics, no shared counter
+}
+
+// K1b — warp-per-node over the work list.
 template <int W>
 __device__ __forceinline__ bool work_pass(const SimDev &d, uint32_t round, uint32_t warp, uint32_t nwarps, int lane,
                                           PbStage &pbs, Ctr &c, uint32_t first_ln, bool fence_remote = true) {
   const uint32_t n_work = d.wl_cnt[ci(round)];
-  const uint32_t par = round & 1;
-  uint2 *rl_out = d.rl + (size_t)par * d.n * d.fanout;
   bool did_remote = false; // this lane stored into a peer GPU's memory
-
   uint32_t next_ln = first_ln;
   for (uint32_t idx = warp; idx < n_work; idx += nwarps) {
     const uint32_t ln = next_ln;
-    const uint32_t self = d.first + ln;
     Row<W> row;
     row_load<W>(row, d, ln, lane);
     pb_load(pbs, d, ln, lane);
     // the next item's list entry is fetched now, and — once it is known, further down — its rows are pulled towards L2:
     // a warp walks its items one after the other, so each dependent round trip it can start early is one it does not wait for
-    if (idx + nwarps < n_work) next_ln = *(volatile const uint32_t *)(d.wl + idx + nwarps);
-    // the row's edge indices travel with the row (narrow rows): the send step below needs the recipients' in-edge
+    const bool have_next = idx + nwarps < n_work;
+    if (have_next) next_ln = *(volatile const uint32_t *)(wl_of(d, round) + idx + nwarps);
+    // the row's edge indices travel with the row (narrow rows): the send step needs the recipients' in-edge
     // indices, and loading them there would be one more dependent memory round trip per item
-    constexpr bool kCarry = W <= 2;
-    uint32_t rix[W];
-    if (kCarry)
-#pragma unroll
-      for (int w = 0; w < W; ++w) rix[w] = d.ridx[(size_t)ln * d.cap + w * 32 + lane];
-    uint32_t td[W], am[W], L = 0;
+    uint32_t rix[W], td[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) {
+      rix[w] = W <= 2 ? d.ridx[(size_t)ln * d.cap + w * 32 + lane] : 0u;
       td[w] = d.meta[(size_t)ln * W + w].z;
-      am[w] = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE);
-      L += __popc(am[w]);
     }
-    // T1 [Q8]: countdown on every Suspect slot; expired -> Dead, broadcast Dead(inc, member,
-    // from = self) in slot order
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      if ((row.st[w] & 3u) == SWIM_SUSPECT) { row.st[w] -= 4u; row.ticked |= 1u << w; } // timer >= 1 while Suspect
-      unsigned em = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT && ((row.st[w] >> 2) & d.tmask) == 0);
-      if (em >> lane & 1u) { row.st[w] = SWIM_DEAD; row.touched |= 1u << w; }
-      while (em) {
-        const int s = __ffs(em) - 1;
-        em &= em - 1;
-        const uint32_t m = __shfl_sync(kFull, row.nb[w], s), i = __shfl_sync(kFull, row.inc[w], s);
-        pb_enqueue(pbs, d, make_rec(m, i, self, SWIM_MSG_DEAD), lane, c.v[SWIM_CTR_PB_DROPPED]);
-        if (lane == 0) ++c.v[SWIM_CTR_DEAD_TIMEOUT];
-      }
-    }
-    // T2: the period's probe targets — kRandomMembers store P [] (Core.hs:239): ONE shuffle of the alive list, take P
-    // (P = cfg.probes_per_round; 1 = SWIM's single probe [Q11]); draw 0 is the node's TARGET word of the group block,
-    // draws 1.. come from a per-node stream. Probe 0's proxies — kRandomMembers store k [] (Core.hs:249), a fresh shuffle
-    // over the same alive list, neither self nor the target excluded — double as piggyback recipients (T4), so they are
-    // drawn whether or not the probe escalates.
-    uint32_t tslots[SWIM_MAX_PROBES], nt = 0, np = 0;
-    uint32_t prox_l = 0; // lane x < np: proxy x of probe 0 (a view slot)
-#pragma unroll
-    for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) tslots[j] = 0;
-    if (L) {
-      nt = d.P < L ? d.P : L;
-      // Every Philox block this item can ask for, in ONE pass of the warp: lane 0 computes the group's TARGET (or
-      // round-robin) block, lanes 1..7 the node's PROXY blocks 0..6 (draws j k + x <= 27), lane 8 its TARGETS block — a
-      // draw is then a shuffle from the lane that holds its block, instead of one warp-wide Philox call per block.
-      const uint4 tab = item_draws<W>(d, round, self, lane);
-      uint32_t tmp[W];
-#pragma unroll
-      for (int w = 0; w < W; ++w) tmp[w] = am[w];
-      uint32_t draw = tab_draw(tab, 0, self & 3);
-#pragma unroll
-      for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
-        if (j >= nt) break;
-        if (j && !(d.flags & SWIM_F_ROUND_ROBIN)) // (round-robin order: one walk, one word, for all probes of the period)
-          draw = tab_draw(tab, 8, j - 1);          // TARGETS draw j - 1 (j - 1 <= 2: block 0)
-        tslots[j] = pick_target_warp<W>(d, tmp, draw, L - j, round, lane);
-        clear_slot<W>(tmp, tslots[j]);
-      }
-#pragma unroll
-      for (int w = 0; w < W; ++w) tmp[w] = am[w];
-      np = d.k < L ? d.k : L;
-      for (uint32_t j = 0; j < np; ++j) {
-        const uint32_t pick = pick_remove_warp<W>(tmp, bounded(tab_draw(tab, 1 + (j >> 2), j & 3), L - j), lane);
-        if ((uint32_t)lane == j) prox_l = pick;
-      }
-      // T3: the probes one after the other (mapM_ probeNode', Core.hs:240) — Ping (Core.hs:246); unlessAck ->
-      // IndirectPings (247-250); unlessAck -> suspectNode (251-254). The incarnations are those of the moment the targets
-      // were chosen; a later probe's proxies are drawn from the store as the earlier probes left it.
-      uint32_t tincs = 0, tnodes = 0; // lane j: incarnation / id of target j as loaded (captured before any suspicion)
-#pragma unroll
-      for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
-        if (j >= nt) break;
-        uint32_t a = 0, b = 0;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-          const uint32_t x = __shfl_sync(kFull, row.inc[w], tslots[j] & 31), y = __shfl_sync(kFull, row.nb[w], tslots[j] & 31);
-          if ((uint32_t)w == (tslots[j] >> 5)) { a = x; b = y; }
-        }
-        if ((uint32_t)lane == j) { tincs = a; tnodes = b; }
-      }
-      uint32_t cur[W], Lc = L; // the alive list as the probes so far left it
-#pragma unroll
-      for (int w = 0; w < W; ++w) cur[w] = am[w];
-#pragma unroll
-      for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j) {
-        if (j >= nt) break;
-        const uint32_t tslot = tslots[j];
-        const bool t_up = (td[tslot >> 5] >> (tslot & 31) & 1u) == 0;
-        const bool acked = t_up && !direct_leg_lost(d, round, self, j);
-        if (acked) continue;
-        uint32_t npj = np;
-        uint32_t ps = (uint32_t)lane < np ? prox_l : 0u; // lane x: proxy x of this probe
-        if (j) { // kRandomMembers store k [] on the store as it is now: draws j k .. j k + k - 1 of the PROXY stream
-          uint32_t t2[W];
-#pragma unroll
-          for (int w = 0; w < W; ++w) t2[w] = cur[w];
-          npj = d.k < Lc ? d.k : Lc;
-          ps = 0;
-          for (uint32_t x = 0; x < npj; ++x) {
-            const uint32_t q = j * d.k + x;
-            const uint32_t pick = pick_remove_warp<W>(t2, bounded(tab_draw(tab, 1 + (q >> 2), q & 3), Lc - x), lane);
-            if ((uint32_t)lane == x) ps = pick;
-          }
-        }
-        if (lane == 0) { ++c.v[SWIM_CTR_DIRECT_FAIL]; c.v[SWIM_CTR_INDIRECT_PINGS] += npj; }
-        bool ok = false;
-        if ((uint32_t)lane < npj && t_up)
-          ok = (td[ps >> 5] >> (ps & 31) & 1u) == 0 && !leg_lost(d, round, self, 1 + j * d.k + lane);
-        if (!__any_sync(kFull, ok)) {
-          // Suspect (memberIncarnation m) (memberName m) with m captured at probe start
-          const uint32_t tinc = __shfl_sync(kFull, tincs, j), tnode = __shfl_sync(kFull, tnodes, j);
-          uint4 rb;
-          uint32_t no_self_inc = 0xFFFFFFFFu; // a probe never targets self
-          if (row_apply<W>(row, d, self, no_self_inc, make_rec(tnode, tinc, 0, SWIM_MSG_SUSPECT), rb, lane,
-                           c.v[SWIM_CTR_REFUTES], false) == 1) {
-            pb_enqueue(pbs, d, rb, lane, c.v[SWIM_CTR_PB_DROPPED]); // yield . Broadcast (Core.hs:254)
-            if (lane == 0) ++c.v[SWIM_CTR_SUSPECT_LOCAL];
-            clear_slot<W>(cur, tslot);
-            --Lc;
-          }
-        }
-      }
-    }
-    row_store<W>(row, d, ln, lane, round);
-#ifndef SWIM_EMU
-    if (idx + nwarps < n_work && lane < 5) { // next item's rows -> L2 (one 128-byte line each at cap 32)
-      const size_t nb = (size_t)next_ln * d.cap;
-      const void *pf = lane == 0 ? (const void *)(d.nbr + nb) : lane == 1 ? (const void *)(d.vinc + nb) : lane == 2 ? (const void *)(d.vst + nb)
-                     : lane == 3 ? (const void *)(d.pb + (size_t)next_ln * d.B) : (const void *)(d.ridx + nb);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-    }
-#endif
-    // T4 [Q5]: the buffer rides on the messages to the target and the first proxies
-    uint2 cand = make_uint2(0xFFFFFFFFu, ln); // lane f < fanout: recipient slot f
-    if (L && pbs.cnt) {
-      // recipients: the probe targets in order, then probe 0's proxies that are no targets, the first `fanout` of them;
-      // lane f carries recipient f
-      uint32_t nr = nt < d.fanout ? nt : d.fanout, rslot = 0;
-#pragma unroll
-      for (uint32_t j = 0; j < SWIM_MAX_PROBES; ++j)
-        if ((uint32_t)lane == j && j < nr) rslot = tslots[j];
-      bool is_target = false; // lane x: proxy x is one of the targets
-#pragma unroll
-      for (uint32_t t = 0; t < SWIM_MAX_PROBES; ++t) is_target |= t < nt && prox_l == tslots[t];
-      unsigned pm = __ballot_sync(kFull, (uint32_t)lane < np && !is_target);
-      while (pm && nr < d.fanout) { // the remaining proxies in draw order
-        const int x = __ffs(pm) - 1;
-        pm &= pm - 1;
-        const uint32_t p = __shfl_sync(kFull, prox_l, x);
-        if ((uint32_t)lane == nr) rslot = p;
-        ++nr;
-      }
-      uint32_t xs = 0xFFFFFFFFu; // exchange-bucket slot when lane f's recipient lives on another shard
-      uint32_t dst_c = 0, ridx_c = 0; // recipient id and in-edge index of lane f's slot, from the lanes that hold them
-      if (kCarry)
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-          const uint32_t a = __shfl_sync(kFull, row.nb[w], rslot & 31), b = __shfl_sync(kFull, rix[w], rslot & 31);
-          if ((uint32_t)w == (rslot >> 5)) { dst_c = a; ridx_c = b; }
-        }
-      uint32_t n_up = 0;
-      if ((uint32_t)lane < nr) {
-        const size_t e = (size_t)ln * d.cap + rslot;
-        const uint32_t dst = kCarry ? dst_c : d.nbr[e], ridx = kCarry ? ridx_c : d.ridx[e];
-        // A datagram to a crashed process is lost (the crashed-member bitmap says so without touching alive[]); one to a
-        // live process is received (counted here), but it is only DELIVERED — flagged and listed for K2 — if one of its
-        // records is about the recipient itself or passes the recipient's membership filter: anything else would run
-        // into `we don't know this node. ignore` (Core.hs:147-148) record by record and change nothing.
-        const bool r_up = (td[rslot >> 5] >> (rslot & 31) & 1u) == 0;
-        n_up = r_up ? 1u : 0u;
-        bool deliver = false;
-        if (r_up) {
-          constexpr uint32_t kBits = 512u * W;
-          const uint32_t *bf = d.bloom + (size_t)dst * (kBits / 32);
-          // two records per trip: their four filter words are in flight together (most envelopes carry one record)
-          for (uint32_t q0 = 0; q0 < pbs.cnt && !deliver; q0 += 2) {
-            const uint32_t xa = pbs.s[q0].x, xb = q0 + 1 < pbs.cnt ? pbs.s[q0 + 1].x : xa;
-            const uint32_t pa0 = bloom_pos(xa, 0, kBits), pa1 = bloom_pos(xa, 1, kBits);
-            const uint32_t pb0 = bloom_pos(xb, 0, kBits), pb1 = bloom_pos(xb, 1, kBits);
-            const uint32_t wa0 = bf[pa0 >> 5], wa1 = bf[pa1 >> 5], wb0 = bf[pb0 >> 5], wb1 = bf[pb1 >> 5];
-            deliver = xa == dst || xb == dst || ((wa0 >> (pa0 & 31) & 1u) && (wa1 >> (pa1 & 31) & 1u)) ||
-                      ((wb0 >> (pb0 & 31) & 1u) && (wb1 >> (pb1 & 31) & 1u));
-          }
-        }
-        const uint32_t owner = d.world == 1 ? 0u : dst / d.per;
-        const uint32_t dl = dst - owner * d.per;
-        if (owner == d.rank) cand.x = dl | (deliver ? 0u : 0x80000000u); // bit 31: sent, nothing for K2 to do
-        if (!deliver) {
-          // dropped at the sender
-        } else if (owner == d.rank) {
-          d.eflag[(size_t)par * d.estride + ridx] = 1; // raise the in-edge flag (i -> dst)
-          if (d.fused) atomicOr(&d.mailbits[(size_t)(round % 3u) * d.mbw + (dl >> 5)], 1u << (dl & 31));
-        } else if (d.p2p) {
-          // fused exchange: flag and receiver-list entry go straight into the owner GPU's memory over NVLink (plain
-          // stores, nothing comes back); the receiver pulls our snapshot
-          d.eflag_p[owner][(size_t)par * d.estride_p[owner] + ridx] = 1;
-          const uint32_t k = atomicAdd(&d.xcnt[owner], 1u);
-          d.rlr_p[owner][((size_t)par * d.world + d.rank) * d.rcap + k] = dl;
-          if (d.fused) atomicOr(&d.mailbits_p[owner][(size_t)(round % 3u) * d.mbw + (dl >> 5)], 1u << (dl & 31));
-          did_remote = true;
-        } else {
-          const uint32_t k = atomicAdd(&d.xsend_cnt[owner], 1u);
-          if (k < d.xcap) {
-            xs = owner * d.xcap + k;
-            d.xsend[(size_t)xs * (1 + d.B)] = make_uint4(ridx, pbs.cnt, self, dl);
-          } else {
-            d.xsend_cnt[d.world] = 1; // overflow: reported by the host as SWIM_ECAP, never silent
-          }
-        }
-      }
-      n_up = __reduce_add_sync(kFull, n_up);
-      const unsigned dm = __ballot_sync(kFull, cand.x < 0x80000000u); // delivered to a local receiver
-      if (dm) { // compact list for K2: one counter bump per sender that delivered anything (few do)
-        uint32_t pos = 0;
-        if (lane == 0) pos = atomicAdd(&d.ncand[ci(round)], (uint32_t)__popc(dm));
-        pos = __shfl_sync(kFull, pos, 0);
-        if (dm >> lane & 1u) d.cl[(size_t)par * d.n * d.fanout + pos + __popc(dm & ((1u << lane) - 1))] = cand;
-      }
-      if (lane == 0) {
-        d.out_cnt[(size_t)par * d.per + ln] = (uint8_t)pbs.cnt;
-        c.v[SWIM_CTR_MSGS] += nr;
-        c.v[SWIM_CTR_RECS_SENT] += nr * pbs.cnt;
-        c.v[SWIM_CTR_MSGS_RECV] += n_up; // envelopes that reach a live process
-      }
-      // snapshot, then one transmission is spent on every record
-      uint4 mine = make_uint4(0, 0, 0, 0);
-      const bool have = (uint32_t)lane < pbs.cnt;
-      if (have) { mine = pbs.s[lane]; d.out[((size_t)par * d.per + ln) * d.B + lane] = mine; }
-      unsigned xm = __ballot_sync(kFull, xs != 0xFFFFFFFFu);
-      while (xm) { // cross-shard envelopes carry the records themselves (staged NCCL path)
-        const int f = __ffs(xm) - 1;
-        xm &= xm - 1;
-        const uint32_t xslot = __shfl_sync(kFull, xs, f);
-        if (have) d.xsend[(size_t)xslot * (1 + d.B) + 1 + lane] = mine;
-      }
-      const bool keep = have && rec_ttl(mine) > 1;
-      const unsigned km = __ballot_sync(kFull, keep);
-      __syncwarp();
-      if (keep) {
-        mine.w -= 1u << 8;
-        pbs.s[__popc(km & ((1u << lane) - 1))] = mine;
-      }
-      pbs.cnt = __popc(km);
-      pbs.dirty = true;
-      __syncwarp();
-    }
-    pb_store(pbs, d, ln, lane);
-    if ((uint32_t)lane < d.fanout) rl_out[(size_t)idx * d.fanout + lane] = cand; // no atomics, no shared counter
+    work_body<W>(d, round, ln, idx, row, rix, td, pbs, c, lane, did_remote, next_ln, have_next);
   }
   if (did_remote && fence_remote) __threadfence_system(); // peer-memory stores are performed before the grid reports completion
   return did_remote;
@@ -1252,7 +1284,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) tick_work_kernel(SimDev 
   if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.ncand[ci(round + 1)] = 0; }
   Ctr c; c.clear();
   PbStage pbs; pbs.s = s_pb[wib];
-  work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_work_entry(d, warp));
+  work_pass<W>(d, round, warp, nwarps, lane, pbs, c, first_work_entry(d, round, warp));
   c.flush(d.ctr, lane);
 }
 
@@ -1397,7 +1429,7 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
                                          tick_round, pings, self); // (a receiver is a live process)
     if (lane == 0) {
       c.v[SWIM_CTR_PINGS] += pings;
-      if (need) d.wl[atomicAdd(&d.wl_cnt[ci(tick_round)], 1u)] = ln;
+      if (need) wl_of(d, tick_round)[atomicAdd(&d.wl_cnt[ci(tick_round)], 1u)] = ln;
     }
   }
 }
@@ -1624,7 +1656,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     else grid_barrier(d, round, 5);
     tl_mark(d, round, 2);
     const uint32_t n_work = d.wl_cnt[ci(round)];
-    const uint32_t first_ln = first_work_entry(d, warp);                  // in flight together with the count
+    const uint32_t first_ln = first_work_entry(d, round, warp);                  // in flight together with the count
     if (mail) { // last round's mail bitmap has been read by every scanner: clear it (its next writers: senders of round + 2)
       uint32_t *mb = d.mailbits + (size_t)((round - 1) % 3u) * d.mbw;
       for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) mb[x] = 0;

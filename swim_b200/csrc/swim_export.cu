@@ -63,7 +63,7 @@ extern "C" int swim_sim_export_round(swim_sim_t *sim, uint8_t *buf, size_t cap, 
   if (n_work == 0) return SWIM_OK;
   const uint32_t F = d.fanout, B = d.B;
   std::vector<uint32_t> wl(n_work), rl((size_t)n_work * F);
-  CUDA_TRY(sim, cudaMemcpy(wl.data(), d.wl, (size_t)n_work * 4, cudaMemcpyDeviceToHost));
+  CUDA_TRY(sim, cudaMemcpy(wl.data(), d.wl + (size_t)par * d.n, (size_t)n_work * 4, cudaMemcpyDeviceToHost));
   {
     // recipient slots {receiver | bit 31 = dropped at the sender (it still went on the wire), sender}
     std::vector<uint2> slots((size_t)n_work * F);

@@ -229,11 +229,13 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
     if ((r = dalloc(sim, &d.meta, slots / 32, 0))) return r;
     if ((r = dalloc(sim, &d.obs_off, (size_t)d.N + 1, 0))) return r;
     if ((r = dalloc(sim, &d.obs_slot, slots, 0))) return r;
-    if ((r = dalloc(sim, &d.wl, n, 0))) return r;
+    if ((r = dalloc(sim, &d.wl, 2 * n, 0))) return r; // [parity]
     if ((r = dalloc(sim, &d.wl_cnt, 4, 0))) return r;
     if ((r = dalloc(sim, &d.ncand, 4, 0))) return r;
     d.mbw = (d.per + 31) / 32;
     if ((r = dalloc(sim, &d.mailbits, 3 * (size_t)d.mbw, 0))) return r;
+    if ((r = dalloc(sim, &d.workbits, 3 * (size_t)d.mbw, 0))) return r;
+    if ((r = dalloc(sim, &d.wl_n, 4, 0))) return r;
     if ((r = dalloc(sim, &d.rl, 2 * n * d.fanout, 0xFF))) return r; // [parity] recipient slots, empty = 0xFFFFFFFF
     if ((r = dalloc(sim, &d.cl, 2 * n * d.fanout, 0xFF))) return r; // [parity] delivered slots, compact
     // {digest, mismatch count} scratch and the counters share one block: swim_sim_observe reads both back in one copy
@@ -778,6 +780,8 @@ static int reset_round_state(swim_sim *sim) {
   CUDA_TRY(sim, cudaMemsetAsync(d.wl_cnt, 0, 16, sim->stream));
   CUDA_TRY(sim, cudaMemsetAsync(d.ncand, 0, 16, sim->stream));
   CUDA_TRY(sim, cudaMemsetAsync(d.mailbits, 0, 3 * (size_t)d.mbw * 4, sim->stream));
+  CUDA_TRY(sim, cudaMemsetAsync(d.workbits, 0, 3 * (size_t)d.mbw * 4, sim->stream));
+  CUDA_TRY(sim, cudaMemsetAsync(d.wl_n, 0, 16, sim->stream));
   CUDA_TRY(sim, cudaMemsetAsync(d.qm, 0, 16, sim->stream));
   CUDA_TRY(sim, cudaMemsetAsync(d.gbar, 0, 4, sim->stream)); // arrival count; the generation word keeps counting
   CUDA_TRY(sim, cudaMemsetAsync(d.xcnt, 0, SWIM_MAX_WORLD * 4, sim->stream));
