@@ -81,11 +81,22 @@ def algorithmic_bytes(cfg_kw, n_nodes, rounds, ctr_delta):
     return floor + 2 * msg_side, floor + msg_side, m_bar, b_bar
 
 
+def timed_kernel_name(steps, world):
+    """Which fused kernel runs the timed rounds: round_kernel_x (one grid barrier per round) for launches of >= 32 rounds on
+    a single shard, the two-phase round_kernel otherwise (swim_sim.cu: kXModeMinRounds); SWIM_XMODE=1 / 0 forces one."""
+    x = os.environ.get("SWIM_XMODE")
+    if x is not None:
+        return "round_kernel_x<1>" if x != "0" else "round_kernel<1>"
+    longest = steps - max(0, CRASH_ROUND - 1 - 5)  # the launch behind the crash events (warm-up 5: rounds 6..9 come first)
+    return "round_kernel_x<1>" if world == 1 and longest >= 32 else "round_kernel<1>"
+
+
 def summarize_timeline(tl, warmup):
     """tl: [rounds, 8] ns stamps of round_kernel's phase boundaries (CTA 0; swim_sim_get_timeline). Per-phase means over
     the rounds that ran the phase; a round committed by a batched quiet scan shares its batch's stamps."""
     scan, work, recv, busy_total, quiet_total, bar3 = [], [], [], [], [], []
     last_scan, last_work, rel1, rel2 = [], [], [], []  # slowest CTA's phase time; release latency of the two barriers
+    x_own, x_last = [], []  # one-barrier rounds: CTA 0's / the slowest CTA's interval
     own = {"scan": [], "work": [], "recv": []}  # CTA 0's own share of a phase (the rest is waiting at the barrier)
     n_busy = n_quiet = 0
     r = 0
@@ -102,6 +113,12 @@ def summarize_timeline(tl, warmup):
             r += span
             continue
         n_busy += 1
+        if t[3] == 0 and t[4] == 1:  # round_kernel_x: ONE interval and one barrier per round (slot 4 holds the busy flag)
+            busy_total.append(t[2] - t[0]); x_own.append(t[1] - t[0])
+            if t[5]:
+                x_last.append(t[5] - t[0]); rel1.append(t[2] - t[5])
+            r += 1
+            continue
         scan.append(t[2] - t[0]); own["scan"].append(t[1] - t[0])
         work.append(t[4] - t[2]); own["work"].append(t[3] - t[2])
         busy_total.append(t[4] - t[0])  # (the receive pass of a round runs inside the next round's scan phase)
@@ -114,12 +131,17 @@ def summarize_timeline(tl, warmup):
             "scan_us": f(scan), "work_us": f(work), "recv_us": f(recv), "recv_rounds": len(recv),
             "cta0_scan_us": f(own["scan"]), "cta0_work_us": f(own["work"]), "cta0_recv_us": f(own["recv"]),
             "busy_us_max": float(np.max(busy_total)) / 1e3 if busy_total else None,
+            "barriers_per_busy_round": 1 if x_own else 2,
+            "cta0_interval_us": f(x_own), "slowest_cta_interval_us": f(x_last),
             "slowest_cta_scan_us": f(last_scan), "slowest_cta_work_us": f(last_work),
             "barrier1_release_us": f(rel1), "barrier2_release_us": f(rel2),
             "what": "in-kernel %globaltimer stamps of CTA 0 at round_kernel's phase boundaries over the timed rounds; a phase "
                     "runs from one grid barrier to the next: scan (+ the receive pass of the round before, on otherwise idle "
                     "warps) | work = K1b; cta0_* is CTA 0's own part of it, slowest_cta_* the arrival of the LAST CTA at the phase's "
-                    "barrier, barrierN_release_us what the barrier itself adds after that"}
+                    "barrier, barrierN_release_us what the barrier itself adds after that. round_kernel_x (default) has ONE "
+                    "interval per round — mail of the round before + K1b + the next round's scan — and one barrier: "
+                    "busy_us / cta0_interval_us / slowest_cta_interval_us / barrier1_release_us describe it, the scan_ / "
+                    "work_ keys stay empty"}
 
 
 def make_roofline(cfg_kw, n_local, ms_per_round, ab_round, m_bar, b_bar, peak, measured_peak, prof, rounds_p, timeline,
@@ -148,15 +170,18 @@ def make_roofline(cfg_kw, n_local, ms_per_round, ab_round, m_bar, b_bar, peak, m
         items_w = max(1.0, msgs / max(1.0, cfg_kw["fanout"] * 0.97) / nwarps)
         items_r = max(1.0, msgs / nwarps)
         hop = calib["hbm_load_ns"] / 1e3
-        floor_busy = 2 * calib["grid_barrier_ns"] / 1e3 + hop * (1 + 2 * items_w)
+        n_bar = timeline.get("barriers_per_busy_round", 2)
+        floor_busy = n_bar * calib["grid_barrier_ns"] / 1e3 + hop * (1 + 2 * items_w)
         floor = {"busy_round_us": floor_busy, "measured_busy_round_us": timeline["busy_us"],
                  "frac_of_floor": floor_busy / timeline["busy_us"] if timeline["busy_us"] else None,
                  "grid_barrier_us": calib["grid_barrier_ns"] / 1e3, "hbm_dependent_load_us": hop,
                  "l2_dependent_load_us": calib.get("l2_load_ns", 0) / 1e3,
-                 "model": "2 grid barriers + dependent-load hops (1 for the scan's records, 2 per K1b item: list entry -> row "
-                          "-> recipients' filters) x K1b items per warp, mean items of the timed rounds; the receive pass "
-                          "overlaps the scan"}
-    return {"bound": "hbm", "kernel": "round_kernel<1>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                 "barriers_per_busy_round": n_bar,
+                 "model": "grid barriers of a busy round (1 with round_kernel_x, 2 with the two-phase round_kernel) + "
+                          "dependent-load hops (1 for the scan's records, 2 per K1b item: list entry -> row -> recipients' "
+                          "filters) x K1b items per warp, mean items of the timed rounds; the receive pass overlaps"}
+    return {"bound": "hbm", "kernel": ("round_kernel_x<1>" if timeline.get("barriers_per_busy_round") == 1 else "round_kernel<1>")
+                      if timeline and timeline.get("busy_rounds") else timed_kernel_name(steps, world), "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if measured_peak else "6650 GB/s (of fallback)",
             "traffic": traffic, "dram_gbs": dram_gbs, "dram_frac": dram_gbs / peak if dram_gbs else None,
@@ -266,7 +291,7 @@ def config_dict(cfg_kw, n, n_gpus, exchange_mode="single"):
             "parallelism": f"shard{n_gpus}" if n_gpus > 1 else "single", "exchange": exchange_mode,
             # rounds decided per batched quiet scan of round_kernel (single shard; 0 = off), DESIGN.md section 5
             "quiet_batch": (min(8, max(0, int(os.environ.get("SWIM_QUIET_BATCH", "4")))) if n_gpus == 1 else 0),
-            "launch_switches": {k: os.environ[k] for k in ("SWIM_PIPELINE", "SWIM_SPLIT", "SWIM_ROUND_KERNEL",
+            "launch_switches": {k: os.environ[k] for k in ("SWIM_PIPELINE", "SWIM_SPLIT", "SWIM_ROUND_KERNEL", "SWIM_XMODE",
                                                             "SWIM_ONE_ROUND_PER_LAUNCH", "SWIM_WPB", "SWIM_QUIET_BATCH") if k in os.environ},
             "l2": "no flush between rounds: consecutive rounds of one simulation share state by definition; "
                   "state arrays total 0.5 GB/GPU (> 126 MB L2), the per-round hot set (packed state rows 32 MB "
@@ -319,16 +344,28 @@ def run_cuda(args):
             print(f"[bench +{time.perf_counter() - t_bench0:7.2f}s] {msg}", file=sys.stderr, flush=True)
 
     # ------------------------------------------------ device-resident timing (value)
-    # One handle, one device-resident checkpoint (swim_sim_save at round 0, events pending): every timing window starts
-    # from the same state and runs the same rounds, so the windows differ only by the machine.
+    # One handle, one device-resident checkpoint (swim_sim_save at round 0): every timing window starts from the same state
+    # and runs the same rounds, so the windows differ only by the machine.
     log(f"workload built: {n} nodes, world {world}")
-    sim = fresh()
+    # ONE handle serves every leg below (the host-side index build of swim_sim_set_view is the expensive part of a handle,
+    # tens of seconds per rank at 8 x C3): the checkpoint is taken at round 0 WITHOUT pending events; a leg that runs the
+    # event trace from the queue does load() + inject(events), the end-to-end leg injects round by round instead.
+    sim = fresh(inject=False)
     # a non-default torch stream: its handle is what the library launches on, so the torch events
     # below bracket the kernels (handle 0 would mean "the handle's private stream" to the C ABI)
     stream = torch.cuda.Stream()
     assert stream.cuda_stream != 0
     sim.set_stream(stream.cuda_stream)
     sim.save()
+
+    def restart(flags=0, inject=True):
+        sim.load()
+        if sim.cfg.flags != flags:
+            sim.set_params(flags=flags)
+        if inject:
+            sim.inject(events)
+
+    restart()
     clocks = ClockSampler(local) if rank == 0 else None  # runs until the end of the e2e region
     # clock spin-up: a fresh process finds the GPU at its idle clock (~1 GHz on this pool) and a 2 ms window is over
     # before the governor reacts; run real rounds for a while first, then go back to the checkpoint. (Not part of the
@@ -341,7 +378,7 @@ def run_cuda(args):
     ctr_delta, launches = None, 0
     for w in range(args.windows):
         barrier()
-        sim.load()
+        restart()
         barrier()
         sim.step(args.warmup)
         c0, l0 = sim.counters(), sim.launch_count()
@@ -375,7 +412,7 @@ def run_cuda(args):
     timeline = None
     if True:  # (sharded runs: stamps exist only on the fused-kernel path, SWIM_ROUND_KERNEL; each rank reports its own CTA 0)
         barrier()
-        sim.load()
+        restart()
         barrier()
         sim.step(args.warmup)
         sim.set_timeline(args.steps)
@@ -387,7 +424,7 @@ def run_cuda(args):
     log("timeline done")
     # ------------------------------------------------ per-kernel timing of the same rounds (split launches)
     barrier()
-    sim.load()
+    restart()
     barrier()
     sim.step(args.warmup)
     sim.set_profile(True)
@@ -403,7 +440,7 @@ def run_cuda(args):
     if not args.no_parity:
         rounds_chk = min(args.warmup + args.steps, 40)
         barrier()
-        sim.load()
+        restart()
         barrier()
         sim.step(rounds_chk)
         dg = sdist.global_digest(sim.digest())
@@ -427,7 +464,6 @@ def run_cuda(args):
                       "digest": f"{dg:016x}", "what": "global state digest + all counters + convergence count of the CUDA run "
                       f"(all {world} shard(s)) == restated C oracle on the same N, seed and event trace"}
             del orc
-    sim.close()
     log(f"parity leg done: {parity['status'] if parity else None}")
     ab_round, ab_tick, m_bar, b_bar = algorithmic_bytes(cfg_kw, n, args.steps, ctr_delta)
     peaks = {}
@@ -443,8 +479,6 @@ def run_cuda(args):
     # ------------------------------------------------ end to end through the C ABI, host buffers
     e2e = None
     if True:
-        sim = fresh(inject=False)
-        sim.save()
         by_round = {}
         for e in events:
             by_round.setdefault(int(e["round"]), []).append(e)
@@ -478,15 +512,16 @@ def run_cuda(args):
         e2e_windows = []
         use_step_observe, e2e_notes = [True], []
         try:  # one probe round outside every timed window: the mapped-memory read-back must work on this box
-            sim.load()
+            restart(inject=False)
             one_round(1)
         except Exception:  # noqa: BLE001
             sim.close()
             sim = fresh(inject=False)
+            sim.set_stream(stream.cuda_stream)
             sim.save()
         for w in range(args.windows):
             barrier()
-            sim.load()
+            restart(inject=False)
             barrier()
             for r in range(1, args.warmup + 1):
                 one_round(r)
@@ -511,7 +546,6 @@ def run_cuda(args):
                "what": "per round: swim_sim_inject(host events, when the round has any) + swim_sim_step_observe(1): one round, then "
                        "the counters and the convergence count written by the device into mapped pinned host memory — host "
                        "wall clock, max over ranks, median of the windows"}
-        sim.close()
     clk = clocks.stop() if clocks else None
     log("e2e done")
 
@@ -519,7 +553,9 @@ def run_cuda(args):
     conv = None
     if rank == 0 or world > 1:
         def rounds_to_convergence(flags):
-            sim = fresh(flags=flags)
+            barrier()
+            restart(flags=flags)
+            barrier()
             sim.step(CRASH_ROUND)
             r = CRASH_ROUND
             mm = None
@@ -536,7 +572,6 @@ def run_cuda(args):
                     break
                 if mm < 64:
                     stride = 1
-            sim.close()
             return (r if mm == 0 else None), mm
 
         r0, mm0 = rounds_to_convergence(0)
@@ -547,6 +582,9 @@ def run_cuda(args):
                 "crash_round": CRASH_ROUND, "rounds_to_convergence_round_robin": r1, "mismatches_at_end_round_robin": mm1}
 
     log(f"convergence done: {conv}")
+    if sim.cfg.flags:
+        sim.set_params(flags=0)
+    sim.close()
     # ------------------------------------------------ second workload: the state machine under load (ring-lattice views)
     # C3's uniformly random views almost never let a receiver know the member a record is about (32 of 2^20), so its
     # dissemination path idles. With ring-lattice views (each node knows its 32 nearest ids) records reach nodes that know

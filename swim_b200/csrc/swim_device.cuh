@@ -597,7 +597,10 @@ struct Ctr {
       if (lane == 0 && x) atomicAdd(&s_ctr[i], x);
     }
     __syncthreads();
-    if (threadIdx.x < SWIM_CTR__COUNT && s_ctr[threadIdx.x]) atomicAdd(&g[threadIdx.x], (unsigned long long)s_ctr[threadIdx.x]);
+    // (the Ping count takes corrections of either sign — round_kernel_x — and is carried modulo 2^32 up to here: extend its sign)
+    if (threadIdx.x < SWIM_CTR__COUNT && s_ctr[threadIdx.x])
+      atomicAdd(&g[threadIdx.x], threadIdx.x == SWIM_CTR_PINGS ? (unsigned long long)(long long)(int32_t)s_ctr[threadIdx.x]
+                                                                : (unsigned long long)s_ctr[threadIdx.x]);
   }
 };
 
@@ -1336,38 +1339,16 @@ static __global__ void peer_barrier_kernel(SimDev d) {
 }
 
 // =================================================================== K2: receive
-// One receiver of `round`: claim, in-edge flags -> sender snapshots (local or peer-GPU memory) -> row_apply per record,
-// re-broadcast enqueue. Loads that do not depend on each other are issued together: (claim, row, buffer, in-list bounds,
-// the snapshot of the sender the slot names) -> (edge flags, sender ids) -> (other senders' snapshots).
-// tick_round != 0 (fused kernel: the mail of `round` is applied during the scan phase of tick_round = round + 1, and the
-// scan leaves the node alone): after the mail, the node's tick decision of tick_round — what K1a would have computed —
-// is taken here from the fresh row, and the node is appended to that round's work list if it needs K1b.
+// The mail of `round` for local node ln, applied to a row and a piggyback buffer that are already loaded: in-edge flags
+// [e0, e1) in ascending sender order -> the senders' snapshots (the one fetched early, local HBM, or a peer GPU's memory)
+// -> row_apply per record, re-broadcast enqueue.
 template <int W>
-__device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32_t ln, bool early, uint32_t snd, int lane,
-                                         PbStage &pbs, Ctr &c, uint32_t tick_round = 0) {
+__device__ __forceinline__ void apply_mail(const SimDev &d, uint32_t round, uint32_t ln, uint32_t e0, uint32_t e1, bool early,
+                                           uint32_t snd, uint4 early_rec, uint32_t early_cnt, Row<W> &row, PbStage &pbs,
+                                           uint32_t &self_inc, int lane, Ctr &c) {
   const uint32_t par = round & 1;
   const size_t ebase = (size_t)par * d.estride;
-  // the claim and every load that depends only on `ln` are issued together (one memory round trip)
-  uint32_t old = 0;
-  if (lane == 0) old = atomicExch(&d.claim[ln], round);
   const uint32_t self = d.first + ln;
-  const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
-  Row<W> row;
-  row_load<W>(row, d, ln, lane);
-  pb_load(pbs, d, ln, lane);
-  uint32_t self_inc = d.self_inc[ln];
-  const uint32_t self_inc0 = self_inc;
-  // A recipient slot names one sender of its receiver; that sender's snapshot is fetched together with the receiver's
-  // row, ahead of the in-edge flags that will ask for it — for the usual envelope (one sender per receiver per round) the
-  // pass is one dependent round trip shorter. The flags still decide what is applied and in which order.
-  uint4 early_rec = make_uint4(0, 0, 0, 0);
-  uint32_t early_cnt = 0;
-  if (early) {
-    if ((uint32_t)lane < d.B) early_rec = d.out[((size_t)par * d.per + snd) * d.B + lane];
-    early_cnt = d.out_cnt[(size_t)par * d.per + snd];
-  }
-  if (__shfl_sync(kFull, old, 0) == round) return; // another warp has this receiver
-  // (a listed receiver is a live process: senders deliver only to members whose crashed-member bit is clear)
   for (uint32_t eb = e0; eb < e1; eb += 32) {
     const uint32_t e = eb + lane;
     uint32_t f = 0, src = 0;
@@ -1410,6 +1391,42 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
       }
     }
   }
+}
+
+
+// One receiver of `round`: claim, in-edge flags -> sender snapshots (local or peer-GPU memory) -> row_apply per record,
+// re-broadcast enqueue. Loads that do not depend on each other are issued together: (claim, row, buffer, in-list bounds,
+// the snapshot of the sender the slot names) -> (edge flags, sender ids) -> (other senders' snapshots).
+// tick_round != 0 (fused kernel: the mail of `round` is applied during the scan phase of tick_round = round + 1, and the
+// scan leaves the node alone): after the mail, the node's tick decision of tick_round — what K1a would have computed —
+// is taken here from the fresh row, and the node is appended to that round's work list if it needs K1b.
+template <int W>
+__device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32_t ln, bool early, uint32_t snd, int lane,
+                                         PbStage &pbs, Ctr &c, uint32_t tick_round = 0) {
+  const uint32_t par = round & 1;
+  const size_t ebase = (size_t)par * d.estride;
+  // the claim and every load that depends only on `ln` are issued together (one memory round trip)
+  uint32_t old = 0;
+  if (lane == 0) old = atomicExch(&d.claim[ln], round);
+  const uint32_t self = d.first + ln;
+  const uint32_t e0 = d.in_off[ln], e1 = d.in_off[ln + 1];
+  Row<W> row;
+  row_load<W>(row, d, ln, lane);
+  pb_load(pbs, d, ln, lane);
+  uint32_t self_inc = d.self_inc[ln];
+  const uint32_t self_inc0 = self_inc;
+  // A recipient slot names one sender of its receiver; that sender's snapshot is fetched together with the receiver's
+  // row, ahead of the in-edge flags that will ask for it — for the usual envelope (one sender per receiver per round) the
+  // pass is one dependent round trip shorter. The flags still decide what is applied and in which order.
+  uint4 early_rec = make_uint4(0, 0, 0, 0);
+  uint32_t early_cnt = 0;
+  if (early) {
+    if ((uint32_t)lane < d.B) early_rec = d.out[((size_t)par * d.per + snd) * d.B + lane];
+    early_cnt = d.out_cnt[(size_t)par * d.per + snd];
+  }
+  if (__shfl_sync(kFull, old, 0) == round) return; // another warp has this receiver
+  // (a listed receiver is a live process: senders deliver only to members whose crashed-member bit is clear)
+  apply_mail<W>(d, round, ln, e0, e1, early, snd, early_rec, early_cnt, row, pbs, self_inc, lane, c);
   row_store<W>(row, d, ln, lane, round);
   pb_store(pbs, d, ln, lane);
   if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
@@ -1686,6 +1703,345 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel(SimDev d) {
     // its bitmap is not needed by anybody: clear it. (The receive pass does not read it, so no barrier in between.)
     uint32_t *mb = d.mailbits + (size_t)((d.round + d.nrounds - 1) % 3u) * d.mbw;
     for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) mb[x] = 0;
+  }
+  c.flush(d.ctr, lane);
+}
+
+// =================================================================== one kernel per round, ONE grid barrier per round
+// round_kernel_x: the two phases of round_kernel merged. Between the barriers B(r-1) and B(r) a warp does, for round r,
+//   * the mail of round r-1 for the receivers it is given (x_node from the delivered-slot lists): apply it, take the node's
+//     FINAL tick decision of round r, run K1b of round r right there if the node needs it, then its tick decision of r+1;
+//   * K1b of round r for its items of the work list of round r (complete and frozen at B(r-1)); a listed node that also has
+//     mail of round r-1 gets it applied first, by the same warp, on the row it has loaded anyway; then the decision of r+1;
+//   * K1a of round r+1 for its slice of all other nodes (neither on the work list of r nor receivers of round r-1: nothing
+//     touches them in this interval) — appending to the work list of r+1.
+// A tick decision of round r+1 taken before B(r) is TENTATIVE for a node that turns out to receive mail in round r: the
+// mail is applied behind B(r), and whoever applies it re-decides (and corrects the Ping count by the difference). Nothing
+// else depends on the order of things inside an interval: a node's row, buffer and meta record are written by exactly one
+// warp per interval, mail flags and snapshots are round-parity double-buffered, and the bitmaps (mail of round r in slot
+// r % 3, work list of round r in slot r % 3) are cleared one interval after their last reader and one before their next
+// writer. Result: bit-identical to round_kernel, one barrier (and one cross-GPU handshake) per round instead of two.
+
+// The tick decision of `tick_round` for a live local node from its freshly updated row (what K1a computes from the meta
+// record): counts its Pings and, if it needs K1b, appends it to that round's work list and marks it in `listbits`.
+template <int W>
+__device__ __forceinline__ void tick_decide(const SimDev &d, uint32_t tick_round, uint32_t ln, const Row<W> &row, uint32_t pbcnt,
+                                            const uint32_t (&td)[W], int lane, Ctr &c, uint32_t *listbits) {
+  const uint32_t self = d.first + ln;
+  uint32_t am[W], sus = 0, L = 0, risk = d.loss_ppm;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    am[w] = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE);
+    sus |= __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT);
+    L += __popc(am[w]);
+    risk |= am[w] & td[w];
+  }
+  bool need = pbcnt != 0 || sus != 0;
+  if (L && risk && !need) { // only now does the decision depend on the node's draws
+    const uint4 x = target_block<W>(d, tick_round, self >> 2);
+    uint32_t ldraw = 0;
+    if (d.loss_ppm) ldraw = word_of(philox4x32_10(make_uint4(tick_round, self >> 2, P_LOSS0, 0), d.key0, d.key1), self & 3);
+    need = probe_fails<W>(d, am, td, L, word_of(x, self & 3), ldraw, tick_round, self);
+  }
+  if (lane == 0) {
+    if (L) c.v[SWIM_CTR_PINGS] += d.P < L ? d.P : L;
+    if (need) {
+      wl_of(d, tick_round)[atomicAdd(&d.wl_cnt[ci(tick_round)], 1u)] = ln;
+      if (listbits) atomicOr(&listbits[ln >> 5], 1u << (ln & 31));
+    }
+  }
+}
+
+// One node of the interval of round `round` (see above). from_wl: the node is item `idx` of the round's work list; else it
+// is a receiver of round - 1 named by a delivered slot (early / snd as in recv_one). mail: round - 1 delivered mail to
+// nodes of this rank at all. decide: take the tick decision of round + 1 (false in the last round of a launch).
+template <int W>
+__device__ __forceinline__ void x_node(const SimDev &d, uint32_t round, uint32_t ln, uint32_t idx, bool from_wl, bool mail, bool early,
+                                       uint32_t snd, int lane, PbStage &pbs, Ctr &c, bool decide, bool &did_remote,
+                                       uint32_t next_ln, bool have_next) {
+  const uint32_t mround = round - 1, mpar = mround & 1;
+  // everything that depends only on `ln` is issued together (one memory round trip)
+  uint32_t old = 0, wbit = 0, mbit = 0;
+  if (!from_wl) {
+    if (lane == 0) old = atomicExch(&d.claim[ln], mround);
+    wbit = d.workbits[(size_t)(round % 3u) * d.mbw + (ln >> 5)] >> (ln & 31) & 1u;
+  } else if (mail) {
+    mbit = d.mailbits[(size_t)(mround % 3u) * d.mbw + (ln >> 5)] >> (ln & 31) & 1u;
+  }
+  Row<W> row;
+  row_load<W>(row, d, ln, lane);
+  pb_load(pbs, d, ln, lane);
+  uint32_t rix[W], td[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    rix[w] = W <= 2 ? d.ridx[(size_t)ln * d.cap + w * 32 + lane] : 0u;
+    td[w] = d.meta[(size_t)ln * W + w].z; // crashed-member bits: events only, not touched by mail or ticks
+  }
+  uint32_t e0 = 0, e1 = 0, self_inc = 0;
+  uint4 early_rec = make_uint4(0, 0, 0, 0);
+  uint32_t early_cnt = 0;
+  if (!from_wl || mail) { // (loaded before the bits are known: a listed node without mail simply does not use them)
+    e0 = d.in_off[ln]; e1 = d.in_off[ln + 1];
+    self_inc = d.self_inc[ln];
+    if (early) {
+      if ((uint32_t)lane < d.B) early_rec = d.out[((size_t)mpar * d.per + snd) * d.B + lane];
+      early_cnt = d.out_cnt[(size_t)mpar * d.per + snd];
+    }
+  }
+  if (!from_wl) {
+    // a receiver that is on this round's work list belongs to the warp that has it as an item; otherwise one warp per receiver
+    if (wbit || __shfl_sync(kFull, old, 0) == mround) return;
+  }
+  const bool has_mail = !from_wl || mbit != 0;
+  bool do_work = from_wl;
+  if (has_mail) {
+    uint32_t l_pre = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) l_pre += __popc(__ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE));
+    const uint32_t self_inc0 = self_inc;
+    apply_mail<W>(d, mround, ln, e0, e1, early, snd, early_rec, early_cnt, row, pbs, self_inc, lane, c);
+    row_store<W>(row, d, ln, lane, mround); // (lastChange = the round of the mail)
+    row.touched = 0;
+    row.ticked = 0;
+    if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
+    // The node's tick decision of `round` was taken before its mail was known: its Pings were counted from the row as it
+    // was then — the row this warp loaded. Correct the count; a receiver that was not listed is decided again.
+    uint32_t am[W], sus = 0, l_post = 0, risk = d.loss_ppm;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      am[w] = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE);
+      sus |= __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT);
+      l_post += __popc(am[w]);
+      risk |= am[w] & td[w];
+    }
+    const uint32_t p_pre = d.P < l_pre ? d.P : l_pre, p_post = d.P < l_post ? d.P : l_post;
+    if (lane == 0) c.v[SWIM_CTR_PINGS] += p_post - p_pre; // (modulo 2^32; Ctr::flush extends the sign of this counter)
+    if (!from_wl) {
+      do_work = pbs.cnt != 0 || sus != 0;
+      if (l_post && risk && !do_work) {
+        const uint32_t self = d.first + ln;
+        const uint4 x = target_block<W>(d, round, self >> 2);
+        uint32_t ldraw = 0;
+        if (d.loss_ppm) ldraw = word_of(philox4x32_10(make_uint4(round, self >> 2, P_LOSS0, 0), d.key0, d.key1), self & 3);
+        do_work = probe_fails<W>(d, am, td, l_post, word_of(x, self & 3), ldraw, round, self);
+      }
+      if (do_work) { // behind the frozen part of the list: nobody walks it, its position carries the node's recipient slots
+        if (lane == 0) {
+          idx = atomicAdd(&d.wl_cnt[ci(round)], 1u);
+          wl_of(d, round)[idx] = ln;
+        }
+        idx = __shfl_sync(kFull, idx, 0);
+      }
+    }
+  }
+  if (do_work) work_body<W>(d, round, ln, idx, row, rix, td, pbs, c, lane, did_remote, next_ln, have_next);
+  else pb_store(pbs, d, ln, lane);
+  if (decide) tick_decide<W>(d, round + 1, ln, row, pbs.cnt, td, lane, c, d.workbits + (size_t)((round + 1) % 3u) * d.mbw);
+}
+
+// grid barrier whose last arrival also freezes a work-list length (*cnt_src -> *cnt_dst) before it releases the grid
+__device__ __forceinline__ void grid_barrier_freeze(const SimDev &d, const uint32_t *cnt_src, uint32_t *cnt_dst, uint32_t tl_round, int tl_slot) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    volatile uint32_t *gen = d.gbar + 1;
+    const uint32_t g = (*barrier_generation())++;
+    __threadfence();
+    if (atomicAdd(d.gbar, 1u) == gridDim.x - 1) {
+      __threadfence();
+      tl_mark_last(d, tl_round, tl_slot);
+      *(volatile uint32_t *)cnt_dst = *(volatile const uint32_t *)cnt_src;
+      d.gbar[0] = 0;
+      __threadfence();
+      atomicAdd(d.gbar + 1, 1u);
+    } else {
+      const long long t0 = clock64();
+      uint32_t polls = 0;
+      while (*gen == g) {
+        if (wait_expired(d, t0, 6000000000ll, polls, 2)) break;
+        __nanosleep(20);
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// the same with the cross-GPU handshake of `mail_round` performed by the last CTA to arrive (see grid_barrier_leader)
+__device__ __forceinline__ void grid_barrier_leader_freeze(const SimDev &d, bool fence_sys, uint32_t mail_round, const uint32_t *cnt_src,
+                                                           uint32_t *cnt_dst, int tl_slot) {
+  SWIM_SHARED_1D(uint32_t, s_last, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (fence_sys) __threadfence_system(); else __threadfence();
+    const bool last = atomicAdd(d.gbar, 1u) == gridDim.x - 1;
+    if (last) { __threadfence(); tl_mark_last(d, mail_round, tl_slot); }
+    s_last[0] = last ? 1u : 0u;
+  }
+  __syncthreads();
+  if (s_last[0]) {
+    peer_handshake_cta(d, mail_round);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      (*barrier_generation())++;
+      *(volatile uint32_t *)cnt_dst = *(volatile const uint32_t *)cnt_src;
+      d.gbar[0] = 0;
+      __threadfence();
+      atomicAdd(d.gbar + 1, 1u);
+    }
+  } else if (threadIdx.x == 0) {
+    volatile uint32_t *gen = d.gbar + 1;
+    const uint32_t g = (*barrier_generation())++;
+    const long long t0 = clock64();
+    uint32_t polls = 0;
+    while (*gen == g) {
+      if (wait_expired(d, t0, kPeerWaitCycles + 6000000000ll, polls, 2)) break;
+      __nanosleep(20);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int W>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) round_kernel_x(SimDev d) {
+  SWIM_SHARED_2D(uint4, s_pb, kWarpsPerBlock, 32);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint32_t warp = blockIdx.x * kWarpsPerBlock + wib, nwarps = gridDim.x * kWarpsPerBlock;
+  pdl_launch();
+  pdl_wait();
+  barrier_begin(d);
+  Ctr c; c.clear();
+  PbStage pbs; pbs.s = s_pb[wib];
+  const bool batching = d.qbatch > 1 && d.world == 1 && d.loss_ppm == 0;
+  const bool sharded = d.world > 1 && d.p2p;
+  const uint32_t last_round = d.round + d.nrounds - 1;
+  bool mail = false;       // round - 1 delivered envelopes to nodes of this rank
+  bool have_wl = false;    // the work list of `round` exists (its length frozen in wl_n)
+  bool known_empty = false; // ... and is known to be empty (a batched quiet scan decided the round)
+  bool wb_prev = false;    // the work list of round - 1 had entries (its bitmap slot wants clearing)
+  bool mail_prev = false;  // round - 2 delivered mail (its bitmap slot wants clearing)
+  uint32_t nb = 0;
+  if (batching && warp == 0 && lane == 0) d.qm[0] = 0;
+  for (uint32_t it = 0; it < d.nrounds; ++it) {
+    const uint32_t round = d.round + it;
+    if (!have_wl) {
+      // K1a of `round` over every node on its own (the first round of a launch, and the first busy round behind a batch of
+      // quiet ones): nothing is pending — no mail, no list — so nothing is skipped
+      if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 1)] = 0; d.ncand[ci(round)] = 0; }
+      uint32_t pings = 0;
+      scan_pass<W>(d, round, warp, nwarps, lane, pings, nullptr, pbs.s, nullptr, d.workbits + (size_t)(round % 3u) * d.mbw);
+      c.v[SWIM_CTR_PINGS] += pings;
+      grid_barrier_freeze(d, d.wl_cnt + ci(round), d.wl_n + ci(round), round, -1);
+      have_wl = true;
+      known_empty = false;
+    }
+    tl_mark(d, round, 0);
+    const uint32_t n_work = known_empty ? 0u : *(volatile const uint32_t *)&d.wl_n[ci(round)];
+    const bool last = round == last_round;
+    if (wb_prev) { // the bitmap of the work list of round - 1: read in the last interval, written again in the next one
+      uint32_t *wb = d.workbits + (size_t)((round - 1) % 3u) * d.mbw;
+      for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) wb[x] = 0;
+    }
+    if (mail_prev) { // the mail bitmap of round - 2 likewise (its next writers: the senders of round + 1)
+      uint32_t *mb = d.mailbits + (size_t)((round - 2) % 3u) * d.mbw;
+      for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) mb[x] = 0;
+    }
+    if (batching && n_work == 0 && !mail && !last) {
+      // `round` is quiet — nothing to apply, nothing to run — and so committed. One pass decides rounds round+1 .. round+Q.
+      // (No list is appended to and no mail counted while rounds are quiet: all counters of the three slots are cleared.)
+      const uint32_t Q = d.qbatch < last_round - round ? d.qbatch : last_round - round;
+      if (warp == 0 && lane == 0) {
+        d.qm[(nb + 1) % 3] = 0;
+        d.wl_cnt[ci(round + 1)] = 0; d.wl_cnt[ci(round + 2)] = 0; d.ncand[ci(round + 1)] = 0;
+      }
+      uint32_t p1 = 0;
+      uint32_t busy = quiet_scan<W>(d, round + 1, Q, warp, nwarps, lane, p1);
+      busy = __reduce_or_sync(kFull, busy);
+      if (lane == 0 && busy) atomicOr(&d.qm[nb % 3], busy);
+      tl_mark(d, round, 1);
+      grid_barrier(d, round, 5);
+      const uint32_t mask = *(volatile uint32_t *)&d.qm[nb % 3];
+      ++nb;
+      const uint32_t fb = mask ? (uint32_t)__ffs(mask) - 1u : Q; // rounds round+1 .. round+fb are quiet too
+      tl_mark(d, round, 2);
+      tl_mark(d, round, 7, fb == Q ? Q : fb + 1); // rounds committed by this pass
+      c.v[SWIM_CTR_PINGS] += p1 * fb;
+      // fb == Q: round+Q is decided (quiet) but not yet committed: it is the next current round, with a list known to be
+      // empty. fb < Q: round+fb+1 is busy: it gets the ordinary scan above.
+      if (fb == Q) { it += Q - 1; known_empty = true; }
+      else { it += fb; have_wl = false; known_empty = false; }
+      wb_prev = false;
+      mail_prev = false;
+      continue;
+    }
+    // ---- the interval of `round`
+    if (warp == 0 && lane == 0) { d.wl_cnt[ci(round + 2)] = 0; d.ncand[ci(round + 1)] = 0; }
+    bool did_remote = false;
+    if (mail) { // receivers of round - 1: from the top warp down (the scan below fills the warps from the bottom up)
+      const uint32_t mpar = (round - 1) & 1;
+      const uint32_t w0 = nwarps - 1 - warp;
+      const uint32_t n_cl = d.ncand[ci(round - 1)];
+      const uint2 *cl_in = d.cl + (size_t)mpar * d.n * d.fanout;
+      for (uint32_t item = w0; item < n_cl; item += nwarps) {
+        const uint2 e = cl_in[item];
+        x_node<W>(d, round, e.x, 0u, false, true, true, e.y, lane, pbs, c, !last, did_remote, 0u, false);
+      }
+      if (d.world > 1) {
+        uint32_t seg_end[SWIM_MAX_WORLD + 1];
+        uint32_t n_recv = 0;
+        seg_end[0] = 0;
+        for (uint32_t a = 0; a < d.world; ++a) {
+          if (a != d.rank) n_recv += d.rcnt[mpar * d.world + a];
+          seg_end[1 + a] = n_recv;
+        }
+        for (uint32_t item = w0; item < n_recv; item += nwarps) {
+          uint32_t a = 0;
+          while (item >= seg_end[1 + a]) ++a;
+          const uint32_t ln = d.rlr[((size_t)mpar * d.world + a) * d.rcap + (item - seg_end[a])];
+          x_node<W>(d, round, ln, 0u, false, true, false, 0u, lane, pbs, c, !last, did_remote, 0u, false);
+        }
+      }
+    }
+    if (n_work) { // K1b of `round` (+ a listed node's own mail) (+ its tick decision of round + 1)
+      const uint32_t *wl = wl_of(d, round);
+      uint32_t next_ln = warp < n_work ? *(volatile const uint32_t *)(wl + warp) : 0u;
+      for (uint32_t idx = warp; idx < n_work; idx += nwarps) {
+        const uint32_t ln = next_ln;
+        const bool have_next = idx + nwarps < n_work;
+        if (have_next) next_ln = *(volatile const uint32_t *)(wl + idx + nwarps);
+        x_node<W>(d, round, ln, idx, true, mail, false, 0u, lane, pbs, c, !last, did_remote, next_ln, have_next);
+      }
+    }
+    if (!last) { // K1a of round + 1 for everybody else
+      uint32_t pings = 0;
+      scan_pass<W>(d, round + 1, warp, nwarps, lane, pings, mail ? d.mailbits + (size_t)((round - 1) % 3u) * d.mbw : nullptr, pbs.s,
+                   n_work ? d.workbits + (size_t)(round % 3u) * d.mbw : nullptr, d.workbits + (size_t)((round + 1) % 3u) * d.mbw);
+      c.v[SWIM_CTR_PINGS] += pings;
+    }
+    tl_mark(d, round, 1);
+    // every flag, snapshot and list entry of the round is written (sharded: ... on every rank — the last CTA talks to the peers)
+    if (sharded) grid_barrier_leader_freeze(d, cta_or(did_remote), round, d.wl_cnt + ci(round + 1), d.wl_n + ci(round + 1), 5);
+    else grid_barrier_freeze(d, d.wl_cnt + ci(round + 1), d.wl_n + ci(round + 1), round, 5);
+    tl_mark(d, round, 2);
+    tl_mark(d, round, 4, (unsigned long long)(n_work || mail)); // 1: a busy round (bench.py tells busy from quiet rounds by it)
+    mail_prev = mail;
+    wb_prev = n_work != 0;
+    // was anything delivered here in this round?
+    uint32_t got = *(volatile uint32_t *)&d.ncand[ci(round)];
+    if (sharded)
+      for (uint32_t a = 0; a < d.world; ++a)
+        if (a != d.rank) got |= *(volatile uint32_t *)&d.rcnt[(round & 1) * d.world + a];
+    mail = got != 0;
+    known_empty = false;
+  }
+  // the last round's mail, before the launch ends (no tick decision: the next launch scans everybody)
+  if (mail) recv_pass<W>(d, last_round, warp, nwarps, lane, pbs, c, 0);
+  // bitmaps still set: the mail of the last two rounds and the work lists (this rank's own affair: all three slots). Never
+  // the mail slot of last + 1: a peer that is already in its next launch may be marking receivers there.
+  for (uint32_t x = warp * 32 + lane; x < d.mbw; x += nwarps * 32) {
+    d.mailbits[(size_t)(last_round % 3u) * d.mbw + x] = 0;
+    d.mailbits[(size_t)((last_round + 2u) % 3u) * d.mbw + x] = 0; // (= last - 1)
+    d.workbits[x] = 0; d.workbits[d.mbw + x] = 0; d.workbits[2 * (size_t)d.mbw + x] = 0;
   }
   c.flush(d.ctr, lane);
 }

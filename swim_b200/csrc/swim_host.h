@@ -45,11 +45,12 @@ struct swim_sim {
   void *d_sargs = nullptr; // scalar-call argument block (swim_scalar.cu)
   std::vector<swim_event_t> events; // pending, sorted by round (stable)
   std::string last_error;
-  int grids[5] = {0, 0, 0, 0, 0}; // one-wave grid sizes of the per-round kernels (filled on first use)
+  int grids[6] = {0, 0, 0, 0, 0, 0}; // one-wave grid sizes of the per-round kernels (filled on first use)
   uint64_t launches = 0;
   bool profile = false;
   // launch-path switches, read from the environment once per handle (swim_sim_create), not once per call
   bool opt_split = false, opt_round_kernel = true, opt_one_round = false;
+  int opt_xmode = -1;                // round_kernel_x (one grid barrier per round): -1 auto (long single-shard launches), 1 always, 0 never
   uint32_t opt_quiet_batch = 4;
   std::vector<cudaEvent_t> prof_events; // pool, reused
   std::vector<std::pair<int, int>> prof_marks; // (phase, index of start event); stop = start + 1

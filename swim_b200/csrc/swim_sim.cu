@@ -171,6 +171,7 @@ extern "C" int swim_sim_create(const swim_config_t *cfg, swim_sim_t **out) {
   if (const char *rk = getenv("SWIM_ROUND_KERNEL")) sim->opt_round_kernel = atoi(rk) != 0;
   sim->opt_one_round = getenv("SWIM_ONE_ROUND_PER_LAUNCH") != nullptr;
   // rounds decided per batched quiet scan of round_kernel (1..8; 0 or 1 turns batching off)
+  if (const char *xm = getenv("SWIM_XMODE")) sim->opt_xmode = atoi(xm) != 0 ? 1 : 0;
   if (const char *qb = getenv("SWIM_QUIET_BATCH")) sim->opt_quiet_batch = (uint32_t)std::min(8l, std::max(0l, strtol(qb, nullptr, 10)));
   if (cfg->device >= 0) {
     rc = [&]() { CUDA_TRY(sim, cudaSetDevice(cfg->device)); return SWIM_OK; }();
@@ -553,6 +554,7 @@ static void prepare_kernels(swim_sim *sim) {
   sim->grids[1] = wave_grid(sim, tick_work_kernel<W>, (size_t)d.n);
   sim->grids[2] = wave_grid(sim, recv_kernel<W>, (size_t)d.n);
   sim->grids[4] = wave_grid(sim, round_kernel<W>, (size_t)d.n);
+  sim->grids[5] = wave_grid(sim, round_kernel_x<W>, (size_t)d.n);
 #ifndef SWIM_EMU
   cudaFuncAttributes a;
   cudaFuncGetAttributes(&a, event_kernel<W>);
@@ -672,10 +674,24 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
       uint32_t nr = rounds - r;
       if (ev_pos < n_ev) nr = std::min<uint32_t>(nr, ev_round[ev_pos] - d.round);
       if (multi_round_off || d.churn_ppm) nr = 1; // churn: events every round
+      nr = std::min<uint32_t>(nr, 65536u); // (per-launch event counts are carried in 32 bits up to the final flush)
       d.nrounds = nr;
       d.qbatch = sim->opt_quiet_batch;
       d.fused = 1;
-      CUDA_TRY(sim, launch_pdl(round_kernel<W>, kgrid, sim->stream, d));
+      // round_kernel_x (one grid barrier per round) pays a scan + barrier of its own at the start of every launch and gains
+      // 2-3 us per lightly loaded busy round: measured on C3 (profiles/r02_ab_j1_*), it wins on long event-free stretches
+      // (444 rounds: 10.5 vs 11.9 us per round) and loses on short launches (16 burst rounds: equal; one round per call, as
+      // in the end-to-end loop: 4 us slower). Default ("auto"): launches of at least kXModeMinRounds rounds on a single
+      // shard; SWIM_XMODE=1 / 0 forces it on (sharded runs included) / off.
+      constexpr uint32_t kXModeMinRounds = 32;
+      const bool use_x = sim->opt_xmode == 1 || (sim->opt_xmode < 0 && d.world == 1 && nr >= kXModeMinRounds);
+      if (use_x) {
+        d.xmode = 1;
+        CUDA_TRY(sim, launch_pdl(round_kernel_x<W>, sim->grids[5], sim->stream, d));
+        d.xmode = 0;
+      } else {
+        CUDA_TRY(sim, launch_pdl(round_kernel<W>, kgrid, sim->stream, d));
+      }
       d.fused = 0;
       ++sim->launches;
       sim->round += nr - 1;

@@ -468,3 +468,48 @@ def test_step_observe_equals_step_plus_observe():
         orc.step(chunk)
         assert c.tolist() == orc.counters().tolist() and mm == orc.mismatches(), sim.round
     assert_same_state(sim, orc, "after step_observe calls")
+
+
+# ---------------------------------------------------------------- round_kernel_x: one grid barrier per round
+def _xmode_case(n, topo, deg, loss, chunks, P=1, flags=0, smax=0, seed=77):
+    cfg = default_config(n_nodes=n, k_indirect=3, fanout=4, pb_cap=8, suspicion_rounds=5, retransmit=8, seed=seed + n,
+                         loss_ppm=loss, flags=flags)
+    cfg.probes_per_round = P
+    if smax:
+        cfg.suspicion_max = smax
+    nbr = generate_topology(topo, n, 32, deg, seed=5)
+    sim, orc = make_pair(cfg, nbr)
+    rng = np.random.default_rng(n)
+    ev = crash_events(3, np.sort(rng.choice(n, size=max(2, n // 50), replace=False)).astype(np.uint32))
+    sim.inject(ev)
+    orc.inject(ev)
+    for c in chunks:
+        sim.step(c)
+        orc.step(c)
+        assert_same_state(sim, orc, f"after {c} more rounds")
+    sim.close()
+
+
+@pytest.mark.parametrize("xmode", ["1", "0"])
+@pytest.mark.parametrize("case", [
+    dict(n=1200, topo="ring", deg=24, loss=0, chunks=[2, 45, 1, 70]),           # dissemination: mail every round
+    dict(n=1500, topo="random", deg=24, loss=0, chunks=[2, 150]),               # sparse knowledge, batched quiet scans behind it
+    dict(n=900, topo="ring", deg=16, loss=30000, chunks=[2, 50]),               # loss: every node depends on its draws
+    dict(n=900, topo="ring", deg=20, loss=0, chunks=[2, 50], P=3),
+    dict(n=900, topo="ring", deg=20, loss=0, chunks=[2, 50], flags=A.F_ROUND_ROBIN | A.F_STRICT_OVERRIDE, smax=12),
+])
+def test_one_barrier_round_kernel(case, xmode, monkeypatch):
+    """round_kernel_x (SWIM_XMODE=1: every fused launch; the default takes it for launches of >= 32 rounds on one shard)
+    against the oracle on long event-free stretches — mail applied behind the barrier by the warp that owns the node,
+    tentative tick decisions corrected, work lists extended while they are walked — and the same cases on the two-phase
+    round_kernel (SWIM_XMODE=0)."""
+    monkeypatch.setenv("SWIM_XMODE", xmode)
+    _xmode_case(**case)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_one_barrier_round_kernel_sharded(world, monkeypatch):
+    monkeypatch.setenv("SWIM_XMODE", "1")
+    monkeypatch.setenv("SWIM_ROUND_KERNEL", "1")
+    run_sharded(world, n=403, chunks=[1, 1, 3, 40], loss=0, deg=24)
+    run_sharded(world, n=300, chunks=[2, 30], loss=20000, deg=20)

@@ -277,3 +277,28 @@ def test_batched_quiet_scans(qbatch, monkeypatch):
         sim.step(chunk)
         orc.step(chunk)
         assert_same_state(sim, orc, f"qbatch {qbatch} after {sim.round} rounds")
+
+
+@pytest.mark.parametrize("xmode", ["1", "0"])
+def test_one_barrier_round_kernel_equals_oracle(xmode, monkeypatch):
+    """round_kernel_x (one grid barrier per round; the default for launches of >= 32 rounds on one shard) and the two-phase
+    round_kernel, each forced for every launch, against the oracle: ring-lattice views (mail every round) and sparse random
+    views through long event-free stretches, every array compared at the chunk boundaries."""
+    import numpy as np
+    from helpers import assert_same_state, crash_events, default_config, generate_topology, make_pair
+    monkeypatch.setenv("SWIM_XMODE", xmode)
+    for n, topo, deg, loss, chunks in [(20000, "ring", 24, 0, [2, 6, 60]), (50000, "random", 32, 0, [2, 1, 130]),
+                                       (6000, "ring", 16, 30000, [2, 40])]:
+        cfg = default_config(n_nodes=n, k_indirect=3, fanout=4, pb_cap=8, suspicion_rounds=5, retransmit=8, seed=4242 + n,
+                             loss_ppm=loss, device=0)
+        nbr = generate_topology(topo, n, 32, deg, seed=5)
+        sim, orc = make_pair(cfg, nbr)
+        rng = np.random.default_rng(n)
+        ev = crash_events(3, np.sort(rng.choice(n, size=n // 50, replace=False)).astype(np.uint32))
+        sim.inject(ev)
+        orc.inject(ev)
+        for c in chunks:
+            sim.step(c)
+            orc.step(c)
+            assert_same_state(sim, orc, f"xmode {xmode} n {n} {topo} after {c} more rounds")
+        sim.close()
