@@ -329,7 +329,7 @@ int swim_sim_step_observe(swim_sim_t *sim, uint32_t rounds, uint64_t *counters, 
 int swim_sim_mismatches(swim_sim_t *sim, uint64_t *count);
 
 /* Device time in ms of the last swim_sim_step / step_async+sync on this handle, measured
- * with CUDA events on the handle's stream. */
+ * with CUDA events on the handle's stream. (swim_sim_step_observe records no events: SWIM_ESTATE after it.) */
 int swim_sim_last_step_ms(const swim_sim_t *sim, float *ms);
 
 /* Number of kernels this handle has launched since create (bench.py's `gpu_launches`). */

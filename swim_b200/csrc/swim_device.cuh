@@ -1415,6 +1415,9 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
   pb_load(pbs, d, ln, lane);
   uint32_t self_inc = d.self_inc[ln];
   const uint32_t self_inc0 = self_inc;
+  uint32_t td[W]; // crashed-member bits (events only, not touched by mail): needed by the tick decision at the very end —
+#pragma unroll    // fetched now, with everything else, so that it is no dependent round trip there
+  for (int w = 0; w < W; ++w) td[w] = tick_round ? d.meta[(size_t)ln * W + w].z : 0u;
   // A recipient slot names one sender of its receiver; that sender's snapshot is fetched together with the receiver's
   // row, ahead of the in-edge flags that will ask for it — for the usual envelope (one sender per receiver per round) the
   // pass is one dependent round trip shorter. The flags still decide what is applied and in which order.
@@ -1431,12 +1434,11 @@ __device__ __forceinline__ void recv_one(const SimDev &d, uint32_t round, uint32
   pb_store(pbs, d, ln, lane);
   if (lane == 0 && self_inc != self_inc0) d.self_inc[ln] = self_inc;
   if (tick_round) {
-    uint32_t am[W], td[W], sus = 0;
+    uint32_t am[W], sus = 0;
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       am[w] = __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_ALIVE);
       sus |= __ballot_sync(kFull, (row.st[w] & 3u) == SWIM_SUSPECT);
-      td[w] = d.meta[(size_t)ln * W + w].z; // crashed-member bits: events only, not touched by mail
     }
     const uint4 x = target_block<W>(d, tick_round, self >> 2);
     uint4 y = make_uint4(0, 0, 0, 0);
@@ -1461,10 +1463,16 @@ __device__ __forceinline__ void recv_pass(const SimDev &d, uint32_t round, uint3
   // items go to the warps from the top down: in the fused kernel this pass shares a phase with the scan, whose node ranges
   // fill the warps from the bottom up (at C3 the last 640 of 4736 warps have no nodes to scan)
   const uint32_t w0 = nwarps - 1 - warp;
-  const uint32_t n_cl = d.ncand[ci(round)];
   const uint2 *cl_in = d.cl + (size_t)par * d.n * d.fanout;
+  // this warp's first entry travels with the list's length (one memory round trip instead of two); only looked at if w0 < n_cl
+  uint2 e_first = make_uint2(0u, 0u);
+  if ((size_t)w0 < (size_t)d.n * d.fanout) {
+    e_first.x = *(volatile const uint32_t *)&cl_in[w0].x;
+    e_first.y = *(volatile const uint32_t *)&cl_in[w0].y;
+  }
+  const uint32_t n_cl = d.ncand[ci(round)];
   for (uint32_t item = w0; item < n_cl; item += nwarps) {
-    const uint2 e = cl_in[item];
+    const uint2 e = item == w0 ? e_first : cl_in[item];
     recv_one<W>(d, round, e.x, true, e.y, lane, pbs, c, tick_round);
   }
   if (d.world > 1) {

@@ -726,7 +726,10 @@ static int run_rounds(swim_sim *sim, uint32_t rounds) {
   return SWIM_OK;
 }
 
-extern "C" int swim_sim_step_async(swim_sim_t *sim, uint32_t rounds) {
+// timed: bracket the call's kernels with the two events swim_sim_last_step_ms reads. swim_sim_step_observe — the per-round
+// call of a study loop — goes without them: two stream operations and two API calls less per round, and nothing between
+// the round kernel and the observe kernel that is chained behind it.
+static int step_async_impl(swim_sim_t *sim, uint32_t rounds, bool timed) {
   if (!sim) return SWIM_EINVAL;
   if (!sim->view_set) { set_error(sim, "swim_sim_step: no view installed (swim_sim_set_view / swim_set_members)"); return SWIM_ESTATE; }
   cudaSetDevice(sim->device);
@@ -737,7 +740,7 @@ extern "C" int swim_sim_step_async(swim_sim_t *sim, uint32_t rounds) {
   if (sim->dev.world > 1 && !sim->connected) { set_error(sim, "swim_sim_step: world > 1 needs swim_sim_ipc_connect or swim_sim_connect"); return SWIM_ESTATE; }
   if (sim->failed) { set_error(sim, "swim_sim_step: an earlier step failed part-way; the handle's device state is undefined"); return SWIM_ESTATE; }
   swim::refresh_peer_tables(sim);
-  CUDA_TRY(sim, cudaEventRecord(sim->ev_start, sim->stream));
+  if (timed) CUDA_TRY(sim, cudaEventRecord(sim->ev_start, sim->stream));
   int rc;
   switch (sim->dev.cap / 32) {
     case 1: rc = run_rounds<1>(sim, rounds); break;
@@ -746,10 +749,12 @@ extern "C" int swim_sim_step_async(swim_sim_t *sim, uint32_t rounds) {
     default: rc = run_rounds<8>(sim, rounds); break;
   }
   if (rc) { sim->failed = true; return rc; } // rounds and events were consumed: no retry on this handle
-  CUDA_TRY(sim, cudaEventRecord(sim->ev_stop, sim->stream));
-  sim->timed = true;
+  if (timed) CUDA_TRY(sim, cudaEventRecord(sim->ev_stop, sim->stream));
+  sim->timed = timed;
   return SWIM_OK;
 }
+
+extern "C" int swim_sim_step_async(swim_sim_t *sim, uint32_t rounds) { return step_async_impl(sim, rounds, true); }
 
 extern "C" int swim_sim_sync(swim_sim_t *sim) {
   if (!sim) return SWIM_EINVAL;
@@ -1198,7 +1203,7 @@ extern "C" int swim_sim_observe(swim_sim_t *sim, uint64_t *counters, size_t n_co
 // synchronising the stream. No memset, no copy-engine operation, no stream synchronisation on the path.
 extern "C" int swim_sim_step_observe(swim_sim_t *sim, uint32_t rounds, uint64_t *counters, size_t n_counters, uint64_t *mismatches) {
   if (!sim) return SWIM_EINVAL;
-  int rc = swim_sim_step_async(sim, rounds);
+  int rc = step_async_impl(sim, rounds, false);
   if (rc) return rc;
   const SimDev &d = sim->dev;
   if (sim->tdead_dirty) { // (cannot be: the step above rebuilt the per-node records)

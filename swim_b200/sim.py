@@ -217,10 +217,16 @@ class Simulator:
 
     def step_observe(self, rounds=1):
         """`rounds` rounds, then (counters, mismatches) — one call, no stream synchronisation (swim_sim_step_observe)."""
-        out = np.zeros(A.CTR_COUNT, dtype=np.uint64)
-        mm = C.c_uint64()
-        check(lib().swim_sim_step_observe(self._h, rounds, out.ctypes.data, A.CTR_COUNT, C.byref(mm)), "swim_sim_step_observe", self._h)
-        return out, mm.value
+        so = getattr(self, "_so", None)
+        if so is None:  # the per-round call of a study loop: its argument objects are made once
+            buf = (C.c_uint64 * A.CTR_COUNT)()
+            mm = C.c_uint64()
+            so = self._so = (buf, mm, C.byref(mm), lib().swim_sim_step_observe)
+        buf, mm, mm_ref, fn = so
+        rc = fn(self._h, rounds, buf, A.CTR_COUNT, mm_ref)
+        if rc:
+            check(rc, "swim_sim_step_observe", self._h)
+        return np.frombuffer(buf, dtype=np.uint64).copy(), mm.value
 
     def export_round(self):
         """The last round's piggyback envelopes as real datagrams in the reference's wire format:
