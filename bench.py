@@ -372,8 +372,15 @@ def run_cuda(args):
     # W warm-up rounds: those are rounds 1..W of the workload and precede every window.)
     barrier()
     t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < args.spinup:
+    while args.spinup > 0:
         sim.step(256)
+        go = time.perf_counter() - t_spin < args.spinup
+        if world > 1:  # every rank must issue the same steps (a shard's kernel waits for its peers): one decision for all
+            t = torch.tensor([int(go)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            go = bool(t.item())
+        if not go:
+            break
     windows = []
     ctr_delta, launches = None, 0
     for w in range(args.windows):
