@@ -765,6 +765,7 @@ extern "C" int swim_sim_sync(swim_sim_t *sim) {
     set_error(sim, err == 1 ? "a cross-GPU wait timed out (a peer rank stopped stepping)"
                    : err == 3 ? "the device-side churn event list overflowed (churn_ppm too high for its capacity)"
                               : "an in-kernel grid barrier timed out");
+    sim->failed = true; // the rounds of that launch ran without their barriers: the device state is undefined
     return SWIM_ESTATE;
   }
   return SWIM_OK;

@@ -32,8 +32,20 @@ for r in rows[hi + 1:]:
     loc = off2line.get(a - base, (None, ''))[0]
     agg[loc][0] += ex; agg[loc][1] += st; tot_ex += ex; tot_st += st
 print('total warp-instructions', tot_ex, 'stall samples', tot_st)
-regions = [('scan_pass', 679, 793), ('quiet_scan', 816, 880), ('work_pass', 892, 1152), ('recv', 1223, 1345), ('barrier', 1369, 1461), ('round_kernel', 1463, 1566),
-           ('philox', 240, 256), ('picks', 257, 310), ('pb', 370, 414), ('row', 417, 552), ('ctr', 554, 575), ('probe/needs', 579, 670), ('misc<240', 1, 239)]
+# regions = the functions of swim_device.cuh, found by their definitions (a line at column 0 that opens one)
+import os
+srcp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'swim_b200', 'csrc', 'swim_device.cuh')
+src_lines = open(srcp).read().splitlines()
+starts = []
+for n, l in enumerate(src_lines, 1):
+    if re.match(r'^(SWIM_HD|__device__|static __global__|__global__|template <)', l):
+        txt = l if '(' in l and not l.startswith('template') else (l + ' ' + (src_lines[n] if n < len(src_lines) else ''))
+        txt = re.sub(r'__launch_bounds__\([^)]*\)', '', txt)
+        m = re.search(r'([A-Za-z_]\w*)\s*\(', re.sub(r'template <[^>]*>', '', txt))
+        if m and m.group(1) not in ('defined',):
+            if not starts or starts[-1][1] != m.group(1):
+                starts.append((n, m.group(1)))
+regions = [(name, a, (starts[k + 1][0] - 1 if k + 1 < len(starts) else len(src_lines))) for k, (a, name) in enumerate(starts)]
 reg = collections.defaultdict(lambda: [0, 0])
 for loc, (ex, st) in agg.items():
     name = 'other'
