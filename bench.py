@@ -359,11 +359,16 @@ def run_cuda(args):
     sim.save()
 
     def restart(flags=0, inject=True):
+        # swim_sim_load moves the round counter back and re-arms the cross-GPU handshake words of THIS rank: it is a collective
+        # — no rank may step before every rank has loaded (a peer's first publication would be wiped out by a late load and
+        # its owner would wait for it until the watchdog fires), so: barrier, load, barrier.
+        barrier()
         sim.load()
         if sim.cfg.flags != flags:
             sim.set_params(flags=flags)
         if inject:
             sim.inject(events)
+        barrier()
 
     restart()
     clocks = ClockSampler(local) if rank == 0 else None  # runs until the end of the e2e region
@@ -384,9 +389,7 @@ def run_cuda(args):
     windows = []
     ctr_delta, launches = None, 0
     for w in range(args.windows):
-        barrier()
         restart()
-        barrier()
         sim.step(args.warmup)
         c0, l0 = sim.counters(), sim.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -418,9 +421,7 @@ def run_cuda(args):
     # ------------------------------------------------ phase timeline of the same rounds (fused kernel, in-kernel timer)
     timeline = None
     if True:  # (sharded runs: stamps exist only on the fused-kernel path, SWIM_ROUND_KERNEL; each rank reports its own CTA 0)
-        barrier()
         restart()
-        barrier()
         sim.step(args.warmup)
         sim.set_timeline(args.steps)
         sim.step(args.steps)
@@ -430,9 +431,7 @@ def run_cuda(args):
 
     log("timeline done")
     # ------------------------------------------------ per-kernel timing of the same rounds (split launches)
-    barrier()
     restart()
-    barrier()
     sim.step(args.warmup)
     sim.set_profile(True)
     sim.step(args.steps)
@@ -446,9 +445,7 @@ def run_cuda(args):
     parity = None
     if not args.no_parity:
         rounds_chk = min(args.warmup + args.steps, 40)
-        barrier()
         restart()
-        barrier()
         sim.step(rounds_chk)
         dg = sdist.global_digest(sim.digest())
         gc = sdist.global_sum(sim.counters())
@@ -518,18 +515,18 @@ def run_cuda(args):
 
         e2e_windows = []
         use_step_observe, e2e_notes = [True], []
+        restart(inject=False)
         try:  # one probe round outside every timed window: the mapped-memory read-back must work on this box
-            restart(inject=False)
             one_round(1)
         except Exception:  # noqa: BLE001
+            if world > 1:  # (a fallback taken by one rank alone would desynchronise the ranks' collectives: fail loudly)
+                raise
             sim.close()
             sim = fresh(inject=False)
             sim.set_stream(stream.cuda_stream)
             sim.save()
         for w in range(args.windows):
-            barrier()
             restart(inject=False)
-            barrier()
             for r in range(1, args.warmup + 1):
                 one_round(r)
             h2d = d2h = 0
@@ -560,9 +557,7 @@ def run_cuda(args):
     conv = None
     if rank == 0 or world > 1:
         def rounds_to_convergence(flags):
-            barrier()
             restart(flags=flags)
-            barrier()
             sim.step(CRASH_ROUND)
             r = CRASH_ROUND
             mm = None
