@@ -51,6 +51,11 @@ if _local_world > 1:
 else:
     os.environ.setdefault("OMP_NUM_THREADS", str(usable_cpus()))
 
+# (two seams for tests/test_bench_dryrun.py, which runs this file's CUDA arm on the emulator, several ranks as threads of one
+# process: where the launcher's environment is read, and where the tensors of the host-side reductions live)
+_ENV = os.environ
+_TENSOR_DEVICE = "cuda"
+
 N_PER_GPU = 1 << 20
 CRASH_ROUND = 10
 CRASH_PPM = 1000  # 0.1 %
@@ -302,9 +307,9 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank = int(_ENV.get("RANK", "0"))
+    world = int(_ENV.get("WORLD_SIZE", "1"))
+    local = int(_ENV.get("LOCAL_RANK", "0"))
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
@@ -381,7 +386,7 @@ def run_cuda(args):
         sim.step(256)
         go = time.perf_counter() - t_spin < args.spinup
         if world > 1:  # every rank must issue the same steps (a shard's kernel waits for its peers): one decision for all
-            t = torch.tensor([int(go)], device="cuda")
+            t = torch.tensor([int(go)], device=_TENSOR_DEVICE)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             go = bool(t.item())
         if not go:
@@ -402,13 +407,13 @@ def run_cuda(args):
         sim.sync()
         c1, l1 = sim.counters(), sim.launch_count()
         if world > 1:
-            t = torch.tensor([ms_w], device="cuda")
+            t = torch.tensor([ms_w], device=_TENSOR_DEVICE)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_w = float(t.item())
         windows.append(ms_w)
         if ctr_delta is None:
             if world > 1:
-                cd = torch.tensor((c1 - c0).astype(np.int64), device="cuda")
+                cd = torch.tensor((c1 - c0).astype(np.int64), device=_TENSOR_DEVICE)
                 dist.all_reduce(cd)
                 ctr_delta = cd.cpu().numpy().astype(np.uint64)
             else:
@@ -538,7 +543,7 @@ def run_cuda(args):
             barrier()
             dt = time.perf_counter() - t0
             if world > 1:
-                t = torch.tensor([dt], device="cuda")
+                t = torch.tensor([dt], device=_TENSOR_DEVICE)
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
             e2e_windows.append(dt)
@@ -567,7 +572,7 @@ def run_cuda(args):
                 r += stride
                 mm = sim.mismatches()
                 if world > 1:
-                    t = torch.tensor([mm], device="cuda", dtype=torch.int64)
+                    t = torch.tensor([mm], device=_TENSOR_DEVICE, dtype=torch.int64)
                     dist.all_reduce(t)
                     mm = int(t.item())
                 if mm == 0:

@@ -77,3 +77,105 @@ def test_cuda_arm_runs_every_leg_on_the_emulator(emulated_bench, steps, xmode, m
     g = line["state_machine_workload"]
     assert g["parity_check"] == "ok" and g["value"] > 0
     assert line["config"]["n_nodes"] == 8192 and "workload" in line["config"]
+
+
+# ---------------------------------------------------------------- the sharded flow: ranks as threads of one process
+class _ThreadDist:
+    """The few torch.distributed calls bench.py and swim_b200/dist.py make, for `world` ranks that are threads of this
+    process (rank = a thread-local): every collective is two passes through one threading.Barrier."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self.bar = threading.Barrier(world, timeout=120)
+        self.tl = threading.local()
+        self.slots = [None] * world
+
+    def _exchange(self, value):
+        self.slots[self.tl.rank] = value
+        self.bar.wait()
+        got = list(self.slots)
+        self.bar.wait()  # everybody has read before the slots are written again
+        return got
+
+    def init_process_group(self, *_a, **_k): pass
+    def destroy_process_group(self, *_a, **_k): pass
+    def is_initialized(self): return True
+    def get_world_size(self, *_a): return self.world
+    def get_rank(self, *_a): return self.tl.rank
+    def get_backend(self, *_a): return "gloo"
+    def barrier(self, *_a, **_k): self.bar.wait()
+
+    def all_reduce(self, t, op=None):
+        import torch
+        vals = torch.stack([v for v in self._exchange(t.clone())])
+        is_max = op is not None and "MAX" in str(op).upper()
+        t.copy_(vals.max(dim=0).values if is_max else vals.sum(dim=0))
+
+    def all_gather_object(self, out, obj):
+        out[:] = self._exchange(obj)
+
+    def broadcast_object_list(self, lst, src=0):
+        got = self._exchange(list(lst))
+        lst[:] = got[src]
+
+
+@pytest.mark.parametrize("world,steps", [(2, 20), (3, 12)])
+def test_sharded_cuda_arm_on_the_emulator(emulated_bench, world, steps, monkeypatch):
+    """bench.py --gpus N with the ranks as threads (each with its own handle on the emulated device, connected through raw
+    peer pointers exactly as ranks of one process are on hardware): the collective structure of every leg — load as a
+    collective, the spin-up that ends on one decision for all ranks, streams drained before barriers, the end-to-end loop
+    one round per call with in-kernel handshakes, parameter change for the round-robin convergence leg. A rank that steps
+    out of line dead-locks here (the barrier times out after 120 s) instead of on the driver's 8-GPU box."""
+    import threading
+    import torch
+    bench = emulated_bench
+    fake = _ThreadDist(world)
+    for name in ("init_process_group", "destroy_process_group", "is_initialized", "get_world_size", "get_rank", "get_backend",
+                 "barrier", "all_reduce", "all_gather_object", "broadcast_object_list"):
+        monkeypatch.setattr(torch.distributed, name, getattr(fake, name))
+    monkeypatch.setattr(bench, "_TENSOR_DEVICE", "cpu")
+    monkeypatch.setenv("SWIM_ROUND_KERNEL", "1")
+
+    class _Env:
+        def get(self, key, default=None):
+            r = fake.tl.rank
+            return {"RANK": str(r), "LOCAL_RANK": str(r), "WORLD_SIZE": str(world), "LOCAL_WORLD_SIZE": str(world)}.get(key, os.environ.get(key, default))
+
+    monkeypatch.setattr(bench, "_ENV", _Env())
+    # ranks never arrive together on a real box: every rank is late by its own amount at the calls that move the round
+    # counter (the race bench.py once lost: a late swim_sim_load wiping out a peer's first publication)
+    from swim_b200.sim import Simulator
+    real_load = Simulator.load
+
+    def late_load(self):
+        time.sleep(0.03 * fake.tl.rank)
+        real_load(self)
+
+    monkeypatch.setattr(Simulator, "load", late_load)
+    lines, errs = [None] * world, []
+
+    def rank_main(r):
+        fake.tl.rank = r
+        args = argparse.Namespace(gpus=world, steps=steps, warmup=5, impl="cuda", nodes_per_gpu=2048, converge_limit=120, no_cpu=True,
+                                  no_parity=False, no_ring=True, windows=2, spinup=0.05, exchange=None)
+        try:
+            lines[r] = bench.run_cuda(args)
+        except BaseException as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+            fake.bar.abort()
+
+    ts = [threading.Thread(target=rank_main, args=(r,), daemon=True) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=600)
+    assert not errs, errs
+    assert not any(t.is_alive() for t in ts), "a rank is stuck"
+    line = lines[0]
+    assert all(ln is None for ln in lines[1:])  # rank 0 alone reports
+    json.dumps(line)
+    assert line["n_gpus"] == world and line["config"]["n_nodes"] == 2048 * world and line["config"]["exchange"] == "p2p"
+    assert line["parity_check"] == "ok", line["parity"]
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["e2e"]["api"] == "swim_sim_step_observe"
+    assert line["convergence"] is not None and line["state_machine_workload"] is None and line["cpu_baseline"] is None
