@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round 2, last call (gpurun --gpus 2): the driver's bench command at N=2 on the final bench.py (one handle for every leg,
-# streams drained before the NCCL barriers, spin-up ended by one decision for all ranks)
+# Round 2, last call (gpurun --gpus 2): the driver's bench command at N=2. It stopped behind the parity leg — the end-to-end
+# probe raced an unsynchronised swim_sim_load against a peer's first publication; bench.py fixed afterwards
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 170 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29721 \
