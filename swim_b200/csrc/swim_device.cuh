@@ -20,8 +20,10 @@
 //     slot; a receiver is claimed once (per-receiver stamp), walks its flags in ascending sender
 //     order and pulls the sender's snapshot — from local HBM or, across shards, from the peer GPU's
 //     HBM over NVLink.
-//   * default launch: round_kernel = K1a | grid barrier | K1b | grid barrier | K2 in one resident wave;
-//     the same passes exist as separate kernels for profiling and the staged NCCL exchange.
+//   * default launch: one resident wave per event-free stretch of rounds. round_kernel: per round (receive of the round
+//     before || K1a) | grid barrier | K1b | grid barrier; round_kernel_x (long single-shard stretches): per round ONE
+//     interval (mail of the round before + K1b + K1a of the next round) and one grid barrier. The same passes exist as
+//     separate kernels for profiling and the staged NCCL exchange.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
