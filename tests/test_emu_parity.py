@@ -513,3 +513,36 @@ def test_one_barrier_round_kernel_sharded(world, monkeypatch):
     monkeypatch.setenv("SWIM_ROUND_KERNEL", "1")
     run_sharded(world, n=403, chunks=[1, 1, 3, 40], loss=0, deg=24)
     run_sharded(world, n=300, chunks=[2, 30], loss=20000, deg=20)
+
+
+# ---------------------------------------------------------------- edge shapes (empty, ragged, minimal, everybody down)
+def test_edge_shapes():
+    """A single node with an empty view; two nodes of which one crashes; every process down; ragged rows (0..6 members) with
+    the smallest parameters the config allows (k = 0, fan-out 1, one-record buffers, S = T = 1) — single-round and
+    multi-round launches, every array against the oracle."""
+    no = 0xFFFFFFFF
+
+    def run(cfg, nbr, ev, chunks):
+        sim, orc = make_pair(cfg, nbr)
+        if ev is not None:
+            sim.inject(ev)
+            orc.inject(ev)
+        for c in chunks:
+            sim.step(c)
+            orc.step(c)
+            assert_same_state(sim, orc, f"after {c} more rounds")
+        sim.close()
+
+    run(default_config(n_nodes=1, seed=5), np.full((1, 32), no, dtype=np.uint32), None, [1, 40])
+    nbr = np.full((2, 32), no, dtype=np.uint32)
+    nbr[0, 0], nbr[1, 0] = 1, 0
+    run(default_config(n_nodes=2, seed=9), nbr, crash_events(3, [1]), [1, 1, 1, 1, 40, 40])
+    n = 300
+    run(default_config(n_nodes=n, seed=11), generate_topology("random", n, 32, 10, seed=2), crash_events(2, list(range(n))), [1, 1, 50])
+    rng = np.random.default_rng(3)
+    nbr = np.full((n, 32), no, dtype=np.uint32)
+    for i in range(n):
+        m = np.sort(rng.choice([x for x in range(n) if x != i], size=i % 7, replace=False))
+        nbr[i, :len(m)] = m
+    run(default_config(n_nodes=n, seed=12, k_indirect=0, fanout=1, pb_cap=1, suspicion_rounds=1, retransmit=1), nbr,
+        crash_events(2, list(range(0, n, 5))), [1, 1, 1, 60])
